@@ -1,0 +1,294 @@
+"""Parity of the CUDA hot path (through the C-ABI) against the golden fixtures produced by the reference and against the
+CPU oracle on the same inputs.  Every test runs twice: `emu` (kernel-logic emulator, CPU, `-m "not gpu"`) and `gpu`
+(the real sm_100a build on the B200, `-m gpu`).
+
+Tolerances (stated per the north star):
+  * pileups, read counts, count tensors                     bit-exact (integers)
+  * bias track (DWM / PWM score)                            |d| <= 1e-9 * max(1, |ref|)   (fp64; only exp2/log2 and sum order differ)
+  * footprint / rolling scores                              rtol 1e-5 (footprint: fp64 prefix differences vs sequential fp32 sums);
+                                                            rolling sums/means reproduce the fp32 accumulator exactly
+  * expected / corrected, PWM mode                          bit-exact against the reference (identical bias input, exact-order LM)
+  * expected / corrected, DWM mode                          rtol 1e-5 + atol 2e-6 on >= 99.9 % of positions, atol 2e-5 everywhere:
+        the window fits differentiate by forward differences (h ~ 1.5e-8), which amplifies the ~1e-13 difference of the
+        bias input (CUDA vs glibc exp2/log2) to ~1e-8 in the fitted parameters -- the reference shows the same scatter
+        against itself under such a perturbation (tests/test_lm_exact.py::test_reference_sensitivity)."""
+import numpy as np
+import pytest
+
+from oracle import restate
+from tobias_b200 import lib
+
+TRACKS = ("uncorrected", "bias", "expected", "corrected")
+
+
+def _cols(a):
+    a = np.asarray(a)
+    return a[:, 0], a[:, 1], a[:, 2]
+
+
+def test_genome_roundtrip(loaded_ctx, golden):
+    for c, seq in enumerate(golden.genome):
+        assert np.array_equal(loaded_ctx.genome_fetch(c, 0, len(seq)), restate.encode(seq))
+    assert np.array_equal(loaded_ctx.genome_fetch(0, 777, 1001), restate.encode(golden.genome[0][777:1778]))
+
+
+def test_count_reads_bit_exact(loaded_ctx, golden):
+    g = golden.atac
+    assert loaded_ctx.count_reads(*_cols(g["nonpeak"])) == int(g["count_nonpeak"])
+    assert loaded_ctx.count_reads(*_cols(g["peakreg"])) == int(g["count_peak"])
+
+
+def test_pileup_bit_exact(loaded_ctx, golden):
+    c, s, e = _cols(golden.atac["outreg"])
+    fwd, rev = loaded_ctx.pileup(c, s - 62, e + 62)
+    off = 0
+    for ci, a, b in zip(c, s - 62, e + 62):
+        f0, r0 = restate.pileup(golden.reads, int(ci), int(a), int(b))
+        assert np.array_equal(fwd[off:off + b - a], f0) and np.array_equal(rev[off:off + b - a], r0)
+        off += b - a
+    assert fwd.sum() > 0 and rev.sum() > 0
+
+
+def test_pileup_empty_and_edges(loaded_ctx, golden):
+    # a region inside an N block holds no reads; a 1-bp region; the first region of a contig
+    fwd, rev = loaded_ctx.pileup([0, 0, 1], [10, 5000, 0], [11, 5001, 300])
+    assert fwd.shape == (302,) and fwd[:1].sum() == 0
+    f0, r0 = restate.pileup(golden.reads, 1, 0, 300)
+    assert np.array_equal(fwd[2:], f0) and np.array_equal(rev[2:], r0)
+    with pytest.raises(lib.TobiasB200Error):
+        loaded_ctx.pileup([0, 0], [500, 100], [600, 200])          # unsorted
+    with pytest.raises(lib.TobiasB200Error):
+        loaded_ctx.pileup([0], [100], [10 ** 9])                   # outside the contig
+
+
+@pytest.mark.parametrize("mode", ["DWM", "PWM"])
+def test_bias_counts_bit_exact(loaded_ctx, golden, mode):
+    g = golden.atac
+    counts, scalars = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=(mode == "DWM"))
+    assert scalars[0] == int(g[mode + "_no_reads"])
+    for si, st in enumerate(("forward", "reverse")):
+        assert np.array_equal(counts[si, 0], g["%s_%s_counts" % (mode, st)]), st
+        assert np.array_equal(counts[si, 1], g["%s_%s_bg_counts" % (mode, st)]), st
+        assert [scalars[1 + 2 * si], scalars[2 + 2 * si]] == list(g["%s_%s_no" % (mode, st)])
+
+
+def test_bias_counts_other_parameters(loaded_ctx, golden):
+    regs = [tuple(int(x) for x in r) for r in golden.atac["nonpeak"]]
+    ref = restate.bias_estimation(golden.reads, golden.genome, regs, golden.lengths, k_flank=5, bg_shift=37, cap=3)
+    counts, scalars = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), k_flank=5, bg_shift=37, cap=3)
+    for si, st in enumerate(("forward", "reverse")):
+        assert np.array_equal(counts[si, 0], ref.bias[st].counts) and np.array_equal(counts[si, 1], ref.bias[st].bg_counts)
+    assert scalars[0] == ref.no_reads
+
+
+def _set_model(ctx, g, mode):
+    for si, st in enumerate(("forward", "reverse")):
+        if mode == "DWM":
+            ctx.set_bias_model(si, True, 25, *[g["DWM_%s_%s" % (st, k)] for k in ("bias_pwm_log", "bg_pwm_log", "bias_dwm_log", "bg_dwm_log")])
+        else:
+            ctx.set_bias_model(si, False, 25, g["PWM_%s_pssm" % st])
+
+
+def _oracle_matrix(g, mode, st):
+    m = restate.Matrix(25, mode)
+    if mode == "DWM":
+        for k in ("bias_pwm_log", "bg_pwm_log", "bias_dwm_log", "bg_dwm_log"):
+            setattr(m, k, g["DWM_%s_%s" % (st, k)])
+    else:
+        m.pssm = g["PWM_%s_pssm" % st]
+    return m
+
+
+@pytest.mark.parametrize("mode", ["DWM", "PWM"])
+def test_score_sequence(loaded_ctx, golden, mode):
+    g = golden.atac
+    _set_model(loaded_ctx, g, mode)
+    for (c, a, b) in ((0, 700, 2300), (1, 12000, 13100), (0, 0, 60)):       # spans N blocks, soft-masked bases, a contig start
+        codes = restate.encode(golden.genome[c][a:b])
+        for si, st in enumerate(("forward", "reverse")):
+            m = _oracle_matrix(g, mode, st)
+            ref = m.score_sequence(codes) if si == 0 else m.score_sequence(restate.revcomp(codes))[::-1]
+            got = loaded_ctx.score_sequence(si, c, a, b)
+            assert np.array_equal(np.isnan(ref), np.isnan(got))
+            v = ~np.isnan(ref)
+            if mode == "PWM":
+                assert np.array_equal(ref[v], got[v])
+            else:
+                assert np.all(np.abs(ref[v] - got[v]) <= 1e-9 * np.maximum(1.0, np.abs(ref[v])))
+
+
+@pytest.mark.parametrize("mode", ["PWM", "DWM"])
+def test_bias_correction_tracks(loaded_ctx, golden, mode):
+    g = golden.atac
+    _set_model(loaded_ctx, g, mode)
+    c, s, e = _cols(g["outreg"])
+    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=True)
+    got = loaded_ctx.correct_download(split_strands=True, as_f64=True)
+    for t in TRACKS:
+        for si, st in enumerate(("forward", "reverse")):
+            ref = g["%s_track_%s_%s" % (mode, t, st)]
+            x = got[t][si]
+            assert x.shape == ref.shape
+            if t == "uncorrected" or mode == "PWM":
+                assert np.array_equal(x, ref), (mode, t, st, np.abs(x - ref).max())
+            elif t == "bias":
+                assert np.all(np.abs(x - ref) <= 1e-9 * np.maximum(1.0, np.abs(ref)))
+            else:
+                d = np.abs(x - ref)
+                ok = d <= 1e-5 * np.abs(ref) + 2e-6
+                assert ok.mean() >= 0.999, (mode, t, st, ok.mean(), d.max())
+                assert d.max() <= 2e-5, (mode, t, st, d.max())
+    pp = got["prepost"]
+    rtol = 1e-12 if mode == "PWM" else 1e-6
+    assert np.allclose(pp[:, :, :4, :], g[mode + "_prepost"][:, :, :4, :], rtol=rtol, atol=1e-9)
+    # what the bigWig writer stores: float32, strands summed
+    both = loaded_ctx.correct_download(split_strands=False, as_f64=False, prepost=False)
+    for t in TRACKS:
+        ref32 = (g["%s_track_%s_forward" % (mode, t)] + g["%s_track_%s_reverse" % (mode, t)]).astype(np.float32)
+        assert both[t].dtype == np.float32
+        if mode == "PWM" or t == "uncorrected":
+            assert np.array_equal(both[t], ref32)
+        else:
+            assert np.all(np.abs(both[t].astype(np.float64) - ref32) <= 1e-5 * np.abs(ref32) + 2e-5)
+
+
+def test_bias_correction_tree_sums_close(loaded_ctx, golden):
+    """lm_exact_order=False (warp-tree sums in the fits): same tracks within the DWM-mode tolerance."""
+    g = golden.atac
+    _set_model(loaded_ctx, g, "PWM")
+    c, s, e = _cols(g["outreg"])
+    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=False)
+    got = loaded_ctx.correct_download(split_strands=True, as_f64=True, prepost=False)
+    for t in ("expected", "corrected"):
+        for si, st in enumerate(("forward", "reverse")):
+            ref = g["PWM_track_%s_%s" % (t, st)]
+            d = np.abs(got[t][si] - ref)
+            assert (d <= 1e-5 * np.abs(ref) + 2e-6).mean() >= 0.999 and d.max() <= 2e-5
+
+
+def test_fit_trace_matches_scipy_exactly_in_pwm_mode(loaded_ctx, golden):
+    g = golden.atac
+    _set_model(loaded_ctx, g, "PWM")
+    c, s, e = _cols(g["outreg"])
+    loaded_ctx.correct_run(c[:3], s[:3], e[:3], correction_factor=1.0, lm_exact_order=True)
+    trace = loaded_ctx.correct_fit_trace()
+    bias = restate.AtacBias(25, "PWM")
+    for st in ("forward", "reverse"):
+        bias.bias[st].pssm = g["PWM_%s_pssm" % st]
+    ref = {"forward": [], "reverse": []}
+    for ci, a, b in zip(c[:3], s[:3], e[:3]):
+        tr = {}
+        restate.bias_correction_region(golden.reads, golden.genome, int(ci), int(a), int(b), bias, trace=tr)
+        for st in ref:
+            ref[st] += tr[st]
+    for si, st in enumerate(("forward", "reverse")):
+        r = np.array(ref[st])
+        fitted = r[:, 4] == 0
+        assert np.array_equal(trace[si, :, 0], r[:, 4])                       # fit / fallback / empty decisions
+        assert np.array_equal(trace[si, fitted, 1], r[fitted, 0]) and np.array_equal(trace[si, fitted, 2], r[fitted, 1])
+        assert np.array_equal(trace[si, fitted, 4], r[fitted, 2]) and np.array_equal(trace[si, fitted, 5], r[fitted, 3])
+
+
+# ------------------------------------------------------------------------------------------------ K4
+def test_rolling_bit_exact(ctx, golden):
+    s = golden.signals
+    b = s["roll_in"]
+    for w in (1, 7, 100):
+        assert np.array_equal(ctx.rolling(b, w, "sum"), s["roll_sum_%d" % w], equal_nan=True)
+        assert np.array_equal(ctx.rolling(b, w, "mean"), s["roll_mean_%d" % w], equal_nan=True)
+    long = np.random.default_rng(0).normal(size=5000)
+    assert np.array_equal(ctx.rolling(long, 100, "sum"), restate.fast_rolling_math(long, 100, "sum"), equal_nan=True)
+
+
+def _fp_close(got, ref):
+    assert np.array_equal(got == 0, ref == 0)
+    nz = ref != 0
+    assert np.all(np.abs(got[nz] - ref[nz]) <= 1e-5 * np.abs(ref[nz]))
+
+
+def test_footprint_against_golden(ctx, golden):
+    s = golden.signals
+    a = s["fp_in"].astype(np.float32)
+    for tag in ("default", "flank100", "narrow"):
+        fmin, fmax, pmin, pmax = [int(x) for x in s["fp_%s_args" % tag]]
+        for as_f64 in (True, False):
+            p = ctx.score_params("footprint", flank=0, flank_min=fmin, flank_max=fmax, fp_min=pmin, fp_max=pmax, as_f64=as_f64)
+            got = ctx.score_regions(a, [a.shape[0]], p)
+            _fp_close(got.astype(np.float64), s["fp_" + tag])
+    p = ctx.score_params("FOS", flank=0, as_f64=True)
+    got = ctx.score_regions(a, [a.shape[0]], p)
+    ref = s["fos_default"]
+    assert np.array_equal(got == 10000, ref == 10000)
+    assert np.allclose(got, ref, rtol=1e-5)
+
+
+def test_footprint_many_regions_and_tiles(ctx):
+    rng = np.random.default_rng(5)
+    lens = [61, 140, 2100, 999, 141]                       # shorter than one scan, exactly one position, multi-tile
+    sig = [np.where(rng.random(n) < 0.5, 0, rng.standard_t(3, size=n)).astype(np.float32) for n in lens]
+    flat = np.concatenate(sig)
+    flat[5] = np.nan
+    p = ctx.score_params("footprint", flank=30, as_f64=True)
+    got = ctx.score_regions(flat, lens, p)
+    off = 0
+    for i, n in enumerate(lens):
+        x = flat[sum(lens[:i]):sum(lens[:i]) + n]
+        ref = restate.calculate_scores_region(x, 30, "footprint")
+        _fp_close(got[off:off + n - 60], ref)
+        off += n - 60
+    assert off == got.shape[0]
+
+
+def test_calculate_scores_against_golden(ctx, golden):
+    sc, g = golden.score, golden.atac
+    sig = sc["signal"]
+    regs = [tuple(int(x) for x in r) for r in g["outreg"]]
+    opts = {
+        "footprint": dict(kind="footprint"), "footprint_smooth": dict(kind="footprint", smooth=5),
+        "footprint_limits": dict(kind="footprint", min_limit=-0.2, max_limit=0.6),
+        "sum_abs": dict(kind="sum", absolute=True, window=100), "mean": dict(kind="mean", window=21), "none": dict(kind="none"),
+    }
+    for tag, opt in opts.items():
+        flank = int(sc["flank_" + tag])
+        ext, lens = [], []
+        for (c, s, e) in regs:
+            x = np.zeros(e - s + 2 * flank, dtype=np.float32)
+            o2 = 0
+            for (c2, s2, e2) in regs:
+                if c2 == c:
+                    a, b = max(s - flank, s2), min(e + flank, e2)
+                    if a < b:
+                        x[a - (s - flank):b - (s - flank)] = sig[o2 + a - s2:o2 + b - s2]
+                o2 += e2 - s2
+            ext.append(x)
+            lens.append(x.shape[0])
+        got = ctx.score_regions(np.concatenate(ext), lens, ctx.score_params(flank=flank, as_f64=True, **opt))
+        ref = sc["out_" + tag]
+        assert got.shape == ref.shape
+        if opt["kind"] == "footprint":
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+            v = ~np.isnan(ref)
+            assert np.all(np.abs(got[v] - ref[v]) <= 1e-5 * np.abs(ref[v]) + 1e-12), tag
+        else:
+            assert np.array_equal(got, ref, equal_nan=True), tag
+
+
+def test_chain_corrected_to_footprints(loaded_ctx, golden):
+    """ATACorrect -> ScoreBigwig chained on the device equals scoring the float32 corrected track."""
+    g, sc = golden.atac, golden.score
+    _set_model(loaded_ctx, g, "DWM")
+    c, s, e = _cols(g["outreg"])
+    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]))
+    both = loaded_ctx.correct_download(split_strands=False, as_f64=False, tracks=("corrected",), prepost=False)["corrected"]
+    loaded_ctx.signal_from_corrected(30, e - s)
+    loaded_ctx.score_run(loaded_ctx.score_params("footprint", flank=30, as_f64=True))
+    got = loaded_ctx.score_download()
+    ext, lens, off = [], [], 0
+    for a, b in zip(s, e):
+        x = np.zeros(b - a + 60, dtype=np.float32)
+        x[30:-30] = both[off:off + b - a]
+        off += b - a
+        ext.append(x)
+        lens.append(x.shape[0])
+    ref = loaded_ctx.score_regions(np.concatenate(ext), lens, loaded_ctx.score_params("footprint", flank=30, as_f64=True))
+    assert np.array_equal(got, ref)

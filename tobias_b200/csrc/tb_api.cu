@@ -1,0 +1,356 @@
+// tb_api.cu -- context management, genome packing/upload, read upload, shared host helpers of libtobias_b200.
+#include "tb_common.cuh"
+
+static char g_init_error[512] = "";
+
+int tb_fail(tb_ctx *ctx, int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    char *dst = ctx ? ctx->err : g_init_error;
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int tb_check(tb_ctx *ctx, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return TB_OK;
+    return tb_fail(ctx, e == cudaErrorMemoryAllocation ? TB_ERR_NOMEM : TB_ERR_CUDA, "CUDA error %d (%s) in %s", (int)e,
+                   cudaGetErrorString(e), what);
+}
+
+int tb_reserve(tb_ctx *ctx, tb_dbuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return TB_OK;
+    if (b.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    want = (want + 255) & ~(size_t)255;
+    TB_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return TB_OK;
+}
+
+void tb_release(tb_dbuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int tb_pinned(tb_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return TB_OK;
+    if (ctx->pinned) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+    }
+    TB_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_cap = bytes;
+    return TB_OK;
+}
+
+int tb_h2d(tb_ctx *ctx, tb_dbuf &dst, const void *src, size_t bytes) {
+    TB_TRY(tb_reserve(ctx, dst, bytes));
+    if (bytes) TB_CUDA(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return TB_OK;
+}
+
+int tb_d2h(tb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes) TB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
+}
+
+int tb_sync(tb_ctx *ctx, const char *what) {
+    TB_TRY(tb_check(ctx, cudaStreamSynchronize(ctx->stream), what));
+    return tb_check(ctx, cudaGetLastError(), what);
+}
+
+void tb_timer_start(tb_ctx *ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
+void tb_timer_stop(tb_ctx *ctx) {
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+}
+
+void tb_mark(tb_ctx *ctx, int i) { cudaEventRecord(ctx->marks[i], ctx->stream); }
+void tb_marks_collect(tb_ctx *ctx, int n_marks) {
+    cudaEventSynchronize(ctx->marks[n_marks - 1]);
+    for (int i = 0; i < 8; i++) ctx->stage_ms[i] = 0.f;
+    for (int i = 0; i + 1 < n_marks; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->marks[i], ctx->marks[i + 1]);
+}
+
+int tb_linear_regions(tb_ctx *ctx, i64 n, const int32_t *contig, const int64_t *start, const int64_t *end,
+                      std::vector<i64> &lstart, std::vector<i64> &lend, bool need_disjoint) {
+    if (ctx->n_contigs == 0) return tb_fail(ctx, TB_ERR_STATE, "no genome: call tb_genome_create first");
+    if (n < 0) return tb_fail(ctx, TB_ERR_ARG, "negative region count");
+    lstart.resize(n);
+    lend.resize(n);
+    for (i64 i = 0; i < n; i++) {
+        int c = contig[i];
+        if (c < 0 || c >= ctx->n_contigs) return tb_fail(ctx, TB_ERR_ARG, "region %lld: contig %d out of range", i, c);
+        if (start[i] < 0 || end[i] > ctx->contig_len[c] || start[i] >= end[i])
+            return tb_fail(ctx, TB_ERR_ARG, "region %lld: [%lld, %lld) is empty or outside contig %d (length %lld)", i,
+                           (i64)start[i], (i64)end[i], c, ctx->contig_len[c]);
+        lstart[i] = ctx->contig_off[c] + start[i];
+        lend[i] = ctx->contig_off[c] + end[i];
+        if (i > 0) {
+            if (lstart[i] < lstart[i - 1] || lend[i] < lend[i - 1])
+                return tb_fail(ctx, TB_ERR_ARG, "regions must be sorted by (contig, start) with ascending ends (region %lld)", i);
+            if (need_disjoint && lstart[i] < lend[i - 1])
+                return tb_fail(ctx, TB_ERR_ARG, "regions must not overlap (region %lld)", i);
+        }
+    }
+    return TB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int tb_abi_version(void) { return 1; }
+
+extern "C" int tb_init(int device, tb_ctx **out) {
+    if (!out) return tb_fail(nullptr, TB_ERR_ARG, "tb_init: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: no usable CUDA device (%s); libtobias_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return tb_fail(nullptr, TB_ERR_ARG, "tb_init: device %d out of range (%d devices)", device, ndev);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    tb_ctx *ctx = new tb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
+    }
+    bool marks_ok = true;
+    for (int i = 0; i < 8; i++) marks_ok = marks_ok && cudaEventCreate(&ctx->marks[i]) == cudaSuccess;
+    if (!marks_ok) {
+        delete ctx;
+        return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
+    }
+    *out = ctx;
+    return TB_OK;
+}
+
+extern "C" void tb_destroy(tb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    tb_dbuf *bufs[] = {&ctx->seq2, &ctx->nmask, &ctx->d_contig_off, &ctx->r_start, &ctx->r_len, &ctx->r_clip, &ctx->r_flags,
+                       &ctx->reg_a, &ctx->reg_b, &ctx->reg_c, &ctx->reg_d, &ctx->reg_e, &ctx->scratch0, &ctx->scratch1,
+                       &ctx->scratch2, &ctx->scratch3, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
+                       &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
+                       &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.tracks, &ctx->cor.prepost,
+                       &ctx->sc.d_ext_off, &ctx->sc.signal, &ctx->sc.work0, &ctx->sc.work1, &ctx->sc.out};
+    for (tb_dbuf *b : bufs) tb_release(*b);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    tb_nccl_teardown(ctx);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->marks[i]);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *tb_last_error(const tb_ctx *ctx) { return ctx ? ctx->err : g_init_error; }
+
+extern "C" int tb_device_info(tb_ctx *ctx, int *sm_count, int64_t *free_bytes, int64_t *total_bytes, int *is_emulator) {
+    if (!ctx) return TB_ERR_ARG;
+    size_t f = 0, t = 0;
+    TB_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+#ifdef TB_EMU
+    if (is_emulator) *is_emulator = 1;
+#else
+    if (is_emulator) *is_emulator = 0;
+#endif
+    return TB_OK;
+}
+
+extern "C" int tb_last_kernel_ms(tb_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return TB_ERR_ARG;
+    *ms = ctx->last_ms;
+    return TB_OK;
+}
+
+extern "C" int tb_stage_ms(tb_ctx *ctx, float *out, int n) {
+    if (!ctx || !out || n < 0) return TB_ERR_ARG;
+    for (int i = 0; i < n; i++) out[i] = i < 8 ? ctx->stage_ms[i] : 0.f;
+    return TB_OK;
+}
+
+extern "C" int tb_launch_count(tb_ctx *ctx, int64_t *n) {
+    if (!ctx || !n) return TB_ERR_ARG;
+    *n = ctx->launches;
+    return TB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ genome
+// ASCII -> (2-bit code, N flag).  One thread packs 32 bases: two u32 words of seq2 and one u32 word of nmask.
+// 128-bit loads of the ASCII staging buffer (32 bases = 2 x uint4), coalesced 4/8-byte stores.
+__device__ __forceinline__ u32 tb_ascii_code(u32 c, u32 &is_n) {
+    c &= 0xDFu;                       // upper-case
+    u32 code = 0;
+    is_n = 0;
+    if (c == 'A') code = 0;
+    else if (c == 'T') code = 1;
+    else if (c == 'C') code = 2;
+    else if (c == 'G') code = 3;
+    else is_n = 1;
+    return code;
+}
+
+__global__ void tb_pack_kernel(const uint8_t *__restrict__ ascii, i64 n, u32 *__restrict__ seq2, u32 *__restrict__ nmask,
+                               i64 base0) {
+    i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;     // group of 32 bases
+    i64 first = g * 32;
+    if (first >= n) return;
+    u32 w0 = 0, w1 = 0, m = 0;
+    if (first + 32 <= n) {
+        const uint4 *p = (const uint4 *)(ascii + first);
+        uint4 a = p[0], b = p[1];
+        u32 words[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            u32 c = (words[i >> 2] >> (8 * (i & 3))) & 0xFFu, isn;
+            u32 code = tb_ascii_code(c, isn);
+            if (i < 16) w0 |= code << (2 * i); else w1 |= code << (2 * (i - 16));
+            m |= isn << i;
+        }
+    } else {
+        for (int i = 0; i < 32; i++) {
+            u32 isn = 1, code = 0;
+            if (first + i < n) code = tb_ascii_code(ascii[first + i], isn);
+            if (i < 16) w0 |= code << (2 * i); else w1 |= code << (2 * (i - 16));
+            m |= isn << i;
+        }
+    }
+    i64 k = base0 + first;            // multiple of 32
+    seq2[(k >> 4)] = w0;
+    seq2[(k >> 4) + 1] = w1;
+    nmask[k >> 5] = m;
+}
+
+__global__ void tb_fetch_codes_kernel(tb_genome_view g, i64 k0, i64 n, uint8_t *out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = tb_is_n(g, k0 + i) ? 4 : (uint8_t)tb_base(g, k0 + i);
+}
+
+static const i64 TB_CONTIG_PAD = 1024;     // >= this many N bases between contigs in the linear space
+
+extern "C" int tb_genome_create(tb_ctx *ctx, int n_contigs, const int64_t *lengths) {
+    if (!ctx) return TB_ERR_ARG;
+    if (n_contigs <= 0 || !lengths) return tb_fail(ctx, TB_ERR_ARG, "tb_genome_create: need at least one contig");
+    ctx->contig_len.assign(lengths, lengths + n_contigs);
+    ctx->contig_off.resize(n_contigs + 1);
+    i64 off = TB_CONTIG_PAD;
+    for (int c = 0; c < n_contigs; c++) {
+        if (lengths[c] <= 0) return tb_fail(ctx, TB_ERR_ARG, "tb_genome_create: contig %d has length %lld", c, (i64)lengths[c]);
+        ctx->contig_off[c] = off;
+        off += lengths[c] + TB_CONTIG_PAD;
+        off = (off + 255) & ~(i64)255;
+    }
+    ctx->contig_off[n_contigs] = off;
+    ctx->genome_bases = off;
+    ctx->n_contigs = n_contigs;
+    size_t seq_bytes = (size_t)(off / 16 + 8) * 4, mask_bytes = (size_t)(off / 32 + 8) * 4;
+    TB_TRY(tb_reserve(ctx, ctx->seq2, seq_bytes));
+    TB_TRY(tb_reserve(ctx, ctx->nmask, mask_bytes));
+    TB_CUDA(ctx, cudaMemsetAsync(ctx->seq2.p, 0, seq_bytes, ctx->stream));
+    TB_CUDA(ctx, cudaMemsetAsync(ctx->nmask.p, 0xFF, mask_bytes, ctx->stream));     // everything is N until uploaded
+    TB_TRY(tb_h2d(ctx, ctx->d_contig_off, ctx->contig_off.data(), sizeof(i64) * (n_contigs + 1)));
+    ctx->cor.valid = false;
+    return tb_sync(ctx, "tb_genome_create");
+}
+
+extern "C" int tb_genome_upload(tb_ctx *ctx, int contig, int64_t offset, const uint8_t *ascii, int64_t n) {
+    if (!ctx) return TB_ERR_ARG;
+    if (ctx->n_contigs == 0) return tb_fail(ctx, TB_ERR_STATE, "tb_genome_upload: call tb_genome_create first");
+    if (contig < 0 || contig >= ctx->n_contigs) return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload: contig %d out of range", contig);
+    if (offset < 0 || (offset & 31) || n < 0 || offset + n > ctx->contig_len[contig])
+        return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload: bad range offset=%lld n=%lld (offset must be a multiple of 32)",
+                       (i64)offset, (i64)n);
+    const i64 CHUNK = (i64)64 << 20;
+    for (i64 done = 0; done < n; done += CHUNK) {
+        i64 m = n - done < CHUNK ? n - done : CHUNK;
+        TB_TRY(tb_reserve(ctx, ctx->staging, (size_t)m + 64));
+        TB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, ascii + done, (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        i64 groups = tb_div_up(m, 32);
+        int block = 256;
+        TB_LAUNCH(ctx, tb_pack_kernel, (unsigned)tb_div_up(groups, block), block, 0, ctx->staging.as<uint8_t>(), m,
+                  ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->contig_off[contig] + offset + done);
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // the host buffer may be reused by the caller
+    }
+    return tb_check(ctx, cudaGetLastError(), "tb_pack_kernel");
+}
+
+extern "C" int tb_genome_fetch(tb_ctx *ctx, int contig, int64_t start, int64_t n, uint8_t *codes_out) {
+    if (!ctx) return TB_ERR_ARG;
+    if (contig < 0 || contig >= ctx->n_contigs || start < 0 || n < 0 || start + n > ctx->contig_len[contig])
+        return tb_fail(ctx, TB_ERR_ARG, "tb_genome_fetch: bad range");
+    if (n == 0) return TB_OK;
+    TB_TRY(tb_reserve(ctx, ctx->scratch0, (size_t)n));
+    tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
+    TB_LAUNCH(ctx, tb_fetch_codes_kernel, (unsigned)tb_div_up(n, 256), 256, 0, g, ctx->contig_off[contig] + start, (i64)n,
+              ctx->scratch0.as<uint8_t>());
+    return tb_d2h(ctx, codes_out, ctx->scratch0.p, (size_t)n);
+}
+
+// ------------------------------------------------------------------------------------------------ reads
+// Host columns are int32 contig-local; the device keeps the linear start (int64), the reference length and
+// the 5' clip so that every kernel works in one coordinate space.
+__global__ void tb_reads_linearise_kernel(i64 n, const int32_t *__restrict__ contig, const int32_t *__restrict__ ref_start,
+                                          const int32_t *__restrict__ ref_end, const i64 *__restrict__ contig_off,
+                                          int n_contigs, i64 *__restrict__ lstart, int32_t *__restrict__ rlen,
+                                          uint8_t *__restrict__ flags) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = contig[i];
+    if (c < 0 || c >= n_contigs) {      // unknown contig: never matches any region
+        lstart[i] = -((i64)1 << 40);
+        rlen[i] = 0;
+        flags[i] = (uint8_t)(flags[i] | TB_READ_SKIP);
+        return;
+    }
+    lstart[i] = contig_off[c] + (i64)ref_start[i];
+    rlen[i] = ref_end[i] - ref_start[i];
+}
+
+extern "C" int tb_reads_upload(tb_ctx *ctx, int64_t n, const int32_t *contig, const int32_t *ref_start,
+                               const int32_t *ref_end, const int32_t *clip5, const uint8_t *flags) {
+    if (!ctx) return TB_ERR_ARG;
+    if (ctx->n_contigs == 0) return tb_fail(ctx, TB_ERR_STATE, "tb_reads_upload: call tb_genome_create first");
+    if (n < 0 || (n > 0 && (!contig || !ref_start || !ref_end || !clip5 || !flags)))
+        return tb_fail(ctx, TB_ERR_ARG, "tb_reads_upload: NULL column");
+    ctx->n_reads = n;
+    ctx->cor.valid = false;
+    if (n == 0) return TB_OK;
+    size_t b4 = (size_t)n * 4;
+    TB_TRY(tb_h2d(ctx, ctx->scratch0, contig, b4));
+    TB_TRY(tb_h2d(ctx, ctx->scratch1, ref_start, b4));
+    TB_TRY(tb_h2d(ctx, ctx->scratch2, ref_end, b4));
+    TB_TRY(tb_h2d(ctx, ctx->r_clip, clip5, b4));
+    TB_TRY(tb_h2d(ctx, ctx->r_flags, flags, (size_t)n));
+    TB_TRY(tb_reserve(ctx, ctx->r_start, (size_t)n * 8));
+    TB_TRY(tb_reserve(ctx, ctx->r_len, b4));
+    TB_LAUNCH(ctx, tb_reads_linearise_kernel, (unsigned)tb_div_up(n, 256), 256, 0, (i64)n, ctx->scratch0.as<int32_t>(),
+              ctx->scratch1.as<int32_t>(), ctx->scratch2.as<int32_t>(), ctx->d_contig_off.as<i64>(), ctx->n_contigs,
+              ctx->r_start.as<i64>(), ctx->r_len.as<int32_t>(), ctx->r_flags.as<uint8_t>());
+    return tb_sync(ctx, "tb_reads_upload");
+}

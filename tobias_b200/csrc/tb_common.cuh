@@ -1,0 +1,187 @@
+// tb_common.cuh -- shared declarations of libtobias_b200 (context, device buffers, launch macro, genome access).
+#pragma once
+
+#ifdef TB_EMU
+#include "cuda_emu.h"      // tests/emu: GPU-less kernel-logic emulator used by the CPU test-suite only
+#define TB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        tb_emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); }); \
+    } while (0)
+#define TB_DYN_SMEM(name) unsigned char *name = tb_emu::S().dyn_smem
+#else
+#include <cuda_runtime.h>
+#define TB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        kernel<<<dim3(grid), dim3(block), (size_t)(smem), (ctx)->stream>>>(__VA_ARGS__); \
+    } while (0)
+#define TB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/tobias_b200.h"
+
+typedef long long i64;
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// A growable device allocation owned by the context.
+struct tb_dbuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// Bias model of one strand, device resident.
+struct tb_model {
+    int is_dwm = -1;
+    int L = 0;
+    tb_dbuf table;       // DWM: U[2 models][L][4][L][4] doubles; PWM: pssm[5][L]
+    std::vector<double> host_raw[4];
+};
+
+struct tb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float last_ms = 0.f;
+    i64 launches = 0;
+    char err[512] = {0};
+
+    // genome
+    int n_contigs = 0;
+    std::vector<i64> contig_len, contig_off;   // linear (padded) offsets in bases
+    i64 genome_bases = 0;
+    tb_dbuf seq2;      // u32 words, 16 bases each
+    tb_dbuf nmask;     // u32 words, 32 bases each
+    tb_dbuf d_contig_off;
+
+    // reads
+    i64 n_reads = 0;
+    tb_dbuf r_start, r_len, r_clip;   // i64 linear start, i32 reference length, i32 5' clip
+    tb_dbuf r_flags;
+
+    // scratch / per-call device tables
+    tb_dbuf reg_a, reg_b, reg_c, reg_d, reg_e;
+    tb_dbuf scratch0, scratch1, scratch2, scratch3;
+    tb_dbuf staging;   // device staging for uploads
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    // models
+    tb_model model[2];
+
+    // state of the last tb_correct_run
+    struct {
+        i64 n_regions = 0, ext_total = 0, out_total = 0, n_windows = 0;
+        int k_flank = 0, window = 0, L = 0;
+        std::vector<i64> ext_start, ext_off, out_off, win_off;   // linear ext start, offsets
+        tb_dbuf d_ext_start, d_ext_end, d_ext_off, d_out_off, d_win_off;
+        tb_dbuf pile;      // u32 [2][ext_total]
+        tb_dbuf biasraw;   // f64 [2][ext_total]
+        tb_dbuf fit;       // f64 [2][n_windows][4]
+        tb_dbuf tracks;    // f64 [4 tracks][2 strands][out_total]
+        tb_dbuf prepost;   // f64 [2][3][5][L]
+        bool valid = false;
+    } cor;
+
+    // state of K4
+    struct {
+        i64 n_regions = 0, ext_total = 0, out_total = 0;
+        std::vector<i64> ext_off, out_off;
+        tb_dbuf d_ext_off;
+        tb_dbuf signal;    // f32 [ext_total]
+        tb_dbuf work0, work1;   // f64 [ext_total]
+        tb_dbuf out;       // trimmed output
+        int out_f64 = 0;
+        int flank = -1;
+        bool have_signal = false, have_out = false;
+    } sc;
+
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+int tb_fail(tb_ctx *ctx, int code, const char *fmt, ...);
+int tb_reserve(tb_ctx *ctx, tb_dbuf &b, size_t bytes);
+void tb_release(tb_dbuf &b);
+int tb_pinned(tb_ctx *ctx, size_t bytes);
+int tb_check(tb_ctx *ctx, cudaError_t e, const char *what);
+int tb_h2d(tb_ctx *ctx, tb_dbuf &dst, const void *src, size_t bytes);          // reserve + async copy on ctx->stream
+int tb_d2h(tb_ctx *ctx, void *dst, const void *src, size_t bytes);            // sync copy
+int tb_sync(tb_ctx *ctx, const char *what);
+void tb_timer_start(tb_ctx *ctx);
+void tb_timer_stop(tb_ctx *ctx);
+void tb_mark(tb_ctx *ctx, int i);                 // record stage boundary i on the context's stream
+void tb_marks_collect(tb_ctx *ctx, int n_marks);  // stage_ms[i] = time between marks i and i+1
+void tb_nccl_teardown(tb_ctx *ctx);
+// regions (contig-local) -> linear coordinates; validates order; returns TB_OK or error
+int tb_linear_regions(tb_ctx *ctx, i64 n, const int32_t *contig, const int64_t *start, const int64_t *end,
+                      std::vector<i64> &lstart, std::vector<i64> &lend, bool need_disjoint);
+
+#define TB_CUDA(ctx, call)                                        \
+    do {                                                          \
+        int _rc = tb_check((ctx), (call), #call);                 \
+        if (_rc != TB_OK) return _rc;                             \
+    } while (0)
+#define TB_TRY(call)                                              \
+    do {                                                          \
+        int _rc = (call);                                         \
+        if (_rc != TB_OK) return _rc;                             \
+    } while (0)
+
+static inline i64 tb_div_up(i64 a, i64 b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------- device helpers
+// Genome: base k of the linear coordinate space lives in seq2[k >> 4] bits 2*(k & 15); N flag in nmask[k >> 5] bit (k & 31).
+struct tb_genome_view {
+    const u32 *seq2;
+    const u32 *nmask;
+    i64 n_bases;
+};
+
+__device__ __forceinline__ int tb_base(const tb_genome_view &g, i64 k) {
+    return (int)((g.seq2[k >> 4] >> (2 * (int)(k & 15))) & 3u);
+}
+__device__ __forceinline__ int tb_is_n(const tb_genome_view &g, i64 k) {
+    return (int)((g.nmask[k >> 5] >> (int)(k & 31)) & 1u);
+}
+// nb (<= 32) bases starting at k as a packed 2-bit word (base i in bits 2i..2i+1)
+__device__ __forceinline__ u64 tb_bases(const tb_genome_view &g, i64 k, int nb) {
+    i64 w = k >> 4;
+    int sh = 2 * (int)(k & 15);
+    u64 lo = (u64)g.seq2[w] | ((u64)g.seq2[w + 1] << 32);
+    u64 v = lo >> sh;
+    if (sh) v |= (u64)g.seq2[w + 2] << (64 - sh);
+    if (nb < 32) v &= (((u64)1 << (2 * nb)) - 1);
+    return v;
+}
+// N flags of nb (<= 32) bases starting at k (bit i = base k+i is N)
+__device__ __forceinline__ u32 tb_nflags(const tb_genome_view &g, i64 k, int nb) {
+    i64 w = k >> 5;
+    int sh = (int)(k & 31);
+    u64 v = (u64)g.nmask[w] | ((u64)g.nmask[w + 1] << 32);
+    u32 r = (u32)(v >> sh);
+    if (nb < 32) r &= ((1u << nb) - 1u);
+    return r;
+}
+// first index i in [0, n) with a[i] > v  (a ascending)
+__device__ __forceinline__ i64 tb_upper_bound(const i64 *a, i64 n, i64 v) {
+    i64 lo = 0, hi = n;
+    while (lo < hi) {
+        i64 mid = (lo + hi) >> 1;
+        if (a[mid] > v) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}

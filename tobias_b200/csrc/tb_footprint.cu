@@ -1,0 +1,498 @@
+// tb_footprint.cu -- K4: ScoreBigwig scoring (multi-width flank-vs-centre footprint scan, rolling sum / mean, smoothing).
+//
+// Reference: calculate_scores, tobias/tools/score_bigwig.py:33-98; tobias_footprint_array, tobias/utils/signals.pyx:184-230;
+// fast_rolling_math, signals.pyx:102-177; FOS_score, signals.pyx:237-282.
+//
+// Footprint scan, gather form of the reference's scatter loop.  With P / N the running sums of max(v,0) / min(v,0) over the
+// fp32-truncated input, a footprint starting at s with flank width fw and footprint width pw scores
+//     score(s,fw,pw) = ( (P[s]-P[s-fw]) + (P[s+pw+fw]-P[s+pw]) ) / (2 fw)  -  (N[s+pw]-N[s]) / pw ,   0 <= s-fw < L-2*fmax-pmax
+// and out[pos] = max(0, max_{fw,pw} max_{s in (pos-pw, pos]} score(s,fw,pw)).  Per tile: a block-wide fp64 scan builds P and N in
+// shared memory (tile-local, so differences keep full precision); for each fw the fp32 window sums W_fw[k] = P[k+fw]-P[k] are
+// staged once in shared memory and every thread (one footprint start s) folds them into 32 register accumulators, one per pw;
+// the footprint term is subtracted; a log-doubling sliding maximum in shared memory spreads each score over its footprint.
+// The reference sums sequentially in fp32; prefix differences rounded to fp32 agree with it to a few ulp (tests: rtol 1e-5).
+#include "tb_common.cuh"
+
+#include <cfloat>
+
+struct tb_sc_view {
+    const i64 *ext_off;      // n+1 offsets of the (flank-extended) regions in the concatenated signal
+    const i64 *out_off;      // n+1 offsets of the trimmed outputs
+    const i64 *tile_off;     // n+1 prefix of tiles per region
+    i64 n_regions;
+    int flank;
+};
+
+struct tb_prep {
+    int absolute, use_min, use_max;
+    double min_limit, max_limit;
+};
+
+// nan_to_num + --absolute + --min-limit / --max-limit (score_bigwig.py:55-64), evaluated in double like the reference
+__device__ __forceinline__ double tb_prep_value(float v, const tb_prep &p) {
+    if (v != v) v = 0.0f;
+    else if (v > FLT_MAX) v = FLT_MAX;
+    else if (v < -FLT_MAX) v = -FLT_MAX;
+    double d = (double)v;
+    if (p.absolute) d = fabs(d);
+    if (p.use_min && d < p.min_limit) d = p.min_limit;
+    if (p.use_max && d > p.max_limit) d = p.max_limit;
+    return d;
+}
+
+// exclusive block scan of two fp64 sequences held in shared memory: a[0..n), b[0..n) -> in place prefix (a[i] = sum of inputs < i),
+// a[n], b[n] receive the totals.  aux needs 2 * blockDim.x doubles.
+__device__ void tb_block_scan2(double *a, double *b, int n, double *aux) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (n + nt - 1) / nt;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    double sa = 0.0, sb = 0.0;
+    for (int i = lo; i < hi; i++) {
+        sa += a[i];
+        sb += b[i];
+    }
+    aux[tid] = sa;
+    aux[nt + tid] = sb;
+    __syncthreads();
+    if (tid < 32) {
+        const int chunk = (nt + 31) / 32;
+        const int c0 = min(nt, tid * chunk), c1 = min(nt, c0 + chunk);
+        double ta = 0.0, tb = 0.0;
+        for (int i = c0; i < c1; i++) {
+            ta += aux[i];
+            tb += aux[nt + i];
+        }
+        double ia = ta, ib = tb;                                  // inclusive scan over lanes
+        for (int d = 1; d < 32; d <<= 1) {
+            double oa = __shfl_up_sync(0xffffffffu, ia, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+            if (tid >= d) {
+                ia += oa;
+                ib += ob;
+            }
+        }
+        double ra = ia - ta, rb = ib - tb;                        // exclusive offset of this lane's chunk
+        for (int i = c0; i < c1; i++) {
+            double va = aux[i], vb = aux[nt + i];
+            aux[i] = ra;
+            aux[nt + i] = rb;
+            ra += va;
+            rb += vb;
+        }
+    }
+    __syncthreads();
+    double ra = aux[tid], rb = aux[nt + tid];
+    for (int i = lo; i < hi; i++) {
+        double va = a[i], vb = b[i];
+        a[i] = ra;
+        b[i] = rb;
+        ra += va;
+        rb += vb;
+    }
+    if (hi == n && lo < n) {
+        a[n] = ra;
+        b[n] = rb;
+    }
+    if (n == 0 && tid == 0) {
+        a[0] = 0.0;
+        b[0] = 0.0;
+    }
+    __syncthreads();
+}
+
+#define TB_K4_THREADS 512
+#define TB_K4_NPW 32
+
+// OUT_MODE 0: trimmed float, 1: trimmed double, 2: untrimmed double work array (smoothing follows)
+template <int OUT_MODE>
+__global__ void __launch_bounds__(TB_K4_THREADS)
+tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_, int pmin_, int pmax_,
+                    void *__restrict__ out_) {
+    TB_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    const int S = TB_K4_THREADS;
+    const int T = S - (pmax_ - 1);                              // outputs per tile
+    const i64 j = tb_upper_bound(V.tile_off, V.n_regions + 1, (i64)blockIdx.x) - 1;
+    const i64 tile = (i64)blockIdx.x - V.tile_off[j];
+    const i64 Lr = V.ext_off[j + 1] - V.ext_off[j];
+    const i64 p0 = tile * T;                                    // first output position of the tile (region coordinates)
+    const i64 smin = p0 - (pmax_ - 1);                          // footprint start handled by thread 0
+    const i64 in0 = smin - fmax_;                               // first loaded position
+    const int n_in = S + 2 * fmax_ + pmax_;
+    const i64 limit = Lr - 2 * (i64)fmax_ - pmax_;              // i = s - fw must be < limit
+    double *P = (double *)smem;                                 // n_in + 1
+    double *N = P + (n_in + 1);                                 // n_in + 1
+    double *aux = N + (n_in + 1);                               // 2 * S
+    float *W = (float *)(aux + 2 * S);                          // n_in
+    float *A = W + n_in;                                        // S
+    float *B = A + S;                                           // S
+    const float *sg = signal + V.ext_off[j];
+
+    for (int i = tid; i < n_in; i += S) {
+        i64 q = in0 + i;
+        float v = 0.0f;
+        if (q >= 0 && q < Lr) v = (float)tb_prep_value(sg[q], prep);      // `val = arr[i+j]` is a C float (signals.pyx:191)
+        P[i] = v > 0.0f ? (double)v : 0.0;
+        N[i] = v < 0.0f ? (double)v : 0.0;
+    }
+    __syncthreads();
+    tb_block_scan2(P, N, n_in, aux);
+
+    const i64 s = smin + tid;                                   // this thread's footprint start
+    const int si = tid + fmax_;                                 // its index in the loaded range
+    float best = 0.0f;                                          // out[pos] for pos = s (footprint_scores starts at 0)
+
+    for (int pw0 = pmin_; pw0 <= pmax_; pw0 += TB_K4_NPW) {
+        const int npw = min(TB_K4_NPW, pmax_ - pw0 + 1);
+        float acc[TB_K4_NPW];
+#pragma unroll
+        for (int c = 0; c < TB_K4_NPW; c++) acc[c] = -INFINITY;
+        for (int fw = fmin_; fw <= fmax_; fw++) {
+            for (int i = tid; i + fw <= n_in; i += S) W[i] = (float)(P[i + fw] - P[i]);
+            __syncthreads();
+            const i64 i0 = s - fw;
+            if (i0 >= 0 && i0 < limit) {
+                const float l = W[si - fw];
+                const float inv = 1.0f / (2.0f * (float)fw);
+                const float *wr = W + si + pw0;
+#pragma unroll
+                for (int c = 0; c < TB_K4_NPW; c++)
+                    if (c < npw) acc[c] = fmaxf(acc[c], (l + wr[c]) * inv);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int c = 0; c < TB_K4_NPW; c++) {
+            if (c < npw) {
+                const int pw = pw0 + c;
+                float sc = -INFINITY;
+                if (acc[c] > -INFINITY) {
+                    float mid = (float)(N[si + pw] - N[si]);
+                    sc = acc[c] - mid * (1.0f / (float)pw);
+                }
+                // sliding maximum over s in (pos - pw, pos]: log-doubling
+                A[tid] = sc;
+                __syncthreads();
+                float *src = A, *dst = B;
+                int span = 1;
+                while (span * 2 <= pw) {
+                    float v = src[tid];
+                    if (tid >= span) v = fmaxf(v, src[tid - span]);
+                    dst[tid] = v;
+                    __syncthreads();
+                    float *t = src; src = dst; dst = t;
+                    span *= 2;
+                }
+                float v = src[tid];
+                int back = pw - span;
+                if (back > 0 && tid >= back) v = fmaxf(v, src[tid - back]);
+                best = fmaxf(best, v);
+                __syncthreads();
+            }
+        }
+    }
+    // thread tid holds out[pos = s]; valid for pos in [p0, p0 + T)
+    if (tid >= pmax_ - 1 && s < Lr) {
+        if (OUT_MODE == 2) {
+            ((double *)out_)[V.ext_off[j] + s] = (double)best;
+        } else if (s >= V.flank && s < Lr - V.flank) {
+            i64 o = V.out_off[j] + (s - V.flank);
+            if (OUT_MODE == 0) ((float *)out_)[o] = best;
+            else ((double *)out_)[o] = (double)best;
+        }
+    }
+}
+
+// FOS_score (signals.pyx:237-282): exclusive width ranges, plain sums, running minimum from 10000.  One thread per output
+// position; tile-local fp64 prefix sums.  Not reachable from the reference CLI (parsers.py:84); kept for API parity.
+template <int OUT_MODE>
+__global__ void __launch_bounds__(TB_K4_THREADS)
+tb_fos_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_, int pmin_, int pmax_,
+              void *__restrict__ out_) {
+    TB_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    const int S = TB_K4_THREADS;
+    const int T = S;
+    const i64 j = tb_upper_bound(V.tile_off, V.n_regions + 1, (i64)blockIdx.x) - 1;
+    const i64 tile = (i64)blockIdx.x - V.tile_off[j];
+    const i64 Lr = V.ext_off[j + 1] - V.ext_off[j];
+    const i64 p0 = tile * T;
+    const i64 in0 = p0 - (pmax_ - 1) - fmax_;
+    const int n_in = S + 2 * (fmax_ + pmax_);
+    const i64 limit = Lr - 2 * (i64)fmax_ - pmax_;
+    double *P = (double *)smem;
+    double *N = P + (n_in + 1);
+    double *aux = N + (n_in + 1);
+    const float *sg = signal + V.ext_off[j];
+    for (int i = tid; i < n_in; i += S) {
+        i64 q = in0 + i;
+        double v = 0.0;
+        if (q >= 0 && q < Lr) v = tb_prep_value(sg[q], prep);
+        P[i] = v;
+        N[i] = 0.0;
+    }
+    __syncthreads();
+    tb_block_scan2(P, N, n_in, aux);
+    const i64 pos = p0 + tid;
+    float best = 10000.0f;
+    if (pos < Lr) {
+        for (int fw = fmin_; fw < fmax_; fw++)
+            for (int pw = pmin_; pw < pmax_; pw++)
+                for (i64 s = pos - pw + 1; s <= pos; s++) {
+                    i64 i0 = s - fw;
+                    if (i0 < 0 || i0 >= limit) continue;
+                    int b = (int)(s - in0);
+                    float left = (float)(P[b] - P[b - fw]), mid = (float)(P[b + pw] - P[b]);
+                    float right = (float)(P[b + pw + fw] - P[b + pw]);
+                    float Lm = (float)(left / (fw * 1.0)), Cm = (float)(mid / (pw * 1.0)), Rm = (float)(right / (fw * 1.0));
+                    float sc = 10000.0f;
+                    if (Cm < Rm && Cm < Lm && Lm > 0 && Rm > 0) sc = (float)((Cm + 1.0) / Lm + (Cm + 1.0) / Rm);
+                    if (sc < best) best = sc;
+                }
+        if (OUT_MODE == 2) ((double *)out_)[V.ext_off[j] + pos] = (double)best;
+        else if (pos >= V.flank && pos < Lr - V.flank) {
+            i64 o = V.out_off[j] + (pos - V.flank);
+            if (OUT_MODE == 0) ((float *)out_)[o] = best;
+            else ((double *)out_)[o] = (double)best;
+        }
+    }
+}
+
+// fast_rolling_math "sum" / "mean" (signals.pyx:149-164): the accumulator is a C float, each += a double add rounded to float.
+// IN_MODE 0: float signal + preprocessing, 1: double array.  is_mean: divide by w (in double).  w == 0: copy (--score none).
+#define TB_ROLL_TILE 1024
+template <int IN_MODE, int OUT_MODE>
+__global__ void tb_rolling_kernel(tb_sc_view V, const void *__restrict__ in_, tb_prep prep, int w, int is_mean,
+                                  void *__restrict__ out_) {
+    TB_DYN_SMEM(smem);
+    double *buf = (double *)smem;                                // TB_ROLL_TILE + w
+    const i64 j = tb_upper_bound(V.tile_off, V.n_regions + 1, (i64)blockIdx.x) - 1;
+    const i64 tile = (i64)blockIdx.x - V.tile_off[j];
+    const i64 Lr = V.ext_off[j + 1] - V.ext_off[j];
+    const i64 p0 = tile * TB_ROLL_TILE;
+    const int lf = w / 2;
+    const i64 in0 = p0 - lf;
+    const int n_in = TB_ROLL_TILE + (w > 0 ? w : 0);
+    for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
+        i64 q = in0 + i;
+        double v = 0.0;
+        if (q >= 0 && q < Lr) {
+            if (IN_MODE == 0) v = tb_prep_value(((const float *)in_)[V.ext_off[j] + q], prep);
+            else v = ((const double *)in_)[V.ext_off[j] + q];
+        }
+        buf[i] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < TB_ROLL_TILE; t += blockDim.x) {
+        i64 pos = p0 + t;
+        if (pos >= Lr) break;
+        double r;
+        if (w <= 0) r = buf[t];
+        else if (pos >= lf && pos - lf + w <= Lr) {
+            float acc = 0.0f;
+            for (int u = 0; u < w; u++) acc = (float)((double)acc + buf[t + u]);
+            r = is_mean ? (double)acc / (w * 1.0) : (double)acc;
+        } else r = (double)NAN;
+        if (OUT_MODE == 2) ((double *)out_)[V.ext_off[j] + pos] = r;
+        else if (pos >= V.flank && pos < Lr - V.flank) {
+            i64 o = V.out_off[j] + (pos - V.flank);
+            if (OUT_MODE == 0) ((float *)out_)[o] = (float)r;
+            else ((double *)out_)[o] = r;
+        }
+    }
+}
+
+// the corrected track of the last tb_correct_run as the float32 signal of the same regions extended by `flank`
+__global__ void tb_corrected_to_signal_kernel(const double *__restrict__ cf, const double *__restrict__ cr, const i64 *__restrict__ out_off,
+                                              const i64 *__restrict__ sig_off, i64 n_regions, i64 total, int flank, float *__restrict__ sig) {
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+        i64 j = tb_upper_bound(sig_off, n_regions + 1, x) - 1;
+        i64 q = x - sig_off[j] - flank;
+        i64 len = out_off[j + 1] - out_off[j];
+        float v = 0.0f;
+        if (q >= 0 && q < len) v = (float)(cf[out_off[j] + q] + cr[out_off[j] + q]);
+        sig[x] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int tb_sc_layout(tb_ctx *ctx, i64 n_regions, const int64_t *ext_len) {
+    auto &S = ctx->sc;
+    S.n_regions = n_regions;
+    S.ext_off.assign(n_regions + 1, 0);
+    for (i64 i = 0; i < n_regions; i++) {
+        if (ext_len[i] <= 0) return tb_fail(ctx, TB_ERR_ARG, "region %lld has length %lld", i, (i64)ext_len[i]);
+        S.ext_off[i + 1] = S.ext_off[i] + ext_len[i];
+    }
+    S.ext_total = S.ext_off[n_regions];
+    S.have_out = false;
+    S.flank = -1;
+    return tb_h2d(ctx, S.d_ext_off, S.ext_off.data(), sizeof(i64) * (n_regions + 1));
+}
+
+extern "C" int tb_signal_upload(tb_ctx *ctx, const float *signal, int64_t n_regions, const int64_t *ext_len) {
+    if (!ctx || (n_regions > 0 && (!signal || !ext_len)) || n_regions < 0) return TB_ERR_ARG;
+    ctx->sc.have_signal = false;
+    TB_TRY(tb_sc_layout(ctx, n_regions, ext_len));
+    TB_TRY(tb_h2d(ctx, ctx->sc.signal, signal, (size_t)ctx->sc.ext_total * sizeof(float)));
+    TB_TRY(tb_sync(ctx, "tb_signal_upload"));
+    ctx->sc.have_signal = true;
+    return TB_OK;
+}
+
+extern "C" int tb_signal_from_corrected(tb_ctx *ctx, int flank) {
+    if (!ctx) return TB_ERR_ARG;
+    auto &C = ctx->cor;
+    if (!C.valid) return tb_fail(ctx, TB_ERR_STATE, "tb_signal_from_corrected: no completed tb_correct_run");
+    if (flank < 0) return tb_fail(ctx, TB_ERR_ARG, "tb_signal_from_corrected: negative flank");
+    std::vector<int64_t> ext_len(C.n_regions);
+    for (i64 i = 0; i < C.n_regions; i++) ext_len[i] = (C.out_off[i + 1] - C.out_off[i]) + 2 * (i64)flank;
+    ctx->sc.have_signal = false;
+    TB_TRY(tb_sc_layout(ctx, C.n_regions, ext_len.data()));
+    auto &S = ctx->sc;
+    TB_TRY(tb_reserve(ctx, S.signal, (size_t)S.ext_total * sizeof(float)));
+    if (S.ext_total > 0) {
+        i64 want = tb_div_up(S.ext_total, 256), capg = (i64)ctx->sm_count * 16;
+        const double *cf = C.tracks.as<double>() + ((i64)3 * 2 + 0) * C.out_total;
+        const double *cr = C.tracks.as<double>() + ((i64)3 * 2 + 1) * C.out_total;
+        TB_LAUNCH(ctx, tb_corrected_to_signal_kernel, (unsigned)(want < capg ? want : capg), 256, 0, cf, cr,
+                  (const i64 *)C.d_out_off.as<i64>(), (const i64 *)S.d_ext_off.as<i64>(), C.n_regions, S.ext_total, flank,
+                  S.signal.as<float>());
+    }
+    TB_TRY(tb_sync(ctx, "tb_signal_from_corrected"));
+    S.have_signal = true;
+    return TB_OK;
+}
+
+template <int IN_MODE>
+static int tb_launch_rolling(tb_ctx *ctx, const tb_sc_view &V, i64 n_tiles, const void *in, const tb_prep &prep, int w, int is_mean,
+                             int out_mode, void *out) {
+    size_t smem = (size_t)(TB_ROLL_TILE + (w > 0 ? w : 0)) * sizeof(double);
+    if (smem > (size_t)200 * 1024) return tb_fail(ctx, TB_ERR_ARG, "rolling window %d too large", w);
+#define TB_ROLL_CASE(OM)                                                                                        \
+    {                                                                                                           \
+        auto k = tb_rolling_kernel<IN_MODE, OM>;                                                                \
+        TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        TB_LAUNCH(ctx, k, (unsigned)n_tiles, 256, smem, V, in, prep, w, is_mean, out);                          \
+    }
+    if (out_mode == 0) TB_ROLL_CASE(0) else if (out_mode == 1) TB_ROLL_CASE(1) else TB_ROLL_CASE(2)
+#undef TB_ROLL_CASE
+    return tb_check(ctx, cudaGetLastError(), "tb_rolling_kernel");
+}
+
+static int tb_tiles(tb_ctx *ctx, const std::vector<i64> &ext_off, i64 per_tile, tb_dbuf &d_tile_off, i64 &n_tiles) {
+    i64 n = (i64)ext_off.size() - 1;
+    std::vector<i64> tile_off(n + 1, 0);
+    for (i64 i = 0; i < n; i++) tile_off[i + 1] = tile_off[i] + tb_div_up(ext_off[i + 1] - ext_off[i], per_tile);
+    n_tiles = tile_off[n];
+    if (n_tiles > 0x7fffffffLL) return tb_fail(ctx, TB_ERR_ARG, "too many tiles (%lld)", n_tiles);
+    return tb_h2d(ctx, d_tile_off, tile_off.data(), sizeof(i64) * (n + 1));
+}
+
+extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
+    if (!ctx || !p) return TB_ERR_ARG;
+    auto &S = ctx->sc;
+    if (!S.have_signal) return tb_fail(ctx, TB_ERR_STATE, "tb_score_run: no signal (tb_signal_upload / tb_signal_from_corrected)");
+    S.have_out = false;
+    if (p->flank < 0) return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: negative flank");
+    const bool fp_like = p->kind == TB_SCORE_FOOTPRINT || p->kind == TB_SCORE_FOS;
+    if (fp_like && (p->flank_min < 1 || p->flank_max < p->flank_min || p->fp_min < 1 || p->fp_max < p->fp_min || p->flank_max > 2048 ||
+                    p->fp_max > 256))
+        return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: need 1 <= flank_min <= flank_max <= 2048 and 1 <= fp_min <= fp_max <= 256");
+    if ((p->kind == TB_SCORE_SUM || p->kind == TB_SCORE_MEAN) && p->window < 1)
+        return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: window must be >= 1");
+    S.out_off.assign(S.n_regions + 1, 0);
+    for (i64 i = 0; i < S.n_regions; i++) {
+        i64 len = S.ext_off[i + 1] - S.ext_off[i] - 2 * (i64)p->flank;
+        if (len <= 0) return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: region %lld shorter than twice the flank", i);
+        S.out_off[i + 1] = S.out_off[i] + len;
+    }
+    S.out_total = S.out_off[S.n_regions];
+    S.out_f64 = p->as_f64 ? 1 : 0;
+    S.flank = p->flank;
+    if (S.n_regions == 0) {
+        S.have_out = true;
+        return TB_OK;
+    }
+    TB_TRY(tb_h2d(ctx, ctx->reg_d, S.out_off.data(), sizeof(i64) * (S.n_regions + 1)));
+    TB_TRY(tb_reserve(ctx, S.out, (size_t)S.out_total * (p->as_f64 ? 8 : 4)));
+    const bool smooth = p->smooth > 1;
+    if (smooth) TB_TRY(tb_reserve(ctx, S.work0, (size_t)S.ext_total * sizeof(double)));
+    tb_prep prep{p->absolute, p->use_min, p->use_max, p->min_limit, p->max_limit};
+    const int first_mode = smooth ? 2 : (p->as_f64 ? 1 : 0);
+    void *first_out = smooth ? S.work0.p : S.out.p;
+    i64 n_tiles = 0;
+
+    tb_timer_start(ctx);
+    if (fp_like) {
+        const bool fos = p->kind == TB_SCORE_FOS;
+        const i64 per_tile = fos ? TB_K4_THREADS : TB_K4_THREADS - (p->fp_max - 1);
+        TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles));
+        tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
+        const int n_in = fos ? TB_K4_THREADS + 2 * (p->flank_max + p->fp_max) : TB_K4_THREADS + 2 * p->flank_max + p->fp_max;
+        size_t smem = (size_t)(2 * (n_in + 1) + 2 * TB_K4_THREADS) * sizeof(double) + (size_t)(n_in + 2 * TB_K4_THREADS) * sizeof(float);
+        if (smem > (size_t)220 * 1024) return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: flank/footprint widths too large for one tile");
+#define TB_FP_CASE(KERNEL, OM)                                                                                              \
+    {                                                                                                                       \
+        auto k = KERNEL<OM>;                                                                                                \
+        TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+        TB_LAUNCH(ctx, k, (unsigned)n_tiles, TB_K4_THREADS, smem, V, (const float *)S.signal.as<float>(), prep, p->flank_min, \
+                  p->flank_max, p->fp_min, p->fp_max, first_out);                                                           \
+    }
+        if (!fos) {
+            if (first_mode == 0) TB_FP_CASE(tb_footprint_kernel, 0) else if (first_mode == 1) TB_FP_CASE(tb_footprint_kernel, 1)
+            else TB_FP_CASE(tb_footprint_kernel, 2)
+        } else {
+            if (first_mode == 0) TB_FP_CASE(tb_fos_kernel, 0) else if (first_mode == 1) TB_FP_CASE(tb_fos_kernel, 1)
+            else TB_FP_CASE(tb_fos_kernel, 2)
+        }
+#undef TB_FP_CASE
+        TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_footprint_kernel"));
+    } else {
+        TB_TRY(tb_tiles(ctx, S.ext_off, TB_ROLL_TILE, ctx->reg_e, n_tiles));
+        tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
+        int w = p->kind == TB_SCORE_NONE ? 0 : p->window;
+        TB_TRY(tb_launch_rolling<0>(ctx, V, n_tiles, S.signal.p, prep, w, p->kind == TB_SCORE_MEAN, first_mode, first_out));
+    }
+    if (smooth) {
+        TB_TRY(tb_tiles(ctx, S.ext_off, TB_ROLL_TILE, ctx->reg_e, n_tiles));
+        tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
+        TB_TRY(tb_launch_rolling<1>(ctx, V, n_tiles, S.work0.p, prep, p->smooth, 1, p->as_f64 ? 1 : 0, S.out.p));
+    }
+    tb_timer_stop(ctx);
+    TB_TRY(tb_sync(ctx, "tb_score_run"));
+    S.have_out = true;
+    return TB_OK;
+}
+
+extern "C" int tb_score_download(tb_ctx *ctx, void *out) {
+    if (!ctx || !out) return TB_ERR_ARG;
+    auto &S = ctx->sc;
+    if (!S.have_out) return tb_fail(ctx, TB_ERR_STATE, "tb_score_download: no completed tb_score_run");
+    return tb_d2h(ctx, out, S.out.p, (size_t)S.out_total * (S.out_f64 ? 8 : 4));
+}
+
+extern "C" int tb_score_regions(tb_ctx *ctx, const float *signal, int64_t n_regions, const int64_t *ext_len, const tb_score_params *p,
+                                void *out) {
+    TB_TRY(tb_signal_upload(ctx, signal, n_regions, ext_len));
+    TB_TRY(tb_score_run(ctx, p));
+    return tb_score_download(ctx, out);
+}
+
+extern "C" int tb_rolling(tb_ctx *ctx, const double *arr, int64_t n, int w, int is_mean, double *out) {
+    if (!ctx || n < 0 || (n > 0 && (!arr || !out))) return TB_ERR_ARG;
+    if (w < 1) return tb_fail(ctx, TB_ERR_ARG, "tb_rolling: w must be >= 1");
+    if (n == 0) return TB_OK;
+    std::vector<i64> off = {0, (i64)n};
+    TB_TRY(tb_h2d(ctx, ctx->reg_a, off.data(), sizeof(i64) * 2));
+    TB_TRY(tb_h2d(ctx, ctx->scratch0, arr, (size_t)n * sizeof(double)));
+    TB_TRY(tb_reserve(ctx, ctx->scratch1, (size_t)n * sizeof(double)));
+    i64 n_tiles = 0;
+    TB_TRY(tb_tiles(ctx, off, TB_ROLL_TILE, ctx->reg_e, n_tiles));
+    tb_sc_view V{ctx->reg_a.as<i64>(), ctx->reg_a.as<i64>(), ctx->reg_e.as<i64>(), 1, 0};
+    tb_prep prep{0, 0, 0, 0.0, 0.0};
+    tb_timer_start(ctx);
+    TB_TRY(tb_launch_rolling<1>(ctx, V, n_tiles, ctx->scratch0.p, prep, w, is_mean, 1, ctx->scratch1.p));
+    tb_timer_stop(ctx);
+    return tb_d2h(ctx, out, ctx->scratch1.p, (size_t)n * sizeof(double));
+}

@@ -1,0 +1,265 @@
+// tb_score.cu -- K3a: per-position Tn5 bias score (DWM / PWM) over 2-bit packed genome sequence.
+//
+// Reference: DiNucleotideMatrix.score_sequence, tobias/utils/sequences.pyx:263-342 (PWM: :123-151), called per
+// strand by bias_correction, tobias/tools/atacorrect_functions.py:254-262 (reverse strand = score of the reverse
+// complement, reversed; NaN -> 0).
+//
+// Reformulation.  For a window with bases S_0..S_{L-1} the reference computes, per model x in {bias, background},
+//     E_x[n][a] = PWM_x[a,n] + sum_{m != n} (DWM_x[S_m, a, m, n] - PWM_x[a,n])                (a = 0..3)
+//     p_x[n]    = E_x[n][S_n] - log2( sum_a 2^E_x[n][a] ),      score = sum_n p_bias[n] - sum_n p_bg[n].
+// With U_x[m][s][n][a] = DWM_x[s,a,m,n] - PWM_x[a,n] (m != n), U_x[n][s][n][a] = PWM_x[a,n], this is
+//     E_x[n][.] = sum_m U_x[m][S_m][n][.]
+// i.e. 25 selected rows of a 100 x 100 table are summed.  The table of BOTH models of one strand (160 KB of fp64 for
+// L = 25) is staged once per block in shared memory and stays resident while the block streams positions
+// (persistent blocks, one per SM, half of them per strand).  Within a warp lane n owns column n: its four
+// accumulators are contiguous (32 B) so every row read is two conflict-free LDS.128, and the base S_m is warp-
+// uniform.  The reverse-strand table is pre-permuted on the host (m -> L-1-m, n -> L-1-n, bases complemented) so
+// that both strands run the same code on forward-oriented k-mers.  All arithmetic is fp64.
+#include "tb_common.cuh"
+
+struct tb_score_regions_view {
+    const i64 *ext_start;   // linear start of each (extended) region
+    const i64 *ext_off;     // offsets into the concatenated position space, n+1 entries
+    i64 n;
+    i64 total;
+};
+
+#define TB_K3A_WPI 2        // windows in flight per warp (independent accumulator sets)
+
+__global__ void tb_score_dwm_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ table_fwd,
+                                    const double *__restrict__ table_rev, int L, int use_smem, int strand_mask, int nan_invalid,
+                                    double *__restrict__ out_fwd, double *__restrict__ out_rev) {
+    TB_DYN_SMEM(smem);
+    const int k_flank = L / 2;
+    const int tbl_doubles = 2 * L * 4 * L * 4;
+    // strands handled by this block: both masks set -> even blocks forward, odd blocks reverse
+    int strand, part, nparts;
+    if (strand_mask == 3) {
+        strand = blockIdx.x & 1;
+        part = blockIdx.x >> 1;
+        nparts = (gridDim.x + 1 - strand) >> 1;
+    } else {
+        strand = strand_mask == 2 ? 1 : 0;
+        part = blockIdx.x;
+        nparts = gridDim.x;
+    }
+    const double *src = strand ? table_rev : table_fwd;
+    const double *U = src;
+    if (use_smem) {
+        double *dst = (double *)smem;
+        for (int i = threadIdx.x; i < tbl_doubles; i += blockDim.x) dst[i] = src[i];
+        U = dst;
+        __syncthreads();
+    }
+    double *out = strand ? out_rev : out_fwd;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const i64 n_units = (R.total + 31) >> 5;              // a unit = 32 consecutive positions
+    const int row = L * 4;                                // doubles per (m, s) row
+    const int nl = lane < L ? lane : L - 1;               // lanes >= L shadow lane L-1 (their result is discarded)
+    const double invalid = nan_invalid ? (double)NAN : 0.0;
+
+    for (i64 unit = (i64)part * warps_per_block + warp; unit < n_units; unit += (i64)nparts * warps_per_block) {
+        i64 pos0 = unit << 5;
+        i64 j = tb_upper_bound(R.ext_off, R.n + 1, pos0) - 1;
+        for (int it = 0; it < 32; it += TB_K3A_WPI) {
+            u64 kmer[TB_K3A_WPI];
+            bool ok[TB_K3A_WPI];
+            i64 pos[TB_K3A_WPI];
+#pragma unroll
+            for (int w = 0; w < TB_K3A_WPI; w++) {
+                pos[w] = pos0 + it + w;
+                ok[w] = false;
+                kmer[w] = 0;
+                if (pos[w] < R.total) {
+                    while (pos[w] >= R.ext_off[j + 1]) j++;
+                    i64 local = pos[w] - R.ext_off[j];
+                    i64 len = R.ext_off[j + 1] - R.ext_off[j];
+                    if (local >= k_flank && local < len - k_flank) {
+                        i64 gp = R.ext_start[j] + local;
+                        if (tb_nflags(g, gp - k_flank, L) == 0) {
+                            kmer[w] = tb_bases(g, gp - k_flank, L);
+                            ok[w] = true;
+                        }
+                    }
+                }
+            }
+            double acc[TB_K3A_WPI][2][4];
+#pragma unroll
+            for (int w = 0; w < TB_K3A_WPI; w++)
+#pragma unroll
+                for (int x = 0; x < 2; x++)
+#pragma unroll
+                    for (int a = 0; a < 4; a++) acc[w][x][a] = 0.0;
+            for (int m = 0; m < L; m++) {
+#pragma unroll
+                for (int w = 0; w < TB_K3A_WPI; w++) {
+                    int s = (int)((kmer[w] >> (2 * m)) & 3u);
+#pragma unroll
+                    for (int x = 0; x < 2; x++) {
+                        const double2 *p = (const double2 *)(U + ((size_t)(x * L + m) * 4 + s) * row + nl * 4);
+                        double2 v0 = p[0], v1 = p[1];
+                        acc[w][x][0] += v0.x;
+                        acc[w][x][1] += v0.y;
+                        acc[w][x][2] += v1.x;
+                        acc[w][x][3] += v1.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < TB_K3A_WPI; w++) {
+                int sn = (int)((kmer[w] >> (2 * nl)) & 3u);
+                double p[2];
+#pragma unroll
+                for (int x = 0; x < 2; x++) {
+                    double cn = exp2(acc[w][x][0]);
+                    cn += exp2(acc[w][x][1]);
+                    cn += exp2(acc[w][x][2]);
+                    cn += exp2(acc[w][x][3]);
+                    double e = sn == 0 ? acc[w][x][0] : sn == 1 ? acc[w][x][1] : sn == 2 ? acc[w][x][2] : acc[w][x][3];
+                    p[x] = e - log2(cn);
+                }
+                double pb = lane < L ? p[0] : 0.0;       // x = 0: bias model, x = 1: background model
+                double pg = lane < L ? p[1] : 0.0;
+                for (int d = 16; d > 0; d >>= 1) {
+                    pb += __shfl_xor_sync(0xffffffffu, pb, d);
+                    pg += __shfl_xor_sync(0xffffffffu, pg, d);
+                }
+                if (lane == 0 && pos[w] < R.total) out[pos[w]] = ok[w] ? pb - pg : invalid;
+            }
+        }
+    }
+}
+
+// PWM: score = sum_m pssm[S_m][m]; one thread per position, table in shared memory.
+__global__ void tb_score_pwm_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ pssm_fwd,
+                                    const double *__restrict__ pssm_rev, int L, int strand_mask, int nan_invalid,
+                                    double *__restrict__ out_fwd, double *__restrict__ out_rev) {
+    TB_DYN_SMEM(smem);
+    double *T = (double *)smem;                  // [2 strands][L][4], reverse strand already permuted to forward orientation
+    for (int i = threadIdx.x; i < 2 * L * 4; i += blockDim.x) {
+        int strand = i / (L * 4), r = i % (L * 4), m = r / 4, s = r % 4;
+        T[i] = strand == 0 ? pssm_fwd[s * L + m] : pssm_rev[(s ^ 1) * L + (L - 1 - m)];
+    }
+    __syncthreads();
+    const int k_flank = L / 2;
+    const double invalid = nan_invalid ? (double)NAN : 0.0;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 pos = (i64)blockIdx.x * blockDim.x + threadIdx.x; pos < R.total; pos += stride) {
+        i64 j = tb_upper_bound(R.ext_off, R.n + 1, pos) - 1;
+        i64 local = pos - R.ext_off[j], len = R.ext_off[j + 1] - R.ext_off[j];
+        bool ok = local >= k_flank && local < len - k_flank;
+        u64 kmer = 0;
+        if (ok) {
+            i64 gp = R.ext_start[j] + local;
+            ok = tb_nflags(g, gp - k_flank, L) == 0;
+            if (ok) kmer = tb_bases(g, gp - k_flank, L);
+        }
+        for (int strand = 0; strand < 2; strand++) {
+            if (!((strand_mask >> strand) & 1)) continue;
+            double sc = invalid;
+            if (ok) {
+                sc = 0.0;
+                if (strand == 0) {
+                    for (int m = 0; m < L; m++) sc += T[m * 4 + (int)((kmer >> (2 * m)) & 3u)];
+                } else {        // read-oriented summation order: m' = 0..L-1  <->  forward offset L-1-m'
+                    for (int m = L - 1; m >= 0; m--) sc += T[L * 4 + m * 4 + (int)((kmer >> (2 * m)) & 3u)];
+                }
+            }
+            (strand ? out_rev : out_fwd)[pos] = sc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, const double *bias_pwm_log,
+                                 const double *bg_pwm_log, const double *bias_dwm_log, const double *bg_dwm_log) {
+    if (!ctx) return TB_ERR_ARG;
+    if (strand < 0 || strand > 1) return tb_fail(ctx, TB_ERR_ARG, "tb_set_bias_model: strand must be 0 or 1");
+    if (L < 1 || L > 31 || !(L & 1)) return tb_fail(ctx, TB_ERR_ARG, "tb_set_bias_model: L must be odd and <= 31");
+    if (!bias_pwm_log || (is_dwm && (!bg_pwm_log || !bias_dwm_log || !bg_dwm_log)))
+        return tb_fail(ctx, TB_ERR_ARG, "tb_set_bias_model: NULL table");
+    tb_model &M = ctx->model[strand];
+    M.is_dwm = is_dwm ? 1 : 0;
+    M.L = L;
+    ctx->cor.valid = false;
+    if (!is_dwm) return tb_h2d(ctx, M.table, bias_pwm_log, sizeof(double) * 5 * L) || tb_sync(ctx, "tb_set_bias_model");
+    // U[x][m][s][n][a]; for the reverse strand the table is expressed on forward-oriented k-mers:
+    //   U'[m'][s'][n'][a'] = U[L-1-m'][s'^1][L-1-n'][a'^1]
+    std::vector<double> U((size_t)2 * L * 4 * L * 4);
+    const double *pwm[2] = {bias_pwm_log, bg_pwm_log};
+    const double *dwm[2] = {bias_dwm_log, bg_dwm_log};
+    for (int x = 0; x < 2; x++)
+        for (int m = 0; m < L; m++)
+            for (int s = 0; s < 4; s++)
+                for (int n = 0; n < L; n++)
+                    for (int a = 0; a < 4; a++) {
+                        int rm = strand ? L - 1 - m : m, rn = strand ? L - 1 - n : n;
+                        int rs = strand ? s ^ 1 : s, ra = strand ? a ^ 1 : a;
+                        double p = pwm[x][ra * L + rn];
+                        double v = rm == rn ? p : dwm[x][(((size_t)rs * 5 + ra) * L + rm) * L + rn] - p;
+                        U[((((size_t)x * L + m) * 4 + s) * L + n) * 4 + a] = v;
+                    }
+    TB_TRY(tb_h2d(ctx, M.table, U.data(), U.size() * sizeof(double)));
+    return tb_sync(ctx, "tb_set_bias_model");
+}
+
+// scores both strands (mask 3) or one; d_out_* are device arrays over the concatenated position space
+int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i64 n_regions, i64 total, int strand_mask,
+                    int nan_invalid, double *d_out_fwd, double *d_out_rev) {
+    int s0 = (strand_mask & 1) ? 0 : 1;
+    tb_model &M0 = ctx->model[s0];
+    for (int s = 0; s < 2; s++)
+        if ((strand_mask >> s) & 1) {
+            if (ctx->model[s].is_dwm < 0) return tb_fail(ctx, TB_ERR_STATE, "no bias model for strand %d: call tb_set_bias_model", s);
+            if (ctx->model[s].is_dwm != M0.is_dwm || ctx->model[s].L != M0.L)
+                return tb_fail(ctx, TB_ERR_STATE, "forward and reverse bias models differ in type or length");
+        }
+    if (total == 0) return TB_OK;
+    tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
+    tb_score_regions_view R{d_ext_start, d_ext_off, n_regions, total};
+    const double *tf = ctx->model[0].table.as<double>(), *tr = ctx->model[1].table.as<double>();
+    if (!tf) tf = tr;
+    if (!tr) tr = tf;
+    int L = M0.L;
+    if (M0.is_dwm) {
+        size_t smem = (size_t)2 * L * 4 * L * 4 * sizeof(double);
+        int use_smem = smem <= (size_t)200 * 1024;
+        auto k = tb_score_dwm_kernel;
+        if (use_smem) TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int block = 512;
+        i64 n_units = (total + 31) >> 5;
+        i64 want = tb_div_up(n_units, block / 32) * (strand_mask == 3 ? 2 : 1);
+        i64 cap = ctx->sm_count;
+        if (strand_mask == 3 && (cap & 1)) cap--;
+        unsigned grid = (unsigned)(want < cap ? want : cap);
+        if (strand_mask == 3 && grid < 2) grid = 2;
+        TB_LAUNCH(ctx, k, grid, block, use_smem ? smem : 0, g, R, tf, tr, L, use_smem, strand_mask, nan_invalid, d_out_fwd, d_out_rev);
+    } else {
+        size_t smem = (size_t)2 * L * 4 * sizeof(double);
+        i64 want = tb_div_up(total, 256), cap = (i64)ctx->sm_count * 8;
+        TB_LAUNCH(ctx, tb_score_pwm_kernel, (unsigned)(want < cap ? want : cap), 256, smem, g, R, tf, tr, L, strand_mask, nan_invalid,
+                  d_out_fwd, d_out_rev);
+    }
+    return tb_check(ctx, cudaGetLastError(), "tb_score kernel");
+}
+
+extern "C" int tb_score_sequence(tb_ctx *ctx, int strand, int contig, int64_t start, int64_t end, double *out) {
+    if (!ctx || !out) return TB_ERR_ARG;
+    if (strand < 0 || strand > 1) return tb_fail(ctx, TB_ERR_ARG, "tb_score_sequence: strand must be 0 or 1");
+    std::vector<i64> ls, le;
+    int32_t c = contig;
+    int64_t s = start, e = end;
+    TB_TRY(tb_linear_regions(ctx, 1, &c, &s, &e, ls, le, false));
+    i64 total = le[0] - ls[0];
+    i64 off[2] = {0, total};
+    TB_TRY(tb_h2d(ctx, ctx->reg_a, ls.data(), sizeof(i64)));
+    TB_TRY(tb_h2d(ctx, ctx->reg_c, off, sizeof(off)));
+    TB_TRY(tb_reserve(ctx, ctx->scratch0, (size_t)total * sizeof(double)));
+    tb_timer_start(ctx);
+    TB_TRY(tb_score_device(ctx, ctx->reg_a.as<i64>(), ctx->reg_c.as<i64>(), 1, total, 1 << strand, 1, ctx->scratch0.as<double>(),
+                           ctx->scratch0.as<double>()));
+    tb_timer_stop(ctx);
+    return tb_d2h(ctx, out, ctx->scratch0.p, (size_t)total * sizeof(double));
+}

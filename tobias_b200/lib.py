@@ -1,0 +1,342 @@
+"""
+ctypes binding of libtobias_b200.so (C-ABI declared in include/tobias_b200.h).
+
+`load()` loads the nvcc-built library from tobias_b200/csrc/ and raises if it is missing or if no
+CUDA device can be initialised -- there is no CPU fallback anywhere in this package.  `Context` wraps
+one `tb_ctx` (one GPU, one stream set; one process per GPU) with numpy-typed methods.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "csrc", "libtobias_b200.so")
+
+TB_READ_REVERSE, TB_READ_5P_MATCH, TB_READ_SKIP = 1, 2, 4
+SCORE_KINDS = {"footprint": 0, "sum": 1, "mean": 2, "none": 3, "FOS": 4}
+TRACKS = ("uncorrected", "bias", "expected", "corrected")
+
+
+class TobiasB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libtobias_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class ScoreParams(C.Structure):
+    _fields_ = [("kind", C.c_int), ("absolute", C.c_int), ("use_min", C.c_int), ("use_max", C.c_int),
+                ("min_limit", C.c_double), ("max_limit", C.c_double), ("window", C.c_int), ("smooth", C.c_int),
+                ("flank_min", C.c_int), ("flank_max", C.c_int), ("fp_min", C.c_int), ("fp_max", C.c_int),
+                ("flank", C.c_int), ("as_f64", C.c_int)]
+
+
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_PROTOS = {
+    "tb_abi_version": (_i, []),
+    "tb_init": (_i, [_i, C.POINTER(_vp)]),
+    "tb_destroy": (None, [_vp]),
+    "tb_last_error": (C.c_char_p, [_vp]),
+    "tb_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i)]),
+    "tb_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
+    "tb_launch_count": (_i, [_vp, C.POINTER(_i64)]),
+    "tb_genome_create": (_i, [_vp, _i, _vp]),
+    "tb_genome_upload": (_i, [_vp, _i, _i64, _vp, _i64]),
+    "tb_genome_fetch": (_i, [_vp, _i, _i64, _i64, _vp]),
+    "tb_reads_upload": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "tb_count_reads": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, C.POINTER(_i64)]),
+    "tb_pileup": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "tb_bias_counts": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tb_nccl_unique_id": (_i, [_vp]),
+    "tb_nccl_init": (_i, [_vp, _vp, _i, _i]),
+    "tb_allreduce_i64": (_i, [_vp, _vp, _i64]),
+    "tb_allreduce_f64": (_i, [_vp, _vp, _i64]),
+    "tb_set_bias_model": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tb_score_sequence": (_i, [_vp, _i, _i, _i64, _i64, _vp]),
+    "tb_correct_run": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _d, _i, _i, _i]),
+    "tb_stage_ms": (_i, [_vp, C.POINTER(C.c_float), _i]),
+    "tb_correct_download": (_i, [_vp, _i, _i, _vp, _vp]),
+    "tb_correct_fit_trace": (_i, [_vp, C.POINTER(_i64), _vp]),
+    "tb_signal_upload": (_i, [_vp, _vp, _i64, _vp]),
+    "tb_score_run": (_i, [_vp, C.POINTER(ScoreParams)]),
+    "tb_score_download": (_i, [_vp, _vp]),
+    "tb_score_regions": (_i, [_vp, _vp, _i64, _vp, C.POINTER(ScoreParams), _vp]),
+    "tb_signal_from_corrected": (_i, [_vp, _i]),
+    "tb_rolling": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+}
+
+_lib = None
+_lib_path = None
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def load(path=None):
+    """Load the C-ABI library (default: the in-tree CUDA build) and declare every prototype.  Raises when the
+    library is missing: build it with `python -m tobias_b200.build` (or __graft_entry__.build())."""
+    global _lib, _lib_path
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if _lib is not None and _lib_path == path:
+        return _lib
+    if not os.path.exists(path):
+        raise FileNotFoundError("%s not found: the CUDA extension is not built (python -m tobias_b200.build); "
+                                "tobias_b200 has no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib, _lib_path = lib, path
+    return lib
+
+
+def loaded_path():
+    return _lib_path
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One tb_ctx: a GPU-resident genome + read set + bias model and the kernels that run over them."""
+
+    def __init__(self, device=0, lib_path=None):
+        self._lib = load(lib_path)
+        h = _vp()
+        rc = self._lib.tb_init(int(device), C.byref(h))
+        if rc != 0:
+            raise TobiasB200Error(rc, (self._lib.tb_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self.n_contigs = 0
+        self.contig_lengths = []
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TobiasB200Error(rc, (self._lib.tb_last_error(self._h) or b"").decode())
+
+    def device_info(self):
+        sm, fr, tot, emu = _i(), _i64(), _i64(), _i()
+        self._ck(self._lib.tb_device_info(self._h, C.byref(sm), C.byref(fr), C.byref(tot), C.byref(emu)))
+        return {"sm_count": sm.value, "free_bytes": fr.value, "total_bytes": tot.value, "is_emulator": bool(emu.value)}
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._ck(self._lib.tb_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = _i64()
+        self._ck(self._lib.tb_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ genome / reads
+    def genome_create(self, lengths):
+        lens = _arr(lengths, np.int64)
+        self._ck(self._lib.tb_genome_create(self._h, int(lens.shape[0]), _ptr(lens)))
+        self.n_contigs = int(lens.shape[0])
+        self.contig_lengths = [int(x) for x in lens]
+
+    def genome_upload(self, contig, ascii_arr, offset=0):
+        a = _arr(ascii_arr, np.uint8)
+        self._ck(self._lib.tb_genome_upload(self._h, int(contig), int(offset), _ptr(a), int(a.shape[0])))
+
+    def genome_load(self, contigs):
+        """contigs: list of uint8 ASCII arrays, one per contig, in contig-id order."""
+        self.genome_create([len(c) for c in contigs])
+        for i, c in enumerate(contigs):
+            self.genome_upload(i, c)
+
+    def genome_fetch(self, contig, start, n):
+        out = np.empty(int(n), dtype=np.uint8)
+        self._ck(self._lib.tb_genome_fetch(self._h, int(contig), int(start), int(n), _ptr(out)))
+        return out
+
+    def reads_upload(self, contig, ref_start, ref_end, clip5, flags):
+        c, s, e = _arr(contig, np.int32), _arr(ref_start, np.int32), _arr(ref_end, np.int32)
+        k, f = _arr(clip5, np.int32), _arr(flags, np.uint8)
+        self._ck(self._lib.tb_reads_upload(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), _ptr(k), _ptr(f)))
+
+    def reads_upload_columns(self, rc):
+        """Upload a tobias_b200.reads.ReadColumns."""
+        flags = (rc.is_reverse.astype(np.uint8) * TB_READ_REVERSE
+                 | rc.five_prime_is_match().astype(np.uint8) * TB_READ_5P_MATCH
+                 | (~rc.usable()).astype(np.uint8) * TB_READ_SKIP)
+        self.reads_upload(rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags)
+
+    # ------------------------------------------------------------------ K1
+    @staticmethod
+    def _regions(contig, start, end):
+        c, s, e = _arr(contig, np.int32), _arr(start, np.int64), _arr(end, np.int64)
+        if not (c.shape == s.shape == e.shape) or c.ndim != 1:
+            raise ValueError("contig/start/end must be 1-D arrays of equal length")
+        return c, s, e
+
+    def count_reads(self, contig, start, end, read_shift=(4, -5)):
+        c, s, e = self._regions(contig, start, end)
+        out = _i64()
+        self._ck(self._lib.tb_count_reads(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), int(read_shift[0]),
+                                          int(read_shift[1]), C.byref(out)))
+        return out.value
+
+    def pileup(self, contig, start, end, read_shift=(4, -5)):
+        c, s, e = self._regions(contig, start, end)
+        total = int((e - s).sum())
+        fwd, rev = np.zeros(total, dtype=np.uint32), np.zeros(total, dtype=np.uint32)
+        self._ck(self._lib.tb_pileup(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), int(read_shift[0]),
+                                     int(read_shift[1]), _ptr(fwd), _ptr(rev)))
+        return fwd, rev
+
+    # ------------------------------------------------------------------ K2
+    def bias_counts(self, contig, start, end, k_flank=12, bg_shift=100, read_shift=(4, -5), cap=10, is_dwm=True):
+        c, s, e = self._regions(contig, start, end)
+        L = 2 * k_flank + 1
+        shape = (2, 2, 5, 5, L, L) if is_dwm else (2, 2, 5, L)
+        counts = np.zeros(shape, dtype=np.int64)
+        scalars = np.zeros(5, dtype=np.int64)
+        self._ck(self._lib.tb_bias_counts(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), int(k_flank), int(bg_shift),
+                                          int(read_shift[0]), int(read_shift[1]), int(cap), int(bool(is_dwm)),
+                                          _ptr(counts), _ptr(scalars)))
+        return counts, scalars
+
+    def nccl_unique_id(self):
+        buf = np.zeros(128, dtype=np.uint8)
+        rc = self._lib.tb_nccl_unique_id(_ptr(buf))
+        if rc != 0:
+            raise TobiasB200Error(rc, (self._lib.tb_last_error(None) or b"").decode())
+        return buf
+
+    def nccl_init(self, unique_id, rank, world_size):
+        uid = _arr(unique_id, np.uint8)
+        self._ck(self._lib.tb_nccl_init(self._h, _ptr(uid), int(rank), int(world_size)))
+
+    def allreduce(self, buf):
+        """In-place sum of an int64 / float64 host array over the ranks (NCCL)."""
+        if buf.dtype == np.int64:
+            self._ck(self._lib.tb_allreduce_i64(self._h, _ptr(buf), int(buf.size)))
+        elif buf.dtype == np.float64:
+            self._ck(self._lib.tb_allreduce_f64(self._h, _ptr(buf), int(buf.size)))
+        else:
+            raise TypeError("allreduce supports int64 and float64 arrays")
+        return buf
+
+    # ------------------------------------------------------------------ K3
+    def set_bias_model(self, strand, is_dwm, L, bias_pwm_log, bg_pwm_log=None, bias_dwm_log=None, bg_dwm_log=None):
+        t = [None if x is None else _arr(x, np.float64) for x in (bias_pwm_log, bg_pwm_log, bias_dwm_log, bg_dwm_log)]
+        self._ck(self._lib.tb_set_bias_model(self._h, int(strand), int(bool(is_dwm)), int(L), _ptr(t[0]), _ptr(t[1]),
+                                             _ptr(t[2]), _ptr(t[3])))
+
+    def score_sequence(self, strand, contig, start, end):
+        out = np.empty(int(end - start), dtype=np.float64)
+        self._ck(self._lib.tb_score_sequence(self._h, int(strand), int(contig), int(start), int(end), _ptr(out)))
+        return out
+
+    def stage_ms(self, n=4):
+        buf = (C.c_float * n)()
+        self._ck(self._lib.tb_stage_ms(self._h, buf, n))
+        return [float(x) for x in buf]
+
+    def correct_run(self, contig, start, end, k_flank=12, window=100, correction_factor=1.0, read_shift=(4, -5),
+                    lm_exact_order=True):
+        c, s, e = self._regions(contig, start, end)
+        self._ck(self._lib.tb_correct_run(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), int(k_flank), int(window),
+                                          float(correction_factor), int(read_shift[0]), int(read_shift[1]),
+                                          int(bool(lm_exact_order))))
+        self._cor_total = int((e - s).sum())
+        self._cor_L = 2 * k_flank + 1
+
+    def correct_download(self, split_strands=False, as_f64=False, tracks=TRACKS, prepost=True):
+        """dict track -> array (split_strands=False) or track -> (forward, reverse); plus 'prepost' [2][3][5][L]."""
+        dt = np.float64 if as_f64 else np.float32
+        ptrs = ((_vp * 2) * 4)()
+        out = {}
+        for t, name in enumerate(TRACKS):
+            if name not in tracks:
+                continue
+            if split_strands:
+                a, b = np.empty(self._cor_total, dtype=dt), np.empty(self._cor_total, dtype=dt)
+                ptrs[t][0], ptrs[t][1] = a.ctypes.data, b.ctypes.data
+                out[name] = (a, b)
+            else:
+                a = np.empty(self._cor_total, dtype=dt)
+                ptrs[t][0] = a.ctypes.data
+                out[name] = a
+        pp = np.zeros((2, 3, 5, self._cor_L), dtype=np.float64) if prepost else None
+        self._ck(self._lib.tb_correct_download(self._h, int(bool(split_strands)), int(bool(as_f64)), ptrs, _ptr(pp)))
+        if prepost:
+            out["prepost"] = pp
+        return out
+
+    def correct_fit_trace(self):
+        n = _i64()
+        self._ck(self._lib.tb_correct_fit_trace(self._h, C.byref(n), None))
+        out = np.zeros((2, n.value, 6), dtype=np.float64)
+        if n.value:
+            self._ck(self._lib.tb_correct_fit_trace(self._h, C.byref(n), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ K4
+    @staticmethod
+    def score_params(kind="footprint", flank=0, absolute=False, min_limit=None, max_limit=None, window=100, smooth=1,
+                     flank_min=10, flank_max=30, fp_min=20, fp_max=50, as_f64=False):
+        return ScoreParams(SCORE_KINDS[kind], int(bool(absolute)), int(min_limit is not None), int(max_limit is not None),
+                           float(min_limit or 0.0), float(max_limit or 0.0), int(window), int(smooth), int(flank_min),
+                           int(flank_max), int(fp_min), int(fp_max), int(flank), int(bool(as_f64)))
+
+    def signal_upload(self, signal, ext_len):
+        sig, ln = _arr(signal, np.float32), _arr(ext_len, np.int64)
+        if int(ln.sum()) != sig.shape[0]:
+            raise ValueError("signal length does not match sum(ext_len)")
+        self._ck(self._lib.tb_signal_upload(self._h, _ptr(sig), int(ln.shape[0]), _ptr(ln)))
+        self._sc_ext = ln
+
+    def signal_from_corrected(self, flank, out_len):
+        self._ck(self._lib.tb_signal_from_corrected(self._h, int(flank)))
+        self._sc_ext = _arr(out_len, np.int64) + 2 * int(flank)
+
+    def score_run(self, params):
+        self._ck(self._lib.tb_score_run(self._h, C.byref(params)))
+        self._sc_params = params
+
+    def score_download(self):
+        p = self._sc_params
+        total = int((self._sc_ext - 2 * p.flank).sum())
+        out = np.empty(total, dtype=np.float64 if p.as_f64 else np.float32)
+        self._ck(self._lib.tb_score_download(self._h, _ptr(out)))
+        return out
+
+    def score_regions(self, signal, ext_len, params):
+        self.signal_upload(signal, ext_len)
+        self.score_run(params)
+        return self.score_download()
+
+    def rolling(self, arr, w, operation="sum"):
+        a = _arr(arr, np.float64)
+        out = np.empty_like(a)
+        self._ck(self._lib.tb_rolling(self._h, _ptr(a), int(a.shape[0]), int(w), int(operation == "mean"), _ptr(out)))
+        return out

@@ -145,7 +145,7 @@ def _insertion_weight(codes, pos, pwm):
         c = codes[idx]
         bad |= c > 3
         w += pwm[np.minimum(c, 3), j]
-    w = np.exp2(w - np.abs(pwm).max(axis=0).sum())
+    w = np.minimum(1.0, np.exp2(w - 0.45 * np.abs(pwm).max(axis=0).sum()))
     w[bad] = 0.02
     return w
 
