@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the TOBIAS per-base hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload hg38|chr50mb|small]
+
+Metric (BASELINE.json): corrected + footprint-scored bp/s -- output-region base pairs (trimmed, strands combined) that went
+through ATACorrect (read counts -> bias estimation -> bias model -> correction) AND ScoreBigwig footprint scoring, per second.
+Workload at N=1: BASELINE.json configs[1], the synthetic hg38-sized genome (24 contigs with hg38 lengths + chrM, 3.1 Gb,
+150 k peaks, 50 M alignment records).  At N>1 the same workload is sharded by contig (strong scaling, config[2]); the only
+collective is the all-reduce of the bias-training counts / normalisation counters (NCCL) and of the verification PWMs.
+
+One "step" = one pass of the whole path over the rank's shard:
+   value : inputs (2-bit genome, read columns) resident in HBM; timed with CUDA events on the library's stream.
+   e2e   : same pass through the public host API with HOST buffers: H2D of the ASCII genome + read columns from pinned
+           memory, all kernels, D2H of the four float32 tracks + the footprint track into pinned memory.
+Host-side region algebra (BED parsing, merge / subtract / split) happens once outside the timed region on both arms.
+
+--impl reference times the reference's own CPU implementation (compiled, unmodified: oracle/_ref) with all host cores on
+a bounded sample of the same workload (two small contigs of the synthetic genome at the same read density).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "corrected+footprint-scored bp/s"
+SEED = 20261019
+K_FLANK, WINDOW, BG_SHIFT, EXTEND, READ_SHIFT = 12, 100, 100, 100, (4, -5)
+FP = dict(flank_min=10, flank_max=30, fp_min=20, fp_max=50)
+
+
+def workload(name):
+    from tobias_b200 import synth
+    if name == "hg38":
+        return dict(lengths=dict(synth.HG38_LENGTHS), n_peaks=150000, n_records=50_000_000,
+                    desc="ATACorrect+ScoreBigwig, synthetic hg38-sized genome (3.1 Gb, 150k peaks, 50M reads)")
+    if name == "chr50mb":
+        return dict(lengths={"chr1": 50_000_000}, n_peaks=20000, n_records=5_000_000,
+                    desc="ATACorrect+ScoreBigwig, synthetic 50 Mb chromosome, 20k 500bp peaks, 5M reads")
+    if name == "small":
+        return dict(lengths={"chr1": 3_000_000, "chr2": 2_000_000, "chrM": 16569}, n_peaks=600, n_records=400000,
+                    desc="small smoke workload (not a benchmark configuration)")
+    raise SystemExit("unknown workload " + name)
+
+
+def shard_contigs(lengths, world):
+    """Greedy longest-first bin packing of contigs onto ranks (deterministic)."""
+    loads = [0] * world
+    owner = {}
+    for name, ln in sorted(lengths.items(), key=lambda kv: (-kv[1], kv[0])):
+        r = min(range(world), key=lambda i: (loads[i], i))
+        owner[name] = r
+        loads[r] += ln
+    return owner
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.samples, self.reasons, self.proc = [], set(), None
+        self.idx = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(s for s, _ in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- B200 arm
+def prepare_shard(args, rank, world):
+    """Synthetic data of this rank's contigs + region tables as arrays (host driver work, untimed)."""
+    import torch
+    from tobias_b200 import synth_torch
+    from tobias_b200.pipeline import prepare_regions
+    from tobias_b200.regions import OneRegion, RegionList, to_arrays
+    wl = workload(args.workload)
+    owner = shard_contigs({n: ln for n, ln in wl["lengths"].items()}, world)
+    mine = {n: ln for n, ln in wl["lengths"].items() if owner[n] == rank}
+    tot = float(sum(wl["lengths"].values()))
+    frac = sum(mine.values()) / tot
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    ds = synth_torch.TorchDataset(SEED + 17 * rank, mine, max(1, int(round(wl["n_peaks"] * frac))),
+                                  int(round(wl["n_records"] * frac)), device=dev, pin=True)
+    names = ds.names
+    chrom_info = {n: ln for n, ln in zip(names, ds.lengths) if n != "chrM"}          # --drop-chroms default
+    peaks = RegionList([OneRegion(list(p)) for p in ds.peaks])
+    regs = prepare_regions(peaks, chrom_info, [n for n in names if n in chrom_info], extend=EXTEND, k_flank=K_FLANK, window=WINDOW)
+    index = {n: i for i, n in enumerate(names)}
+    arrays = {k: to_arrays(sorted(regs[k], key=lambda r: (index[r.chrom], r.start, r.end)), index)
+              for k in ("peak_regions", "nonpeak_regions", "input_regions", "output_regions")}
+    return ds, arrays, wl
+
+
+def allreduce_np(buf, device):
+    """Sum a host int64/float64 array over ranks with NCCL (torch.distributed plumbing); no-op at world size 1."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return buf
+    t = torch.from_numpy(buf).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    buf[...] = t.cpu().numpy()
+    return buf
+
+
+def run_step(eng, arrays, device, resident, host=None, out=None):
+    """One pass of the hot path over this rank's shard.  Returns (AtacBias, stage_ms list)."""
+    from tobias_b200.pipeline import AtacBias, STRANDS
+    ctx = eng.ctx
+    if not resident:                      # e2e: inputs come from (pinned) host buffers every step
+        ctx.genome_create(host["lengths"])
+        for i, g in enumerate(host["genome"]):
+            ctx.genome_upload(i, g)
+        ctx.reads_upload(*host["reads"])
+    # --- normalisation counters + bias-training counts, then the one exchange step of the path
+    reads_peaks = ctx.count_reads(*arrays["peak_regions"], READ_SHIFT)
+    reads_nonpeaks = ctx.count_reads(*arrays["nonpeak_regions"], READ_SHIFT)
+    counts, scalars = ctx.bias_counts(*arrays["input_regions"], K_FLANK, BG_SHIFT, READ_SHIFT, 10, True)
+    k2_ms = ctx.last_kernel_ms()
+    packed = np.concatenate([counts.ravel(), scalars, np.array([reads_peaks, reads_nonpeaks], dtype=np.int64)])
+    allreduce_np(packed, device)
+    counts = packed[:counts.size].reshape(counts.shape)
+    scalars = packed[counts.size:counts.size + 5]
+    reads_peaks, reads_nonpeaks = int(packed[-2]), int(packed[-1])
+    reads_total = reads_peaks + reads_nonpeaks
+    bias = AtacBias(2 * K_FLANK + 1, "DWM")
+    for si, st in enumerate(STRANDS):
+        m = bias.bias[st]
+        m.counts = counts[si, 0].astype(np.float64)
+        m.bg_counts = counts[si, 1].astype(np.float64)
+        m.prepare_mat()                   # host numpy, identical on every rank
+    bias.no_reads = int(scalars[0])
+    bias.correction_factor = (10000000 / reads_total) * (reads_total / reads_peaks)      # atacorrect.py:298-300
+    eng.set_bias(bias)
+    # --- correction + footprints of this rank's output regions
+    c, s, e = arrays["output_regions"]
+    ctx.correct_run(c, s, e, K_FLANK, WINDOW, bias.correction_factor, READ_SHIFT, True)
+    stage = ctx.stage_ms(4)
+    ctx.signal_from_corrected(FP["flank_max"], e - s)
+    ctx.score_run(ctx.score_params("footprint", flank=FP["flank_max"], **FP))
+    k4_ms = ctx.last_kernel_ms()
+    if not resident:
+        ctx.correct_download(split_strands=False, as_f64=False, prepost=True, out=out["tracks"])
+        ctx.score_download(out=out["footprint"])
+    return bias, {"K1_pileup": stage[0], "K3a_score": stage[1], "K3b_fit": stage[2], "K3c_correct": stage[3],
+                  "K2_counts": k2_ms, "K4_footprint": k4_ms}
+
+
+def bench_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from tobias_b200.pipeline import Engine
+    t_setup = time.time()
+    ds, arrays, wl = prepare_shard(args, rank, world)
+    eng = Engine(local)
+    ctx = eng.ctx
+    eng.names, eng.index, eng.lengths = ds.names, {n: i for i, n in enumerate(ds.names)}, ds.lengths
+    rc = ds.reads
+    from tobias_b200 import lib
+    flags = (rc.is_reverse.astype(np.uint8) * lib.TB_READ_REVERSE | rc.five_prime_is_match().astype(np.uint8) * lib.TB_READ_5P_MATCH
+             | (~rc.usable()).astype(np.uint8) * lib.TB_READ_SKIP)
+    cols = []
+    for a in (rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags):          # pinned copies of the read columns
+        p = ctx.pinned_empty(a.shape, a.dtype)
+        p[...] = a
+        cols.append(p)
+    host = {"lengths": ds.lengths, "genome": ds.genome, "reads": cols}
+    c, s, e = arrays["output_regions"]
+    out_bp = int((e - s).sum())
+    out = {"tracks": {t: ctx.pinned_empty((out_bp,), np.float32) for t in lib.TRACKS}, "footprint": ctx.pinned_empty((out_bp,), np.float32)}
+    h2d = sum(int(g.nbytes) for g in ds.genome) + sum(int(a.nbytes) for a in cols) + sum(int(x.nbytes) for v in arrays.values() for x in v)
+    d2h = 5 * out_bp * 4 + 2 * 3 * 5 * 25 * 8
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, n_warm, n_steps):
+        stages, last = None, None
+        for _ in range(n_warm):
+            last, stages = run_step(eng, arrays, device, resident, host, out)
+        barrier()
+        launches0 = ctx.launch_count()
+        ctx.timer_begin()
+        t0 = time.perf_counter()
+        acc = {}
+        for _ in range(n_steps):
+            last, stages = run_step(eng, arrays, device, resident, host, out)
+            for k, v in stages.items():
+                acc[k] = acc.get(k, 0.0) + v
+        ms = ctx.timer_end()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms, wall], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), {k: v / n_steps for k, v in acc.items()}, ctx.launch_count() - launches0, last
+
+    # resident inputs for `value`
+    run_step(eng, arrays, device, False, host, out)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_res, wall_res, stages, launches, bias = timed(True, args.warmup, args.steps)
+    clocks = sampler.stop()
+    ms_e2e, wall_e2e, _, _, _ = timed(False, max(1, min(args.warmup, 2)), args.steps)
+
+    tot_bp = torch.tensor([out_bp, int((arrays["output_regions"][2] - arrays["output_regions"][1] + 124).sum())], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tot_bp)
+    total_out_bp, total_ext_bp = float(tot_bp[0]), float(tot_bp[1])
+    value = total_out_bp * args.steps / (ms_res * 1e-3)
+    e2e_value = total_out_bp * args.steps / (ms_e2e * 1e-3)
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    # algorithmic bytes per unit; per-rank units for per-rank launch durations
+    ext_bp = float(tot_bp[1] / world)
+    n_reads = float(len(rc))
+    alg = {"K1_pileup": 5.0 * n_reads + 8.0 * ext_bp, "K2_counts": 5.0 * n_reads, "K3a_score": 16.375 * ext_bp,
+           "K3b_fit": 24.0 * ext_bp, "K3c_correct": 25.9 * out_bp, "K4_footprint": 8.0 * out_bp}
+    dom = max(stages, key=lambda k: stages[k])
+    achieved = alg[dom] / (stages[dom] * 1e-3) / 1e9
+    per_stage = {k: {"ms": round(v, 4), "alg_GBps": round(alg[k] / (v * 1e-3) / 1e9, 2) if v > 0 else None} for k, v in stages.items()}
+    result = {
+        "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "out_bp_total": int(total_out_bp), "extended_bp_total": int(total_ext_bp),
+                   "reads_this_rank": int(len(rc)), "score_mat": "DWM", "k_flank": K_FLANK, "window": WINDOW,
+                   "footprint": FP, "lm_exact_order": True, "sharding": "contigs over %d rank(s), count all-reduce only" % world,
+                   "l2": "inputs (2-bit genome + read columns + per-position arrays) far exceed the 126 MB L2; no flush needed"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "bp/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "K3a (DWM scoring) and K3b (LM fits) are fp64-compute bound, K4 fp32/SMEM bound (SURVEY 8d); bytes-based fractions are reported for every stage in `stages`"},
+        "stages": per_stage, "wall_ms_per_step": wall_res / args.steps, "setup_s": round(setup_s, 1),
+        "correction_factor": bias.correction_factor,
+    }
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        try:
+            result["cpu_baseline"] = cpu_reference(args, steps=1, warmup=0)["cpu_baseline"]
+        except Exception as ex:          # the baseline is a report, never a reason to lose the GPU number
+            result["cpu_baseline"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(result))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def _ref_worker(task):
+    """Runs inside a pool worker: the compiled, unmodified reference on one chunk of regions."""
+    kind, regions, params = task
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    R = ref.regions
+    regs = R.RegionList([R.OneRegion(list(r)) for r in regions])
+    if kind == "count":
+        return ref.atacorrect_functions.count_reads(regs, params)
+    if kind == "estimate":
+        return ref.atacorrect_functions.bias_estimation(regs, params)
+    if kind == "correct":
+        class Q:
+            def __init__(self):
+                self.items = []
+
+            def put(self, x):
+                self.items.append(x)
+        q = Q()
+        params.qs = {"corrected:both": q}
+        ref.atacorrect_functions.bias_correction(regs, params, params.bias_obj)
+        fp_bp = 0
+        for (_k, _reg, sig) in q.items:                    # ScoreBigwig footprint scoring of the corrected track
+            ext = np.zeros(sig.shape[0] + 60)
+            ext[30:-30] = sig.astype(np.float32)
+            ref.signals.tobias_footprint_array(ext, 10, 30, 20, 50)
+            fp_bp += sig.shape[0]
+        return fp_bp
+    raise ValueError(kind)
+
+
+def cpu_reference(args, steps, warmup):
+    import multiprocessing as mp
+    import types
+    from tobias_b200 import synth_torch
+    from tobias_b200.pipeline import prepare_regions
+    from tobias_b200.regions import OneRegion, RegionList
+    from oracle import ref_loader
+    ref_loader.load()
+    cores = os.cpu_count() or 1
+    wl = workload(args.workload)
+    # bounded sample: the two smallest autosome-like contigs of the workload at the workload's read / peak density
+    names = [n for n in wl["lengths"] if n != "chrM"]
+    sample_names = sorted(names, key=lambda n: wl["lengths"][n])[:2] if len(names) > 2 else names
+    tot = float(sum(wl["lengths"].values()))
+    cap = 24_000_000 if args.workload == "hg38" else 6_000_000
+    lengths = {n: min(wl["lengths"][n], cap) for n in sample_names}
+    frac = sum(lengths.values()) / tot
+    ds = synth_torch.TorchDataset(SEED + 999, lengths, max(4, int(wl["n_peaks"] * frac)), int(wl["n_records"] * frac), device="cpu")
+    tmp = tempfile.mkdtemp(prefix="tb_ref_")
+    from tobias_b200.io.fasta import write_fasta
+    fa = os.path.join(tmp, "sample.fa")
+    write_fasta(fa, zip(ds.names, ds.genome))
+    npz = os.path.join(tmp, "sample_reads.npz")
+    ds.reads.save(npz)
+    chrom_info = dict(zip(ds.names, ds.lengths))
+    regs = prepare_regions(RegionList([OneRegion(list(p)) for p in ds.peaks]), chrom_info, ds.names, extend=EXTEND, k_flank=K_FLANK, window=WINDOW)
+    params = types.SimpleNamespace(bam=npz, genome=fa, k_flank=K_FLANK, bg_shift=BG_SHIFT, read_shift=list(READ_SHIFT), score_mat="DWM",
+                                   verbosity=0, log_q=None, window=WINDOW, split_strands=False, qs={}, bias_obj=None)
+    out_all = [tuple(r[:3]) for r in regs["output_regions"]]
+    n_out = min(len(out_all), max(cores * 24, 48))
+    rng = np.random.default_rng(1)
+    out_sample = [out_all[i] for i in sorted(rng.choice(len(out_all), n_out, replace=False))]
+    inp = [tuple(r[:3]) for r in regs["input_regions"]]
+    pk = [tuple(r[:3]) for r in regs["peak_regions"]]
+    npk = [tuple(r[:3]) for r in regs["nonpeak_regions"]]
+
+    def chunks(lst, n):
+        per = max(1, -(-len(lst) // n))
+        return [lst[i:i + per] for i in range(0, len(lst), per)]
+
+    results = []
+    ctxmp = mp.get_context("fork")
+    with ctxmp.Pool(cores) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            n_split = cores * 4
+            reads_peaks = sum(pool.map(_ref_worker, [("count", ch, params) for ch in chunks(pk, n_split)]))
+            reads_nonpeaks = sum(pool.map(_ref_worker, [("count", ch, params) for ch in chunks(npk, n_split)]))
+            t_count = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            parts = pool.map(_ref_worker, [("estimate", ch, params) for ch in chunks(inp, n_split)])
+            bias = parts[0]
+            for p in parts[1:]:
+                bias.join(p)
+            for st in ("forward", "reverse"):
+                bias.bias[st].prepare_mat()
+            total = reads_peaks + reads_nonpeaks
+            bias.correction_factor = (10000000 / total) * (total / max(reads_peaks, 1))
+            t_est = time.perf_counter() - t0
+            params.bias_obj = bias
+            t0 = time.perf_counter()
+            done = pool.map(_ref_worker, [("correct", ch, params) for ch in chunks(out_sample, n_split)])
+            t_corr = time.perf_counter() - t0
+            params.bias_obj = None
+            sample_bp = int(sum(done))
+            all_bp = sum(e - s for _, s, e in out_all)
+            # counts + estimation cover the whole sample genome; correction + footprints cover `sample_bp` of its `all_bp`
+            t_full = t_count + t_est + t_corr * (all_bp / float(sample_bp))
+            if it >= warmup:
+                results.append((all_bp / t_full, t_count, t_est, t_corr, sample_bp, all_bp))
+    value = float(np.mean([r[0] for r in results]))
+    r = results[-1]
+    sample = ("contigs %s (%.1f Mb) of the synthetic workload at its read/peak density: count_reads + bias_estimation over all %d input regions "
+              "(%d records), bias_correction + footprint scoring over %d of %d output regions (%d of %d bp), scaled by bp; stage seconds "
+              "count=%.1f estimate=%.1f correct+footprint=%.1f" % ("+".join(ds.names), sum(ds.lengths) / 1e6, len(inp), len(ds.reads), n_out,
+                                                                  len(out_all), r[4], r[5], r[1], r[2], r[3]))
+    return {"value": value, "cpu_baseline": {"value": value, "unit": "bp/s", "cores": cores, "kind": "reference", "sample": sample},
+            "ms_per_step": 1e3 * (r[1] + r[2] + r[3]), "wl": wl}
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        res = cpu_reference(args, steps=args.steps, warmup=min(args.warmup, 1))
+    except Exception as ex:
+        print(json.dumps({"impl": "reference", "unavailable": repr(ex)}))
+        return
+    out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": {"workload": res["wl"]["desc"], "score_mat": "DWM", "k_flank": K_FLANK,
+                                                           "window": WINDOW, "footprint": FP},
+           "cpu_baseline": res["cpu_baseline"],
+           "e2e": {"value": res["value"], "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hg38", choices=["hg38", "chr50mb", "small"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_b200(args)
+
+
+if __name__ == "__main__":
+    main()

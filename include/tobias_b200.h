@@ -57,6 +57,12 @@ int tb_last_kernel_ms(tb_ctx *ctx, float *ms);
 /* per-stage device times (ms) of the most recent multi-kernel call; tb_correct_run: { K1 pileup, K3a score, K3b fit,
  * K3c correct }, tb_bias_counts: { scatter, scan+accumulate } (summed over chunks) */
 int tb_stage_ms(tb_ctx *ctx, float *out, int n);
+/* CUDA-event stopwatch on the context's stream spanning any sequence of calls (device time line, host gaps included) */
+int tb_timer_begin(tb_ctx *ctx);
+int tb_timer_end(tb_ctx *ctx, float *ms);
+/* page-locked host memory for the caller's input / output buffers (full-speed, truly asynchronous copies) */
+int tb_host_alloc(tb_ctx *ctx, int64_t bytes, void **out);
+int tb_host_free(tb_ctx *ctx, void *p);
 /* number of kernel launches issued by this context so far */
 int tb_launch_count(tb_ctx *ctx, int64_t *n);
 

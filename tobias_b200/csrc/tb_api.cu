@@ -188,6 +188,28 @@ extern "C" int tb_last_kernel_ms(tb_ctx *ctx, float *ms) {
     return TB_OK;
 }
 
+extern "C" int tb_timer_begin(tb_ctx *ctx) {
+    if (!ctx) return TB_ERR_ARG;
+    return tb_check(ctx, cudaEventRecord(ctx->marks[6], ctx->stream), "tb_timer_begin");
+}
+
+extern "C" int tb_timer_end(tb_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return TB_ERR_ARG;
+    TB_CUDA(ctx, cudaEventRecord(ctx->marks[7], ctx->stream));
+    TB_CUDA(ctx, cudaEventSynchronize(ctx->marks[7]));
+    return tb_check(ctx, cudaEventElapsedTime(ms, ctx->marks[6], ctx->marks[7]), "tb_timer_end");
+}
+
+extern "C" int tb_host_alloc(tb_ctx *ctx, int64_t bytes, void **out) {
+    if (!ctx || !out || bytes < 0) return TB_ERR_ARG;
+    return tb_check(ctx, cudaMallocHost(out, (size_t)(bytes > 0 ? bytes : 1)), "tb_host_alloc");
+}
+
+extern "C" int tb_host_free(tb_ctx *ctx, void *p) {
+    if (!ctx) return TB_ERR_ARG;
+    return p ? tb_check(ctx, cudaFreeHost(p), "tb_host_free") : TB_OK;
+}
+
 extern "C" int tb_stage_ms(tb_ctx *ctx, float *out, int n) {
     if (!ctx || !out || n < 0) return TB_ERR_ARG;
     for (int i = 0; i < n; i++) out[i] = i < 8 ? ctx->stage_ms[i] : 0.f;

@@ -40,6 +40,10 @@ _PROTOS = {
     "tb_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i)]),
     "tb_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "tb_launch_count": (_i, [_vp, C.POINTER(_i64)]),
+    "tb_timer_begin": (_i, [_vp]),
+    "tb_timer_end": (_i, [_vp, C.POINTER(C.c_float)]),
+    "tb_host_alloc": (_i, [_vp, _i64, C.POINTER(_vp)]),
+    "tb_host_free": (_i, [_vp, _vp]),
     "tb_genome_create": (_i, [_vp, _i, _vp]),
     "tb_genome_upload": (_i, [_vp, _i, _i64, _vp, _i64]),
     "tb_genome_fetch": (_i, [_vp, _i, _i64, _i64, _vp]),
@@ -121,6 +125,9 @@ class Context:
     # ------------------------------------------------------------------ plumbing
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._lib.tb_host_free(self._h, p)
+            self._pinned = []
             self._lib.tb_destroy(self._h)
             self._h = None
 
@@ -154,6 +161,25 @@ class Context:
         n = _i64()
         self._ck(self._lib.tb_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def timer_begin(self):
+        self._ck(self._lib.tb_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        self._ck(self._lib.tb_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array backed by page-locked host memory owned by this context (freed on close)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = _vp()
+        self._ck(self._lib.tb_host_alloc(self._h, n, C.byref(p)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     # ------------------------------------------------------------------ genome / reads
     def genome_create(self, lengths):
@@ -270,11 +296,11 @@ class Context:
         self._cor_total = int((e - s).sum())
         self._cor_L = 2 * k_flank + 1
 
-    def correct_download(self, split_strands=False, as_f64=False, tracks=TRACKS, prepost=True):
+    def correct_download(self, split_strands=False, as_f64=False, tracks=TRACKS, prepost=True, out=None):
         """dict track -> array (split_strands=False) or track -> (forward, reverse); plus 'prepost' [2][3][5][L]."""
         dt = np.float64 if as_f64 else np.float32
         ptrs = ((_vp * 2) * 4)()
-        out = {}
+        out_bufs, out = out, {}          # `out`: optional dict track -> preallocated (e.g. pinned) array, strands combined
         for t, name in enumerate(TRACKS):
             if name not in tracks:
                 continue
@@ -283,9 +309,10 @@ class Context:
                 ptrs[t][0], ptrs[t][1] = a.ctypes.data, b.ctypes.data
                 out[name] = (a, b)
             else:
-                a = np.empty(self._cor_total, dtype=dt)
+                a = out_bufs[name] if out_bufs is not None else np.empty(self._cor_total, dtype=dt)
+                assert a.dtype == dt and a.size >= self._cor_total and a.flags.c_contiguous
                 ptrs[t][0] = a.ctypes.data
-                out[name] = a
+                out[name] = a[:self._cor_total]
         pp = np.zeros((2, 3, 5, self._cor_L), dtype=np.float64) if prepost else None
         self._ck(self._lib.tb_correct_download(self._h, int(bool(split_strands)), int(bool(as_f64)), ptrs, _ptr(pp)))
         if prepost:
@@ -323,10 +350,14 @@ class Context:
         self._ck(self._lib.tb_score_run(self._h, C.byref(params)))
         self._sc_params = params
 
-    def score_download(self):
+    def score_download(self, out=None):
         p = self._sc_params
         total = int((self._sc_ext - 2 * p.flank).sum())
-        out = np.empty(total, dtype=np.float64 if p.as_f64 else np.float32)
+        dt = np.float64 if p.as_f64 else np.float32
+        if out is None:
+            out = np.empty(total, dtype=dt)
+        assert out.dtype == dt and out.size >= total and out.flags.c_contiguous
+        out = out[:total]
         self._ck(self._lib.tb_score_download(self._h, _ptr(out)))
         return out
 
