@@ -37,6 +37,7 @@ METRIC = "corrected+footprint-scored bp/s"
 SEED = 20261019
 K_FLANK, WINDOW, BG_SHIFT, EXTEND, READ_SHIFT = 12, 100, 100, 100, (4, -5)
 FP = dict(flank_min=10, flank_max=30, fp_min=20, fp_max=50)
+LM_EXACT = False      # --lm-exact: MINPACK-order sums in the window fits (bit-faithful to scipy on identical inputs, slower)
 
 
 def workload(name):
@@ -170,7 +171,7 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
     eng.set_bias(bias)
     # --- correction + footprints of this rank's output regions
     c, s, e = arrays["output_regions"]
-    ctx.correct_run(c, s, e, K_FLANK, WINDOW, bias.correction_factor, READ_SHIFT, True)
+    ctx.correct_run(c, s, e, K_FLANK, WINDOW, bias.correction_factor, READ_SHIFT, LM_EXACT)
     stage = ctx.stage_ms(4)
     ctx.signal_from_corrected(FP["flank_max"], e - s)
     ctx.score_run(ctx.score_params("footprint", flank=FP["flank_max"], **FP))
@@ -282,7 +283,7 @@ def bench_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "out_bp_total": int(total_out_bp), "extended_bp_total": int(total_ext_bp),
                    "reads_this_rank": int(len(rc)), "score_mat": "DWM", "k_flank": K_FLANK, "window": WINDOW,
-                   "footprint": FP, "lm_exact_order": True, "sharding": "contigs over %d rank(s), count all-reduce only" % world,
+                   "footprint": FP, "lm_exact_order": LM_EXACT, "sharding": "contigs over %d rank(s), count all-reduce only" % world,
                    "l2": "inputs (2-bit genome + read columns + per-position arrays) far exceed the 126 MB L2; no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "bp/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -443,7 +444,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hg38", choices=["hg38", "chr50mb", "small"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lm-exact", action="store_true")
     args = ap.parse_args()
+    global LM_EXACT
+    LM_EXACT = bool(args.lm_exact)
     if args.impl == "reference":
         bench_reference(args)
     else:

@@ -1,0 +1,261 @@
+"""
+`TOBIAS ATACorrect` on the B200: same arguments, same output files, same STATS log lines as the reference driver
+(tobias/tools/atacorrect.py:53-487), with the multiprocessing fan-out over region chunks replaced by batched GPU stages
+(tobias_b200.pipeline.Engine).  Under torchrun (one process per GPU) contigs are sharded over the ranks; the only
+collectives are the all-reduces of the count tensors / normalisation counters and of the verification PWMs, and rank 0
+gathers the tracks for the bigWig writers (tobias_b200.dist).
+"""
+import argparse
+import itertools
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+
+from . import lib
+from .dist import Comm, shard_contigs
+from .io.bam import read_bam
+from .io.bigwig import BigWigWriter
+from .io.fasta import FastaFile
+from .logger import TobiasLogger
+from .parsers import add_atacorrect_arguments
+from .pipeline import AtacBias, Engine, STRANDS, prepare_regions, prepost_to_matrices
+from .regions import RegionList
+
+
+def check_files(paths, action="r"):
+    for p in paths:
+        if p is None:
+            continue
+        if action == "r" and not os.path.exists(p):
+            sys.exit("ERROR: {0} does not exist".format(p))
+        if action == "w":
+            d = os.path.dirname(os.path.abspath(p))
+            if os.path.exists(p) and not os.access(p, os.W_OK):
+                sys.exit("ERROR: {0} could not be opened for writing".format(p))
+            if not os.path.isdir(d):
+                sys.exit("ERROR: directory {0} does not exist".format(d))
+
+
+def write_track(path, header, regions, values, region_offsets):
+    """bigwig_writer semantics (tobias/utils/utilities.py:129-232): regions in header order, non-zero positions only,
+    float32 values, span 1.  `values` is the concatenated track, region i at region_offsets[i]."""
+    order = {c: i for i, (c, _) in enumerate(header)}
+    idx = sorted(range(len(regions)), key=lambda i: (order[regions[i].chrom], regions[i].start))
+    w = BigWigWriter(path)
+    w.add_header(header)
+    for i in idx:
+        r = regions[i]
+        sig = values[region_offsets[i]:region_offsets[i] + (r.end - r.start)]
+        nz = np.flatnonzero(sig)
+        if nz.size:
+            w.add_entries(r.chrom, nz.astype(np.int64) + r.start, sig[nz])
+    w.close()
+
+
+def run_atacorrect(args):
+    if args.bam is None:
+        sys.exit("Error: No .bam-file given")
+    if args.genome is None:
+        sys.exit("Error: No .fasta-file given")
+    if args.peaks is None:
+        sys.exit("Error: No .peaks-file given")
+    comm = Comm.init_from_env()
+    root = comm.rank == 0
+    args.prefix = os.path.splitext(os.path.basename(args.bam))[0] if args.prefix is None else args.prefix
+    args.outdir = os.path.abspath(args.outdir) if args.outdir else os.path.abspath(os.getcwd())
+    tracks = [t for t in ("uncorrected", "bias", "expected", "corrected") if t not in args.track_off]
+    strands_out = ["forward", "reverse"] if args.split_strands else ["both"]
+    output_bws = {}
+    for track in tracks:
+        output_bws[track] = {}
+        for strand in strands_out:
+            elements = [args.prefix, track] if strand == "both" else [args.prefix, track, strand]
+            output_bws[track][strand] = os.path.join(args.outdir, "{0}.bw".format("_".join(elements)))
+    bigwigs = [output_bws[t][s] for (t, s) in itertools.product(tracks, strands_out)]
+    figures_f = os.path.join(args.outdir, "{0}_atacorrect.pdf".format(args.prefix))
+    output_files = list(OrderedDict.fromkeys(bigwigs + [figures_f]))
+
+    logger = TobiasLogger("ATACorrect", args.verbosity if root else 0)
+    logger.begin()
+    parser = add_atacorrect_arguments(argparse.ArgumentParser())
+    logger.arguments_overview(parser, args)
+    logger.output_files(output_files)
+
+    logger.info("----- Processing input data -----")
+    check_files([args.bam, args.genome, args.peaks, args.regions_in, args.regions_out, args.blacklist, args.bias_pkl], "r")
+    if root:
+        os.makedirs(args.outdir, exist_ok=True)
+    comm.barrier()
+    check_files(bigwigs, "w")
+
+    logger.info("Reading info from .bam file")
+    reads = read_bam(args.bam)
+    bam_references = list(reads.references)
+    bam_chrom_info = dict(zip(reads.references, reads.lengths))
+    logger.info("Reading info from .fasta file")
+    fasta = FastaFile(args.genome)
+    fasta_chrom_info = dict(zip(fasta.references, fasta.lengths))
+    chrom_in_common = set(bam_chrom_info).intersection(fasta_chrom_info)
+    for chrom in chrom_in_common:
+        if bam_chrom_info[chrom] != fasta_chrom_info[chrom]:
+            logger.warning("(Fastafile)\t{0} has length {1}".format(chrom, fasta_chrom_info[chrom]))
+            logger.warning("(Bamfile)\t{0} has length {1}".format(chrom, bam_chrom_info[chrom]))
+            sys.exit("Error: .bam and .fasta have different chromosome lengths. Please make sure the genome file is similar to the one used in mapping.")
+    not_in_fasta = set(bam_references) - set(fasta_chrom_info)
+    if len(not_in_fasta) > 1:
+        logger.warning("The following contigs in --bam did not have sequences in --fasta: {0}. NOTE: These contigs will be skipped in calculation and output.".format(not_in_fasta))
+    bam_references = [r for r in bam_references if r in fasta_chrom_info]
+    chrom_in_common = [r for r in bam_references]
+    kept = [c for c in chrom_in_common if c not in args.drop_chroms]
+    dropped = set(chrom_in_common) - set(kept)
+    bam_references = kept
+    if dropped:
+        logger.info("The following contigs were dropped from analysis because they were found in '--drop-chroms': {0}".format(list(dropped)))
+    else:
+        logger.warning("No additional chromosomes were removed. Consider using '--drop-chroms' to remove mitochondrial and/or other unwanted contigs.")
+    if len(bam_references) == 0:
+        logger.error("No common contigs left to run ATACorrect on. Please check that '--bam' and '--fasta' are matching.")
+        sys.exit()
+
+    logger.info("Processing input/output regions")
+    chrom_info = {c: bam_chrom_info[c] for c in bam_references}
+    rd = prepare_regions(RegionList().from_bed(args.peaks), chrom_info, bam_references, extend=args.extend, k_flank=args.k_flank,
+                         window=args.window,
+                         regions_in=RegionList().from_bed(args.regions_in) if args.regions_in else None,
+                         regions_out=RegionList().from_bed(args.regions_out) if args.regions_out else None,
+                         blacklist=RegionList().from_bed(args.blacklist) if args.blacklist else None)
+    genome_bp = sum(r.get_length() for r in rd["genome"])
+    for key in rd:
+        total_bp = sum(r.get_length() for r in rd[key])
+        logger.stats("{0}: {1} regions | {2} bp | {3:.2f}% coverage".format(key, len(rd[key]), total_bp, total_bp / genome_bp * 100))
+    if min(len(rd[k]) for k in ("input_regions", "output_regions", "peak_regions", "nonpeak_regions")) == 0:
+        logger.error("No regions found - exiting!")
+        sys.exit()
+
+    # ---- shard by contig, make this rank's data resident on its GPU
+    owner = shard_contigs(chrom_info, comm.world)
+    mine = [c for c in bam_references if owner[c] == comm.rank]
+    local = {k: RegionList([r for r in rd[k] if owner[r.chrom] == comm.rank]) for k in
+             ("input_regions", "output_regions", "peak_regions", "nonpeak_regions")}
+    device = int(os.environ.get("LOCAL_RANK", args.device))
+    eng = Engine(device)
+    eng.load_genome_fasta(fasta, mine)
+    name_to_old = {n: i for i, n in enumerate(reads.references)}
+    sel = np.isin(reads.chrom_id, [name_to_old[c] for c in mine])
+    eng.load_reads(reads.select(sel))
+    read_shift = tuple(args.read_shift)
+
+    logger.comment("")
+    logger.info("----- Estimating normalization factors -----")
+    if not args.norm_off:
+        logger.info("Counting reads in peak regions")
+        logger.info("Counting reads in nonpeak regions")
+        cnt = np.array([eng.count_reads(local["peak_regions"], read_shift), eng.count_reads(local["nonpeak_regions"], read_shift)], dtype=np.int64)
+        comm.allreduce_sum(cnt)
+        reads_peaks, reads_nonpeaks = int(cnt[0]), int(cnt[1])
+        reads_total = reads_peaks + reads_nonpeaks
+        logger.stats("TOTAL_READS\t{0}".format(reads_total))
+        logger.stats("PEAK_READS\t{0}".format(reads_peaks))
+        logger.stats("NONPEAK_READS\t{0}".format(reads_nonpeaks))
+        lib_norm = 10000000 / reads_total
+        frip = reads_peaks / reads_total
+        correct_factor = lib_norm * (1 / frip)
+        logger.stats("LIB_NORM\t{0:.5f}".format(lib_norm))
+        logger.stats("FRiP\t{0:.5f}".format(frip))
+    else:
+        logger.info("Normalization was switched off")
+        correct_factor = 1.0
+    logger.stats("CORRECTION_FACTOR:\t{0:.5f}".format(correct_factor))
+
+    logger.comment("")
+    if args.bias_pkl is None:
+        logger.info("Started estimation of sequence bias...")
+        bias_obj = eng.estimate_bias(local["input_regions"], args.k_flank, args.bg_shift, read_shift, args.score_mat)
+        packed = bias_obj.pack_counts()
+        comm.allreduce_sum(packed)
+        bias_obj.unpack_counts(packed)
+        logger.debug("Bias estimated\tno_reads: {0}".format(bias_obj.no_reads))
+    else:
+        logger.info("Loading sequence bias from '--bias-pkl' file...")
+        bias_obj = AtacBias().from_pickle(args.bias_pkl)
+    bias_obj.correction_factor = correct_factor
+    logger.info("Finalizing bias motif for scoring")
+    for strand in STRANDS:
+        bias_obj.bias[strand].prepare_mat()
+    if root:
+        bias_obj.to_pickle(os.path.join(args.outdir, args.prefix + "_AtacBias.pickle"))
+
+    logger.comment("")
+    logger.info("----- Correcting reads from .bam within output regions -----")
+    eng.set_bias(bias_obj)
+    out_regions = local["output_regions"]
+    out_regions.loc_sort(mine)
+    lm_exact = bool(args.lm_exact) or args.score_mat == "PWM"
+    n_out = len(out_regions)
+    if n_out:
+        eng.correct(out_regions, bias_obj, args.k_flank, args.window, read_shift, lm_exact)
+        got = eng.tracks(split_strands=args.split_strands, as_f64=False, tracks=tracks, prepost=True)
+        prepost = got["prepost"]
+    else:
+        got, prepost = {}, np.zeros((2, 3, 5, 2 * args.k_flank + 1))
+    comm.allreduce_sum(prepost)
+
+    # ---- rank 0 gathers and writes the bigWigs (header = contigs in BAM order, like the reference)
+    header = [(c, bam_chrom_info[c]) for c in bam_references]
+    reg_tbl = np.array([(bam_references.index(r.chrom), r.start, r.end) for r in out_regions], dtype=np.int64).reshape(-1, 3)
+    all_tbl = comm.gather_arrays(reg_tbl.ravel())
+    for track in tracks:
+        for si, strand in enumerate(strands_out):
+            vals = got[track][si] if (args.split_strands and n_out) else (got[track] if n_out else np.zeros(0, np.float32))
+            parts = comm.gather_arrays(np.ascontiguousarray(vals))
+            if root:
+                from .regions import OneRegion
+                regs, offs, off = [], [], 0
+                for tbl in all_tbl:
+                    for cid, s, e in tbl.reshape(-1, 3):
+                        regs.append(OneRegion([bam_references[int(cid)], int(s), int(e)]))
+                for tbl in all_tbl:
+                    for cid, s, e in tbl.reshape(-1, 3):
+                        offs.append(off)
+                        off += int(e - s)
+                logger.info("Closing {0} (this might take some time)".format(output_bws[track][strand]))
+                write_track(output_bws[track][strand], header, regs, np.concatenate(parts) if parts else np.zeros(0, np.float32), offs)
+
+    logger.comment("")
+    logger.info("Verifying bias correction")
+    pre_bias, post_bias = prepost_to_matrices(prepost, 2 * args.k_flank + 1)
+    for strand in STRANDS:
+        abssum = np.abs(np.sum(post_bias[strand].neg_counts, axis=0))                 # atacorrect.py:461-466
+        post_bias[strand].neg_counts = post_bias[strand].neg_counts + abssum
+        post_bias[strand].counts += post_bias[strand].neg_counts
+        pre_bias[strand].prepare_mat()
+        post_bias[strand].prepare_mat()
+        pre_var = np.mean(np.var(pre_bias[strand].bias_pwm, axis=1)[:4])
+        post_var = np.mean(np.var(post_bias[strand].bias_pwm, axis=1)[:4])
+        logger.stats("BIAS\tpre-bias variance {0}:\t{1:.7f}".format(strand, pre_var))
+        logger.stats("BIAS\tpost-bias variance {0}:\t{1:.7f}".format(strand, post_var))
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        logger.warning("matplotlib is not available: {0} was not written".format(figures_f))
+    eng.close()
+    fasta.close()
+    logger.end()
+    return {"correction_factor": correct_factor, "bias": bias_obj, "pre_bias": pre_bias, "post_bias": post_bias}
+
+
+def main(argv=None):
+    parser = add_atacorrect_arguments(argparse.ArgumentParser())
+    from .parsers import add_underscore_options
+    add_underscore_options(parser)
+    args = parser.parse_args(argv)
+    if argv is None and len(sys.argv[1:]) == 0:
+        parser.print_help()
+        sys.exit()
+    run_atacorrect(args)
+
+
+if __name__ == '__main__':
+    main()

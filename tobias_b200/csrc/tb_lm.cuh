@@ -369,14 +369,16 @@ __device__ void tb_lm_fit_warp(const double (&x)[PPL], const double (&y)[PPL], i
             double temp = par[0], h = eps * fabs(temp);
             if (h == 0.0) h = eps;
             tb_relu_residuals<PPL>(x, y, temp + h, par[1], c0);
+            double hinv = 1.0 / h;            // tree mode only: one reciprocal instead of PPL divisions (<= 1 ulp, like the sums)
 #pragma unroll
-            for (int q = 0; q < PPL; q++) c0[q] = (c0[q] - fvec[q]) / h;
+            for (int q = 0; q < PPL; q++) c0[q] = SEQ ? (c0[q] - fvec[q]) / h : (c0[q] - fvec[q]) * hinv;
             temp = par[1];
             h = eps * fabs(temp);
             if (h == 0.0) h = eps;
             tb_relu_residuals<PPL>(x, y, par[0], temp + h, c1);
+            hinv = 1.0 / h;
 #pragma unroll
-            for (int q = 0; q < PPL; q++) c1[q] = (c1[q] - fvec[q]) / h;
+            for (int q = 0; q < PPL; q++) c1[q] = SEQ ? (c1[q] - fvec[q]) / h : (c1[q] - fvec[q]) * hinv;
             nfev += 2;
         }
         // ---- qrfac with column pivoting
@@ -399,8 +401,9 @@ __device__ void tb_lm_fit_warp(const double (&x)[PPL], const double (&y)[PPL], i
         double ajnorm = rdiag0;
         if (ajnorm != 0.0) {
             if (tb_elem<PPL>(c0, 0) < 0.0) ajnorm = -ajnorm;
+            const double ainv = 1.0 / ajnorm;
 #pragma unroll
-            for (int q = 0; q < PPL; q++) c0[q] /= ajnorm;
+            for (int q = 0; q < PPL; q++) c0[q] = SEQ ? c0[q] / ajnorm : c0[q] * ainv;
             if (lane == 0) c0[0] += 1.0;
             double s = tb_dot_warp<PPL, SEQ>(c0, c1, m, lane, 0, wbuf);
             double temp = s / tb_elem<PPL>(c0, 0);
@@ -411,9 +414,10 @@ __device__ void tb_lm_fit_warp(const double (&x)[PPL], const double (&y)[PPL], i
         double ajnorm1 = tb_enorm_warp<PPL, SEQ>(c1, m, lane, 1, wbuf);
         if (ajnorm1 != 0.0) {
             if (tb_elem<PPL>(c1, 1) < 0.0) ajnorm1 = -ajnorm1;
+            const double ainv1 = 1.0 / ajnorm1;
 #pragma unroll
             for (int q = 0; q < PPL; q++)
-                if (lane + 32 * q >= 1) c1[q] /= ajnorm1;
+                if (lane + 32 * q >= 1) c1[q] = SEQ ? c1[q] / ajnorm1 : c1[q] * ainv1;
             if (lane == 1) c1[0] += 1.0;
         }
         r[1][1] = -ajnorm1;

@@ -12,7 +12,7 @@
 // i.e. 25 selected rows of a 100 x 100 table are summed.  The table of BOTH models of one strand (160 KB of fp64 for
 // L = 25) is staged once per block in shared memory and stays resident while the block streams positions
 // (persistent blocks, one per SM, half of them per strand).  Within a warp lane n owns column n: its four
-// accumulators are contiguous (32 B) so every row read is two conflict-free LDS.128, and the base S_m is warp-
+// accumulators come from two 16-byte halves stored [half][n] so every row read is two conflict-free LDS.128, and S_m is warp-
 // uniform.  The reverse-strand table is pre-permuted on the host (m -> L-1-m, n -> L-1-n, bases complemented) so
 // that both strands run the same code on forward-oriented k-mers.  All arithmetic is fp64.
 #include "tb_common.cuh"
@@ -26,7 +26,7 @@ struct tb_score_regions_view {
 
 #define TB_K3A_WPI 2        // windows in flight per warp (independent accumulator sets)
 
-__global__ void tb_score_dwm_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ table_fwd,
+__global__ void __launch_bounds__(768, 1) tb_score_dwm_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ table_fwd,
                                     const double *__restrict__ table_rev, int L, int use_smem, int strand_mask, int nan_invalid,
                                     double *__restrict__ out_fwd, double *__restrict__ out_rev) {
     TB_DYN_SMEM(smem);
@@ -98,8 +98,9 @@ __global__ void tb_score_dwm_kernel(tb_genome_view g, tb_score_regions_view R, c
                     int s = (int)((kmer[w] >> (2 * m)) & 3u);
 #pragma unroll
                     for (int x = 0; x < 2; x++) {
-                        const double2 *p = (const double2 *)(U + ((size_t)(x * L + m) * 4 + s) * row + nl * 4);
-                        double2 v0 = p[0], v1 = p[1];
+                        // row layout [half][n][2]: lane n reads 16 B at n*16 -> conflict-free LDS.128 (a 32-B stride would 2-way conflict)
+                        const double2 *p = (const double2 *)(U + ((size_t)(x * L + m) * 4 + s) * row) + nl;
+                        double2 v0 = p[0], v1 = p[L];
                         acc[w][x][0] += v0.x;
                         acc[w][x][1] += v0.y;
                         acc[w][x][2] += v1.x;
@@ -185,7 +186,7 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
     M.L = L;
     ctx->cor.valid = false;
     if (!is_dwm) return tb_h2d(ctx, M.table, bias_pwm_log, sizeof(double) * 5 * L) || tb_sync(ctx, "tb_set_bias_model");
-    // U[x][m][s][n][a]; for the reverse strand the table is expressed on forward-oriented k-mers:
+    // U[x][m][s][a>>1][n][a&1] (see the kernel for the layout); for the reverse strand the table is expressed on forward-oriented k-mers:
     //   U'[m'][s'][n'][a'] = U[L-1-m'][s'^1][L-1-n'][a'^1]
     std::vector<double> U((size_t)2 * L * 4 * L * 4);
     const double *pwm[2] = {bias_pwm_log, bg_pwm_log};
@@ -199,7 +200,7 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                         int rs = strand ? s ^ 1 : s, ra = strand ? a ^ 1 : a;
                         double p = pwm[x][ra * L + rn];
                         double v = rm == rn ? p : dwm[x][(((size_t)rs * 5 + ra) * L + rm) * L + rn] - p;
-                        U[((((size_t)x * L + m) * 4 + s) * L + n) * 4 + a] = v;
+                        U[(((((size_t)x * L + m) * 4 + s) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)] = v;
                     }
     TB_TRY(tb_h2d(ctx, M.table, U.data(), U.size() * sizeof(double)));
     return tb_sync(ctx, "tb_set_bias_model");
@@ -228,7 +229,7 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
         int use_smem = smem <= (size_t)200 * 1024;
         auto k = tb_score_dwm_kernel;
         if (use_smem) TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int block = 512;
+        int block = 768;                  // 24 warps: 82 registers/thread fit once per SM next to the 160 KB table
         i64 n_units = (total + 31) >> 5;
         i64 want = tb_div_up(n_units, block / 32) * (strand_mask == 3 ? 2 : 1);
         i64 cap = ctx->sm_count;
