@@ -290,7 +290,7 @@ template <class T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o
 
 /* ---- runtime API subset ---- */
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 16; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     memset(p, 0, sizeof(*p));
     p->multiProcessorCount = 4;

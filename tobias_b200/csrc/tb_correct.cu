@@ -292,7 +292,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     const int L = ctx->model[0].L;
     if (L != 2 * k_flank + 1) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: k_flank %d does not match the model length %d", k_flank, L);
     std::vector<i64> ls, le;
-    TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, true));
+    TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
     const int f_extend = k_flank + window / 2;
     auto &C = ctx->cor;
     C.n_regions = n_regions;

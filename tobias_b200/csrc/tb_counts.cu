@@ -157,7 +157,7 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     memset(counts_out, 0, n_out * sizeof(int64_t));
     memset(scalars_out, 0, 5 * sizeof(int64_t));
     std::vector<i64> ls, le;
-    TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, true));
+    TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
     if (n_regions == 0 || ctx->n_reads == 0) return TB_OK;
 
     const i64 ext = (i64)k_flank + bg_shift;

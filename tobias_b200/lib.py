@@ -81,6 +81,8 @@ def load(path=None):
     """Load the C-ABI library (default: the in-tree CUDA build) and declare every prototype.  Raises when the
     library is missing: build it with `python -m tobias_b200.build` (or __graft_entry__.build())."""
     global _lib, _lib_path
+    if path is None and _lib is not None:
+        return _lib                      # whatever was loaded first stays (the CUDA build unless a test loaded the emulator)
     path = os.path.abspath(path or DEFAULT_LIB)
     if _lib is not None and _lib_path == path:
         return _lib
