@@ -40,8 +40,7 @@ def load():
     if _loaded is not None:
         return _loaded
     from . import build_ref
-    if not build_ref.is_built():
-        build_ref.build()
+    build_ref.build()          # no-op when oracle/_ref is complete (restores .pyc files a file sync may have dropped)
     _install_shims()
     if REF not in sys.path:
         sys.path.insert(0, REF)

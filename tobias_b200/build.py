@@ -33,14 +33,19 @@ def is_current():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False, ptxas_info=False):
-    if is_current() and not force:
+def build(force=False, verbose=False, ptxas_info=False, extra_flags=(), out=None):
+    """extra_flags / out: build a tuning variant next to the product library (used by kernel experiments only)."""
+    global LIB
+    if out is None and is_current() and not force:
         return LIB
+    lib_path = out or LIB
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if out is not None:
+            obj = obj[:-2] + "." + os.path.basename(out) + ".o"
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -55,9 +60,12 @@ def build(force=False, verbose=False, ptxas_info=False):
             print(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
-    return LIB
+    if out is not None:
+        for o in objs:
+            os.remove(o)
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -36,11 +36,14 @@ __device__ __forceinline__ int tb_n_windows(i64 reg_len, int k_flank, int window
 
 // ------------------------------------------------------------------------------------------------ K3b
 #define TB_FIT_WARPS 8      // warps per block of the fit kernel
+#ifndef TB_FIT_MINBLOCKS
+#define TB_FIT_MINBLOCKS 2  // resident blocks per SM the register allocation is tuned for
+#endif
 
 // SEQ = 1: the m-term sums of the fit run in MINPACK's sequential order (bit-faithful to scipy's lmdif on identical
 // inputs, verified window by window in tests/test_lm_exact.py); SEQ = 0: warp-tree sums (faster, ~1 ulp per sum).
 template <int PPL, bool SEQ>
-__global__ void tb_fit_kernel(tb_cor_view V, const u32 *__restrict__ pile, const double *__restrict__ biasraw,
+__global__ void __launch_bounds__(TB_FIT_WARPS * 32, TB_FIT_MINBLOCKS) tb_fit_kernel(tb_cor_view V, const u32 *__restrict__ pile, const double *__restrict__ biasraw,
                               double *__restrict__ fit) {
     __shared__ double wbuf_all[SEQ ? TB_FIT_WARPS * 32 * PPL : 1];
     double *wbuf = SEQ ? wbuf_all + (threadIdx.x >> 5) * 32 * PPL : wbuf_all;
