@@ -299,6 +299,13 @@ def bench_b200(args):
             result["cpu_baseline"] = cpu_reference(args, steps=1, warmup=0)["cpu_baseline"]
         except Exception as ex:          # the baseline is a report, never a reason to lose the GPU number
             result["cpu_baseline"] = {"error": repr(ex)}
+    if args.fit_stats and rank == 0:      # diagnostic: distribution of the window fits of the last step (stderr)
+        tr = eng.ctx.correct_fit_trace()
+        mode, nf, info = tr[:, :, 0].ravel().astype(int), tr[:, :, 5].ravel(), tr[:, :, 4].ravel().astype(int)
+        f = nf[mode < 2]
+        sys.stderr.write("fit stats: windows %d modes %s info %s nfev mean %.2f p50 %.0f p90 %.0f p99 %.0f p999 %.0f max %.0f\n" % (
+            nf.size, np.bincount(mode, minlength=3).tolist(), np.bincount(info[mode < 2]).tolist(), f.mean(),
+            *np.percentile(f, [50, 90, 99, 99.9]), f.max()))
     if rank == 0:
         print(json.dumps(result))
     eng.close()
@@ -445,9 +452,11 @@ def main():
     ap.add_argument("--workload", default="hg38", choices=["hg38", "chr50mb", "small"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lm-exact", action="store_true")
+    ap.add_argument("--fit-stats", action="store_true")
+    ap.add_argument("--lm-mode", type=int, default=None, help="2 / 3: first-generation warp-per-window fit kernels (comparison runs)")
     args = ap.parse_args()
     global LM_EXACT
-    LM_EXACT = bool(args.lm_exact)
+    LM_EXACT = args.lm_mode if args.lm_mode is not None else int(bool(args.lm_exact))
     if args.impl == "reference":
         bench_reference(args)
     else:

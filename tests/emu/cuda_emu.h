@@ -279,6 +279,12 @@ inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline long long __double_as_longlong(double d) { long long i; memcpy(&i, &d, 8); return i; }
 inline double __longlong_as_double(long long i) { double d; memcpy(&d, &i, 8); return d; }
+inline int __double2hiint(double d) { long long i; memcpy(&i, &d, 8); return (int)(i >> 32); }
+inline int __double2loint(double d) { long long i; memcpy(&i, &d, 8); return (int)(i & 0xffffffffll); }
+inline double __hiloint2double(int hi, int lo) {
+    unsigned long long i = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+    double d; memcpy(&d, &i, 8); return d;
+}
 
 template <class T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }

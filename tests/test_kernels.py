@@ -152,18 +152,22 @@ def test_bias_correction_tracks(loaded_ctx, golden, mode):
             assert np.all(np.abs(both[t].astype(np.float64) - ref32) <= 1e-5 * np.abs(ref32) + 2e-5)
 
 
-def test_bias_correction_tree_sums_close(loaded_ctx, golden):
-    """lm_exact_order=False (warp-tree sums in the fits): same tracks within the DWM-mode tolerance."""
+@pytest.mark.parametrize("lm_mode", [2, 3])
+def test_bias_correction_warp_kernels(loaded_ctx, golden, lm_mode):
+    """first-generation warp-per-window fit kernels (2: warp-tree sums, 3: MINPACK-order sums), kept for comparison runs:
+    same tracks within the DWM-mode tolerance (bit-identical for mode 3)."""
     g = golden.atac
     _set_model(loaded_ctx, g, "PWM")
     c, s, e = _cols(g["outreg"])
-    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=False)
+    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=lm_mode)
     got = loaded_ctx.correct_download(split_strands=True, as_f64=True, prepost=False)
     for t in ("expected", "corrected"):
         for si, st in enumerate(("forward", "reverse")):
             ref = g["PWM_track_%s_%s" % (t, st)]
             d = np.abs(got[t][si] - ref)
             assert (d <= 1e-5 * np.abs(ref) + 2e-6).mean() >= 0.999 and d.max() <= 2e-5
+            if lm_mode == 3:
+                assert np.array_equal(got[t][si], ref)
 
 
 def test_fit_trace_matches_scipy_exactly_in_pwm_mode(loaded_ctx, golden):

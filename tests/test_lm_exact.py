@@ -23,7 +23,7 @@ def relu(x, a, b):
 @pytest.fixture(scope="module")
 def harness(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("lm") / "lm_harness")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I", os.path.join(ROOT, "tests", "emu"), "-I",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=off", "-I", os.path.join(ROOT, "tests", "emu"), "-I",
                            os.path.join(ROOT, "tobias_b200", "csrc"), os.path.join(ROOT, "tests", "lm_harness.cpp"), "-o", out])
     return out
 
@@ -87,9 +87,11 @@ def _run(harness, windows, seq, tmp):
     return [(float(f[0]), float(f[1]), int(f[2]), int(f[3]), int(f[4])) for f in (ln.split() for ln in lines if ln.strip())]
 
 
-def test_exact_order_reproduces_scipy_bit_for_bit(harness, tmp_path):
-    windows = _windows(160)
-    got = _run(harness, windows, 1, str(tmp_path))
+@pytest.mark.parametrize("form", [2, 1])
+def test_exact_order_reproduces_scipy_bit_for_bit(harness, tmp_path, form):
+    """form 2: thread-per-window kernel core (the default path); form 1: warp-per-window with MINPACK-order sums."""
+    windows = _windows(160 if form == 1 else 640)
+    got = _run(harness, windows, form, str(tmp_path))
     assert len(got) == len(windows)
     n_fallback = 0
     for (x, y), g in zip(windows, got):

@@ -11,6 +11,7 @@
 //                              trimmed per-strand tracks (:381-383)
 #include "tb_common.cuh"
 #include "tb_lm.cuh"
+#include "tb_lm_thread.cuh"
 
 int tb_pileup_device(tb_ctx *ctx, i64 n_regions, const i64 *d_lstart, const i64 *d_lend, const i64 *d_off, i64 total,
                      int shift_fwd, int shift_rev, u32 *d_out);
@@ -117,6 +118,161 @@ __global__ void __launch_bounds__(TB_FIT_WARPS * 32, TB_FIT_MINBLOCKS) tb_fit_ke
             o[5] = pnfev;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ K3b, thread form
+// One THREAD per window (tb_lm_thread.cuh).  A block owns a chunk of consecutive windows of one strand (host-built
+// table: <= TB_FITT_WIN windows, <= TB_FITT_SEG region segments, <= TB_FIT_Q tile slots), stages their positions once
+// into a transposed shared-memory tile (bias f64 + signal u32 = 12 B per position, 120 B per additional window) and
+// lets its threads pull windows from a shared counter: a lane that finishes a fit takes the next window at the top of
+// the next round, so the 32 lanes of a warp stay busy although fits need 2..18 outer iterations.  Every round runs the
+// same phase sequence (QR | trial | finish); lanes skip the phases they do not need.
+#ifndef TB_FITT_THREADS
+#define TB_FITT_THREADS 256
+#endif
+#ifndef TB_FITT_WIN
+#define TB_FITT_WIN 768
+#endif
+#define TB_FITT_SEG 32
+#ifndef TB_FITT_MINBLOCKS
+#define TB_FITT_MINBLOCKS 2
+#endif
+#define TB_FITT_SMEM ((size_t)10 * TB_FIT_Q * (sizeof(double) + sizeof(u32)) + (size_t)TB_FITT_WIN * sizeof(double))
+
+__global__ void __launch_bounds__(TB_FITT_THREADS, TB_FITT_MINBLOCKS)
+    tb_fit_thread_kernel(tb_cor_view V, const i64 *__restrict__ chunk_w0, const u32 *__restrict__ pile,
+                         const double *__restrict__ biasraw, double *__restrict__ fit) {
+    TB_DYN_SMEM(smem);
+    double *tx = (double *)smem;                               // [10][TB_FIT_Q] bias
+    double *sf0 = tx + 10 * TB_FIT_Q;                          // [TB_FITT_WIN]  residual norm at p0, -1 = empty window
+    u32 *ty = (u32 *)(sf0 + TB_FITT_WIN);                      // [10][TB_FIT_Q] signal
+    __shared__ int seg_w0[TB_FITT_SEG + 1], seg_q0[TB_FITT_SEG], seg_np[TB_FITT_SEG];
+    __shared__ i64 seg_pos[TB_FITT_SEG];
+    __shared__ int n_seg, next;
+    const int m = V.window;
+    const int strand = blockIdx.y;
+    const i64 w_first = chunk_w0[blockIdx.x];
+    const int n_win = (int)(chunk_w0[blockIdx.x + 1] - w_first);
+    if (threadIdx.x == 0) {
+        i64 wg = w_first, wend = w_first + n_win;
+        i64 j = tb_upper_bound(V.win_off, V.n_regions + 1, wg) - 1;
+        int s = 0, q = 0;
+        while (wg < wend && s < TB_FITT_SEG) {
+            i64 jw = wg - V.win_off[j];
+            i64 hi = V.win_off[j + 1] < wend ? V.win_off[j + 1] : wend;
+            int n = (int)(hi - wg);
+            if (n > 0) {
+                seg_w0[s] = (int)(wg - w_first);
+                seg_q0[s] = q;
+                seg_pos[s] = (i64)strand * V.ext_total + V.ext_off[j] + V.k_flank + (i64)TB_STEP * jw;
+                seg_np[s] = TB_STEP * (n - 1) + m;
+                q += (seg_np[s] + 9) / 10;
+                s++;
+                wg += n;
+            }
+            j++;
+        }
+        seg_w0[s] = n_win;
+        n_seg = s;
+        next = 0;
+    }
+    __syncthreads();
+    for (int s = 0; s < n_seg; s++) {
+        const i64 pos = seg_pos[s];
+        const int np = seg_np[s], q0 = seg_q0[s];
+        for (int lp = threadIdx.x; lp < np; lp += blockDim.x) {
+            const int slot = (lp % 10) * TB_FIT_Q + q0 + lp / 10;
+            tx[slot] = biasraw[pos + lp];
+            ty[slot] = pile[pos + lp];
+        }
+    }
+    __syncthreads();
+    // residual norm at p0 and the empty-window test of every window of the chunk, all lanes busy
+    for (int cw = threadIdx.x; cw < n_win; cw += blockDim.x) {
+        int s = 0;
+        while (cw >= seg_w0[s + 1]) s++;
+        const int q = seg_q0[s] + (cw - seg_w0[s]);
+        sf0[cw] = tb_lmt_fnorm0(tb_win_ref{tx + q, ty + q}, m);
+    }
+    __syncthreads();
+
+    tb_lmt S;
+    tb_win_ref W{tx, ty};
+    double *rec = fit;
+    bool active = true, need_new = true, need_qr = false;
+    while (active) {
+        if (need_new) {
+            for (;;) {
+                const int cw = atomicAdd(&next, 1);
+                if (cw >= n_win) {
+                    active = false;
+                    break;
+                }
+                rec = fit + ((i64)strand * V.n_windows + w_first + cw) * TB_FIT_REC;
+                const double f0 = sf0[cw];
+                if (f0 >= 0.0) {                                   // signalmax > 0 (:290)
+                    int s = 0;
+                    while (cw >= seg_w0[s + 1]) s++;
+                    const int q = seg_q0[s] + (cw - seg_w0[s]);
+                    W.x = tx + q;
+                    W.y = ty + q;
+                    tb_lmt_init(S, f0);
+                    need_new = false;
+                    need_qr = true;
+                    break;
+                }
+                rec[0] = 2.0;                                      // np.zeros (:304)
+                rec[1] = rec[2] = rec[3] = rec[4] = rec[5] = 0.0;
+            }
+        }
+        if (active) {
+            if (need_qr) {
+                tb_lmt_qr(S, W, m);
+                need_qr = false;
+            }
+            if (S.info == 0) need_qr = tb_lmt_trial(S, W, m);
+            if (S.info != 0) {
+                double mode, pa, pb, pmax;
+                tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
+                rec[0] = mode;
+                rec[1] = pa;
+                rec[2] = pb;
+                rec[3] = pmax;
+                rec[4] = (double)S.info;
+                rec[5] = (double)S.nfev;
+                need_new = true;
+            }
+        }
+    }
+}
+
+// chunk table of tb_fit_thread_kernel: windows [w0[c], w0[c+1]) with bounded window count, segment count and tile slots
+static void tb_fit_chunks(const std::vector<i64> &win_off, int window, std::vector<i64> &w0) {
+    const int qm = (window + 9) / 10;
+    w0.clear();
+    w0.push_back(0);
+    int nw = 0, nq = 0, ns = 0;
+    const i64 n_regions = (i64)win_off.size() - 1;
+    for (i64 j = 0; j < n_regions; j++) {
+        i64 left = win_off[j + 1] - win_off[j], at = win_off[j];
+        while (left > 0) {
+            i64 room = TB_FITT_WIN - nw;
+            i64 roomq = (i64)TB_FIT_Q - nq - qm + 1;
+            if (roomq < room) room = roomq;
+            if (room <= 0 || ns == TB_FITT_SEG) {
+                w0.push_back(at);
+                nw = nq = ns = 0;
+                continue;
+            }
+            i64 n = left < room ? left : room;
+            nw += (int)n;
+            nq += (int)n - 1 + qm;
+            ns++;
+            at += n;
+            left -= n;
+        }
+    }
+    if (w0.back() != win_off[n_regions]) w0.push_back(win_off[n_regions]);
 }
 
 // ------------------------------------------------------------------------------------------------ K3c
@@ -358,7 +514,19 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     tb_mark(ctx, 2);
     tb_cor_view V{C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), C.d_out_off.as<i64>(), C.d_win_off.as<i64>(),
                   n_regions, C.ext_total, C.out_total, C.n_windows, k_flank, window, L, f_extend};
-    {
+    if (lm_exact_order < 2 && window <= 10 * (TB_FIT_Q - 2)) {
+        // thread-per-window fits in MINPACK's own summation order (bit-faithful to scipy on identical input)
+        std::vector<i64> w0;
+        tb_fit_chunks(C.win_off, window, w0);
+        TB_TRY(tb_h2d(ctx, ctx->reg_c, w0.data(), sizeof(i64) * w0.size()));
+        const size_t smem = TB_FITT_SMEM;
+        auto kf = tb_fit_thread_kernel;
+        TB_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TB_LAUNCH(ctx, kf, dim3((unsigned)(w0.size() - 1), 2), TB_FITT_THREADS, smem, V, (const i64 *)ctx->reg_c.as<i64>(),
+                  (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(), C.fit.as<double>());
+        TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_fit_thread_kernel"));
+    } else {
+        const int seq_sums = lm_exact_order != 2;       // warp-per-window kernels: 2 = tree sums, 3 = MINPACK-order sums
         int block = TB_FIT_WARPS * 32;
         i64 want = tb_div_up(2 * C.n_windows, block / 32), capg = (i64)ctx->sm_count * 8;
         unsigned grid = (unsigned)(want < capg ? want : capg);
@@ -368,7 +536,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_LAUNCH(ctx, kf, grid, block, 0, V, (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),      \
                   C.fit.as<double>());                                                                                    \
     }
-        if (lm_exact_order) {
+        if (seq_sums) {
             if (window <= 128) TB_FIT_CASE(4, true) else if (window <= 256) TB_FIT_CASE(8, true) else TB_FIT_CASE(16, true)
         } else {
             if (window <= 128) TB_FIT_CASE(4, false) else if (window <= 256) TB_FIT_CASE(8, false) else TB_FIT_CASE(16, false)

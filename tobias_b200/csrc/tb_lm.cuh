@@ -144,7 +144,7 @@ __device__ __forceinline__ double tb_dot_warp(const double (&a)[PPL], const doub
 }
 
 // MINPACK enorm for the 2-vectors of the trust-region algebra (three-accumulator form).
-__device__ __forceinline__ double tb_enorm2(double x0, double x1) {
+__device__ __noinline__ double tb_enorm2(double x0, double x1) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
     const double agiant = rgiant / 2.0;
@@ -237,7 +237,7 @@ __device__ __forceinline__ void tb_qrsolv2(double (&r)[2][2], const int (&ipvt)[
 }
 
 // lmpar for n = 2.
-__device__ __forceinline__ void tb_lmpar2(double (&r)[2][2], const int (&ipvt)[2], const double (&diag)[2],
+__device__ __noinline__ void tb_lmpar2(double (&r)[2][2], const int (&ipvt)[2], const double (&diag)[2],
                                           const double (&qtb)[2], double delta, double &par, double (&x)[2],
                                           double (&sdiag)[2]) {
     const double dwarf = 2.2250738585072014e-308, p1 = 0.1, p001 = 0.001;

@@ -1,0 +1,475 @@
+// tb_lm_thread.cuh -- K3b core, thread-per-window form: ONE THREAD fits  signal ~ max(0, a*bias + b)  on one window.
+//
+// Same algorithm and same decisions as tb_lm.cuh (scipy.optimize.curve_fit -> leastsq -> MINPACK lmdif with scipy's
+// settings, called by the reference at tobias/tools/atacorrect_functions.py:292), restated so that a thread needs NO
+// m-vector storage: MINPACK keeps fvec, wa4 and the m x 2 Jacobian / Householder vectors in memory; here every
+// element of them is recomputed from the window's (bias, signal) pair whenever a pass over the window needs it, with
+// exactly the operations MINPACK applied to it, so each element has the same bits every time it is formed.  The
+// m-term sums run in index order in one thread -- MINPACK's own order -- so the fit reproduces scipy bit for bit
+// (tests/test_lm_exact.py) while the 32 lanes of a warp work on 32 different windows (no shuffles, no redundant
+// trust-region algebra).
+//
+// Passes over the window per outer iteration: A column norms of the forward-difference Jacobian (fdjac2 + qrfac's
+// enorm), B Householder column 0 applied to column 1 and to fvec, C norm of the remaining column, D second component
+// of Q^T fvec; per inner iteration one pass for the trial residual norm.
+//
+// Divisions by a pass-invariant divisor d (h of fdjac2, the Householder norms) use the precomputed IEEE reciprocal and
+// one fused correction step (q = a*(1/d); r = fma(-q, d, a); q + r*(1/d)), which returns the correctly rounded
+// quotient a/d (Markstein's theorem; checked against the divide instruction on 1.6e9 operand pairs).
+#pragma once
+#include "tb_common.cuh"
+#include "tb_lm.cuh"
+
+#ifndef TB_FIT_Q
+#define TB_FIT_Q 864        // q-slots of the shared-memory tile (10 positions each)
+#endif
+
+// Window point i = 10 u + v of this thread's window lives at x[v * TB_FIT_Q + u] (bias, f64) / y[v * TB_FIT_Q + u]
+// (signal, u32 counts): consecutive windows start 10 positions apart, so consecutive windows read consecutive slots.
+struct tb_win_ref {
+    const double *x;
+    const u32 *y;
+};
+// exact u32 -> double without a conversion instruction: (2^52 + k) - 2^52
+__device__ __forceinline__ double tb_u32_to_double(u32 k) {
+    return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0;
+}
+
+// for (i = 0; i < m; i++) body(i, ex = bias[i], ey = signal[i] as double, eyi = signal[i] as u32).  Kept compact on
+// purpose (no unrolling): the kernel is a sequence of such passes and must stay resident in the instruction cache.
+#ifndef TB_FIT_UNROLL
+#define TB_FIT_UNROLL 1
+#endif
+#define TB_PRAGMA_(x) _Pragma(#x)
+#define TB_PRAGMA(x) TB_PRAGMA_(x)
+#define TB_FOR_POINTS(W, m, i, ...)                                            \
+    for (int _u = 0; _u * 10 < (m); _u++) {                                    \
+        const int _nv = (m) - _u * 10 < 10 ? (m) - _u * 10 : 10;               \
+        const double *_px = (W).x + _u;                                        \
+        const u32 *_py = (W).y + _u;                                           \
+        TB_PRAGMA(unroll TB_FIT_UNROLL)                                        \
+        for (int _v = 0; _v < _nv; _v++, _px += TB_FIT_Q, _py += TB_FIT_Q) {   \
+            const int i = _u * 10 + _v;                                        \
+            const double ex = *_px;                                            \
+            const u32 eyi = *_py;                                              \
+            const double ey = tb_u32_to_double(eyi);                           \
+            __VA_ARGS__                                                        \
+        }                                                                      \
+    }
+
+// a / d with dinv = 1.0 / d (correctly rounded, see header)
+__device__ __forceinline__ double tb_div_inv(double a, double d, double dinv) {
+    double q = a * dinv;
+    double r = fma(-q, d, a);
+    return fma(r, dinv, q);
+}
+
+// MINPACK enorm as a streaming accumulator (three sums: large / intermediate / small components).  A component whose
+// exponent is surely inside (3.834e-20, 1.304e19 / n) is squared and added in line (integer test of the high word);
+// exact zeros are skipped (they change nothing in MINPACK's small branch); anything else takes the out-of-line path
+// with MINPACK's full classification, which practically never runs.
+struct tb_enorm_acc {
+    double s1, s2, s3, x1max, x3max;
+};
+__device__ __noinline__ tb_enorm_acc tb_enorm_rare(tb_enorm_acc t, double xabs, double agiant) {
+    if (xabs > 3.834e-20 && xabs < agiant) {
+        t.s2 += xabs * xabs;
+    } else if (xabs <= 3.834e-20) {
+        if (xabs > t.x3max) {
+            double q = t.x3max / xabs;
+            t.s3 = 1.0 + t.s3 * (q * q);
+            t.x3max = xabs;
+        } else if (xabs != 0.0) {
+            double q = xabs / t.x3max;
+            t.s3 += q * q;
+        }
+    } else {
+        if (xabs > t.x1max) {
+            double q = t.x1max / xabs;
+            t.s1 = 1.0 + t.s1 * (q * q);
+            t.x1max = xabs;
+        } else {
+            double q = xabs / t.x1max;
+            t.s1 += q * q;
+        }
+    }
+    return t;
+}
+__device__ __noinline__ double tb_enorm_result(tb_enorm_acc t) {
+    if (t.s1 != 0.0) return t.x1max * sqrt(t.s1 + (t.s2 / t.x1max) / t.x1max);
+    if (t.s2 != 0.0) {
+        if (t.s2 >= t.x3max) return sqrt(t.s2 * (1.0 + (t.x3max / t.s2) * (t.x3max * t.s3)));
+        return sqrt(t.x3max * ((t.s2 / t.x3max) + (t.x3max * t.s3)));
+    }
+    return t.x3max * sqrt(t.s3);
+}
+__device__ __forceinline__ void tb_enorm_init(tb_enorm_acc &t) { t.s1 = t.s2 = t.s3 = t.x1max = t.x3max = 0.0; }
+// n = number of components of the whole vector (sets MINPACK's agiant); n <= 512 keeps the in-line range test valid
+__device__ __forceinline__ void tb_enorm_add(tb_enorm_acc &t, double v, int n) {
+    const u32 hi = (u32)__double2hiint(v) & 0x7fffffffu;
+    if (hi - 0x3BF00000u < 0x43500000u - 0x3BF00000u) t.s2 += v * v;             // 2^-64 <= |v| < 2^54
+    else if ((hi | (u32)__double2loint(v)) != 0u) t = tb_enorm_rare(t, fabs(v), 1.304e19 / (double)n);
+}
+
+// state of one fit between passes
+struct tb_lmt {
+    double par0, par1, fnorm, diag0, diag1, delta, lmp, xnorm, gnorm;
+    double r00, r01, r11, qtf0, qtf1, acn0, acn1;
+    int ipvt0, iter, nfev, info;
+};
+
+// max(0, t) as the reference's np.maximum(0.0, t) for every finite t (and -0.0 -> 0.0): clears negative values by their
+// sign bit on the integer pipe instead of a double-precision compare + select
+__device__ __forceinline__ double tb_relu(double t) {
+    long long b = __double_as_longlong(t);
+    b &= ~(b >> 63);
+    return __longlong_as_double(b);
+}
+__device__ __forceinline__ double tb_relu_res(double a, double b, double x, double y) {
+    return tb_relu(__dadd_rn(__dmul_rn(a, x), b)) - y;          // np.maximum(0.0, a*x + b) - ydata
+}
+
+// residual norm at the start point p0 = (1, 1) and max(signal) of one window; returns -1 when the window holds no signal
+__device__ __forceinline__ double tb_lmt_fnorm0(const tb_win_ref W, int m) {
+    tb_enorm_acc n;
+    tb_enorm_init(n);
+    u32 ymax = 0;
+    TB_FOR_POINTS(W, m, i, {
+        ymax = eyi > ymax ? eyi : ymax;
+        tb_enorm_add(n, tb_relu_res(1.0, 1.0, ex, ey), m);
+    })
+    return ymax > 0 ? tb_enorm_result(n) : -1.0;
+}
+
+__device__ __forceinline__ void tb_lmt_init(tb_lmt &S, double fnorm0) {
+    S.par0 = 1.0;
+    S.par1 = 1.0;
+    S.fnorm = fnorm0;
+    S.diag0 = S.diag1 = 0.0;
+    S.delta = S.lmp = S.xnorm = S.gnorm = 0.0;
+    S.r00 = S.r01 = S.r11 = S.qtf0 = S.qtf1 = S.acn0 = S.acn1 = 0.0;
+    S.ipvt0 = 0;
+    S.iter = 1;
+    S.nfev = 1;
+    S.info = 0;
+}
+
+// per-point quantities of one outer iteration: residual f, pivot column P and other column Q of the forward-difference
+// Jacobian (fdjac2: column j = (fvec(x + h_j e_j) - fvec) / h_j).  (pa, pb) / (qa, qb) are the perturbed parameter
+// pairs of the pivot / other column, so the pivoting costs no per-point selects.
+struct tb_jac {
+    double a, b, pa, pb, ph, phinv, qa, qb, qh, qhinv;
+    __device__ __forceinline__ void eval(double x, double y, double &f, double &P, double &Q) const {
+        f = tb_relu(__dadd_rn(__dmul_rn(a, x), b)) - y;
+        double fp = tb_relu(__dadd_rn(__dmul_rn(pa, x), pb)) - y;
+        double fq = tb_relu(__dadd_rn(__dmul_rn(qa, x), qb)) - y;
+        P = tb_div_inv(fp - f, ph, phinv);
+        Q = tb_div_inv(fq - f, qh, qhinv);
+    }
+};
+
+// fdjac2 + qrfac + Q^T fvec + scaled gradient norm (lmdif outer-loop head).  Sets S.info = 4 when gnorm <= gtol.
+__device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) {
+    const double epsmch = 2.220446049250313e-16, factor = 100.0, gtol = 0.0;
+    const double eps = sqrt(epsmch);
+    tb_jac J;
+    J.a = S.par0;
+    J.b = S.par1;
+    {
+        double h = eps * fabs(S.par0);
+        if (h == 0.0) h = eps;
+        J.ph = h;
+        J.pa = S.par0 + h;
+        J.pb = S.par1;
+        J.phinv = 1.0 / h;
+        h = eps * fabs(S.par1);
+        if (h == 0.0) h = eps;
+        J.qh = h;
+        J.qa = S.par0;
+        J.qb = S.par1 + h;
+        J.qhinv = 1.0 / h;
+    }
+    S.nfev += 2;
+    // ---- pass A: column norms (column 0 = d/da as P, column 1 = d/db as Q)
+    tb_enorm_acc n0, n1;
+    tb_enorm_init(n0);
+    tb_enorm_init(n1);
+    double j00 = 0.0, j10 = 0.0;
+    TB_FOR_POINTS(W, m, i, {
+        double f, j0, j1;
+        J.eval(ex, ey, f, j0, j1);
+        if (i == 0) {
+            j00 = j0;
+            j10 = j1;
+        }
+        tb_enorm_add(n0, j0, m);
+        tb_enorm_add(n1, j1, m);
+    })
+    S.acn0 = tb_enorm_result(n0);
+    S.acn1 = tb_enorm_result(n1);
+    const bool swap = S.acn1 > S.acn0;            // column pivoting
+    S.ipvt0 = swap ? 1 : 0;
+    if (swap) {
+        double t;
+        t = J.pa; J.pa = J.qa; J.qa = t;
+        t = J.pb; J.pb = J.qb; J.qb = t;
+        t = J.ph; J.ph = J.qh; J.qh = t;
+        t = J.phinv; J.phinv = J.qhinv; J.qhinv = t;
+    }
+    double ajnorm = swap ? S.acn1 : S.acn0;
+    const bool have0 = ajnorm != 0.0;
+    double a00 = swap ? j10 : j00;
+    if (have0 && a00 < 0.0) ajnorm = -ajnorm;
+    double ainv = 0.0, temp = 0.0, tq0 = 0.0;
+    // ---- pass B: Householder vector of the pivot column, its products with the other column and with fvec
+    if (have0) {
+        ainv = 1.0 / ajnorm;
+        double s = 0.0, sf = 0.0;
+        TB_FOR_POINTS(W, m, i, {
+            double f, P, Q;
+            J.eval(ex, ey, f, P, Q);
+            double c0 = tb_div_inv(P, ajnorm, ainv);
+            if (i == 0) {
+                c0 += 1.0;
+                a00 = c0;
+            }
+            s += __dmul_rn(c0, Q);
+            sf += __dmul_rn(c0, f);
+        })
+        temp = s / a00;
+        if (a00 != 0.0) tq0 = -sf / a00;
+    }
+    S.r00 = -ajnorm;
+    // ---- pass C: remaining column, its norm below the first row
+    tb_enorm_acc nc;
+    tb_enorm_init(nc);
+    double c11 = 0.0;
+    TB_FOR_POINTS(W, m, i, {
+        double f, P, Q;
+        J.eval(ex, ey, f, P, Q);
+        double c1 = Q;
+        if (have0) {
+            double c0 = tb_div_inv(P, ajnorm, ainv);
+            if (i == 0) c0 += 1.0;
+            c1 = Q - __dmul_rn(temp, c0);
+        }
+        if (i == 0) S.r01 = c1;
+        else {
+            if (i == 1) c11 = c1;
+            tb_enorm_add(nc, c1, m - 1);
+        }
+    })
+    double ajnorm1 = tb_enorm_result(nc);
+    const bool have1 = ajnorm1 != 0.0;
+    double ainv1 = 0.0;
+    if (have1) {
+        if (c11 < 0.0) ajnorm1 = -ajnorm1;
+        ainv1 = 1.0 / ajnorm1;
+    }
+    S.r11 = -ajnorm1;
+    // ---- first iteration: scaling and trust-region radius
+    if (S.iter == 1) {
+        S.diag0 = S.acn0 == 0.0 ? 1.0 : S.acn0;
+        S.diag1 = S.acn1 == 0.0 ? 1.0 : S.acn1;
+        S.xnorm = tb_enorm2(S.diag0 * S.par0, S.diag1 * S.par1);
+        S.delta = factor * S.xnorm;
+        if (S.delta == 0.0) S.delta = factor;
+    }
+    // ---- pass D: qtf = first two components of Q^T fvec
+    {
+        const bool app0 = have0 && a00 != 0.0;
+        double s1 = 0.0, w0 = 0.0, w1 = 0.0, a11 = c11;
+        TB_FOR_POINTS(W, m, i, {
+            double f, P, Q;
+            J.eval(ex, ey, f, P, Q);
+            double c0 = P, c1 = Q;
+            if (have0) {
+                c0 = tb_div_inv(P, ajnorm, ainv);
+                if (i == 0) c0 += 1.0;
+                c1 = Q - __dmul_rn(temp, c0);
+            }
+            double w = f;
+            if (app0) w = f + __dmul_rn(c0, tq0);
+            if (i == 0) w0 = w;
+            else {
+                if (have1) {
+                    c1 = tb_div_inv(c1, ajnorm1, ainv1);
+                    if (i == 1) c1 += 1.0;
+                }
+                if (i == 1) {
+                    w1 = w;
+                    a11 = c1;
+                }
+                s1 += __dmul_rn(c1, w);
+            }
+        })
+        S.qtf0 = w0;
+        if (a11 != 0.0) {
+            double t1 = -s1 / a11;
+            w1 += __dmul_rn(a11, t1);
+        }
+        S.qtf1 = w1;
+    }
+    // ---- norm of the scaled gradient
+    double gnorm = 0.0;
+    if (S.fnorm != 0.0) {
+        const double acnp0 = swap ? S.acn1 : S.acn0, acnp1 = swap ? S.acn0 : S.acn1;
+        if (acnp0 != 0.0) {
+            double s = 0.0;
+            s += S.r00 * (S.qtf0 / S.fnorm);
+            gnorm = fmax(gnorm, fabs(s / acnp0));
+        }
+        if (acnp1 != 0.0) {
+            double s = 0.0;
+            s += S.r01 * (S.qtf0 / S.fnorm);
+            s += S.r11 * (S.qtf1 / S.fnorm);
+            gnorm = fmax(gnorm, fabs(s / acnp1));
+        }
+    }
+    S.gnorm = gnorm;
+    if (gnorm <= gtol) {
+        S.info = 4;
+        return;
+    }
+    S.diag0 = fmax(S.diag0, S.acn0);
+    S.diag1 = fmax(S.diag1, S.acn1);
+}
+
+// one inner iteration of lmdif: lmpar step, trial residual, trust-region update, termination tests.
+// returns true when the step was accepted (the next round starts with tb_lmt_qr); S.info != 0 ends the fit.
+__device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int m) {
+    const double epsmch = 2.220446049250313e-16;
+    const double ftol = 1.49012e-8, xtol = 1.49012e-8;
+    const double p1 = 0.1, p5 = 0.5, p25 = 0.25, p75 = 0.75, p0001 = 1e-4;
+    const int maxfev = 600;
+    double r[2][2] = {{S.r00, S.r01}, {0.0, S.r11}};
+    const int ipvt[2] = {S.ipvt0, 1 - S.ipvt0};
+    const double diag[2] = {S.diag0, S.diag1};
+    const double qtf[2] = {S.qtf0, S.qtf1};
+    double wa1[2], wa2[2], wa3[2];
+    tb_lmpar2(r, ipvt, diag, qtf, S.delta, S.lmp, wa1, wa2);
+    const double par[2] = {S.par0, S.par1};
+    for (int j = 0; j < 2; j++) {
+        wa1[j] = -wa1[j];
+        wa2[j] = par[j] + wa1[j];
+        wa3[j] = diag[j] * wa1[j];
+    }
+    double pnorm = tb_enorm2(wa3[0], wa3[1]);
+    if (S.iter == 1) S.delta = fmin(S.delta, pnorm);
+    tb_enorm_acc n;
+    tb_enorm_init(n);
+    {
+        const double ta = wa2[0], tb_ = wa2[1];
+        TB_FOR_POINTS(W, m, i, { tb_enorm_add(n, tb_relu_res(ta, tb_, ex, ey), m); })
+    }
+    S.nfev++;
+    const double fnorm1 = tb_enorm_result(n);
+    double actred = -1.0;
+    if (p1 * fnorm1 < S.fnorm) {
+        double t = fnorm1 / S.fnorm;
+        actred = 1.0 - t * t;
+    }
+    r[0][0] = S.r00;
+    r[0][1] = S.r01;
+    r[1][1] = S.r11;
+    for (int j = 0; j < 2; j++) {
+        wa3[j] = 0.0;
+        double temp = wa1[ipvt[j]];
+        for (int i = 0; i <= j; i++) wa3[i] += r[i][j] * temp;
+    }
+    double temp1 = tb_enorm2(wa3[0], wa3[1]) / S.fnorm;
+    double temp2 = sqrt(S.lmp) * pnorm / S.fnorm;
+    double prered = temp1 * temp1 + temp2 * temp2 / p5;
+    double dirder = -(temp1 * temp1 + temp2 * temp2);
+    double ratio = 0.0;
+    if (prered != 0.0) ratio = actred / prered;
+    if (ratio <= p25) {
+        double temp;
+        if (actred >= 0.0) temp = p5;
+        else temp = p5 * dirder / (dirder + p5 * actred);
+        if (p1 * fnorm1 >= S.fnorm || temp < p1) temp = p1;
+        S.delta = temp * fmin(S.delta, pnorm / p1);
+        S.lmp /= temp;
+    } else if (S.lmp == 0.0 || ratio >= p75) {
+        S.delta = pnorm / p5;
+        S.lmp = p5 * S.lmp;
+    }
+    const bool accepted = ratio >= p0001;
+    if (accepted) {
+        S.par0 = wa2[0];
+        S.par1 = wa2[1];
+        S.xnorm = tb_enorm2(S.diag0 * S.par0, S.diag1 * S.par1);
+        S.fnorm = fnorm1;
+        S.iter++;
+    }
+    int info = 0;
+    if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0) info = 1;
+    if (S.delta <= xtol * S.xnorm) info = 2;
+    if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0 && info == 2) info = 3;
+    if (info == 0) {
+        if (S.nfev >= maxfev) info = 5;
+        if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
+        if (S.delta <= epsmch * S.xnorm) info = 7;
+        if (S.gnorm <= epsmch) info = 8;
+    }
+    S.info = info;
+    return accepted;
+}
+
+// scipy's post-conditions (ier in {1,2,3,4}; inv(R) exists and the covariance holds no NaN) and the window record:
+// mode 0: usable fit (a, b), mode 1: the reference's fallback (atacorrect_functions.py:296-299); pmax = max(prediction).
+// The prediction max(0, a*x + b) is monotonic in x (rounding is monotonic), so its maximum sits at max(x) or min(x).
+__device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref W, int m, double &mode, double &pa, double &pb,
+                                              double &pmax) {
+    int usable = (S.info >= 1 && S.info <= 4) ? 1 : 0;
+    if (usable) {
+        if (S.r00 == 0.0 || S.r11 == 0.0) usable = 0;
+        else {
+            double i00 = 1.0 / S.r00, i11 = 1.0 / S.r11;
+            double i01 = -i11 * (i00 * S.r01);
+            double c00 = i00 * i00 + i01 * i01, c01 = i01 * i11, c11 = i11 * i11;
+            if (c00 != c00 || c01 != c01 || c11 != c11) usable = 0;
+        }
+    }
+    double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
+    TB_FOR_POINTS(W, m, i, {
+        xmax = fmax(xmax, ex);
+        xmin = fmin(xmin, ex);
+        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
+        (void)ey;
+    })
+    if (usable) {
+        const double a = S.par0, b = S.par1;
+        mode = 0.0;
+        pa = a;
+        pb = b;
+        double t = __dadd_rn(__dmul_rn(a, a < 0.0 ? xmin : xmax), b);
+        pmax = t > 0.0 ? t : 0.0;
+    } else {
+        mode = 1.0;
+        pa = 0.0;
+        pb = bmin;
+        double t = xmax - bmin;                                 // max_i max(0, x_i - bmin)
+        pmax = t < 0.0 ? 0.0 : t;
+    }
+}
+
+// complete fit of one window by one thread (test harness entry; the kernel interleaves the phases across lanes)
+__device__ __forceinline__ void tb_lm_fit_thread(const tb_win_ref W, int m, tb_lm_result &res) {
+    tb_lmt S;
+    double f0 = tb_lmt_fnorm0(W, m);
+    tb_lmt_init(S, f0 < 0.0 ? 0.0 : f0);
+    for (;;) {
+        tb_lmt_qr(S, W, m);
+        if (S.info) break;
+        while (!tb_lmt_trial(S, W, m) && !S.info) {}
+        if (S.info) break;
+    }
+    double mode, pa, pb, pmax;
+    tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
+    res.a = S.par0;
+    res.b = S.par1;
+    res.info = S.info;
+    res.nfev = S.nfev;
+    res.usable = mode == 0.0 ? 1 : 0;
+}

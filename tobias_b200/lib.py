@@ -294,7 +294,7 @@ class Context:
         c, s, e = self._regions(contig, start, end)
         self._ck(self._lib.tb_correct_run(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), int(k_flank), int(window),
                                           float(correction_factor), int(read_shift[0]), int(read_shift[1]),
-                                          int(bool(lm_exact_order))))
+                                          int(lm_exact_order)))
         self._cor_total = int((e - s).sum())
         self._cor_L = 2 * k_flank + 1
 
