@@ -141,6 +141,7 @@ extern "C" int tb_init(int device, tb_ctx **out) {
         delete ctx;
         return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
     }
+    { const char *e2 = getenv("TB_K3A_SUM_FORM"); ctx->force_sum_form = (e2 && e2[0] == '1') ? 1 : 0; }   // comparison runs only
     *out = ctx;
     return TB_OK;
 }
@@ -151,7 +152,8 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     tb_dbuf *bufs[] = {&ctx->seq2, &ctx->nmask, &ctx->d_contig_off, &ctx->r_start, &ctx->r_len, &ctx->r_clip, &ctx->r_flags,
                        &ctx->reg_a, &ctx->reg_b, &ctx->reg_c, &ctx->reg_d, &ctx->reg_e, &ctx->scratch0, &ctx->scratch1,
-                       &ctx->scratch2, &ctx->scratch3, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
+                       &ctx->scratch2, &ctx->scratch3, &ctx->scratch4, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
+                       &ctx->model[0].vtable, &ctx->model[1].vtable,
                        &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
                        &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.tracks, &ctx->cor.prepost,
                        &ctx->sc.d_ext_off, &ctx->sc.signal, &ctx->sc.work0, &ctx->sc.work1, &ctx->sc.out};

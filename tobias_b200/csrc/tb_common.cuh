@@ -45,6 +45,7 @@ struct tb_model {
     int is_dwm = -1;
     int L = 0;
     tb_dbuf table;       // DWM: U[2 models][L][4][L][4] doubles; PWM: pssm[5][L]
+    tb_dbuf vtable;      // DWM: V[2 models][16 * (L / 2) + 4 rows][L][4] doubles = 2^(pair / single rows of U), see tb_score.cu
     std::vector<double> host_raw[4];
 };
 
@@ -74,7 +75,7 @@ struct tb_ctx {
 
     // scratch / per-call device tables
     tb_dbuf reg_a, reg_b, reg_c, reg_d, reg_e;
-    tb_dbuf scratch0, scratch1, scratch2, scratch3;
+    tb_dbuf scratch0, scratch1, scratch2, scratch3, scratch4;
     tb_dbuf staging;   // device staging for uploads
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -109,6 +110,7 @@ struct tb_ctx {
         bool have_signal = false, have_out = false;
     } sc;
 
+    int force_sum_form = 0;     // K3a: 1 = first-generation sum-form kernel (comparison runs; TB_K3A_SUM_FORM=1)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
 };

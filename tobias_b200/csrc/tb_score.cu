@@ -133,6 +133,171 @@ __global__ void __launch_bounds__(768, 1) tb_score_dwm_kernel(tb_genome_view g, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K3a, product form
+// The scoring kernel above is bound by shared-memory bandwidth (25 row reads of 800 B per model and window) and pays
+// 100 exp2 + 25 log2 per model and window.  Second formulation, same mathematics:
+//   * rows are grouped in PAIRS of window offsets: T[p][d] = U[2p][d & 3] + U[2p+1][d >> 2] for the 16 dinucleotides d
+//     (+ 4 single rows for the last offset): 13 row reads instead of 25 for L = 25;
+//   * the table holds V = 2^T, so 2^E[n][a] = prod_groups V[g][d_g][n][a] is a product of 13 table entries -- no exp2 at
+//     all -- and the per-model score  sum_n (E[n][S_n] - log2 sum_a 2^E[n][a])  =  log2 prod_n (2^E[n][S_n] / Z[n])  needs
+//     two log2 per window (of the products of the 25 selected terms and of the 25 normalisers, exponents carried apart).
+// One model of one strand (157 KB for L = 25) is resident per block; the four (strand, model) classes of blocks write
+// partial scores that tb_score_combine_kernel subtracts (bias - background).  A warp owns 32 consecutive positions;
+// per window lane l multiplies the 16-byte chunks l and 32 + l of each row ([n][a] order: chunk c = (n, a >> 1)), i.e.
+// a row costs 7 shared-memory wavefronts (6.25 ideal); lane w of the warp finishes window w (log2) and the 32 results
+// leave as one coalesced store.  Relative error of a product of 13 correctly rounded factors ~ 2e-15, i.e. ~1e-14
+// absolute on the score -- the same order as the sum form's difference to the reference's libm.
+#define TB_K3A2_THREADS 1024
+#define TB_K3A2_WPI 2
+
+__device__ __forceinline__ void tb_split_exp(double v, double &mant, int &ex) {      // v = mant * 2^ex, mant in [1, 2)  (v > 0, normal)
+    int hi = __double2hiint(v);
+    ex = ((hi >> 20) & 0x7ff) - 1023;
+    mant = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(v));
+}
+
+__global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
+    tb_score_dwm2_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ vt_fwd, const double *__restrict__ vt_rev,
+                         int L, int strand_mask, double *__restrict__ part) {
+    TB_DYN_SMEM(smem);
+    const int k_flank = L / 2, P = L / 2;
+    const int rows = 16 * P + 4, row = 4 * L;                 // doubles per row
+    const int nclass = strand_mask == 3 ? 4 : 2;
+    const int cls = blockIdx.x % nclass;
+    const int bpart = blockIdx.x / nclass, nparts = (gridDim.x - cls + nclass - 1) / nclass;
+    const int strand = strand_mask == 3 ? (cls >> 1) : (strand_mask == 2 ? 1 : 0);
+    const int model = cls & 1;
+    {
+        const double2 *src = (const double2 *)((strand ? vt_rev : vt_fwd) + (size_t)model * rows * row);
+        double2 *dst = (double2 *)smem;
+        for (int i = threadIdx.x; i < rows * row / 2; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const double2 *V = (const double2 *)smem;                 // chunk c of row r at V[r * 2L + c]
+    double *out = part + (size_t)(strand * 2 + model) * R.total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int nchunk = 2 * L;
+    const bool hasB = 32 + lane < nchunk;
+    const int half = lane & 1, nA = lane >> 1, nB = 16 + (lane >> 1);
+    const i64 n_units = (R.total + 31) >> 5;
+
+    for (i64 unit = (i64)bpart * wpb + warp; unit < n_units; unit += (i64)nparts * wpb) {
+        const i64 pos0 = unit << 5;
+        i64 j = tb_upper_bound(R.ext_off, R.n + 1, pos0) - 1;
+        double my_sel = 1.0, my_z = 1.0;
+        int my_de = 0;
+        bool my_ok = false;
+        for (int it = 0; it < 32; it += TB_K3A2_WPI) {
+            u64 kmer[TB_K3A2_WPI];
+            bool ok[TB_K3A2_WPI];
+#pragma unroll
+            for (int w = 0; w < TB_K3A2_WPI; w++) {
+                const i64 pos = pos0 + it + w;
+                ok[w] = false;
+                kmer[w] = 0;
+                if (pos < R.total) {
+                    while (pos >= R.ext_off[j + 1]) j++;
+                    i64 local = pos - R.ext_off[j];
+                    i64 len = R.ext_off[j + 1] - R.ext_off[j];
+                    if (local >= k_flank && local < len - k_flank) {
+                        i64 gp = R.ext_start[j] + local;
+                        if (tb_nflags(g, gp - k_flank, L) == 0) {
+                            kmer[w] = tb_bases(g, gp - k_flank, L);
+                            ok[w] = true;
+                        }
+                    }
+                }
+            }
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < TB_K3A2_WPI; w++) any = any || ok[w];
+            if (!any) continue;                                // warp-uniform
+            double a0[TB_K3A2_WPI], a1[TB_K3A2_WPI], b0[TB_K3A2_WPI], b1[TB_K3A2_WPI];
+#pragma unroll
+            for (int w = 0; w < TB_K3A2_WPI; w++) a0[w] = a1[w] = b0[w] = b1[w] = 1.0;
+            for (int p = 0; p < P; p++) {
+#pragma unroll
+                for (int w = 0; w < TB_K3A2_WPI; w++) {
+                    const int d = (int)((kmer[w] >> (4 * p)) & 15u);
+                    const double2 *r = V + (size_t)(p * 16 + d) * nchunk + lane;
+                    double2 va = r[0];
+                    a0[w] *= va.x;
+                    a1[w] *= va.y;
+                    if (hasB) {
+                        double2 vb = r[32];
+                        b0[w] *= vb.x;
+                        b1[w] *= vb.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < TB_K3A2_WPI; w++) {
+                const int d = (int)((kmer[w] >> (4 * P)) & 3u);
+                const double2 *r = V + (size_t)(P * 16 + d) * nchunk + lane;
+                double2 va = r[0];
+                a0[w] *= va.x;
+                a1[w] *= va.y;
+                if (hasB) {
+                    double2 vb = r[32];
+                    b0[w] *= vb.x;
+                    b1[w] *= vb.y;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < TB_K3A2_WPI; w++) {
+                // column totals: Z = sum_a 2^E[n][a], selected term 2^E[n][S_n]; the two halves of a column sit in lanes l, l^1
+                const int sA = (int)((kmer[w] >> (2 * nA)) & 3u), sB = (int)((kmer[w] >> (2 * nB)) & 3u);
+                double zA = a0[w] + a1[w], zB = b0[w] + b1[w];
+                double selA = (sA >> 1) == half ? ((sA & 1) ? a1[w] : a0[w]) : 0.0;
+                double selB = (sB >> 1) == half ? ((sB & 1) ? b1[w] : b0[w]) : 0.0;
+                zA += __shfl_xor_sync(0xffffffffu, zA, 1);
+                zB += __shfl_xor_sync(0xffffffffu, zB, 1);
+                selA += __shfl_xor_sync(0xffffffffu, selA, 1);
+                selB += __shfl_xor_sync(0xffffffffu, selB, 1);
+                double msel, mz, t;
+                int esel, ez, e;
+                tb_split_exp(selA, msel, esel);
+                tb_split_exp(zA, mz, ez);
+                if (nB < L) {
+                    tb_split_exp(selB, t, e);
+                    msel *= t;
+                    esel += e;
+                    tb_split_exp(zB, t, e);
+                    mz *= t;
+                    ez += e;
+                }
+                int de = esel - ez;
+                for (int dlt = 2; dlt < 32; dlt <<= 1) {           // product over the 16 lane pairs (each pair holds equal values)
+                    msel *= __shfl_xor_sync(0xffffffffu, msel, dlt);
+                    mz *= __shfl_xor_sync(0xffffffffu, mz, dlt);
+                    de += __shfl_xor_sync(0xffffffffu, de, dlt);
+                }
+                if (lane == it + w) {
+                    my_sel = msel;
+                    my_z = mz;
+                    my_de = de;
+                    my_ok = ok[w];
+                }
+            }
+        }
+        if (pos0 + lane < R.total)
+            out[pos0 + lane] = my_ok ? (log2(my_sel) - log2(my_z)) + (double)my_de : (double)NAN;
+    }
+}
+
+// score = partial(bias model) - partial(background model); NaN partials mark windows without a score
+__global__ void tb_score_combine_kernel(const double *__restrict__ part, i64 total, int strand_mask, int nan_invalid,
+                                        double *__restrict__ out_fwd, double *__restrict__ out_rev) {
+    const double invalid = nan_invalid ? (double)NAN : 0.0;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+        for (int strand = 0; strand < 2; strand++)
+            if ((strand_mask >> strand) & 1) {
+                double b = part[(size_t)(strand * 2) * total + i], gq = part[(size_t)(strand * 2 + 1) * total + i];
+                (strand ? out_rev : out_fwd)[i] = (b != b || gq != gq) ? invalid : b - gq;
+            }
+}
+
 // PWM: score = sum_m pssm[S_m][m]; one thread per position, table in shared memory.
 __global__ void tb_score_pwm_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ pssm_fwd,
                                     const double *__restrict__ pssm_rev, int L, int strand_mask, int nan_invalid,
@@ -203,6 +368,29 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                         U[(((((size_t)x * L + m) * 4 + s) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)] = v;
                     }
     TB_TRY(tb_h2d(ctx, M.table, U.data(), U.size() * sizeof(double)));
+    // product-form table (tb_score_dwm2_kernel): V[x][row][n][a] = 2^(U[2p][d & 3] + U[2p+1][d >> 2]) for row = 16 p + d,
+    // and 2^U[L-1][d] for the four last rows; same forward-oriented indexing as U
+    {
+        const int P = L / 2, rows = 16 * P + 4;
+        auto u = [&](int x, int m, int s_, int n, int a) {
+            return U[(((((size_t)x * L + m) * 4 + s_) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)];
+        };
+        std::vector<double> Vt((size_t)2 * rows * L * 4);
+        for (int x = 0; x < 2; x++)
+            for (int r = 0; r < rows; r++)
+                for (int n = 0; n < L; n++)
+                    for (int a = 0; a < 4; a++) {
+                        double t;
+                        if (r < 16 * P) {
+                            int p = r >> 4, d = r & 15;
+                            t = u(x, 2 * p, d & 3, n, a) + u(x, 2 * p + 1, d >> 2, n, a);
+                        } else {
+                            t = u(x, L - 1, r - 16 * P, n, a);
+                        }
+                        Vt[(((size_t)x * rows + r) * L + n) * 4 + a] = exp2(t);
+                    }
+        TB_TRY(tb_h2d(ctx, M.vtable, Vt.data(), Vt.size() * sizeof(double)));
+    }
     return tb_sync(ctx, "tb_set_bias_model");
 }
 
@@ -224,7 +412,27 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
     if (!tf) tf = tr;
     if (!tr) tr = tf;
     int L = M0.L;
-    if (M0.is_dwm) {
+    const size_t smem2 = (size_t)(16 * (L / 2) + 4) * 4 * L * sizeof(double);
+    if (M0.is_dwm && smem2 <= (size_t)227 * 1024 && !ctx->force_sum_form) {
+        // product form: one (strand, model) table per block, partial scores, then bias - background
+        const int nclass = strand_mask == 3 ? 4 : 2;
+        TB_TRY(tb_reserve(ctx, ctx->scratch4, (size_t)4 * total * sizeof(double)));
+        auto k = tb_score_dwm2_kernel;
+        TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        i64 n_units = (total + 31) >> 5;
+        i64 want = tb_div_up(n_units, TB_K3A2_THREADS / 32) * nclass;
+        i64 cap = ctx->sm_count - ctx->sm_count % nclass;
+        unsigned grid = (unsigned)(want < cap ? want : cap);
+        if (grid < (unsigned)nclass) grid = nclass;
+        const double *vf = ctx->model[0].vtable.as<double>(), *vr = ctx->model[1].vtable.as<double>();
+        if (!vf) vf = vr;
+        if (!vr) vr = vf;
+        TB_LAUNCH(ctx, k, grid, TB_K3A2_THREADS, smem2, g, R, vf, vr, L, strand_mask, ctx->scratch4.as<double>());
+        TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_score_dwm2_kernel"));
+        i64 wantc = tb_div_up(total, 256), capc = (i64)ctx->sm_count * 8;
+        TB_LAUNCH(ctx, tb_score_combine_kernel, (unsigned)(wantc < capc ? wantc : capc), 256, 0,
+                  (const double *)ctx->scratch4.as<double>(), total, strand_mask, nan_invalid, d_out_fwd, d_out_rev);
+    } else if (M0.is_dwm) {
         size_t smem = (size_t)2 * L * 4 * L * 4 * sizeof(double);
         int use_smem = smem <= (size_t)200 * 1024;
         auto k = tb_score_dwm_kernel;
