@@ -81,6 +81,20 @@ def test_bias_counts_other_parameters(loaded_ctx, golden):
     assert scalars[0] == ref.no_reads
 
 
+def test_bias_counts_in_several_slab_chunks(loaded_ctx, golden, monkeypatch):
+    """The multiplicity slab is processed in chunks of regions when it does not fit the memory budget; a tiny budget forces
+    many chunks (each with its own record range) and the site-list growth path -- same integers."""
+    g = golden.atac
+    monkeypatch.setenv("TB_K2_SLAB_BUDGET", "20000")
+    counts, scalars = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)
+    monkeypatch.delenv("TB_K2_SLAB_BUDGET")
+    assert scalars[0] == int(g["DWM_no_reads"])
+    for si, st in enumerate(("forward", "reverse")):
+        assert np.array_equal(counts[si, 0], g["DWM_%s_counts" % st]) and np.array_equal(counts[si, 1], g["DWM_%s_bg_counts" % st])
+    counts2, scalars2 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)           # slab left clean by the chunked run
+    assert np.array_equal(counts, counts2) and np.array_equal(scalars, scalars2)
+
+
 def _set_model(ctx, g, mode):
     for si, st in enumerate(("forward", "reverse")):
         if mode == "DWM":

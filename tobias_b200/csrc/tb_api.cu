@@ -153,7 +153,7 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     tb_dbuf *bufs[] = {&ctx->seq2, &ctx->nmask, &ctx->d_contig_off, &ctx->r_start, &ctx->r_len, &ctx->r_clip, &ctx->r_flags,
                        &ctx->reg_a, &ctx->reg_b, &ctx->reg_c, &ctx->reg_d, &ctx->reg_e, &ctx->scratch0, &ctx->scratch1,
                        &ctx->scratch2, &ctx->scratch3, &ctx->scratch4, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
-                       &ctx->model[0].vtable, &ctx->model[1].vtable,
+                       &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_slab, &ctx->k2_sites,
                        &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
                        &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.tracks, &ctx->cor.prepost,
                        &ctx->sc.d_ext_off, &ctx->sc.signal, &ctx->sc.work0, &ctx->sc.work1, &ctx->sc.out};
@@ -342,10 +342,12 @@ extern "C" int tb_genome_fetch(tb_ctx *ctx, int contig, int64_t start, int64_t n
 __global__ void tb_reads_linearise_kernel(i64 n, const int32_t *__restrict__ contig, const int32_t *__restrict__ ref_start,
                                           const int32_t *__restrict__ ref_end, const i64 *__restrict__ contig_off,
                                           int n_contigs, i64 *__restrict__ lstart, int32_t *__restrict__ rlen,
-                                          uint8_t *__restrict__ flags) {
+                                          uint8_t *__restrict__ flags, int *__restrict__ stats) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int c = contig[i];
+    // stats[0] = longest reference span, stats[1] = 1 when the records are not sorted by (contig, start)
+    if (i > 0 && (contig[i - 1] > c || (contig[i - 1] == c && ref_start[i - 1] > ref_start[i]))) stats[1] = 1;
     if (c < 0 || c >= n_contigs) {      // unknown contig: never matches any region
         lstart[i] = -((i64)1 << 40);
         rlen[i] = 0;
@@ -354,6 +356,7 @@ __global__ void tb_reads_linearise_kernel(i64 n, const int32_t *__restrict__ con
     }
     lstart[i] = contig_off[c] + (i64)ref_start[i];
     rlen[i] = ref_end[i] - ref_start[i];
+    if (rlen[i] > stats[0]) atomicMax(&stats[0], rlen[i]);
 }
 
 extern "C" int tb_reads_upload(tb_ctx *ctx, int64_t n, const int32_t *contig, const int32_t *ref_start,
@@ -373,8 +376,14 @@ extern "C" int tb_reads_upload(tb_ctx *ctx, int64_t n, const int32_t *contig, co
     TB_TRY(tb_h2d(ctx, ctx->r_flags, flags, (size_t)n));
     TB_TRY(tb_reserve(ctx, ctx->r_start, (size_t)n * 8));
     TB_TRY(tb_reserve(ctx, ctx->r_len, b4));
+    TB_TRY(tb_reserve(ctx, ctx->reg_e, 2 * sizeof(int)));
+    TB_CUDA(ctx, cudaMemsetAsync(ctx->reg_e.p, 0, 2 * sizeof(int), ctx->stream));
     TB_LAUNCH(ctx, tb_reads_linearise_kernel, (unsigned)tb_div_up(n, 256), 256, 0, (i64)n, ctx->scratch0.as<int32_t>(),
               ctx->scratch1.as<int32_t>(), ctx->scratch2.as<int32_t>(), ctx->d_contig_off.as<i64>(), ctx->n_contigs,
-              ctx->r_start.as<i64>(), ctx->r_len.as<int32_t>(), ctx->r_flags.as<uint8_t>());
+              ctx->r_start.as<i64>(), ctx->r_len.as<int32_t>(), ctx->r_flags.as<uint8_t>(), ctx->reg_e.as<int>());
+    int stats[2] = {0, 0};
+    TB_TRY(tb_d2h(ctx, stats, ctx->reg_e.p, sizeof(stats)));
+    ctx->max_read_len = stats[0];
+    ctx->reads_sorted = stats[1] == 0;
     return tb_sync(ctx, "tb_reads_upload");
 }

@@ -72,6 +72,9 @@ struct tb_ctx {
     i64 n_reads = 0;
     tb_dbuf r_start, r_len, r_clip;   // i64 linear start, i32 reference length, i32 5' clip
     tb_dbuf r_flags;
+    bool reads_sorted = false;        // records sorted by (contig, start): lets K2 narrow the record range of a region chunk
+    i64 max_read_len = 0;             // longest reference span of a record (bounds the records a region chunk can see)
+    tb_dbuf k2_slab, k2_sites;        // K2: multiplicity slab (kept all-zero between calls) and site list
 
     // scratch / per-call device tables
     tb_dbuf reg_a, reg_b, reg_c, reg_d, reg_e;

@@ -9,12 +9,16 @@
 //     k_flank + bg_shift and clipped to the contig (:142-143)  -- reference quirk, kept
 //   * bias k-mer at the cut site, background k-mer bg_shift upstream of the read (:170-175)
 //
-// Two kernels.  (1) scatter: one thread per record, integer atomics into a per-(region, strand) multiplicity slab.
-// (2) scan + accumulate: blocks stream the slab with coalesced loads, compact the non-zero sites into a shared-
-// memory list of 2-bit packed k-mers, then every thread owns one (m, n) position pair and updates its private
-// 16-entry (Sm, Sn) counter column in shared memory -- conflict-free, no atomics in the inner loop (the tensor is
-// symmetric, so only m <= n is accumulated; the reverse strand is accumulated in forward orientation and
-// reverse-complemented by an index permutation on the host).  Everything is integer: bit-exact in any order.
+// Two kernels over a per-(region, strand) multiplicity slab (u32 per position of every extended region, both strands).
+// (1) scatter: one thread per record, an integer atomic per (record, overlapped region); the thread that finds the
+// slot at zero appends the site (region, strand, slab slot) to a global site list (warp-aggregated append), so the
+// slab is never scanned -- it is touched only where reads fall.  (2) accumulate: persistent blocks take batches of
+// sites: phase A, one thread per site, reads the final multiplicity (and zeroes the slot again: the slab cleans itself),
+// forms the bias / background k-mers into a shared-memory list; phase B, one WARP per k-mer, lanes spread over the
+// L(L+1)/2 position pairs (m <= n; the tensor is symmetric), one shared-memory integer atomic per pair -- the atomics
+// return nothing, so the loop runs at the issue / shared-atomic rate (first version: one thread per pair walking the
+// list as a read-modify-write chain, 844 cycles per k-mer).  The reverse strand is accumulated in forward orientation
+// and reverse-complemented by an index permutation on the host.  Everything is integer: bit-exact in any order.
 #include "tb_common.cuh"
 
 struct tb_reads_view2 {
@@ -30,67 +34,112 @@ struct tb_k2_regions {
     const i64 *es, *ee;    // extended + clipped bounds (linear)
     const i64 *soff;       // slab offset of each region (relative to the chunk), n+1 entries
     i64 n;                 // regions in this chunk
-    i64 slab_len;          // entries per strand in this chunk
+    i64 slab_len;          // entries per strand in this chunk (< 2^31)
 };
 
-__global__ void tb_k2_scatter_kernel(tb_reads_view2 r, tb_k2_regions R, int shift_fwd, int shift_rev, u32 *__restrict__ slab) {
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += stride) {
-        uint8_t f = r.flags[i];
-        if ((f & TB_READ_SKIP) || !(f & TB_READ_5P_MATCH)) continue;
-        int rev = (f & TB_READ_REVERSE) ? 1 : 0;
-        i64 rs = r.lstart[i], re = rs + r.rlen[i];
-        i64 p = rev ? re + r.clip[i] + shift_rev : rs - r.clip[i] + shift_fwd;
-        for (i64 j = tb_upper_bound(R.e, R.n, rs); j < R.n && R.s[j] < re; j++) {
-            if (p >= R.es[j] && p <= R.ee[j] - 2)                        // start < cutsite < end on the extended region
-                atomicAdd(&slab[(i64)rev * R.slab_len + R.soff[j] + (p - R.es[j])], 1u);
+// site record: region (chunk-local) in the high word, strand in bit 31, slab slot (per strand) in bits 0..30
+__device__ __forceinline__ u64 tb_k2_site(i64 j, int rev, i64 x) { return ((u64)j << 32) | ((u64)rev << 31) | (u64)x; }
+
+// ctr[0] = number of sites appended, ctr[1] = overflow flag (list capacity exceeded)
+__global__ void tb_k2_scatter_kernel(tb_reads_view2 r, tb_k2_regions R, i64 read_lo, i64 read_hi, int shift_fwd, int shift_rev,
+                                     u32 *__restrict__ slab, u64 *__restrict__ sites, i64 site_cap, unsigned long long *__restrict__ ctr) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 n_round = read_lo + ((read_hi - read_lo + 31) / 32) * 32;         // whole warps iterate together
+    for (i64 i = read_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool live = i < read_hi;
+        i64 rs = 0, re = 0, p = 0, j = R.n;
+        int rev = 0;
+        if (live) {
+            uint8_t f = r.flags[i];
+            live = !(f & TB_READ_SKIP) && (f & TB_READ_5P_MATCH);
+            if (live) {
+                rev = (f & TB_READ_REVERSE) ? 1 : 0;
+                rs = r.lstart[i];
+                re = rs + r.rlen[i];
+                p = rev ? re + r.clip[i] + shift_rev : rs - r.clip[i] + shift_fwd;
+                j = tb_upper_bound(R.e, R.n, rs);
+            }
+        }
+        for (;;) {                                          // regions the alignment overlaps (usually one)
+            const bool more = live && j < R.n && R.s[j] < re;
+            if (!__any_sync(FULL, more)) break;
+            bool fresh = false;
+            i64 x = 0;
+            if (more && p >= R.es[j] && p <= R.ee[j] - 2) { // start < cutsite < end on the extended region
+                x = R.soff[j] + (p - R.es[j]);
+                fresh = atomicAdd(&slab[(i64)rev * R.slab_len + x], 1u) == 0u;
+            }
+            const unsigned nz = __ballot_sync(FULL, fresh);
+            if (nz) {
+                const int leader = __ffs((int)nz) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(&ctr[0], (unsigned long long)__popc(nz));
+                base = __shfl_sync(FULL, base, leader);
+                if (fresh) {
+                    const i64 slot = (i64)base + __popc(nz & ((1u << lane) - 1u));
+                    if (slot < site_cap) sites[slot] = tb_k2_site(j, rev, x);
+                    else ctr[1] = 1ull;
+                }
+            }
+            if (more) j++;
         }
     }
 }
 
-#define TB_K2_TILE 1024
+#define TB_K2_BATCH 2048         // sites per batch of a block (2 per thread); the k-mer list holds 2 per site
+#define TB_K2_PAIR_ITERS 16      // ceil(31 * 32 / 2 / 32): pair slots per lane for L <= 31
 
 // layout of the accumulators: DWM: acc[tbl][code = Sm*4+Sn][pair]   PWM: acc[tbl][S (0..4)][m]
 template <int IS_DWM>
-__global__ void tb_k2_accumulate_kernel(tb_genome_view g, tb_k2_regions R, const u32 *__restrict__ slab, int k_flank,
-                                        int bg_shift, int cap, i64 n_tiles, u64 *__restrict__ g_acc, u64 *__restrict__ g_scalars) {
+__global__ void __launch_bounds__(1024, 1)
+    tb_k2_accumulate_kernel(tb_genome_view g, tb_k2_regions R, u32 *__restrict__ slab, const u64 *__restrict__ sites, i64 n_sites,
+                            int k_flank, int bg_shift, int cap, u64 *__restrict__ g_acc, u64 *__restrict__ g_scalars) {
     TB_DYN_SMEM(smem);
     const int L = 2 * k_flank + 1;
     const int npairs = L * (L + 1) / 2;
     const int n_acc = IS_DWM ? 4 * 16 * npairs : 4 * 5 * L;
     int *acc = (int *)smem;
-    u64 *list = (u64 *)(smem + (((size_t)n_acc * 4 + 15) & ~(size_t)15));
-    uint8_t *meta = (uint8_t *)(list + 4 * TB_K2_TILE);
-    __shared__ int n_list;
+    u64 *list = (u64 *)(smem + (((size_t)n_acc * 4 + 15) & ~(size_t)15));      // [2 * TB_K2_BATCH] k-mers
+    uint8_t *meta = (uint8_t *)(list + 2 * TB_K2_BATCH);                       // tbl | w << 2, 0xff = no k-mer
     __shared__ int sc[5];            // no_reads, no_bias_f, no_bg_f, no_bias_r, no_bg_r
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
     for (int i = tid; i < n_acc; i += blockDim.x) acc[i] = 0;
     if (tid < 5) sc[tid] = 0;
-    // (m, n) pair owned by this thread (m <= n), row-major over the upper triangle
-    int pm = 0, pn = 0;
-    if (IS_DWM && tid < npairs) {
-        int t = tid, m = 0;
-        while (t >= L - m) { t -= L - m; m++; }
-        pm = m;
-        pn = m + t;
+    // pairs owned by this lane in phase B: t = lane + 32 * it  ->  bit offsets of bases m and n in the packed k-mer
+    u32 pair_sh[TB_K2_PAIR_ITERS];
+    if (IS_DWM) {
+#pragma unroll
+        for (int it = 0; it < TB_K2_PAIR_ITERS; it++) {
+            int t = lane + 32 * it, m = 0;
+            pair_sh[it] = 0xffffffffu;
+            if (t < npairs) {
+                int rr = t;
+                while (rr >= L - m) { rr -= L - m; m++; }
+                pair_sh[it] = (u32)(2 * m) | ((u32)(2 * (m + rr)) << 8);
+            }
+        }
     }
     __syncthreads();
+    i64 drained = 0;
 
-    for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (tid == 0) n_list = 0;
-        __syncthreads();
-        i64 x0 = tile * TB_K2_TILE;
-        for (int y = tid; y < 2 * TB_K2_TILE; y += blockDim.x) {
-            int strand = y / TB_K2_TILE;
-            i64 x = x0 + (y - strand * TB_K2_TILE);
-            if (x >= R.slab_len) continue;
-            u32 cnt = slab[(i64)strand * R.slab_len + x];
-            if (cnt == 0) continue;
-            int w = (int)(cnt < (u32)cap ? cnt : (u32)cap);
-            i64 j = tb_upper_bound(R.soff, R.n + 1, x) - 1;              // region owning slab slot x
-            i64 es = R.es[j], ee = R.ee[j];
-            i64 gp = es + (x - R.soff[j]);
+    for (i64 b0 = (i64)blockIdx.x * TB_K2_BATCH; b0 < n_sites; b0 += (i64)gridDim.x * TB_K2_BATCH) {
+        // ---- phase A: one thread per site
+        for (int k = tid; k < TB_K2_BATCH; k += blockDim.x) {
+            if (IS_DWM) meta[2 * k] = meta[2 * k + 1] = 0xff;
+            if (b0 + k >= n_sites) continue;
+            const u64 site = sites[b0 + k];
+            const i64 j = (i64)(site >> 32), x = (i64)(site & 0x7fffffffu);
+            const int strand = (int)((site >> 31) & 1u);
+            u32 *slot = slab + (i64)strand * R.slab_len + x;
+            const u32 cnt = *slot;
+            *slot = 0u;                                                  // the slab is all-zero again after this kernel
+            const int w = (int)(cnt < (u32)cap ? cnt : (u32)cap);
+            const i64 es = R.es[j], ee = R.ee[j];
+            const i64 gp = es + (x - R.soff[j]);
             atomicAdd(&sc[0], w);
             for (int which = 0; which < 2; which++) {                    // 0: bias k-mer, 1: background k-mer
                 i64 c = which == 0 ? gp : (strand ? gp + bg_shift : gp - bg_shift);
@@ -104,9 +153,8 @@ __global__ void tb_k2_accumulate_kernel(tb_genome_view g, tb_k2_regions R, const
                 int tbl = strand * 2 + which;
                 if (IS_DWM) {
                     if (valid && nf == 0) {
-                        int slot = atomicAdd(&n_list, 1);
-                        list[slot] = kmer;
-                        meta[slot] = (uint8_t)(tbl | (w << 2));
+                        list[2 * k + which] = kmer;
+                        meta[2 * k + which] = (uint8_t)(tbl | (w << 2));
                         atomicAdd(&sc[1 + tbl], w);
                     }
                 } else {
@@ -126,21 +174,50 @@ __global__ void tb_k2_accumulate_kernel(tb_genome_view g, tb_k2_regions R, const
                 }
             }
         }
+        if (!IS_DWM) continue;
         __syncthreads();
-        if (IS_DWM && tid < npairs) {
-            int nl = n_list;
-            for (int e = 0; e < nl; e++) {
-                u64 kmer = list[e];
-                int mt = meta[e];
-                int code = (int)(((kmer >> (2 * pm)) & 3u) * 4 + ((kmer >> (2 * pn)) & 3u));
-                acc[((mt & 3) * 16 + code) * npairs + tid] += (mt >> 2);
+        // ---- phase B: one warp per k-mer, lanes over the position pairs
+        for (int e = warp; e < 2 * TB_K2_BATCH; e += nwarps) {
+            const int mt = meta[e];
+            if (mt == 0xff) continue;
+            const u64 kmer = list[e];
+            const int w = mt >> 2;
+            int *a = acc + (mt & 3) * 16 * npairs + lane;
+#pragma unroll
+            for (int it = 0; it < TB_K2_PAIR_ITERS; it++) {
+                const u32 sh = pair_sh[it];
+                if (sh != 0xffffffffu) {
+                    int code = (int)(((kmer >> (sh & 255u)) & 3u) * 4 + ((kmer >> (sh >> 8)) & 3u));
+                    atomicAdd(a + code * npairs + 32 * it, w);
+                }
             }
         }
+        drained += 2 * TB_K2_BATCH;
         __syncthreads();
+        if (drained * cap > ((i64)1 << 30)) {                            // keep the int accumulators far from overflow
+            for (int i = tid; i < n_acc; i += blockDim.x) {
+                if (acc[i]) atomicAdd(&g_acc[i], (u64)(i64)acc[i]);
+                acc[i] = 0;
+            }
+            drained = 0;
+            __syncthreads();
+        }
     }
+    __syncthreads();
     for (int i = tid; i < n_acc; i += blockDim.x)
         if (acc[i]) atomicAdd(&g_acc[i], (u64)(i64)acc[i]);
     if (tid < 5 && sc[tid]) atomicAdd(&g_scalars[tid], (u64)(i64)sc[tid]);
+}
+
+// first record index with lstart >= v (records are sorted by linear start)
+__global__ void tb_k2_read_bound_kernel(const i64 *__restrict__ lstart, i64 n, i64 v, i64 *__restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    i64 lo = 0, hi = n;
+    while (lo < hi) {
+        i64 mid = (lo + hi) >> 1;
+        if (lstart[mid] >= v) hi = mid; else lo = mid + 1;
+    }
+    *out = lo;
 }
 
 extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end,
@@ -168,18 +245,29 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         es[i] = ls[i] - ext < lo ? lo : ls[i] - ext;
         ee[i] = le[i] + ext > hi ? hi : le[i] + ext;
     }
-    TB_TRY(tb_reserve(ctx, ctx->scratch1, (n_acc + 8) * sizeof(u64)));
-    TB_CUDA(ctx, cudaMemsetAsync(ctx->scratch1.p, 0, (n_acc + 8) * sizeof(u64), ctx->stream));
+    TB_TRY(tb_reserve(ctx, ctx->scratch1, (n_acc + 16) * sizeof(u64)));
+    TB_CUDA(ctx, cudaMemsetAsync(ctx->scratch1.p, 0, (n_acc + 16) * sizeof(u64), ctx->stream));
     u64 *d_acc = ctx->scratch1.as<u64>();
     u64 *d_sc = d_acc + n_acc;
+    unsigned long long *d_ctr = (unsigned long long *)(d_acc + n_acc + 8);      // [0] sites, [1] overflow, [2] read bound
 
     tb_reads_view2 rv{ctx->r_start.as<i64>(), ctx->r_len.as<int32_t>(), ctx->r_clip.as<int32_t>(), ctx->r_flags.as<uint8_t>(),
                       ctx->n_reads};
     tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
-    const i64 SLAB_BUDGET = (i64)1 << 27;       // entries per strand per chunk (1 GiB of u32 for both strands)
-    size_t smem = ((n_acc * 4 + 15) & ~(size_t)15) + (size_t)4 * TB_K2_TILE * 9;
-    int block = is_dwm ? ((npairs + 31) / 32) * 32 : 256;
-    if (block < 128) block = 128;
+    // slab entries per strand per chunk: as much as a quarter of the free memory allows (hg38 non-peak space: 3.0e9 positions,
+    // 24 GB for both strands -> one or two chunks on a 180 GB B200), at most 2^31 - 1 (site records hold 31 bits)
+    i64 SLAB_BUDGET;
+    {
+        size_t free_b = 0, total_b = 0;
+        TB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        free_b += ctx->k2_slab.cap;
+        SLAB_BUDGET = (i64)(free_b / 4 / (2 * sizeof(u32)));
+        if (SLAB_BUDGET < ((i64)1 << 22)) SLAB_BUDGET = (i64)1 << 22;
+        if (SLAB_BUDGET > (((i64)1 << 31) - 1)) SLAB_BUDGET = ((i64)1 << 31) - 1;
+        const char *ev = getenv("TB_K2_SLAB_BUDGET");            // tests: force several chunks
+        if (ev && atoll(ev) > 0) SLAB_BUDGET = atoll(ev);
+    }
+    size_t smem = ((n_acc * 4 + 15) & ~(size_t)15) + (size_t)2 * TB_K2_BATCH * 9;
     if (is_dwm) {
         auto k = tb_k2_accumulate_kernel<1>;
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -187,6 +275,7 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         auto k = tb_k2_accumulate_kernel<0>;
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    i64 site_cap = ctx->n_reads + ctx->n_reads / 4 + 1024;       // one site per (record, overlapped region) at most; grown on overflow
 
     tb_timer_start(ctx);
     i64 j0 = 0;
@@ -199,30 +288,61 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
             soff.push_back(len);
             j1++;
         }
+        if (len > (((i64)1 << 31) - 1)) return tb_fail(ctx, TB_ERR_ARG, "tb_bias_counts: region %lld longer than 2^31", j0);
         i64 nr = j1 - j0;
         TB_TRY(tb_h2d(ctx, ctx->reg_a, ls.data() + j0, sizeof(i64) * nr));
         TB_TRY(tb_h2d(ctx, ctx->reg_b, le.data() + j0, sizeof(i64) * nr));
         TB_TRY(tb_h2d(ctx, ctx->reg_c, es.data() + j0, sizeof(i64) * nr));
         TB_TRY(tb_h2d(ctx, ctx->reg_d, ee.data() + j0, sizeof(i64) * nr));
         TB_TRY(tb_h2d(ctx, ctx->reg_e, soff.data(), sizeof(i64) * (nr + 1)));
-        TB_TRY(tb_reserve(ctx, ctx->scratch0, (size_t)len * 2 * sizeof(u32)));
-        TB_CUDA(ctx, cudaMemsetAsync(ctx->scratch0.p, 0, (size_t)len * 2 * sizeof(u32), ctx->stream));
+        {   // the slab is kept all-zero between uses (the accumulate kernel zeroes what the scatter touched)
+            void *before = ctx->k2_slab.p;
+            TB_TRY(tb_reserve(ctx, ctx->k2_slab, (size_t)len * 2 * sizeof(u32)));
+            if (ctx->k2_slab.p != before) TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_slab.p, 0, ctx->k2_slab.cap, ctx->stream));
+        }
         tb_k2_regions R{ctx->reg_a.as<i64>(), ctx->reg_b.as<i64>(), ctx->reg_c.as<i64>(), ctx->reg_d.as<i64>(),
                         ctx->reg_e.as<i64>(), nr, len};
-        {
-            i64 want = tb_div_up(rv.n, 256), capg = (i64)ctx->sm_count * 16;
-            TB_LAUNCH(ctx, tb_k2_scatter_kernel, (unsigned)(want < capg ? want : capg), 256, 0, rv, R, shift_fwd, shift_rev,
-                      ctx->scratch0.as<u32>());
+        // records that can overlap this chunk: start in [first region start - longest alignment, last region end)
+        i64 read_lo = 0, read_hi = rv.n;
+        if ((j0 > 0 || j1 < n_regions) && ctx->reads_sorted) {
+            i64 bounds[2];
+            TB_LAUNCH(ctx, tb_k2_read_bound_kernel, 1, 32, 0, rv.lstart, rv.n, ls[j0] - ctx->max_read_len, (i64 *)(d_ctr + 2));
+            TB_LAUNCH(ctx, tb_k2_read_bound_kernel, 1, 32, 0, rv.lstart, rv.n, le[j1 - 1], (i64 *)(d_ctr + 3));
+            TB_TRY(tb_d2h(ctx, bounds, d_ctr + 2, sizeof(bounds)));
+            read_lo = bounds[0];
+            read_hi = bounds[1];
         }
-        i64 n_tiles = tb_div_up(len, TB_K2_TILE);
-        i64 capg = (i64)ctx->sm_count * (is_dwm ? 1 : 2);
-        unsigned grid = (unsigned)(n_tiles < capg ? n_tiles : capg);
-        if (is_dwm) {
-            auto k = tb_k2_accumulate_kernel<1>;
-            TB_LAUNCH(ctx, k, grid, block, smem, g, R, (const u32 *)ctx->scratch0.as<u32>(), k_flank, bg_shift, cap, n_tiles, d_acc, d_sc);
-        } else {
-            auto k = tb_k2_accumulate_kernel<0>;
-            TB_LAUNCH(ctx, k, grid, block, smem, g, R, (const u32 *)ctx->scratch0.as<u32>(), k_flank, bg_shift, cap, n_tiles, d_acc, d_sc);
+        for (;;) {
+            TB_TRY(tb_reserve(ctx, ctx->k2_sites, (size_t)site_cap * sizeof(u64)));
+            TB_CUDA(ctx, cudaMemsetAsync(d_ctr, 0, 2 * sizeof(u64), ctx->stream));
+            i64 n_rd = read_hi - read_lo;
+            if (n_rd > 0) {
+                i64 want = tb_div_up(n_rd, 256), capg = (i64)ctx->sm_count * 16;
+                TB_LAUNCH(ctx, tb_k2_scatter_kernel, (unsigned)(want < capg ? want : capg), 256, 0, rv, R, read_lo, read_hi, shift_fwd,
+                          shift_rev, ctx->k2_slab.as<u32>(), ctx->k2_sites.as<u64>(), site_cap, d_ctr);
+            }
+            unsigned long long hc[2];
+            TB_TRY(tb_d2h(ctx, hc, d_ctr, sizeof(hc)));
+            i64 n_sites = (i64)hc[0];
+            if (hc[1]) {       // site list too small (records spanning many tiny regions): clean the slab, grow, redo the chunk
+                TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_slab.p, 0, ctx->k2_slab.cap, ctx->stream));
+                site_cap = n_sites + n_sites / 8 + 1024;
+                continue;
+            }
+            if (n_sites > 0) {
+                i64 n_batches = tb_div_up(n_sites, TB_K2_BATCH);
+                unsigned grid = (unsigned)(n_batches < ctx->sm_count ? n_batches : ctx->sm_count);
+                if (is_dwm) {
+                    auto k = tb_k2_accumulate_kernel<1>;
+                    TB_LAUNCH(ctx, k, grid, 1024, smem, g, R, ctx->k2_slab.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(), n_sites, k_flank,
+                              bg_shift, cap, d_acc, d_sc);
+                } else {
+                    auto k = tb_k2_accumulate_kernel<0>;
+                    TB_LAUNCH(ctx, k, grid, 1024, smem, g, R, ctx->k2_slab.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(), n_sites, k_flank,
+                              bg_shift, cap, d_acc, d_sc);
+                }
+            }
+            break;
         }
         TB_TRY(tb_sync(ctx, "tb_bias_counts chunk"));      // region tables are reused by the next chunk
         j0 = j1;
