@@ -6,6 +6,7 @@
 #include "tb_common.cuh"
 #include "tb_lm.cuh"
 #include "tb_lm_thread.cuh"
+#define TB_FIT_Q 64
 #include <vector>
 struct fake_ctx { long launches; };
 static double gx[128], gy[128];
@@ -21,7 +22,7 @@ void kern() {
                 gtx[(i % 10) * TB_FIT_Q + i / 10] = gx[i];
                 gty[(i % 10) * TB_FIT_Q + i / 10] = (unsigned)gy[i];
             }
-            tb_win_ref W{gtx, gty};
+            tb_win_ref W{gtx, gty, TB_FIT_Q};
             tb_lm_fit_thread(W, gm, gres);
         }
         return;

@@ -155,7 +155,8 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
                        &ctx->scratch2, &ctx->scratch3, &ctx->scratch4, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
                        &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_slab, &ctx->k2_sites,
                        &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
-                       &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.tracks, &ctx->cor.prepost,
+                       &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.fitg_x, &ctx->cor.fitg_y, &ctx->cor.fitg_st,
+                       &ctx->cor.fitg_sti, &ctx->cor.fitg_wq, &ctx->cor.fitg_lists, &ctx->cor.tracks, &ctx->cor.prepost,
                        &ctx->sc.d_ext_off, &ctx->sc.signal, &ctx->sc.work0, &ctx->sc.work1, &ctx->sc.out};
     for (tb_dbuf *b : bufs) tb_release(*b);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

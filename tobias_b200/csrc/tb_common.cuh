@@ -94,7 +94,8 @@ struct tb_ctx {
         tb_dbuf d_ext_start, d_ext_end, d_ext_off, d_out_off, d_win_off;
         tb_dbuf pile;      // u32 [2][ext_total]
         tb_dbuf biasraw;   // f64 [2][ext_total]
-        tb_dbuf fit;       // f64 [2][n_windows][4]
+        tb_dbuf fit;       // f64 [2][n_windows][6]
+        tb_dbuf fitg_x, fitg_y, fitg_st, fitg_sti, fitg_wq, fitg_lists;   // K3b round form: transposed window data, fit state, work lists
         tb_dbuf tracks;    // f64 [4 tracks][2 strands][out_total]
         tb_dbuf prepost;   // f64 [2][3][5][L]
         bool valid = false;

@@ -120,159 +120,140 @@ __global__ void __launch_bounds__(TB_FIT_WARPS * 32, TB_FIT_MINBLOCKS) tb_fit_ke
     }
 }
 
-// ------------------------------------------------------------------------------------------------ K3b, thread form
-// One THREAD per window (tb_lm_thread.cuh).  A block owns a chunk of consecutive windows of one strand (host-built
-// table: <= TB_FITT_WIN windows, <= TB_FITT_SEG region segments, <= TB_FIT_Q tile slots), stages their positions once
-// into a transposed shared-memory tile (bias f64 + signal u32 = 12 B per position, 120 B per additional window) and
-// lets its threads pull windows from a shared counter: a lane that finishes a fit takes the next window at the top of
-// the next round, so the 32 lanes of a warp stay busy although fits need 2..18 outer iterations.  Every round runs the
-// same phase sequence (QR | trial | finish); lanes skip the phases they do not need.
-#ifndef TB_FITT_THREADS
-#define TB_FITT_THREADS 256
-#endif
-#ifndef TB_FITT_WIN
-#define TB_FITT_WIN 768
-#endif
-#define TB_FITT_SEG 32
-#ifndef TB_FITT_MINBLOCKS
-#define TB_FITT_MINBLOCKS 2
-#endif
-#define TB_FITT_SMEM ((size_t)10 * TB_FIT_Q * (sizeof(double) + sizeof(u32)) + (size_t)TB_FITT_WIN * sizeof(double))
+// ------------------------------------------------------------------------------------------------ K3b, round form
+// One THREAD per window (tb_lm_thread.cuh); the fits advance in ROUNDS over the whole launch: the state of a
+// fit (16 doubles + 4 ints) lives in HBM between rounds and every round runs over compacted lists of the windows
+// that still need work -- list Q (next step: Jacobian/QR + trial) and list T (trial only, after a rejected step) -- so
+// the 32 lanes of every warp always execute the same phase on live windows; nothing waits for a neighbour's longer
+// fit.  The window data are read through L1 from a transposed copy (plane v = position mod 10, slot q = window index
+// + 9 per preceding region), in which the lanes of a warp (consecutive windows) read consecutive addresses.
+#define TB_FITG_NST 16
 
-__global__ void __launch_bounds__(TB_FITT_THREADS, TB_FITT_MINBLOCKS)
-    tb_fit_thread_kernel(tb_cor_view V, const i64 *__restrict__ chunk_w0, const u32 *__restrict__ pile,
-                         const double *__restrict__ biasraw, double *__restrict__ fit) {
-    TB_DYN_SMEM(smem);
-    double *tx = (double *)smem;                               // [10][TB_FIT_Q] bias
-    double *sf0 = tx + 10 * TB_FIT_Q;                          // [TB_FITT_WIN]  residual norm at p0, -1 = empty window
-    u32 *ty = (u32 *)(sf0 + TB_FITT_WIN);                      // [10][TB_FIT_Q] signal
-    __shared__ int seg_w0[TB_FITT_SEG + 1], seg_q0[TB_FITT_SEG], seg_np[TB_FITT_SEG];
-    __shared__ i64 seg_pos[TB_FITT_SEG];
-    __shared__ int n_seg, next;
-    const int m = V.window;
+struct tb_fitg_view {
+    double *st;             // [TB_FITG_NST][n_slots] fit state, structure of arrays
+    int4 *sti;              // [n_slots] ipvt0, iter, nfev, info
+    u32 *wq;                // [n_slots] tile slot q of each window
+    const double *gx;       // [10][qtot] bias
+    const u32 *gy;          // [10][qtot] signal
+    i64 qtot, n_slots;
+};
+
+__device__ __forceinline__ void tb_fitg_load(const tb_fitg_view &G, i64 slot, tb_lmt &S) {
+    const double *p = G.st + slot;
+    const i64 n = G.n_slots;
+    S.par0 = p[0 * n]; S.par1 = p[1 * n]; S.fnorm = p[2 * n]; S.diag0 = p[3 * n]; S.diag1 = p[4 * n]; S.delta = p[5 * n];
+    S.lmp = p[6 * n]; S.xnorm = p[7 * n]; S.gnorm = p[8 * n]; S.r00 = p[9 * n]; S.r01 = p[10 * n]; S.r11 = p[11 * n];
+    S.qtf0 = p[12 * n]; S.qtf1 = p[13 * n]; S.acn0 = p[14 * n]; S.acn1 = p[15 * n];
+    int4 v = G.sti[slot];
+    S.ipvt0 = v.x; S.iter = v.y; S.nfev = v.z; S.info = v.w;
+}
+__device__ __forceinline__ void tb_fitg_store(const tb_fitg_view &G, i64 slot, const tb_lmt &S) {
+    double *p = G.st + slot;
+    const i64 n = G.n_slots;
+    p[0 * n] = S.par0; p[1 * n] = S.par1; p[2 * n] = S.fnorm; p[3 * n] = S.diag0; p[4 * n] = S.diag1; p[5 * n] = S.delta;
+    p[6 * n] = S.lmp; p[7 * n] = S.xnorm; p[8 * n] = S.gnorm; p[9 * n] = S.r00; p[10 * n] = S.r01; p[11 * n] = S.r11;
+    p[12 * n] = S.qtf0; p[13 * n] = S.qtf1; p[14 * n] = S.acn0; p[15 * n] = S.acn1;
+    G.sti[slot] = int4{S.ipvt0, S.iter, S.nfev, S.info};
+}
+// warp-aggregated append of `slot` to list[ctr] for the lanes with `want`; every lane of the warp must call it
+__device__ __forceinline__ void tb_fitg_append(bool want, u32 slot, u32 *__restrict__ list, unsigned long long *ctr) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned mask = __ballot_sync(FULL, want);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(ctr, (unsigned long long)__popc(mask));
+    base = __shfl_sync(FULL, base, leader);
+    if (want) list[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+}
+
+// transposed copy of (bias, signal) of every window position; one block per (region, strand)
+__global__ void tb_fitg_transpose_kernel(tb_cor_view V, const u32 *__restrict__ pile, const double *__restrict__ biasraw, i64 qs,
+                                         i64 qtot, int qm, double *__restrict__ gx, u32 *__restrict__ gy) {
+    const i64 j = blockIdx.x;
     const int strand = blockIdx.y;
-    const i64 w_first = chunk_w0[blockIdx.x];
-    const int n_win = (int)(chunk_w0[blockIdx.x + 1] - w_first);
-    if (threadIdx.x == 0) {
-        i64 wg = w_first, wend = w_first + n_win;
-        i64 j = tb_upper_bound(V.win_off, V.n_regions + 1, wg) - 1;
-        int s = 0, q = 0;
-        while (wg < wend && s < TB_FITT_SEG) {
-            i64 jw = wg - V.win_off[j];
-            i64 hi = V.win_off[j + 1] < wend ? V.win_off[j + 1] : wend;
-            int n = (int)(hi - wg);
-            if (n > 0) {
-                seg_w0[s] = (int)(wg - w_first);
-                seg_q0[s] = q;
-                seg_pos[s] = (i64)strand * V.ext_total + V.ext_off[j] + V.k_flank + (i64)TB_STEP * jw;
-                seg_np[s] = TB_STEP * (n - 1) + m;
-                q += (seg_np[s] + 9) / 10;
-                s++;
-                wg += n;
-            }
-            j++;
-        }
-        seg_w0[s] = n_win;
-        n_seg = s;
-        next = 0;
+    const i64 nw = V.win_off[j + 1] - V.win_off[j];
+    if (nw <= 0) return;
+    const i64 q0 = (i64)strand * qs + V.win_off[j] + (i64)(qm - 1) * j;
+    const i64 pos = (i64)strand * V.ext_total + V.ext_off[j] + V.k_flank;
+    const int np = (int)(TB_STEP * (nw - 1)) + V.window;
+    for (int lp = threadIdx.x; lp < np; lp += blockDim.x) {
+        const i64 at = (i64)(lp % 10) * qtot + q0 + lp / 10;
+        gx[at] = biasraw[pos + lp];
+        gy[at] = pile[pos + lp];
     }
-    __syncthreads();
-    for (int s = 0; s < n_seg; s++) {
-        const i64 pos = seg_pos[s];
-        const int np = seg_np[s], q0 = seg_q0[s];
-        for (int lp = threadIdx.x; lp < np; lp += blockDim.x) {
-            const int slot = (lp % 10) * TB_FIT_Q + q0 + lp / 10;
-            tx[slot] = biasraw[pos + lp];
-            ty[slot] = pile[pos + lp];
-        }
-    }
-    __syncthreads();
-    // residual norm at p0 and the empty-window test of every window of the chunk, all lanes busy
-    for (int cw = threadIdx.x; cw < n_win; cw += blockDim.x) {
-        int s = 0;
-        while (cw >= seg_w0[s + 1]) s++;
-        const int q = seg_q0[s] + (cw - seg_w0[s]);
-        sf0[cw] = tb_lmt_fnorm0(tb_win_ref{tx + q, ty + q}, m);
-    }
-    __syncthreads();
+}
 
-    tb_lmt S;
-    tb_win_ref W{tx, ty};
-    double *rec = fit;
-    bool active = true, need_new = true, need_qr = false;
-    while (active) {
-        if (need_new) {
-            for (;;) {
-                const int cw = atomicAdd(&next, 1);
-                if (cw >= n_win) {
-                    active = false;
-                    break;
-                }
-                rec = fit + ((i64)strand * V.n_windows + w_first + cw) * TB_FIT_REC;
-                const double f0 = sf0[cw];
-                if (f0 >= 0.0) {                                   // signalmax > 0 (:290)
-                    int s = 0;
-                    while (cw >= seg_w0[s + 1]) s++;
-                    const int q = seg_q0[s] + (cw - seg_w0[s]);
-                    W.x = tx + q;
-                    W.y = ty + q;
-                    tb_lmt_init(S, f0);
-                    need_new = false;
-                    need_qr = true;
-                    break;
-                }
-                rec[0] = 2.0;                                      // np.zeros (:304)
+// per window: tile slot, residual norm at p0, empty-window record, initial state, first Q list
+__global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int qm, double *__restrict__ fit, u32 *__restrict__ listq,
+                                    unsigned long long *ctr) {
+    const i64 n_round = ((G.n_slots + 31) / 32) * 32;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += stride) {
+        bool live = false;
+        if (slot < G.n_slots) {
+            const int strand = slot >= V.n_windows ? 1 : 0;
+            const i64 wg = slot - (i64)strand * V.n_windows;
+            const i64 j = tb_upper_bound(V.win_off, V.n_regions + 1, wg) - 1;
+            const i64 q = (i64)strand * qs + wg + (i64)(qm - 1) * j;
+            G.wq[slot] = (u32)q;
+            const double f0 = tb_lmt_fnorm0(tb_win_ref{G.gx + q, G.gy + q, G.qtot}, V.window);
+            if (f0 >= 0.0) {                                           // signalmax > 0 (:290)
+                tb_lmt S;
+                tb_lmt_init(S, f0);
+                tb_fitg_store(G, slot, S);
+                live = true;
+            } else {
+                double *rec = fit + slot * TB_FIT_REC;
+                rec[0] = 2.0;                                          // np.zeros (:304)
                 rec[1] = rec[2] = rec[3] = rec[4] = rec[5] = 0.0;
             }
         }
-        if (active) {
-            if (need_qr) {
-                tb_lmt_qr(S, W, m);
-                need_qr = false;
-            }
-            if (S.info == 0) need_qr = tb_lmt_trial(S, W, m);
+        tb_fitg_append(live, (u32)slot, listq, ctr);
+    }
+}
+
+// one round over a list: WITH_QR: outer-iteration head + trial; else trial only.  ctr[0] / ctr[1]: next Q / T list sizes
+#ifndef TB_FITG_MINBLOCKS
+#define TB_FITG_MINBLOCKS 4
+#endif
+template <bool WITH_QR>
+__global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
+    tb_fitg_round_kernel(tb_fitg_view G, int m, const u32 *__restrict__ list, i64 n_list, double *__restrict__ fit,
+                         u32 *__restrict__ nextq, u32 *__restrict__ nextt, unsigned long long *ctr) {
+    const i64 n_round = ((n_list + 31) / 32) * 32;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += stride) {
+        bool to_q = false, to_t = false;
+        u32 slot = 0;
+        if (k < n_list) {
+            slot = list[k];
+            tb_lmt S;
+            tb_fitg_load(G, slot, S);
+            const i64 q = G.wq[slot];
+            const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
+            if (WITH_QR) tb_lmt_qr(S, W, m);
+            bool accepted = false;
+            if (S.info == 0) accepted = tb_lmt_trial(S, W, m);
             if (S.info != 0) {
                 double mode, pa, pb, pmax;
                 tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
+                double *rec = fit + (i64)slot * TB_FIT_REC;
                 rec[0] = mode;
                 rec[1] = pa;
                 rec[2] = pb;
                 rec[3] = pmax;
                 rec[4] = (double)S.info;
                 rec[5] = (double)S.nfev;
-                need_new = true;
+            } else {
+                tb_fitg_store(G, slot, S);
+                to_q = accepted;
+                to_t = !accepted;
             }
         }
+        tb_fitg_append(to_q, slot, nextq, ctr);
+        tb_fitg_append(to_t, slot, nextt, ctr + 1);
     }
-}
-
-// chunk table of tb_fit_thread_kernel: windows [w0[c], w0[c+1]) with bounded window count, segment count and tile slots
-static void tb_fit_chunks(const std::vector<i64> &win_off, int window, std::vector<i64> &w0) {
-    const int qm = (window + 9) / 10;
-    w0.clear();
-    w0.push_back(0);
-    int nw = 0, nq = 0, ns = 0;
-    const i64 n_regions = (i64)win_off.size() - 1;
-    for (i64 j = 0; j < n_regions; j++) {
-        i64 left = win_off[j + 1] - win_off[j], at = win_off[j];
-        while (left > 0) {
-            i64 room = TB_FITT_WIN - nw;
-            i64 roomq = (i64)TB_FIT_Q - nq - qm + 1;
-            if (roomq < room) room = roomq;
-            if (room <= 0 || ns == TB_FITT_SEG) {
-                w0.push_back(at);
-                nw = nq = ns = 0;
-                continue;
-            }
-            i64 n = left < room ? left : room;
-            nw += (int)n;
-            nq += (int)n - 1 + qm;
-            ns++;
-            at += n;
-            left -= n;
-        }
-    }
-    if (w0.back() != win_off[n_regions]) w0.push_back(win_off[n_regions]);
 }
 
 // ------------------------------------------------------------------------------------------------ K3c
@@ -514,17 +495,55 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     tb_mark(ctx, 2);
     tb_cor_view V{C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), C.d_out_off.as<i64>(), C.d_win_off.as<i64>(),
                   n_regions, C.ext_total, C.out_total, C.n_windows, k_flank, window, L, f_extend};
-    if (lm_exact_order < 2 && window <= 10 * (TB_FIT_Q - 2)) {
-        // thread-per-window fits in MINPACK's own summation order (bit-faithful to scipy on identical input)
-        std::vector<i64> w0;
-        tb_fit_chunks(C.win_off, window, w0);
-        TB_TRY(tb_h2d(ctx, ctx->reg_c, w0.data(), sizeof(i64) * w0.size()));
-        const size_t smem = TB_FITT_SMEM;
-        auto kf = tb_fit_thread_kernel;
-        TB_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TB_LAUNCH(ctx, kf, dim3((unsigned)(w0.size() - 1), 2), TB_FITT_THREADS, smem, V, (const i64 *)ctx->reg_c.as<i64>(),
-                  (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(), C.fit.as<double>());
-        TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_fit_thread_kernel"));
+    if (lm_exact_order < 2) {
+        // round form (default): state in HBM, compacted work lists, one host read-back of two counters per round
+        const int qm = (window + 9) / 10;
+        const i64 qs = C.n_windows + (i64)(qm - 1) * n_regions, qtot = 2 * qs, n_slots = 2 * C.n_windows;
+        if (qtot >= ((i64)1 << 32)) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: too many windows for one launch");
+        TB_TRY(tb_reserve(ctx, C.fitg_x, (size_t)10 * qtot * sizeof(double)));
+        TB_TRY(tb_reserve(ctx, C.fitg_y, (size_t)10 * qtot * sizeof(u32)));
+        TB_TRY(tb_reserve(ctx, C.fitg_st, (size_t)TB_FITG_NST * n_slots * sizeof(double)));
+        TB_TRY(tb_reserve(ctx, C.fitg_sti, (size_t)n_slots * sizeof(int4)));
+        TB_TRY(tb_reserve(ctx, C.fitg_wq, (size_t)n_slots * sizeof(u32)));
+        TB_TRY(tb_reserve(ctx, C.fitg_lists, (size_t)4 * n_slots * sizeof(u32) + 64));
+        u32 *lists = C.fitg_lists.as<u32>();
+        u32 *lq[2] = {lists, lists + n_slots}, *lt[2] = {lists + 2 * n_slots, lists + 3 * n_slots};
+        unsigned long long *ctr = (unsigned long long *)(lists + 4 * n_slots);       // [0] Q, [1] T of the list being built
+        tb_fitg_view G{C.fitg_st.as<double>(), C.fitg_sti.as<int4>(), C.fitg_wq.as<u32>(), C.fitg_x.as<double>(),
+                       C.fitg_y.as<u32>(), qtot, n_slots};
+        TB_LAUNCH(ctx, tb_fitg_transpose_kernel, dim3((unsigned)n_regions, 2), 256, 0, V, (const u32 *)C.pile.as<u32>(),
+                  (const double *)C.biasraw.as<double>(), qs, qtot, qm, C.fitg_x.as<double>(), C.fitg_y.as<u32>());
+        TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        {
+            i64 want = tb_div_up(n_slots, 128), capg = (i64)ctx->sm_count * 16;
+            TB_LAUNCH(ctx, tb_fitg_init_kernel, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lq[0], ctr);
+        }
+        unsigned long long hc[2] = {0, 0};
+        TB_TRY(tb_d2h(ctx, hc, ctr, sizeof(hc)));
+        i64 nq = (i64)hc[0], nt = 0;
+        int cur = 0;
+        for (int round = 0; nq + nt > 0; round++) {
+            if (round > 700) return tb_fail(ctx, TB_ERR_STATE, "tb_correct_run: window fits did not terminate");
+            TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            const i64 capg = (i64)ctx->sm_count * TB_FITG_MINBLOCKS;
+            if (nq > 0) {
+                i64 want = tb_div_up(nq, 128);
+                auto kq = tb_fitg_round_kernel<true>;
+                TB_LAUNCH(ctx, kq, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lq[cur], nq, C.fit.as<double>(),
+                          lq[cur ^ 1], lt[cur ^ 1], ctr);
+            }
+            if (nt > 0) {
+                i64 want = tb_div_up(nt, 128);
+                auto kt = tb_fitg_round_kernel<false>;
+                TB_LAUNCH(ctx, kt, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lt[cur], nt, C.fit.as<double>(),
+                          lq[cur ^ 1], lt[cur ^ 1], ctr);
+            }
+            TB_TRY(tb_d2h(ctx, hc, ctr, sizeof(hc)));
+            nq = (i64)hc[0];
+            nt = (i64)hc[1];
+            cur ^= 1;
+        }
+        TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_fitg_round_kernel"));
     } else {
         const int seq_sums = lm_exact_order != 2;       // warp-per-window kernels: 2 = tree sums, 3 = MINPACK-order sums
         int block = TB_FIT_WARPS * 32;

@@ -20,15 +20,12 @@
 #include "tb_common.cuh"
 #include "tb_lm.cuh"
 
-#ifndef TB_FIT_Q
-#define TB_FIT_Q 864        // q-slots of the shared-memory tile (10 positions each)
-#endif
-
-// Window point i = 10 u + v of this thread's window lives at x[v * TB_FIT_Q + u] (bias, f64) / y[v * TB_FIT_Q + u]
+// Window point i = 10 u + v of this thread's window lives at x[v * stride + u] (bias, f64) / y[v * stride + u]
 // (signal, u32 counts): consecutive windows start 10 positions apart, so consecutive windows read consecutive slots.
 struct tb_win_ref {
     const double *x;
     const u32 *y;
+    i64 stride;             // distance between the planes v = 0..9
 };
 // exact u32 -> double without a conversion instruction: (2^52 + k) - 2^52
 __device__ __forceinline__ double tb_u32_to_double(u32 k) {
@@ -42,13 +39,45 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
 #endif
 #define TB_PRAGMA_(x) _Pragma(#x)
 #define TB_PRAGMA(x) TB_PRAGMA_(x)
+#ifndef TB_FIT_PREFETCH
+#define TB_FIT_PREFETCH 1       // load point i + 1 while point i is being processed (hides the L1 / shared-memory latency)
+#endif
+#if TB_FIT_PREFETCH
+#define TB_FOR_POINTS(W, m, i, ...)                                            \
+    {                                                                          \
+        const double *_px = (W).x;                                             \
+        const u32 *_py = (W).y;                                                \
+        double _nx = *_px;                                                     \
+        u32 _ny = *_py;                                                        \
+        int _v = 0;                                                            \
+        TB_PRAGMA(unroll TB_FIT_UNROLL)                                        \
+        for (int i = 0; i < (m); i++) {                                        \
+            const double ex = _nx;                                             \
+            const u32 eyi = _ny;                                               \
+            if (++_v == 10) {                                                  \
+                _v = 0;                                                        \
+                _px -= 9 * (W).stride - 1;                                     \
+                _py -= 9 * (W).stride - 1;                                     \
+            } else {                                                           \
+                _px += (W).stride;                                             \
+                _py += (W).stride;                                             \
+            }                                                                  \
+            if (i + 1 < (m)) {                                                 \
+                _nx = *_px;                                                    \
+                _ny = *_py;                                                    \
+            }                                                                  \
+            const double ey = tb_u32_to_double(eyi);                           \
+            __VA_ARGS__                                                        \
+        }                                                                      \
+    }
+#else
 #define TB_FOR_POINTS(W, m, i, ...)                                            \
     for (int _u = 0; _u * 10 < (m); _u++) {                                    \
         const int _nv = (m) - _u * 10 < 10 ? (m) - _u * 10 : 10;               \
         const double *_px = (W).x + _u;                                        \
         const u32 *_py = (W).y + _u;                                           \
         TB_PRAGMA(unroll TB_FIT_UNROLL)                                        \
-        for (int _v = 0; _v < _nv; _v++, _px += TB_FIT_Q, _py += TB_FIT_Q) {   \
+        for (int _v = 0; _v < _nv; _v++, _px += (W).stride, _py += (W).stride) { \
             const int i = _u * 10 + _v;                                        \
             const double ex = *_px;                                            \
             const u32 eyi = *_py;                                              \
@@ -56,6 +85,7 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
             __VA_ARGS__                                                        \
         }                                                                      \
     }
+#endif
 
 // a / d with dinv = 1.0 / d (correctly rounded, see header)
 __device__ __forceinline__ double tb_div_inv(double a, double d, double dinv) {
