@@ -136,19 +136,22 @@ __global__ void __launch_bounds__(768, 1) tb_score_dwm_kernel(tb_genome_view g, 
 // ------------------------------------------------------------------------------------------------ K3a, product form
 // The scoring kernel above is bound by shared-memory bandwidth (25 row reads of 800 B per model and window) and pays
 // 100 exp2 + 25 log2 per model and window.  Second formulation, same mathematics:
-//   * rows are grouped in PAIRS of window offsets: T[p][d] = U[2p][d & 3] + U[2p+1][d >> 2] for the 16 dinucleotides d
-//     (+ 4 single rows for the last offset): 13 row reads instead of 25 for L = 25;
-//   * the table holds V = 2^T, so 2^E[n][a] = prod_groups V[g][d_g][n][a] is a product of 13 table entries -- no exp2 at
+//   * rows are grouped: PAIRS of window offsets, T[p][d] = U[2p][d & 3] + U[2p+1][d >> 2] for the 16 dinucleotides d, and
+//     one last group holding the remaining 3 offsets (64 trinucleotide rows) when the table still fits the SM, else the
+//     last single offset (4 rows): 12 row reads instead of 25 for L = 25 (192 KB of table);
+//   * the table holds V = 2^T, so 2^E[n][a] = prod_groups V[g][d_g][n][a] is a product of 12 table entries -- no exp2 at
 //     all -- and the per-model score  sum_n (E[n][S_n] - log2 sum_a 2^E[n][a])  =  log2 prod_n (2^E[n][S_n] / Z[n])  needs
 //     two log2 per window (of the products of the 25 selected terms and of the 25 normalisers, exponents carried apart).
-// One model of one strand (157 KB for L = 25) is resident per block; the four (strand, model) classes of blocks write
-// partial scores that tb_score_combine_kernel subtracts (bias - background).  A warp owns 32 consecutive positions;
-// per window lane l multiplies the 16-byte chunks l and 32 + l of each row ([n][a] order: chunk c = (n, a >> 1)), i.e.
-// a row costs 7 shared-memory wavefronts (6.25 ideal); lane w of the warp finishes window w (log2) and the 32 results
-// leave as one coalesced store.  Relative error of a product of 13 correctly rounded factors ~ 2e-15, i.e. ~1e-14
-// absolute on the score -- the same order as the sum form's difference to the reference's libm.
-#define TB_K3A2_THREADS 1024
-#define TB_K3A2_WPI 2
+// One model of one strand is resident per block; the four (strand, model) classes of blocks write partial scores that
+// tb_score_combine_kernel subtracts (bias - background).  A warp owns 32 consecutive positions: lane w prepares window
+// w (region lookup, N test, packed k-mer) and finishes it (log2, one coalesced store of the 32 results); in between the
+// warp walks the windows four at a time, lane l multiplying the 16-byte chunks l and 32 + l of each row ([n][a] order:
+// chunk c = (n, a >> 1)), i.e. a row costs 7 shared-memory wavefronts (6.25 ideal).  The cross-lane products of the four
+// windows are reduced together (each butterfly level halves the number of windows a lane still carries), 12.75 shuffles
+// per window instead of 28.  Relative error of a product of 12 correctly rounded factors ~ 2e-15, i.e. ~1e-14 absolute
+// on the score -- the same order as the sum form's difference to the reference's libm.
+#define TB_K3A2_THREADS 768
+#define TB_K3A2_WPI 4
 
 __device__ __forceinline__ void tb_split_exp(double v, double &mant, int &ex) {      // v = mant * 2^ex, mant in [1, 2)  (v > 0, normal)
     int hi = __double2hiint(v);
@@ -156,12 +159,25 @@ __device__ __forceinline__ void tb_split_exp(double v, double &mant, int &ex) { 
     mant = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(v));
 }
 
+// number of pair groups and the width (2 or 6 bits) of the last group for model length L
+static inline void tb_k3a2_groups(int L, int &np, int &lastbits) {
+    size_t rows3 = (size_t)16 * ((L - 3) / 2) + 64;
+    if (L >= 3 && rows3 * 4 * L * sizeof(double) <= (size_t)227 * 1024) {
+        np = (L - 3) / 2;
+        lastbits = 6;
+    } else {
+        np = L / 2;
+        lastbits = 2;
+    }
+}
+
 __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     tb_score_dwm2_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ vt_fwd, const double *__restrict__ vt_rev,
-                         int L, int strand_mask, double *__restrict__ part) {
+                         int L, int np, int lastbits, int strand_mask, double *__restrict__ part) {
     TB_DYN_SMEM(smem);
-    const int k_flank = L / 2, P = L / 2;
-    const int rows = 16 * P + 4, row = 4 * L;                 // doubles per row
+    const unsigned FULL = 0xffffffffu;
+    const int k_flank = L / 2;
+    const int rows = 16 * np + (1 << lastbits), row = 4 * L;  // doubles per row
     const int nclass = strand_mask == 3 ? 4 : 2;
     const int cls = blockIdx.x % nclass;
     const int bpart = blockIdx.x / nclass, nparts = (gridDim.x - cls + nclass - 1) / nclass;
@@ -173,53 +189,58 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
         for (int i = threadIdx.x; i < rows * row / 2; i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
-    const double2 *V = (const double2 *)smem;                 // chunk c of row r at V[r * 2L + c]
     double *out = part + (size_t)(strand * 2 + model) * R.total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int nchunk = 2 * L;
     const bool hasB = 32 + lane < nchunk;
-    const int half = lane & 1, nA = lane >> 1, nB = 16 + (lane >> 1);
+    const double2 *V = (const double2 *)smem + lane;          // chunk c of row r at V[r * 2L + c - lane]
+    const int half = lane & 1;
+    const int ncol = half ? 16 + (lane >> 1) : (lane >> 1);   // column this lane completes in the epilogue
+    const bool colok = ncol < L;
+    const int lastsh = 4 * np;
+    const u32 lastmask = (1u << lastbits) - 1u;
+    const double2 *Vlast = V + (size_t)(16 * np) * nchunk;
     const i64 n_units = (R.total + 31) >> 5;
 
     for (i64 unit = (i64)bpart * wpb + warp; unit < n_units; unit += (i64)nparts * wpb) {
         const i64 pos0 = unit << 5;
-        i64 j = tb_upper_bound(R.ext_off, R.n + 1, pos0) - 1;
-        double my_sel = 1.0, my_z = 1.0;
-        int my_de = 0;
-        bool my_ok = false;
-        for (int it = 0; it < 32; it += TB_K3A2_WPI) {
-            u64 kmer[TB_K3A2_WPI];
-            bool ok[TB_K3A2_WPI];
-#pragma unroll
-            for (int w = 0; w < TB_K3A2_WPI; w++) {
-                const i64 pos = pos0 + it + w;
-                ok[w] = false;
-                kmer[w] = 0;
-                if (pos < R.total) {
-                    while (pos >= R.ext_off[j + 1]) j++;
-                    i64 local = pos - R.ext_off[j];
-                    i64 len = R.ext_off[j + 1] - R.ext_off[j];
-                    if (local >= k_flank && local < len - k_flank) {
-                        i64 gp = R.ext_start[j] + local;
-                        if (tb_nflags(g, gp - k_flank, L) == 0) {
-                            kmer[w] = tb_bases(g, gp - k_flank, L);
-                            ok[w] = true;
-                        }
+        // ---- lane w prepares window w of the unit
+        u32 klo = 0, khi = 0;
+        bool okl = false;
+        {
+            const i64 pos = pos0 + lane;
+            if (pos < R.total) {
+                i64 j = tb_upper_bound(R.ext_off, R.n + 1, pos) - 1;
+                i64 local = pos - R.ext_off[j];
+                i64 len = R.ext_off[j + 1] - R.ext_off[j];
+                if (local >= k_flank && local < len - k_flank) {
+                    i64 gp = R.ext_start[j] + local;
+                    if (tb_nflags(g, gp - k_flank, L) == 0) {
+                        u64 km = tb_bases(g, gp - k_flank, L);
+                        klo = (u32)km;
+                        khi = (u32)(km >> 32);
+                        okl = true;
                     }
                 }
             }
-            bool any = false;
-#pragma unroll
-            for (int w = 0; w < TB_K3A2_WPI; w++) any = any || ok[w];
-            if (!any) continue;                                // warp-uniform
+        }
+        const unsigned okmask = __ballot_sync(FULL, okl);
+        double my_sel = 1.0, my_z = 1.0;
+        int my_de = 0;
+        for (int it = 0; it < 32; it += TB_K3A2_WPI) {
+            if (((okmask >> it) & ((1u << TB_K3A2_WPI) - 1u)) == 0u) continue;       // warp-uniform
+            u64 kmer[TB_K3A2_WPI];
             double a0[TB_K3A2_WPI], a1[TB_K3A2_WPI], b0[TB_K3A2_WPI], b1[TB_K3A2_WPI];
 #pragma unroll
-            for (int w = 0; w < TB_K3A2_WPI; w++) a0[w] = a1[w] = b0[w] = b1[w] = 1.0;
-            for (int p = 0; p < P; p++) {
+            for (int w = 0; w < TB_K3A2_WPI; w++) {
+                kmer[w] = (u64)__shfl_sync(FULL, klo, it + w) | ((u64)__shfl_sync(FULL, khi, it + w) << 32);
+                a0[w] = a1[w] = b0[w] = b1[w] = 1.0;
+            }
+            for (int p = 0; p < np; p++) {
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
-                    const int d = (int)((kmer[w] >> (4 * p)) & 15u);
-                    const double2 *r = V + (size_t)(p * 16 + d) * nchunk + lane;
+                    const int d = (int)((u32)(kmer[w] >> (4 * p)) & 15u);
+                    const double2 *r = V + (p * 16 + d) * nchunk;
                     double2 va = r[0];
                     a0[w] *= va.x;
                     a1[w] *= va.y;
@@ -232,8 +253,8 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
             }
 #pragma unroll
             for (int w = 0; w < TB_K3A2_WPI; w++) {
-                const int d = (int)((kmer[w] >> (4 * P)) & 3u);
-                const double2 *r = V + (size_t)(P * 16 + d) * nchunk + lane;
+                const int d = (int)((u32)(kmer[w] >> lastsh) & lastmask);
+                const double2 *r = Vlast + d * nchunk;
                 double2 va = r[0];
                 a0[w] *= va.x;
                 a1[w] *= va.y;
@@ -243,45 +264,63 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                     b1[w] *= vb.y;
                 }
             }
+            // ---- column totals.  Lane l holds half (l & 1) of columns l >> 1 (a) and 16 + (l >> 1) (b); the even lane of a pair
+            // completes column a, the odd lane column b: Z = sum_a 2^E[n][a] and the selected term 2^E[n][S_n]
+            double msel[TB_K3A2_WPI], mz[TB_K3A2_WPI];
+            int de[TB_K3A2_WPI];
 #pragma unroll
             for (int w = 0; w < TB_K3A2_WPI; w++) {
-                // column totals: Z = sum_a 2^E[n][a], selected term 2^E[n][S_n]; the two halves of a column sit in lanes l, l^1
-                const int sA = (int)((kmer[w] >> (2 * nA)) & 3u), sB = (int)((kmer[w] >> (2 * nB)) & 3u);
-                double zA = a0[w] + a1[w], zB = b0[w] + b1[w];
-                double selA = (sA >> 1) == half ? ((sA & 1) ? a1[w] : a0[w]) : 0.0;
-                double selB = (sB >> 1) == half ? ((sB & 1) ? b1[w] : b0[w]) : 0.0;
-                zA += __shfl_xor_sync(0xffffffffu, zA, 1);
-                zB += __shfl_xor_sync(0xffffffffu, zB, 1);
-                selA += __shfl_xor_sync(0xffffffffu, selA, 1);
-                selB += __shfl_xor_sync(0xffffffffu, selB, 1);
-                double msel, mz, t;
-                int esel, ez, e;
-                tb_split_exp(selA, msel, esel);
-                tb_split_exp(zA, mz, ez);
-                if (nB < L) {
-                    tb_split_exp(selB, t, e);
-                    msel *= t;
-                    esel += e;
-                    tb_split_exp(zB, t, e);
-                    mz *= t;
-                    ez += e;
+                const int sA = (int)((u32)(kmer[w] >> (2 * (lane >> 1))) & 3u), sB = (int)((u32)(kmer[w] >> (2 * (16 + (lane >> 1)))) & 3u);
+                const double zA = a0[w] + a1[w], zB = b0[w] + b1[w];
+                const double selA = (sA >> 1) == half ? ((sA & 1) ? a1[w] : a0[w]) : 0.0;
+                const double selB = (sB >> 1) == half ? ((sB & 1) ? b1[w] : b0[w]) : 0.0;
+                double z = (half ? zB : zA) + __shfl_xor_sync(FULL, half ? zA : zB, 1);
+                double sel = (half ? selB : selA) + __shfl_xor_sync(FULL, half ? selA : selB, 1);
+                int es = 0, ez = 0;
+                msel[w] = 1.0;
+                mz[w] = 1.0;
+                if (colok) {
+                    tb_split_exp(sel, msel[w], es);
+                    tb_split_exp(z, mz[w], ez);
                 }
-                int de = esel - ez;
-                for (int dlt = 2; dlt < 32; dlt <<= 1) {           // product over the 16 lane pairs (each pair holds equal values)
-                    msel *= __shfl_xor_sync(0xffffffffu, msel, dlt);
-                    mz *= __shfl_xor_sync(0xffffffffu, mz, dlt);
-                    de += __shfl_xor_sync(0xffffffffu, de, dlt);
-                }
-                if (lane == it + w) {
-                    my_sel = msel;
-                    my_z = mz;
-                    my_de = de;
-                    my_ok = ok[w];
-                }
+                de[w] = es - ez;
+            }
+            // ---- products over the 32 lanes, four windows at once: after level 16 a lane carries two windows, after level 8 one
+            static_assert(TB_K3A2_WPI == 4, "the reduction below is written for four windows in flight");
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+            double ps[2], pz[2];
+            int pe[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {          // windows (0,1) -> ps[0], windows (2,3) -> ps[1]
+                const int wk = 2 * h, ws = 2 * h + 1;
+                double ks = up16 ? msel[ws] : msel[wk], kz = up16 ? mz[ws] : mz[wk];
+                int ke = up16 ? de[ws] : de[wk];
+                ps[h] = ks * __shfl_xor_sync(FULL, up16 ? msel[wk] : msel[ws], 16);
+                pz[h] = kz * __shfl_xor_sync(FULL, up16 ? mz[wk] : mz[ws], 16);
+                pe[h] = ke + __shfl_xor_sync(FULL, up16 ? de[wk] : de[ws], 16);
+            }
+            double rs = (up8 ? ps[1] : ps[0]) * __shfl_xor_sync(FULL, up8 ? ps[0] : ps[1], 8);
+            double rz = (up8 ? pz[1] : pz[0]) * __shfl_xor_sync(FULL, up8 ? pz[0] : pz[1], 8);
+            int re = (up8 ? pe[1] : pe[0]) + __shfl_xor_sync(FULL, up8 ? pe[0] : pe[1], 8);
+#pragma unroll
+            for (int dlt = 4; dlt > 0; dlt >>= 1) {
+                rs *= __shfl_xor_sync(FULL, rs, dlt);
+                rz *= __shfl_xor_sync(FULL, rz, dlt);
+                re += __shfl_xor_sync(FULL, re, dlt);
+            }
+            // lanes with (bit 4, bit 3) = (b4, b3) now hold window it + b4 + 2 * b3; hand the results to lanes it .. it + 3
+            const int k = (lane - it) & 3;
+            const int srcl = ((k & 1) << 4) | ((k >> 1) << 3);
+            const double gs = __shfl_sync(FULL, rs, srcl), gz = __shfl_sync(FULL, rz, srcl);
+            const int ge = __shfl_sync(FULL, re, srcl);
+            if (lane >= it && lane < it + TB_K3A2_WPI) {
+                my_sel = gs;
+                my_z = gz;
+                my_de = ge;
             }
         }
         if (pos0 + lane < R.total)
-            out[pos0 + lane] = my_ok ? (log2(my_sel) - log2(my_z)) + (double)my_de : (double)NAN;
+            out[pos0 + lane] = okl ? (log2(my_sel) - log2(my_z)) + (double)my_de : (double)NAN;
     }
 }
 
@@ -368,10 +407,13 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                         U[(((((size_t)x * L + m) * 4 + s) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)] = v;
                     }
     TB_TRY(tb_h2d(ctx, M.table, U.data(), U.size() * sizeof(double)));
-    // product-form table (tb_score_dwm2_kernel): V[x][row][n][a] = 2^(U[2p][d & 3] + U[2p+1][d >> 2]) for row = 16 p + d,
-    // and 2^U[L-1][d] for the four last rows; same forward-oriented indexing as U
+    // product-form table (tb_score_dwm2_kernel): V[x][row][n][a] = 2^(sum of the U rows of the group); pair group p: row 16 p + d,
+    // offsets 2p (d & 3) and 2p + 1 (d >> 2); last group: the remaining 3 offsets (64 rows) or the last offset (4 rows);
+    // same forward-oriented indexing as U
     {
-        const int P = L / 2, rows = 16 * P + 4;
+        int np, lastbits;
+        tb_k3a2_groups(L, np, lastbits);
+        const int rows = 16 * np + (1 << lastbits);
         auto u = [&](int x, int m, int s_, int n, int a) {
             return U[(((((size_t)x * L + m) * 4 + s_) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)];
         };
@@ -381,11 +423,13 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                 for (int n = 0; n < L; n++)
                     for (int a = 0; a < 4; a++) {
                         double t;
-                        if (r < 16 * P) {
+                        if (r < 16 * np) {
                             int p = r >> 4, d = r & 15;
                             t = u(x, 2 * p, d & 3, n, a) + u(x, 2 * p + 1, d >> 2, n, a);
                         } else {
-                            t = u(x, L - 1, r - 16 * P, n, a);
+                            int d = r - 16 * np, m0 = 2 * np;
+                            t = u(x, m0, d & 3, n, a);
+                            if (lastbits == 6) t = (t + u(x, m0 + 1, (d >> 2) & 3, n, a)) + u(x, m0 + 2, d >> 4, n, a);
                         }
                         Vt[(((size_t)x * rows + r) * L + n) * 4 + a] = exp2(t);
                     }
@@ -412,7 +456,9 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
     if (!tf) tf = tr;
     if (!tr) tr = tf;
     int L = M0.L;
-    const size_t smem2 = (size_t)(16 * (L / 2) + 4) * 4 * L * sizeof(double);
+    int k3a_np, k3a_lastbits;
+    tb_k3a2_groups(L, k3a_np, k3a_lastbits);
+    const size_t smem2 = (size_t)(16 * k3a_np + (1 << k3a_lastbits)) * 4 * L * sizeof(double);
     if (M0.is_dwm && smem2 <= (size_t)227 * 1024 && !ctx->force_sum_form) {
         // product form: one (strand, model) table per block, partial scores, then bias - background
         const int nclass = strand_mask == 3 ? 4 : 2;
@@ -427,7 +473,7 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
         const double *vf = ctx->model[0].vtable.as<double>(), *vr = ctx->model[1].vtable.as<double>();
         if (!vf) vf = vr;
         if (!vr) vr = vf;
-        TB_LAUNCH(ctx, k, grid, TB_K3A2_THREADS, smem2, g, R, vf, vr, L, strand_mask, ctx->scratch4.as<double>());
+        TB_LAUNCH(ctx, k, grid, TB_K3A2_THREADS, smem2, g, R, vf, vr, L, k3a_np, k3a_lastbits, strand_mask, ctx->scratch4.as<double>());
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_score_dwm2_kernel"));
         i64 wantc = tb_div_up(total, 256), capc = (i64)ctx->sm_count * 8;
         TB_LAUNCH(ctx, tb_score_combine_kernel, (unsigned)(wantc < capc ? wantc : capc), 256, 0,
