@@ -265,151 +265,249 @@ __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w)
 }
 
 #define TB_K3C_TILE 512
+#define TB_K3C_THREADS 256
 
-__global__ void tb_correct_kernel(tb_genome_view g, tb_cor_view V, const int32_t *__restrict__ tile_region,
-                                  const int32_t *__restrict__ tile_start, const u32 *__restrict__ pile,
-                                  const double *__restrict__ biasraw, const double *__restrict__ fit, double cf,
-                                  double *__restrict__ tracks, double *__restrict__ prepost) {
+// Persistent blocks walk the (region, 512-bp tile) list.  Per tile and strand:
+//   1. signal + bias prediction (mean of the 10 window predictions) over the tile widened by 2 * window; integer prefix
+//      sums of the signal and of its non-zero flags, list of the non-zero positions
+//   2. expected / raw corrected over the tile widened by window.  rolling sum of the signal: the reference's float
+//      accumulator is exact on integers below 2^24, so the integer prefix difference is the same number (sequential loop
+//      beyond that); rolling sum of the bias prediction: sequential float-rounded accumulation, as the reference
+//   3. rescale factor and outputs.  sum of uncorrected = signal * cf: adding 0.0 never changes the accumulator, so only
+//      the non-zero signal positions are accumulated, in order; |corrected| and corrected+ sums: sequential
+//   4. verification counts: pre / post(+) / post(-) weights of every valid position are left in shared memory; lane m of
+//      a warp then owns k-mer offset m and adds the weights of the warp's strip of positions into 12 private (weight kind,
+//      base) accumulators -- no atomics in the loop (first version: 25 x 3 shared-memory fp64 atomics = CAS loops per position)
+__global__ void __launch_bounds__(TB_K3C_THREADS)
+    tb_correct_kernel(tb_genome_view g, tb_cor_view V, const int32_t *__restrict__ tile_region,
+                      const int32_t *__restrict__ tile_start, i64 n_tiles, const u32 *__restrict__ pile,
+                      const double *__restrict__ biasraw, const double *__restrict__ fit, double cf,
+                      double *__restrict__ tracks, double *__restrict__ prepost) {
     TB_DYN_SMEM(smem);
     const int w = V.window, k = V.k_flank, L = V.L;
     const int lf = w / 2;
     const int overlaps = w / TB_STEP;
-    const i64 j = tile_region[blockIdx.x];
-    const int t0 = tile_start[blockIdx.x];
-    const int Lr = (int)(V.ext_off[j + 1] - V.ext_off[j]);
-    const int nwin = tb_n_windows(Lr, k, w);
-    const int t1 = min(Lr, t0 + TB_K3C_TILE);                 // tile = [t0, t1)
-    const int c0 = max(0, t0 - w), c1 = min(Lr, t1 + w);      // domain of the raw corrected signal
-    const int d0 = max(0, c0 - w), d1 = min(Lr, c1 + w);      // domain of signal / bias prediction
     const int cap = TB_K3C_TILE + 4 * w;
-    double *sig = (double *)smem;              // [d0, d1)
-    double *bp = sig + cap;                    // [d0, d1)  mean window prediction
+    double *sig = (double *)smem;              // [d0, d1)  signal;            phase 4: pre weights of [t0, t1)
+    double *bp = sig + cap;                    // [d0, d1)  mean prediction;   phase 4: post(+) weights
     double *unc = bp + cap;                    // [c0, c1)  signal * cf
     double *cor = unc + cap;                   // [c0, c1)  uncorrected - expected
-    double *expd = cor + cap;                  // [t0, t1)
-    double *ver = expd + cap;                  // [3][4][L] verification accumulators
+    double *expd = cor + cap;                  // [t0, t1)  expected;          phase 4: post(-) weights
+    double *ver = expd + cap;                  // [2 strands][3][4][L] verification accumulators of this block
+    u32 *psum = (u32 *)(ver + 2 * 3 * 4 * L);  // [cap + 1] prefix sums of the signal over [d0, d1)
+    u32 *pcnt = psum + cap + 1;                // [cap + 1] prefix counts of its non-zero positions
+    u32 *wsum = pcnt + cap + 1;                // [2][32] warp totals of the block scan
+    unsigned short *nzpos = (unsigned short *)(wsum + 64);      // [cap] non-zero positions (relative to d0)
+    uint8_t *bases = (uint8_t *)(nzpos + cap);                  // [TB_K3C_TILE + L] base codes of [t0 - k, t1 + k)
     const int tid = threadIdx.x, nt = blockDim.x;
-    const i64 gext = V.ext_off[j];
-    const i64 gstart = V.ext_start[j];
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
-    for (int strand = 0; strand < 2; strand++) {
-        const u32 *ps = pile + (i64)strand * V.ext_total + gext;
-        const double *br = biasraw + (i64)strand * V.ext_total + gext;
-        const double *ft = fit + ((i64)strand * V.n_windows + V.win_off[j]) * TB_FIT_REC;
-        for (int i = tid; i < 3 * 4 * L; i += nt) ver[i] = 0.0;
-        // ---- signal and bias_prediction = nanmean over the `overlaps` rows (:279-309)
-        for (int q = d0 + tid; q < d1; q += nt) {
-            sig[q - d0] = (double)ps[q];
-            double x = br[q];
-            double sum = 0.0;
-            int cnt = 0;
-            int jmax = q >= k ? (q - k) / TB_STEP : -1;
-            if (jmax > nwin - 1) jmax = nwin - 1;
-            for (int r = 0; r < overlaps; r++) {
-                double val = 0.0;
-                bool have = false;
-                if (jmax >= r) {
-                    int jw = jmax - ((jmax - r) % overlaps);       // last window of row r starting at or before q
-                    if (k + TB_STEP * jw + w > q) {
-                        have = true;
-                        const double *f = ft + (i64)jw * TB_FIT_REC;
-                        double mode = f[0], mx = f[3];
-                        if (mode == 0.0) {
-                            double t = __dadd_rn(__dmul_rn(f[1], x), f[2]);
-                            val = t > 0.0 ? t : 0.0;
-                            if (mx > 0.0) val = val / mx;
-                        } else if (mode == 1.0) {
-                            double t = x - f[2];
-                            val = t < 0.0 ? 0.0 : t;
-                            if (mx > 0.0) val = val / mx;
-                        }
+    for (int i = tid; i < 2 * 3 * 4 * L; i += nt) ver[i] = 0.0;
+    __syncthreads();
+
+    for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const i64 j = tile_region[tile];
+        const int t0 = tile_start[tile];
+        const int Lr = (int)(V.ext_off[j + 1] - V.ext_off[j]);
+        const int nwin = tb_n_windows(Lr, k, w);
+        const int t1 = min(Lr, t0 + TB_K3C_TILE);                 // tile = [t0, t1)
+        const int c0 = max(0, t0 - w), c1 = min(Lr, t1 + w);      // domain of the raw corrected signal
+        const int d0 = max(0, c0 - w), d1 = min(Lr, c1 + w);      // domain of signal / bias prediction
+        const int nd = d1 - d0;
+        const i64 gext = V.ext_off[j];
+        const i64 gstart = V.ext_start[j];
+        // base codes of the tile (+- k_flank), shared by both strands
+        for (int i = tid; i < t1 - t0 + 2 * k; i += nt) {
+            i64 gp = gstart + t0 - k + i;
+            bases[i] = (gp >= 0 && gp < g.n_bases) ? (uint8_t)tb_base(g, gp) : (uint8_t)0;
+        }
+
+        for (int strand = 0; strand < 2; strand++) {
+            const u32 *ps = pile + (i64)strand * V.ext_total + gext;
+            const double *br = biasraw + (i64)strand * V.ext_total + gext;
+            const double *ft = fit + ((i64)strand * V.n_windows + V.win_off[j]) * TB_FIT_REC;
+            // ---- 1. signal, bias_prediction = nanmean over the `overlaps` rows (:279-309), prefix sums
+            const int per = (nd + nt - 1) / nt;                   // consecutive positions per thread in the scan
+            {
+                u32 s_loc = 0, c_loc = 0;
+                for (int e = 0; e < per; e++) {
+                    int i = tid * per + e;
+                    if (i < nd) {
+                        u32 v = ps[d0 + i];
+                        s_loc += v;
+                        c_loc += v != 0u;
                     }
                 }
-                // rows k_flank.. start as NaN (:280 indexes rows): uncovered cells there do not count
-                if (have || r < k) {
-                    sum += val;
-                    cnt++;
+                u32 s_inc = s_loc, c_inc = c_loc;
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 a = __shfl_up_sync(0xffffffffu, s_inc, d), b = __shfl_up_sync(0xffffffffu, c_inc, d);
+                    if (lane >= d) {
+                        s_inc += a;
+                        c_inc += b;
+                    }
                 }
-            }
-            bp[q - d0] = cnt > 0 ? sum / (double)cnt : (double)NAN;
-        }
-        __syncthreads();
-        // ---- expected and raw corrected signal on [c0, c1) (:314-328)
-        for (int q = c0 + tid; q < c1; q += nt) {
-            double ssum = 0.0, bsum = 1.0, probas = 0.0;
-            if (q >= lf && q - lf + w <= Lr) {
-                ssum = tb_roll_f32(sig, q - lf - d0, w);
-                double b = tb_roll_f32(bp, q - lf - d0, w);
-                bool null = !(fabs(b) > 1e-8);                 // isclose(bias_sum, 0) or NaN
-                if (!null) {
-                    bsum = b;
-                    probas = bp[q - d0] / bsum;
+                if (lane == 31) {
+                    wsum[warp] = s_inc;
+                    wsum[32 + warp] = c_inc;
                 }
-            }
-            double e = ssum * probas;
-            double u = sig[q - d0] * cf;
-            e = e * cf;
-            unc[q - c0] = u;
-            cor[q - c0] = u - e;
-            if (q >= t0 && q < t1) expd[q - t0] = e;
-        }
-        __syncthreads();
-        // ---- rescale (:331-350), outputs, verification counts (:358-373)
-        for (int q = t0 + tid; q < t1; q += nt) {
-            double c = cor[q - c0];
-            double u = unc[q - c0];
-            double scale = 1.0;
-            if (q >= lf && q - lf + w <= Lr) {
-                int first = q - lf - c0;
-                float au = 0.0f, aa = 0.0f, ap = 0.0f;
-                for (int t = 0; t < w; t++) {
-                    double cv = cor[first + t];
-                    au = (float)((double)au + unc[first + t]);
-                    aa = (float)((double)aa + fabs(cv));
-                    ap = (float)((double)ap + (cv < 0.0 ? 0.0 : cv));
+                __syncthreads();
+                u32 s_off = s_inc - s_loc, c_off = c_inc - c_loc;
+                for (int ww = 0; ww < warp; ww++) {
+                    s_off += wsum[ww];
+                    c_off += wsum[32 + ww];
                 }
-                double usum = au, asum = aa, psum = ap;
-                double nsum = asum - psum;
-                if (psum != 0.0) {
-                    scale = (usum - nsum) / psum;
-                    if (scale < 1.0) scale = 1.0;
-                }
-            }
-            if (c > 0.0) c = c * scale;
-            if (q >= V.f_extend && q < Lr - V.f_extend) {
-                i64 o = V.out_off[j] + (q - V.f_extend);
-                tracks[((i64)0 * 2 + strand) * V.out_total + o] = u;
-                tracks[((i64)1 * 2 + strand) * V.out_total + o] = br[q];
-                tracks[((i64)2 * 2 + strand) * V.out_total + o] = expd[q - t0];
-                tracks[((i64)3 * 2 + strand) * V.out_total + o] = c;
-            }
-            if (q > k && q < Lr - k - 1 && (u != 0.0 || c != 0.0)) {
-                i64 gp = gstart + q;
-                if (tb_nflags(g, gp - k, L) == 0) {
-                    u64 kmer = tb_bases(g, gp - k, L);
-                    for (int m = 0; m < L; m++) {
-                        int s = (int)((kmer >> (2 * m)) & 3u);
-                        int mm = m;
-                        if (strand) {
-                            s ^= 1;
-                            mm = L - 1 - m;
-                        }
-                        if (u > 0.0) atomicAdd(&ver[(0 * 4 + s) * L + mm], u);           // pre_bias counts
-                        if (c > 0.0) atomicAdd(&ver[(1 * 4 + s) * L + mm], c);           // post_bias counts
-                        else atomicAdd(&ver[(2 * 4 + s) * L + mm], c);                   // post_bias neg_counts
+                if (tid == 0) psum[0] = pcnt[0] = 0;
+                for (int e = 0; e < per; e++) {
+                    int i = tid * per + e;
+                    if (i < nd) {
+                        u32 v = ps[d0 + i];
+                        if (v != 0u) nzpos[c_off] = (unsigned short)i;
+                        s_off += v;
+                        c_off += v != 0u;
+                        psum[i + 1] = s_off;
+                        pcnt[i + 1] = c_off;
+                        sig[i] = (double)v;
                     }
                 }
             }
-        }
-        __syncthreads();
-        for (int i = tid; i < 3 * 4 * L; i += nt) {
-            double v = ver[i];
-            if (v != 0.0) {
-                int which = i / (4 * L), rem = i % (4 * L);
-                atomicAdd(&prepost[((i64)strand * 3 + which) * 5 * L + rem], v);
+            for (int q = d0 + tid; q < d1; q += nt) {
+                double x = br[q];
+                double sum = 0.0;
+                int cnt = 0;
+                int jmax = q >= k ? (q - k) / TB_STEP : -1;
+                if (jmax > nwin - 1) jmax = nwin - 1;
+                for (int r = 0; r < overlaps; r++) {
+                    double val = 0.0;
+                    bool have = false;
+                    if (jmax >= r) {
+                        int jw = jmax - ((jmax - r) % overlaps);       // last window of row r starting at or before q
+                        if (k + TB_STEP * jw + w > q) {
+                            have = true;
+                            const double *f = ft + (i64)jw * TB_FIT_REC;
+                            double mode = f[0], mx = f[3];
+                            if (mode == 0.0) {
+                                double t = __dadd_rn(__dmul_rn(f[1], x), f[2]);
+                                val = t > 0.0 ? t : 0.0;
+                                if (mx > 0.0) val = val / mx;
+                            } else if (mode == 1.0) {
+                                double t = x - f[2];
+                                val = t < 0.0 ? 0.0 : t;
+                                if (mx > 0.0) val = val / mx;
+                            }
+                        }
+                    }
+                    // rows k_flank.. start as NaN (:280 indexes rows): uncovered cells there do not count
+                    if (have || r < k) {
+                        sum += val;
+                        cnt++;
+                    }
+                }
+                bp[q - d0] = cnt > 0 ? sum / (double)cnt : (double)NAN;
             }
+            __syncthreads();
+            // ---- 2. expected and raw corrected signal on [c0, c1) (:314-328)
+            for (int q = c0 + tid; q < c1; q += nt) {
+                double ssum = 0.0, bsum = 1.0, probas = 0.0;
+                if (q >= lf && q - lf + w <= Lr) {
+                    const int first = q - lf - d0;
+                    const u32 isum = psum[first + w] - psum[first];
+                    ssum = isum < (1u << 24) ? (double)isum : tb_roll_f32(sig, first, w);
+                    double b = tb_roll_f32(bp, first, w);
+                    bool null = !(fabs(b) > 1e-8);                 // isclose(bias_sum, 0) or NaN
+                    if (!null) {
+                        bsum = b;
+                        probas = bp[q - d0] / bsum;
+                    }
+                }
+                double e = ssum * probas;
+                double u = sig[q - d0] * cf;
+                e = e * cf;
+                unc[q - c0] = u;
+                cor[q - c0] = u - e;
+                if (q >= t0 && q < t1) expd[q - t0] = e;
+            }
+            __syncthreads();
+            // ---- 3. rescale (:331-350), outputs, verification weights (:358-373)
+            for (int q = t0 + tid; q < t1; q += nt) {
+                double c = cor[q - c0];
+                double u = unc[q - c0];
+                double scale = 1.0;
+                if (q >= lf && q - lf + w <= Lr) {
+                    int first = q - lf - c0;
+                    float au = 0.0f, aa = 0.0f, ap = 0.0f;
+                    for (int t = 0; t < w; t++) {
+                        double cv = cor[first + t];
+                        aa = (float)((double)aa + fabs(cv));
+                        ap = (float)((double)ap + (cv < 0.0 ? 0.0 : cv));
+                    }
+                    {   // uncorrected: only non-zero signal positions move the accumulator
+                        const int fd = q - lf - d0;
+                        for (u32 z = pcnt[fd]; z < pcnt[fd + w]; z++) au = (float)((double)au + unc[(int)nzpos[z] + d0 - c0]);
+                    }
+                    double usum = au, asum = aa, psum_ = ap;
+                    double nsum = asum - psum_;
+                    if (psum_ != 0.0) {
+                        scale = (usum - nsum) / psum_;
+                        if (scale < 1.0) scale = 1.0;
+                    }
+                }
+                if (c > 0.0) c = c * scale;
+                const double e = expd[q - t0];
+                if (q >= V.f_extend && q < Lr - V.f_extend) {
+                    i64 o = V.out_off[j] + (q - V.f_extend);
+                    tracks[((i64)0 * 2 + strand) * V.out_total + o] = u;
+                    tracks[((i64)1 * 2 + strand) * V.out_total + o] = br[q];
+                    tracks[((i64)2 * 2 + strand) * V.out_total + o] = e;
+                    tracks[((i64)3 * 2 + strand) * V.out_total + o] = c;
+                }
+                bool valid = q > k && q < Lr - k - 1 && (u != 0.0 || c != 0.0);
+                if (valid) valid = tb_nflags(g, gstart + q - k, L) == 0;
+                // sig / bp are not read in this phase and expd[q - t0] only by this thread: they now carry the weights of phase 4
+                sig[q - t0] = (valid && u > 0.0) ? u : 0.0;       // pre_bias counts
+                bp[q - t0] = (valid && c > 0.0) ? c : 0.0;        // post_bias counts
+                expd[q - t0] = (valid && !(c > 0.0)) ? c : 0.0;   // post_bias neg_counts
+            }
+            __syncthreads();
+            // ---- 4. verification counts: lane m owns offset m of the k-mer around every position of the warp's strip
+            {
+                const int n_pos = t1 - t0;
+                const int strip = (n_pos + nwarps - 1) / nwarps;
+                const int qa = warp * strip, qb = min(n_pos, qa + strip);
+                double acc[3][4];
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int s = 0; s < 4; s++) acc[a][s] = 0.0;
+                if (lane < L) {
+                    for (int q = qa; q < qb; q++) {
+                        const double v0 = sig[q], v1 = bp[q], v2 = expd[q];
+                        if (v0 == 0.0 && v1 == 0.0 && v2 == 0.0) continue;            // warp-uniform
+                        const int s = bases[q + lane];
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (s == b) {
+                                acc[0][b] += v0;
+                                acc[1][b] += v1;
+                                acc[2][b] += v2;
+                            }
+                    }
+                    const int mm = strand ? L - 1 - lane : lane;
+#pragma unroll
+                    for (int a = 0; a < 3; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (acc[a][b] != 0.0) atomicAdd(&ver[((strand * 3 + a) * 4 + (strand ? (b ^ 1) : b)) * L + mm], acc[a][b]);
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
+    }
+    for (int i = tid; i < 2 * 3 * 4 * L; i += nt) {
+        double v = ver[i];
+        if (v != 0.0) {
+            int sw = i / (4 * L), rem = i % (4 * L);          // sw = strand * 3 + which
+            atomicAdd(&prepost[(i64)sw * 5 * L + rem], v);
+        }
     }
 }
 
@@ -566,11 +664,17 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     tb_mark(ctx, 3);
     {
         tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
-        size_t smem = ((size_t)5 * (TB_K3C_TILE + 4 * window) + 3 * 4 * L) * sizeof(double);
+        const size_t capk = TB_K3C_TILE + 4 * window;
+        size_t smem = ((size_t)5 * capk + 2 * 3 * 4 * L) * sizeof(double) + (2 * (capk + 1) + 64) * sizeof(u32) + capk * 2 + TB_K3C_TILE + L + 16;
         auto kc = tb_correct_kernel;
         TB_CUDA(ctx, cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TB_LAUNCH(ctx, kc, (unsigned)tile_region.size(), 256, smem, g, V, (const int32_t *)ctx->reg_a.as<int32_t>(),
-                  (const int32_t *)ctx->reg_b.as<int32_t>(), (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),
+        const i64 n_tiles = (i64)tile_region.size();
+        i64 per_sm = (i64)(220 * 1024) / (i64)(smem + 1024);
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        const i64 capg = (i64)ctx->sm_count * per_sm;
+        TB_LAUNCH(ctx, kc, (unsigned)(n_tiles < capg ? n_tiles : capg), TB_K3C_THREADS, smem, g, V, (const int32_t *)ctx->reg_a.as<int32_t>(),
+                  (const int32_t *)ctx->reg_b.as<int32_t>(), n_tiles, (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),
                   (const double *)C.fit.as<double>(), correction_factor, C.tracks.as<double>(), C.prepost.as<double>());
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_correct_kernel"));
     }
