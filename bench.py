@@ -144,11 +144,21 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
     """One pass of the hot path over this rank's shard.  Returns (AtacBias, stage_ms list)."""
     from tobias_b200.pipeline import AtacBias, STRANDS
     ctx = eng.ctx
+    trace = os.environ.get("TB_BENCH_TRACE") and not resident      # diagnostic: host wall clock per phase of an e2e step (stderr)
+    marks = [("start", time.perf_counter())]
+
+    def mark(name):
+        if trace:
+            import torch
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
     if not resident:                      # e2e: inputs come from (pinned) host buffers every step
         ctx.genome_create(host["lengths"])
         for i, g in enumerate(host["genome"]):
             ctx.genome_upload(i, g)
+        mark("genome_h2d")
         ctx.reads_upload(*host["reads"])
+        mark("reads_h2d")
     # --- normalisation counters + bias-training counts, then the one exchange step of the path
     reads_peaks = ctx.count_reads(*arrays["peak_regions"], READ_SHIFT)
     reads_nonpeaks = ctx.count_reads(*arrays["nonpeak_regions"], READ_SHIFT)
@@ -169,16 +179,27 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
     bias.no_reads = int(scalars[0])
     bias.correction_factor = (10000000 / reads_total) * (reads_total / reads_peaks)      # atacorrect.py:298-300
     eng.set_bias(bias)
+    mark("counts+model")
     # --- correction + footprints of this rank's output regions
     c, s, e = arrays["output_regions"]
     ctx.correct_run(c, s, e, K_FLANK, WINDOW, bias.correction_factor, READ_SHIFT, LM_EXACT)
     stage = ctx.stage_ms(4)
+    mark("correct_run")
+    if not resident:                      # the four tracks travel to the host while the footprint kernels run
+        ctx.correct_download(split_strands=False, as_f64=False, prepost=True, out=out["tracks"], wait=False)
+        if trace:
+            marks.append(("download_begin(no sync)", time.perf_counter()))
     ctx.signal_from_corrected(FP["flank_max"], e - s)
     ctx.score_run(ctx.score_params("footprint", flank=FP["flank_max"], **FP))
     k4_ms = ctx.last_kernel_ms()
+    mark("footprints")
     if not resident:
-        ctx.correct_download(split_strands=False, as_f64=False, prepost=True, out=out["tracks"])
+        ctx.correct_download_wait()
+        mark("tracks_d2h_wait")
         ctx.score_download(out=out["footprint"])
+        mark("footprint_d2h")
+    if trace:
+        sys.stderr.write("e2e trace (ms): " + ", ".join("%s %.1f" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])) + "\n")
     return bias, {"K1_pileup": stage[0], "K3a_score": stage[1], "K3b_fit": stage[2], "K3c_correct": stage[3],
                   "K2_counts": k2_ms, "K4_footprint": k4_ms}
 

@@ -145,6 +145,11 @@ int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const 
  * prepost_out (may be NULL): double [2 strands][3][5][L] = verification PWM counts
  * (atacorrect_functions.py:358-373): [0] pre counts, [1] post counts, [2] post neg_counts. */
 int tb_correct_download(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out);
+/* Asynchronous form: _begin enqueues the packing and the device-to-host copies on a second stream, ordered after the
+ * work already submitted; kernels launched afterwards (tb_signal_from_corrected, tb_score_run) overlap with the copies.
+ * The host buffers (pinned for real overlap) are complete when _wait returns.  tb_correct_download = _begin + _wait. */
+int tb_correct_download_begin(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out);
+int tb_correct_download_wait(tb_ctx *ctx);
 /* per-window fit diagnostics of the last tb_correct_run (tests): double [2 strands][n_windows_total][6] =
  * { mode (0 fit, 1 fallback, 2 empty window), a, b (bias_min for mode 1), max(prediction), MINPACK info, nfev };
  * n may be queried with out=NULL. */

@@ -310,3 +310,10 @@ def test_chain_corrected_to_footprints(loaded_ctx, golden):
         lens.append(x.shape[0])
     ref = loaded_ctx.score_regions(np.concatenate(ext), lens, loaded_ctx.score_params("footprint", flank=30, as_f64=True))
     assert np.array_equal(got, ref)
+    # asynchronous download: copies enqueued before the footprint kernels, complete after the wait
+    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]))
+    later = loaded_ctx.correct_download(split_strands=False, as_f64=False, tracks=("corrected", "expected"), prepost=True, wait=False)
+    loaded_ctx.signal_from_corrected(30, e - s)
+    loaded_ctx.score_run(loaded_ctx.score_params("footprint", flank=30, as_f64=True))
+    loaded_ctx.correct_download_wait()
+    assert np.array_equal(later["corrected"], both) and np.array_equal(loaded_ctx.score_download(), got)

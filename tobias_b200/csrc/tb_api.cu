@@ -131,7 +131,8 @@ extern "C" int tb_init(int device, tb_ctx **out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
         return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
     }
@@ -150,6 +151,9 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int t = 0; t < 4; t++)
+        for (int s2 = 0; s2 < 2; s2++) tb_release(ctx->cor.dl[t][s2]);
     tb_dbuf *bufs[] = {&ctx->seq2, &ctx->nmask, &ctx->d_contig_off, &ctx->r_start, &ctx->r_len, &ctx->r_clip, &ctx->r_flags,
                        &ctx->reg_a, &ctx->reg_b, &ctx->reg_c, &ctx->reg_d, &ctx->reg_e, &ctx->scratch0, &ctx->scratch1,
                        &ctx->scratch2, &ctx->scratch3, &ctx->scratch4, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
@@ -160,10 +164,13 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
                        &ctx->sc.d_ext_off, &ctx->sc.signal, &ctx->sc.work0, &ctx->sc.work1, &ctx->sc.out};
     for (tb_dbuf *b : bufs) tb_release(*b);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->cor.pp_pinned) cudaFreeHost(ctx->cor.pp_pinned);
     tb_nccl_teardown(ctx);
     for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->marks[i]);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_copy);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

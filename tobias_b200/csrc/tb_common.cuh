@@ -8,6 +8,7 @@
         (ctx)->launches++;                                                               \
         tb_emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); }); \
     } while (0)
+#define TB_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...) TB_LAUNCH(ctx, kernel, grid, block, smem, __VA_ARGS__)
 #define TB_DYN_SMEM(name) unsigned char *name = tb_emu::S().dyn_smem
 #else
 #include <cuda_runtime.h>
@@ -15,6 +16,11 @@
     do {                                                                                 \
         (ctx)->launches++;                                                               \
         kernel<<<dim3(grid), dim3(block), (size_t)(smem), (ctx)->stream>>>(__VA_ARGS__); \
+    } while (0)
+#define TB_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                          \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        kernel<<<dim3(grid), dim3(block), (size_t)(smem), (strm)>>>(__VA_ARGS__);        \
     } while (0)
 #define TB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -53,7 +59,8 @@ struct tb_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device-to-host copies that overlap with later kernels (tb_correct_download_begin)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float last_ms = 0.f;
@@ -98,6 +105,8 @@ struct tb_ctx {
         tb_dbuf fitg_x, fitg_y, fitg_st, fitg_sti, fitg_wq, fitg_lists;   // K3b round form: transposed window data, fit state, work lists
         tb_dbuf tracks;    // f64 [4 tracks][2 strands][out_total]
         tb_dbuf prepost;   // f64 [2][3][5][L]
+        tb_dbuf dl[4][2];  // packed tracks on their way to the host
+        double *pp_pinned = nullptr, *pp_dst = nullptr;   // pinned staging of prepost, caller's destination (set by _begin)
         bool valid = false;
     } cor;
 

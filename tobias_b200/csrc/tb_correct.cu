@@ -686,35 +686,69 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     return TB_OK;
 }
 
-extern "C" int tb_correct_download(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out) {
+// Enqueues the packing kernels and device-to-host copies of the requested tracks on the context's copy stream, ordered
+// after everything already submitted to the compute stream.  Kernels launched afterwards (footprint scoring) overlap
+// with the copies; tb_correct_download_wait blocks until the host buffers are complete.
+extern "C" int tb_correct_download_begin(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out) {
     if (!ctx || !tracks) return TB_ERR_ARG;
     auto &C = ctx->cor;
     if (!C.valid) return tb_fail(ctx, TB_ERR_STATE, "tb_correct_download: no completed tb_correct_run");
     const size_t esz = as_f64 ? 8 : 4;
     const i64 n = C.out_total;
+    for (int t = 0; t < 4; t++)
+        for (int s = 0; s < 2; s++)
+            if (tracks[t][s] && !split_strands && s == 1)
+                return tb_fail(ctx, TB_ERR_ARG, "tb_correct_download: tracks[t][1] must be NULL unless split_strands");
+    if (n > 0)
+        for (int t = 0; t < 4; t++)
+            for (int s = 0; s < 2; s++)
+                if (tracks[t][s]) TB_TRY(tb_reserve(ctx, C.dl[t][s], (size_t)n * esz));
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
     if (n > 0) {
-        TB_TRY(tb_reserve(ctx, ctx->scratch0, (size_t)n * esz));
+        // all packing kernels first (they run before the caller's next kernels fill the SMs), then the copies back to back
         for (int t = 0; t < 4; t++)
             for (int s = 0; s < 2; s++) {
-                void *dst = tracks[t][s];
-                if (!dst) continue;
-                if (!split_strands && s == 1) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_download: tracks[t][1] must be NULL unless split_strands");
+                if (!tracks[t][s]) continue;
                 const double *a = C.tracks.as<double>() + ((i64)t * 2 + (split_strands ? s : 0)) * n;
                 const double *b = split_strands ? nullptr : C.tracks.as<double>() + ((i64)t * 2 + 1) * n;
                 i64 want = tb_div_up(n, 256), capg = (i64)ctx->sm_count * 16;
                 unsigned grid = (unsigned)(want < capg ? want : capg);
                 if (as_f64) {
                     auto kp = tb_pack_track_kernel<double>;
-                    TB_LAUNCH(ctx, kp, grid, 256, 0, a, b, n, ctx->scratch0.as<double>());
+                    TB_LAUNCH_ON(ctx, ctx->copy_stream, kp, grid, 256, 0, a, b, n, C.dl[t][s].as<double>());
                 } else {
                     auto kp = tb_pack_track_kernel<float>;
-                    TB_LAUNCH(ctx, kp, grid, 256, 0, a, b, n, ctx->scratch0.as<float>());
+                    TB_LAUNCH_ON(ctx, ctx->copy_stream, kp, grid, 256, 0, a, b, n, C.dl[t][s].as<float>());
                 }
-                TB_TRY(tb_d2h(ctx, dst, ctx->scratch0.p, (size_t)n * esz));
             }
+        for (int t = 0; t < 4; t++)
+            for (int s = 0; s < 2; s++)
+                if (tracks[t][s])
+                    TB_CUDA(ctx, cudaMemcpyAsync(tracks[t][s], C.dl[t][s].p, (size_t)n * esz, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
-    if (prepost_out) TB_TRY(tb_d2h(ctx, prepost_out, C.prepost.p, (size_t)2 * 3 * 5 * C.L * sizeof(double)));
-    return tb_sync(ctx, "tb_correct_download");
+    C.pp_dst = prepost_out;
+    if (prepost_out) {      // through a pinned staging buffer: a copy into pageable memory would block the host until the stream drains
+        if (!C.pp_pinned) TB_CUDA(ctx, cudaMallocHost((void **)&C.pp_pinned, (size_t)2 * 3 * 5 * 32 * sizeof(double)));
+        TB_CUDA(ctx, cudaMemcpyAsync(C.pp_pinned, C.prepost.p, (size_t)2 * 3 * 5 * C.L * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->copy_stream));
+    }
+    return tb_check(ctx, cudaGetLastError(), "tb_correct_download_begin");
+}
+
+extern "C" int tb_correct_download_wait(tb_ctx *ctx) {
+    if (!ctx) return TB_ERR_ARG;
+    TB_TRY(tb_check(ctx, cudaStreamSynchronize(ctx->copy_stream), "tb_correct_download_wait"));
+    if (ctx->cor.pp_dst) {
+        memcpy(ctx->cor.pp_dst, ctx->cor.pp_pinned, (size_t)2 * 3 * 5 * ctx->cor.L * sizeof(double));
+        ctx->cor.pp_dst = nullptr;
+    }
+    return tb_check(ctx, cudaGetLastError(), "tb_correct_download_wait");
+}
+
+extern "C" int tb_correct_download(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out) {
+    TB_TRY(tb_correct_download_begin(ctx, split_strands, as_f64, tracks, prepost_out));
+    return tb_correct_download_wait(ctx);
 }
 
 extern "C" int tb_correct_fit_trace(tb_ctx *ctx, int64_t *n_windows_total, double *out) {

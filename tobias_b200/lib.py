@@ -60,6 +60,8 @@ _PROTOS = {
     "tb_correct_run": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _d, _i, _i, _i]),
     "tb_stage_ms": (_i, [_vp, C.POINTER(C.c_float), _i]),
     "tb_correct_download": (_i, [_vp, _i, _i, _vp, _vp]),
+    "tb_correct_download_begin": (_i, [_vp, _i, _i, _vp, _vp]),
+    "tb_correct_download_wait": (_i, [_vp]),
     "tb_correct_fit_trace": (_i, [_vp, C.POINTER(_i64), _vp]),
     "tb_signal_upload": (_i, [_vp, _vp, _i64, _vp]),
     "tb_score_run": (_i, [_vp, C.POINTER(ScoreParams)]),
@@ -298,8 +300,10 @@ class Context:
         self._cor_total = int((e - s).sum())
         self._cor_L = 2 * k_flank + 1
 
-    def correct_download(self, split_strands=False, as_f64=False, tracks=TRACKS, prepost=True, out=None):
-        """dict track -> array (split_strands=False) or track -> (forward, reverse); plus 'prepost' [2][3][5][L]."""
+    def correct_download(self, split_strands=False, as_f64=False, tracks=TRACKS, prepost=True, out=None, wait=True):
+        """dict track -> array (split_strands=False) or track -> (forward, reverse); plus 'prepost' [2][3][5][L].
+        wait=False: the copies are only enqueued (they overlap with kernels launched afterwards); the arrays are complete
+        after correct_download_wait()."""
         dt = np.float64 if as_f64 else np.float32
         ptrs = ((_vp * 2) * 4)()
         out_bufs, out = out, {}          # `out`: optional dict track -> preallocated (e.g. pinned) array, strands combined
@@ -316,10 +320,16 @@ class Context:
                 ptrs[t][0] = a.ctypes.data
                 out[name] = a[:self._cor_total]
         pp = np.zeros((2, 3, 5, self._cor_L), dtype=np.float64) if prepost else None
-        self._ck(self._lib.tb_correct_download(self._h, int(bool(split_strands)), int(bool(as_f64)), ptrs, _ptr(pp)))
+        fn = self._lib.tb_correct_download if wait else self._lib.tb_correct_download_begin
+        self._ck(fn(self._h, int(bool(split_strands)), int(bool(as_f64)), ptrs, _ptr(pp)))
         if prepost:
             out["prepost"] = pp
+        self._pending_download = None if wait else (ptrs, out)         # keeps the destination arrays alive
         return out
+
+    def correct_download_wait(self):
+        self._ck(self._lib.tb_correct_download_wait(self._h))
+        self._pending_download = None
 
     def correct_fit_trace(self):
         n = _i64()
