@@ -257,6 +257,21 @@ def test_footprint_many_regions_and_tiles(ctx):
     assert off == got.shape[0]
 
 
+def test_footprint_width_ranges_and_tile_sizes(ctx):
+    """more than 32 footprint widths (second batch: per-width sliding maximum), a single width, regions of very different
+    lengths (the host picks the block size from them) -- against the oracle's restatement of tobias_footprint_array."""
+    rng = np.random.default_rng(11)
+    for lens, args in (([900, 180, 2500], (5, 12, 10, 60)), ([760] * 5, (10, 30, 20, 50)), ([300, 4000], (3, 3, 7, 7))):
+        sig = [np.where(rng.random(n) < 0.6, 0, rng.normal(0, 1.0, size=n)).round(4).astype(np.float32) for n in lens]
+        p = ctx.score_params("footprint", flank=0, flank_min=args[0], flank_max=args[1], fp_min=args[2], fp_max=args[3], as_f64=True)
+        got = ctx.score_regions(np.concatenate(sig), lens, p)
+        off = 0
+        for x in sig:
+            ref = restate.tobias_footprint_array(x.astype(np.float64), *args)
+            _fp_close(got[off:off + x.shape[0]], ref)
+            off += x.shape[0]
+
+
 def test_calculate_scores_against_golden(ctx, golden):
     sc, g = golden.score, golden.atac
     sig = sc["signal"]

@@ -103,13 +103,19 @@ __device__ void tb_block_scan2(double *a, double *b, int n, double *aux) {
 #define TB_K4_NPW 32
 
 // OUT_MODE 0: trimmed float, 1: trimmed double, 2: untrimmed double work array (smoothing follows)
+// The block size S (= blockDim.x, chosen by the host to fit the region lengths) sets the tile: S footprint starts,
+// S - (pmax - 1) outputs.  W is double buffered (one barrier per flank width).  Spreading a score over its footprint:
+// with g[c] = max_{pw >= pmin + c} score(s, pw) (suffix maximum over the widths, in registers),
+//     out[pos] = max( max_{d < pmin} g[0](pos - d),  max_{c >= 1} g[c](pos - (pmin - 1 + c)) )
+// i.e. one shared-memory exchange per width instead of a log-doubling sliding maximum per width (all widths of one batch
+// of 32; wider ranges fall back to the per-width sliding maximum).
 template <int OUT_MODE>
 __global__ void __launch_bounds__(TB_K4_THREADS)
 tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_, int pmin_, int pmax_,
                     void *__restrict__ out_) {
     TB_DYN_SMEM(smem);
     const int tid = threadIdx.x;
-    const int S = TB_K4_THREADS;
+    const int S = blockDim.x;
     const int T = S - (pmax_ - 1);                              // outputs per tile
     const i64 j = tb_upper_bound(V.tile_off, V.n_regions + 1, (i64)blockIdx.x) - 1;
     const i64 tile = (i64)blockIdx.x - V.tile_off[j];
@@ -122,8 +128,9 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
     double *P = (double *)smem;                                 // n_in + 1
     double *N = P + (n_in + 1);                                 // n_in + 1
     double *aux = N + (n_in + 1);                               // 2 * S
-    float *W = (float *)(aux + 2 * S);                          // n_in
-    float *A = W + n_in;                                        // S
+    float *W0 = (float *)(aux + 2 * S);                         // n_in, two buffers
+    float *W1 = W0 + n_in;
+    float *A = W1 + n_in;                                       // S
     float *B = A + S;                                           // S
     const float *sg = signal + V.ext_off[j];
 
@@ -140,6 +147,8 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
     const i64 s = smin + tid;                                   // this thread's footprint start
     const int si = tid + fmax_;                                 // its index in the loaded range
     float best = 0.0f;                                          // out[pos] for pos = s (footprint_scores starts at 0)
+    const bool one_batch = pmax_ - pmin_ + 1 <= TB_K4_NPW;
+    int wbuf = 0;
 
     for (int pw0 = pmin_; pw0 <= pmax_; pw0 += TB_K4_NPW) {
         const int npw = min(TB_K4_NPW, pmax_ - pw0 + 1);
@@ -147,8 +156,10 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
 #pragma unroll
         for (int c = 0; c < TB_K4_NPW; c++) acc[c] = -INFINITY;
         for (int fw = fmin_; fw <= fmax_; fw++) {
+            float *W = wbuf ? W1 : W0;
+            wbuf ^= 1;
             for (int i = tid; i + fw <= n_in; i += S) W[i] = (float)(P[i + fw] - P[i]);
-            __syncthreads();
+            __syncthreads();                                    // the other buffer is rewritten only after the next barrier
             const i64 i0 = s - fw;
             if (i0 >= 0 && i0 < limit) {
                 const float l = W[si - fw];
@@ -158,36 +169,64 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
                 for (int c = 0; c < TB_K4_NPW; c++)
                     if (c < npw) acc[c] = fmaxf(acc[c], (l + wr[c]) * inv);
             }
-            __syncthreads();
         }
+        // acc[c] -> score of (s, pw0 + c)
 #pragma unroll
         for (int c = 0; c < TB_K4_NPW; c++) {
-            if (c < npw) {
+            float sc = -INFINITY;
+            if (c < npw && acc[c] > -INFINITY) {
                 const int pw = pw0 + c;
-                float sc = -INFINITY;
-                if (acc[c] > -INFINITY) {
-                    float mid = (float)(N[si + pw] - N[si]);
-                    sc = acc[c] - mid * (1.0f / (float)pw);
-                }
-                // sliding maximum over s in (pos - pw, pos]: log-doubling
-                A[tid] = sc;
-                __syncthreads();
-                float *src = A, *dst = B;
-                int span = 1;
-                while (span * 2 <= pw) {
-                    float v = src[tid];
-                    if (tid >= span) v = fmaxf(v, src[tid - span]);
-                    dst[tid] = v;
-                    __syncthreads();
-                    float *t = src; src = dst; dst = t;
-                    span *= 2;
-                }
-                float v = src[tid];
-                int back = pw - span;
-                if (back > 0 && tid >= back) v = fmaxf(v, src[tid - back]);
-                best = fmaxf(best, v);
-                __syncthreads();
+                float mid = (float)(N[si + pw] - N[si]);
+                sc = acc[c] - mid * (1.0f / (float)pw);
             }
+            acc[c] = sc;
+        }
+        if (one_batch) {
+            // suffix maxima over the widths
+#pragma unroll
+            for (int c = TB_K4_NPW - 2; c >= 0; c--) acc[c] = fmaxf(acc[c], acc[c + 1]);
+            __syncthreads();
+            A[tid] = acc[0];
+            __syncthreads();
+            for (int d = 0; d < pmin_ && d <= tid; d++) best = fmaxf(best, A[tid - d]);
+            float *cur = B;
+#pragma unroll
+            for (int c = 1; c < TB_K4_NPW; c++) {
+                if (c < npw) {                                  // block-uniform
+                    cur[tid] = acc[c];
+                    __syncthreads();
+                    const int d = pmin_ - 1 + c;
+                    if (tid >= d) best = fmaxf(best, cur[tid - d]);
+                    cur = cur == A ? B : A;
+                }
+            }
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int c = 0; c < TB_K4_NPW; c++) {
+                if (c < npw) {
+                    const int pw = pw0 + c;
+                    // sliding maximum over s in (pos - pw, pos]: log-doubling
+                    __syncthreads();
+                    A[tid] = acc[c];
+                    __syncthreads();
+                    float *src = A, *dst = B;
+                    int span = 1;
+                    while (span * 2 <= pw) {
+                        float v = src[tid];
+                        if (tid >= span) v = fmaxf(v, src[tid - span]);
+                        dst[tid] = v;
+                        __syncthreads();
+                        float *t = src; src = dst; dst = t;
+                        span *= 2;
+                    }
+                    float v = src[tid];
+                    int back = pw - span;
+                    if (back > 0 && tid >= back) v = fmaxf(v, src[tid - back]);
+                    best = fmaxf(best, v);
+                }
+            }
+            __syncthreads();
         }
     }
     // thread tid holds out[pos = s]; valid for pos in [p0, p0 + T)
@@ -426,17 +465,33 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
     tb_timer_start(ctx);
     if (fp_like) {
         const bool fos = p->kind == TB_SCORE_FOS;
-        const i64 per_tile = fos ? TB_K4_THREADS : TB_K4_THREADS - (p->fp_max - 1);
+        // footprint scan: block size = tile size, picked to waste the fewest thread slots on these region lengths
+        int bs = TB_K4_THREADS;
+        if (!fos) {
+            double best_cost = -1.0;
+            for (int cand = 128; cand <= TB_K4_THREADS; cand += 32) {
+                const i64 per = cand - (p->fp_max - 1);
+                if (per < 32) continue;
+                double cost = 0.0;
+                for (i64 i = 0; i < S.n_regions; i++) cost += (double)tb_div_up(S.ext_off[i + 1] - S.ext_off[i], per);
+                cost *= (double)(cand + 2 * p->flank_max + p->fp_max);         // slots incl. the halo every tile re-scans
+                if (best_cost < 0.0 || cost < best_cost) {
+                    best_cost = cost;
+                    bs = cand;
+                }
+            }
+        }
+        const i64 per_tile = fos ? bs : bs - (p->fp_max - 1);
         TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles));
         tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
-        const int n_in = fos ? TB_K4_THREADS + 2 * (p->flank_max + p->fp_max) : TB_K4_THREADS + 2 * p->flank_max + p->fp_max;
-        size_t smem = (size_t)(2 * (n_in + 1) + 2 * TB_K4_THREADS) * sizeof(double) + (size_t)(n_in + 2 * TB_K4_THREADS) * sizeof(float);
+        const int n_in = fos ? bs + 2 * (p->flank_max + p->fp_max) : bs + 2 * p->flank_max + p->fp_max;
+        size_t smem = (size_t)(2 * (n_in + 1) + 2 * bs) * sizeof(double) + (size_t)(2 * n_in + 2 * bs) * sizeof(float);
         if (smem > (size_t)220 * 1024) return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: flank/footprint widths too large for one tile");
 #define TB_FP_CASE(KERNEL, OM)                                                                                              \
     {                                                                                                                       \
         auto k = KERNEL<OM>;                                                                                                \
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
-        TB_LAUNCH(ctx, k, (unsigned)n_tiles, TB_K4_THREADS, smem, V, (const float *)S.signal.as<float>(), prep, p->flank_min, \
+        TB_LAUNCH(ctx, k, (unsigned)n_tiles, bs, smem, V, (const float *)S.signal.as<float>(), prep, p->flank_min, \
                   p->flank_max, p->fp_min, p->fp_max, first_out);                                                           \
     }
         if (!fos) {
