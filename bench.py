@@ -298,6 +298,14 @@ def bench_b200(args):
     dom = max(stages, key=lambda k: stages[k])
     achieved = alg[dom] / (stages[dom] * 1e-3) / 1e9
     per_stage = {k: {"ms": round(v, 4), "alg_GBps": round(alg[k] / (v * 1e-3) / 1e9, 2) if v > 0 else None} for k, v in stages.items()}
+    try:                                   # binding unit of every kernel, from the committed ncu summary of this round (not a live measurement)
+        roofs = json.load(open(os.path.join(ROOT, "profiles", "r01_roofs.json")))
+        for k in per_stage:
+            if k in roofs:
+                per_stage[k]["bound"] = roofs[k]["bound"]
+                per_stage[k]["bound_util_pct_ncu"] = roofs[k]["bound_util_pct"]
+    except Exception:
+        roofs = {}
     result = {
         "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -311,7 +319,10 @@ def bench_b200(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "note": "K3a (DWM scoring) and K3b (LM fits) are fp64-compute bound, K4 fp32/SMEM bound (SURVEY 8d); bytes-based fractions are reported for every stage in `stages`"},
+                     "binding_unit": roofs.get(dom, {}).get("bound"), "binding_unit_util_pct_ncu": roofs.get(dom, {}).get("bound_util_pct"),
+                     "note": "achieved = algorithmic bytes of the stage (SURVEY 8d) / its CUDA-event time (all launches of the stage); none of K2-K4 is "
+                             "HBM bound -- the unit that binds each kernel and its ncu utilisation are in `stages` (profiles/r01_summary.md); "
+                             "traffic: no --set full capture of this exact launch (chr50mb capture in profiles/r01_roofs.json)"},
         "stages": per_stage, "wall_ms_per_step": wall_res / args.steps, "setup_s": round(setup_s, 1),
         "correction_factor": bias.correction_factor,
     }
