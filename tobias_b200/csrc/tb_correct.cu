@@ -597,7 +597,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         // round form (default): state in HBM, compacted work lists, one host read-back of two counters per round
         const int qm = (window + 9) / 10;
         const i64 qs = C.n_windows + (i64)(qm - 1) * n_regions, qtot = 2 * qs, n_slots = 2 * C.n_windows;
-        if (qtot >= ((i64)1 << 32)) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: too many windows for one launch");
+        if (10 * qtot >= ((i64)1 << 32)) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: too many windows for one launch");
         TB_TRY(tb_reserve(ctx, C.fitg_x, (size_t)10 * qtot * sizeof(double)));
         TB_TRY(tb_reserve(ctx, C.fitg_y, (size_t)10 * qtot * sizeof(u32)));
         TB_TRY(tb_reserve(ctx, C.fitg_st, (size_t)TB_FITG_NST * n_slots * sizeof(double)));

@@ -32,60 +32,32 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
     return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0;
 }
 
-// for (i = 0; i < m; i++) body(i, ex = bias[i], ey = signal[i] as double, eyi = signal[i] as u32).  Kept compact on
-// purpose (no unrolling): the kernel is a sequence of such passes and must stay resident in the instruction cache.
-#ifndef TB_FIT_UNROLL
-#define TB_FIT_UNROLL 1
-#endif
-#define TB_PRAGMA_(x) _Pragma(#x)
-#define TB_PRAGMA(x) TB_PRAGMA_(x)
-#ifndef TB_FIT_PREFETCH
-#define TB_FIT_PREFETCH 1       // load point i + 1 while point i is being processed (hides the L1 / shared-memory latency)
-#endif
-#if TB_FIT_PREFETCH
-#define TB_FOR_POINTS(W, m, i, ...)                                            \
+// for (i = i0; i < m; i++) body(i, ex = bias[i], ey = signal[i] as double, eyi = signal[i] as u32), i0 < 10.  Kept compact
+// on purpose (no unrolling): the kernel is a sequence of such passes and must stay resident in the instruction cache.
+// Point i + 1 is loaded while point i is processed (hides the L1 latency); offsets are 32-bit element indices
+// (the host checks 10 * stride < 2^32).
+#define TB_FOR_POINTS_FROM(W, m, i0, i, ...)                                   \
     {                                                                          \
-        const double *_px = (W).x;                                             \
-        const u32 *_py = (W).y;                                                \
-        double _nx = *_px;                                                     \
-        u32 _ny = *_py;                                                        \
-        int _v = 0;                                                            \
-        TB_PRAGMA(unroll TB_FIT_UNROLL)                                        \
-        for (int i = 0; i < (m); i++) {                                        \
+        const u32 _st = (u32)(W).stride, _wrap = 9u * _st - 1u;                \
+        u32 _off = (u32)(i0) * _st;                                            \
+        double _nx = (W).x[_off];                                              \
+        u32 _ny = (W).y[_off];                                                 \
+        int _v = (i0);                                                         \
+        for (int i = (i0); i < (m); i++) {                                     \
             const double ex = _nx;                                             \
             const u32 eyi = _ny;                                               \
-            if (++_v == 10) {                                                  \
-                _v = 0;                                                        \
-                _px -= 9 * (W).stride - 1;                                     \
-                _py -= 9 * (W).stride - 1;                                     \
-            } else {                                                           \
-                _px += (W).stride;                                             \
-                _py += (W).stride;                                             \
-            }                                                                  \
+            const bool _w10 = ++_v == 10;                                      \
+            _off = _w10 ? _off - _wrap : _off + _st;                           \
+            _v = _w10 ? 0 : _v;                                                \
             if (i + 1 < (m)) {                                                 \
-                _nx = *_px;                                                    \
-                _ny = *_py;                                                    \
+                _nx = (W).x[_off];                                             \
+                _ny = (W).y[_off];                                             \
             }                                                                  \
             const double ey = tb_u32_to_double(eyi);                           \
             __VA_ARGS__                                                        \
         }                                                                      \
     }
-#else
-#define TB_FOR_POINTS(W, m, i, ...)                                            \
-    for (int _u = 0; _u * 10 < (m); _u++) {                                    \
-        const int _nv = (m) - _u * 10 < 10 ? (m) - _u * 10 : 10;               \
-        const double *_px = (W).x + _u;                                        \
-        const u32 *_py = (W).y + _u;                                           \
-        TB_PRAGMA(unroll TB_FIT_UNROLL)                                        \
-        for (int _v = 0; _v < _nv; _v++, _px += (W).stride, _py += (W).stride) { \
-            const int i = _u * 10 + _v;                                        \
-            const double ex = *_px;                                            \
-            const u32 eyi = *_py;                                              \
-            const double ey = tb_u32_to_double(eyi);                           \
-            __VA_ARGS__                                                        \
-        }                                                                      \
-    }
-#endif
+#define TB_FOR_POINTS(W, m, i, ...) TB_FOR_POINTS_FROM(W, m, 0, i, __VA_ARGS__)
 
 // a / d with dinv = 1.0 / d (correctly rounded, see header)
 __device__ __forceinline__ double tb_div_inv(double a, double d, double dinv) {
@@ -151,9 +123,9 @@ struct tb_lmt {
 // max(0, t) as the reference's np.maximum(0.0, t) for every finite t (and -0.0 -> 0.0): clears negative values by their
 // sign bit on the integer pipe instead of a double-precision compare + select
 __device__ __forceinline__ double tb_relu(double t) {
-    long long b = __double_as_longlong(t);
-    b &= ~(b >> 63);
-    return __longlong_as_double(b);
+    const int hi = __double2hiint(t);
+    const int keep = ~(hi >> 31);                                // all ones for a clear sign bit
+    return __hiloint2double(hi & keep, __double2loint(t) & keep);
 }
 __device__ __forceinline__ double tb_relu_res(double a, double b, double x, double y) {
     return tb_relu(__dadd_rn(__dmul_rn(a, x), b)) - y;          // np.maximum(0.0, a*x + b) - ydata
@@ -220,18 +192,18 @@ __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) 
         J.qhinv = 1.0 / h;
     }
     S.nfev += 2;
+    // the first two rows take part in the Householder bookkeeping (signs, +1 on the diagonal, R's entries)
+    const double x0 = W.x[0], y0 = tb_u32_to_double(W.y[0]);
+    const double x1 = W.x[W.stride], y1 = tb_u32_to_double(W.y[W.stride]);
+    double f0, f1, j00, j10;
+    J.eval(x0, y0, f0, j00, j10);
     // ---- pass A: column norms (column 0 = d/da as P, column 1 = d/db as Q)
     tb_enorm_acc n0, n1;
     tb_enorm_init(n0);
     tb_enorm_init(n1);
-    double j00 = 0.0, j10 = 0.0;
     TB_FOR_POINTS(W, m, i, {
         double f, j0, j1;
         J.eval(ex, ey, f, j0, j1);
-        if (i == 0) {
-            j00 = j0;
-            j10 = j1;
-        }
         tb_enorm_add(n0, j0, m);
         tb_enorm_add(n1, j1, m);
     })
@@ -248,21 +220,20 @@ __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) 
     }
     double ajnorm = swap ? S.acn1 : S.acn0;
     const bool have0 = ajnorm != 0.0;
-    double a00 = swap ? j10 : j00;
+    const double P0 = swap ? j10 : j00, Q0 = swap ? j00 : j10;
+    double a00 = P0;
     if (have0 && a00 < 0.0) ajnorm = -ajnorm;
     double ainv = 0.0, temp = 0.0, tq0 = 0.0;
     // ---- pass B: Householder vector of the pivot column, its products with the other column and with fvec
     if (have0) {
         ainv = 1.0 / ajnorm;
-        double s = 0.0, sf = 0.0;
+        a00 = tb_div_inv(P0, ajnorm, ainv) + 1.0;
+        double s = 0.0, sf = 0.0, inc = 1.0;
         TB_FOR_POINTS(W, m, i, {
             double f, P, Q;
             J.eval(ex, ey, f, P, Q);
-            double c0 = tb_div_inv(P, ajnorm, ainv);
-            if (i == 0) {
-                c0 += 1.0;
-                a00 = c0;
-            }
+            double c0 = tb_div_inv(P, ajnorm, ainv) + inc;       // + 1 on the first row only (adding 0.0 elsewhere changes no sum)
+            inc = 0.0;
             s += __dmul_rn(c0, Q);
             sf += __dmul_rn(c0, f);
         })
@@ -270,24 +241,31 @@ __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) 
         if (a00 != 0.0) tq0 = -sf / a00;
     }
     S.r00 = -ajnorm;
-    // ---- pass C: remaining column, its norm below the first row
+    const bool app0 = have0 && a00 != 0.0;
+    // rows 0 and 1 of the updated second column and of Q0^T fvec
+    double P1, Q1;
+    J.eval(x1, y1, f1, P1, Q1);
+    double c10 = Q0, c11 = Q1, w0 = f0, w1 = f1;
+    if (have0) {
+        const double c01 = tb_div_inv(P1, ajnorm, ainv);
+        c10 = Q0 - __dmul_rn(temp, a00);
+        c11 = Q1 - __dmul_rn(temp, c01);
+        if (app0) {
+            w0 = f0 + __dmul_rn(a00, tq0);
+            w1 = f1 + __dmul_rn(c01, tq0);
+        }
+    }
+    S.r01 = c10;
+    // ---- pass C: norm of the remaining column below the first row
     tb_enorm_acc nc;
     tb_enorm_init(nc);
-    double c11 = 0.0;
-    TB_FOR_POINTS(W, m, i, {
+    tb_enorm_add(nc, c11, m - 1);
+    TB_FOR_POINTS_FROM(W, m, 2, i, {
         double f, P, Q;
         J.eval(ex, ey, f, P, Q);
         double c1 = Q;
-        if (have0) {
-            double c0 = tb_div_inv(P, ajnorm, ainv);
-            if (i == 0) c0 += 1.0;
-            c1 = Q - __dmul_rn(temp, c0);
-        }
-        if (i == 0) S.r01 = c1;
-        else {
-            if (i == 1) c11 = c1;
-            tb_enorm_add(nc, c1, m - 1);
-        }
+        if (have0) c1 = Q - __dmul_rn(temp, tb_div_inv(P, ajnorm, ainv));
+        tb_enorm_add(nc, c1, m - 1);
     })
     double ajnorm1 = tb_enorm_result(nc);
     const bool have1 = ajnorm1 != 0.0;
@@ -307,31 +285,21 @@ __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) 
     }
     // ---- pass D: qtf = first two components of Q^T fvec
     {
-        const bool app0 = have0 && a00 != 0.0;
-        double s1 = 0.0, w0 = 0.0, w1 = 0.0, a11 = c11;
-        TB_FOR_POINTS(W, m, i, {
+        double a11 = c11;
+        if (have1) a11 = tb_div_inv(c11, ajnorm1, ainv1) + 1.0;
+        double s1 = 0.0;
+        s1 += __dmul_rn(a11, w1);
+        TB_FOR_POINTS_FROM(W, m, 2, i, {
             double f, P, Q;
             J.eval(ex, ey, f, P, Q);
-            double c0 = P, c1 = Q;
+            double c1 = Q, w = f;
             if (have0) {
-                c0 = tb_div_inv(P, ajnorm, ainv);
-                if (i == 0) c0 += 1.0;
+                const double c0 = tb_div_inv(P, ajnorm, ainv);
                 c1 = Q - __dmul_rn(temp, c0);
+                if (app0) w = f + __dmul_rn(c0, tq0);
             }
-            double w = f;
-            if (app0) w = f + __dmul_rn(c0, tq0);
-            if (i == 0) w0 = w;
-            else {
-                if (have1) {
-                    c1 = tb_div_inv(c1, ajnorm1, ainv1);
-                    if (i == 1) c1 += 1.0;
-                }
-                if (i == 1) {
-                    w1 = w;
-                    a11 = c1;
-                }
-                s1 += __dmul_rn(c1, w);
-            }
+            if (have1) c1 = tb_div_inv(c1, ajnorm1, ainv1);
+            s1 += __dmul_rn(c1, w);
         })
         S.qtf0 = w0;
         if (a11 != 0.0) {
