@@ -93,6 +93,10 @@ def test_bias_counts_in_several_slab_chunks(loaded_ctx, golden, monkeypatch):
         assert np.array_equal(counts[si, 0], g["DWM_%s_counts" % st]) and np.array_equal(counts[si, 1], g["DWM_%s_bg_counts" % st])
     counts2, scalars2 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)           # slab left clean by the chunked run
     assert np.array_equal(counts, counts2) and np.array_equal(scalars, scalars2)
+    monkeypatch.setenv("TB_K2_SITE_CAP", "100")                                            # site list too small: regrown, chunk redone
+    counts3, scalars3 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)
+    monkeypatch.delenv("TB_K2_SITE_CAP")
+    assert np.array_equal(counts, counts3) and np.array_equal(scalars, scalars3)
 
 
 def _set_model(ctx, g, mode):

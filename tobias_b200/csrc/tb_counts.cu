@@ -276,6 +276,10 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     i64 site_cap = ctx->n_reads + ctx->n_reads / 4 + 1024;       // one site per (record, overlapped region) at most; grown on overflow
+    {
+        const char *ev = getenv("TB_K2_SITE_CAP");                // tests: force the overflow / regrow path
+        if (ev && atoll(ev) > 0) site_cap = atoll(ev);
+    }
 
     tb_timer_start(ctx);
     i64 j0 = 0;

@@ -36,6 +36,11 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
 // on purpose (no unrolling): the kernel is a sequence of such passes and must stay resident in the instruction cache.
 // Point i + 1 is loaded while point i is processed (hides the L1 latency); offsets are 32-bit element indices
 // (the host checks 10 * stride < 2^32).
+#ifndef TB_FIT_UNROLL
+#define TB_FIT_UNROLL 1
+#endif
+#define TB_PRAGMA_(x) _Pragma(#x)
+#define TB_PRAGMA(x) TB_PRAGMA_(x)
 #define TB_FOR_POINTS_FROM(W, m, i0, i, ...)                                   \
     {                                                                          \
         const u32 _st = (u32)(W).stride, _wrap = 9u * _st - 1u;                \
@@ -43,6 +48,7 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
         double _nx = (W).x[_off];                                              \
         u32 _ny = (W).y[_off];                                                 \
         int _v = (i0);                                                         \
+        TB_PRAGMA(unroll TB_FIT_UNROLL)                                        \
         for (int i = (i0); i < (m); i++) {                                     \
             const double ex = _nx;                                             \
             const u32 eyi = _ny;                                               \
