@@ -7,6 +7,7 @@ batched over ALL regions of a shard in a few kernel launches instead of the refe
 Used by the worker-function mirrors (tobias_b200/atacorrect_functions.py, score_bigwig.py), by the CLI drivers, by
 bench.py and by the multi-GPU layer (tobias_b200/dist.py).
 """
+import io
 import pickle
 from copy import deepcopy
 
@@ -14,9 +15,49 @@ import numpy as np
 
 from . import lib
 from .regions import OneRegion, RegionList, to_arrays
-from .sequences import SequenceMatrix
+from .sequences import DiNucleotideMatrix, NucleotideMatrix, SequenceMatrix
 
 STRANDS = ("forward", "reverse")
+
+# ---- <prefix>_AtacBias.pickle compatibility (tobias/tools/atacorrect_functions.py:62-76, atacorrect.py:316-354) ----
+# The reference pickles plain instances of tobias.tools.atacorrect_functions.AtacBias holding
+# tobias.utils.sequences.{DiNucleotideMatrix,NucleotideMatrix}; the attribute names are the same here, so compatibility is a
+# matter of class paths: pickles are WRITTEN with the reference's paths (loadable by `TOBIAS ATACorrect --bias-pkl` of the
+# reference) and READ with either set of paths, without TOBIAS being installed and without touching sys.modules.
+_REF_ATACBIAS = ("tobias.tools.atacorrect_functions", "AtacBias")
+_REF_SEQ = "tobias.utils.sequences"
+
+
+class _RefPathPickler(pickle._Pickler):
+    """Pure-Python pickler that writes this package's bias classes under the reference's module paths."""
+
+    def save_global(self, obj, name=None):
+        path = _ref_path_of(obj)
+        if path is None:
+            return super().save_global(obj, name)
+        self.write(pickle.GLOBAL + path[0].encode() + b"\n" + path[1].encode() + b"\n")
+        self.memoize(obj)
+
+    dispatch = dict(pickle._Pickler.dispatch)
+    dispatch[type] = save_global
+
+
+class _RefPathUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if (module, name) == _REF_ATACBIAS:
+            return AtacBias
+        if module == _REF_SEQ and name in ("DiNucleotideMatrix", "NucleotideMatrix", "SequenceMatrix"):
+            return {"DiNucleotideMatrix": DiNucleotideMatrix, "NucleotideMatrix": NucleotideMatrix, "SequenceMatrix": SequenceMatrix}[name]
+        return super().find_class(module, name)
+
+
+def _ref_path_of(obj):
+    if obj is AtacBias:
+        return _REF_ATACBIAS
+    for cls in (DiNucleotideMatrix, NucleotideMatrix, SequenceMatrix):
+        if obj is cls:
+            return (_REF_SEQ, cls.__name__)
+    return None
 
 
 class AtacBias:
@@ -35,13 +76,22 @@ class AtacBias:
         self.no_reads += obj.no_reads
 
     def to_pickle(self, f):
+        """Writes a pickle the reference's `--bias-pkl` loads (same class paths and attribute names)."""
+        buf = io.BytesIO()
+        _RefPathPickler(buf, protocol=2).dump(self)
         with open(f, "wb") as handle:
-            pickle.dump(self, handle)
+            handle.write(buf.getvalue())
         return self
 
     def from_pickle(self, f):
+        """Reads a pickle written by the reference's ATACorrect or by this package."""
         with open(f, "rb") as handle:
-            return pickle.load(handle)
+            obj = _RefPathUnpickler(handle).load()
+        if not isinstance(obj, AtacBias):
+            raise ValueError("%s does not hold an AtacBias object" % f)
+        if not hasattr(obj, "correction_factor"):
+            obj.correction_factor = 1.0
+        return obj
 
     # ---- flat int64 view of everything that is summed across shards (exact: all entries are integers) ----
     def pack_counts(self):
