@@ -37,7 +37,7 @@ METRIC = "corrected+footprint-scored bp/s"
 SEED = 20261019
 K_FLANK, WINDOW, BG_SHIFT, EXTEND, READ_SHIFT = 12, 100, 100, 100, (4, -5)
 FP = dict(flank_min=10, flank_max=30, fp_min=20, fp_max=50)
-LM_EXACT = 0          # fit kernel: 0 / 1 = thread-per-window rounds in MINPACK order (default); --lm-mode 2 / 3 = first-generation warp kernels
+LM_EXACT = 0          # fit kernel: 0 = one-pass outer iterations (DWM default), 1 = MINPACK-exact arithmetic (--lm-exact); --lm-mode 2 / 3 = first-generation warp kernels
 
 
 def workload(name):

@@ -129,10 +129,11 @@ int tb_score_sequence(tb_ctx *ctx, int strand, int contig, int64_t start, int64_
 
 /* bias_correction (tobias/tools/atacorrect_functions.py:191-410) over all OUTPUT regions [start, end) at once
  * (each is extended internally by k_flank + window/2, which must stay inside its contig).
- * lm_exact_order 0 or 1: one thread per window fit, sums in MINPACK's sequential order -- bit-faithful to scipy's
- * lmdif on identical inputs (the default and the fast path; the flag's two values are kept for ABI compatibility).
- * 2 / 3 select the first-generation warp-per-window kernels (2: warp-tree sums, 3: MINPACK-order sums), kept for
- * comparison runs only.
+ * Window fits: one thread per window, rounds over compacted work lists.  lm_exact_order = 1: MINPACK's own
+ * arithmetic and summation order -- bit-faithful to scipy's lmdif on identical inputs (PWM mode: tracks bit-identical to the
+ * reference).  0: the outer-iteration head uses the five inner products of the Jacobian columns (one pass instead of four):
+ * same iteration and decisions, parameters ~1e-8 apart, the scatter a 1e-13 change of the bias input causes in the reference
+ * itself (what the DWM bias input carries anyway).  2 / 3 select the first-generation warp-per-window kernels (comparison runs).
  * Device-side only; results stay in HBM until tb_correct_download.  Regions sorted by (contig, start), and
  * non-overlapping before extension. */
 int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start,

@@ -170,10 +170,11 @@ def test_bias_correction_tracks(loaded_ctx, golden, mode):
             assert np.all(np.abs(both[t].astype(np.float64) - ref32) <= 1e-5 * np.abs(ref32) + 2e-5)
 
 
-@pytest.mark.parametrize("lm_mode", [2, 3])
-def test_bias_correction_warp_kernels(loaded_ctx, golden, lm_mode):
-    """first-generation warp-per-window fit kernels (2: warp-tree sums, 3: MINPACK-order sums), kept for comparison runs:
-    same tracks within the DWM-mode tolerance (bit-identical for mode 3)."""
+@pytest.mark.parametrize("lm_mode", [0, 2, 3])
+def test_bias_correction_other_fit_kernels(loaded_ctx, golden, lm_mode):
+    """lm_exact_order = 0: one-pass (inner product) outer iterations, the DWM default; 2 / 3: first-generation warp-per-window
+    kernels (warp-tree sums / MINPACK-order sums), kept for comparison runs: same tracks within the DWM-mode tolerance even on
+    the bit-exact PWM bias input (bit-identical for mode 3)."""
     g = golden.atac
     _set_model(loaded_ctx, g, "PWM")
     c, s, e = _cols(g["outreg"])

@@ -104,9 +104,12 @@ def test_exact_order_reproduces_scipy_bit_for_bit(harness, tmp_path, form):
     assert n_fallback >= 20          # the OptimizeWarning / RuntimeError branch is exercised
 
 
-def test_tree_sums_follow_the_same_fit(harness, tmp_path):
-    windows = _windows(96, seed=9)
-    got = _run(harness, windows, 0, str(tmp_path))
+@pytest.mark.parametrize("form", [4, 0])
+def test_fast_forms_follow_the_same_fit(harness, tmp_path, form):
+    """form 4: thread-per-window kernel core with the one-pass (inner product) outer-iteration head (lm_exact_order=0);
+    form 0: first-generation warp kernel with tree sums.  Same usable / fallback decisions, predictions within 1e-5."""
+    windows = _windows(96 if form == 0 else 480, seed=9)
+    got = _run(harness, windows, form, str(tmp_path))
     for (x, y), g in zip(windows, got):
         ref = _scipy(x, y)
         assert g[4] == ref[4]

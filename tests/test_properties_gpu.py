@@ -141,6 +141,29 @@ def test_correction_identities_determinism_and_batching(work):
     assert set(np.unique(trace[:, :, 0])) <= {0.0, 1.0, 2.0}
 
 
+def test_fast_and_exact_fits_agree(work):
+    """lm_exact_order = 0 (one-pass outer iterations, DWM default) against 1 (MINPACK-exact arithmetic) on ~200k window fits:
+    same fit / fallback / empty decisions except for a handful of windows, tracks within the DWM-mode tolerance."""
+    ctx, ds, arrays = work
+    _model(ctx, arrays)
+    c, s, e = arrays["output_regions"]
+    ctx.correct_run(c, s, e, correction_factor=1.0, lm_exact_order=1)
+    a = ctx.correct_download(split_strands=True, as_f64=True, prepost=False)
+    ta = ctx.correct_fit_trace()
+    ctx.correct_run(c, s, e, correction_factor=1.0, lm_exact_order=0)
+    b = ctx.correct_download(split_strands=True, as_f64=True, prepost=False)
+    tb = ctx.correct_fit_trace()
+    assert (ta[:, :, 0] != tb[:, :, 0]).mean() < 1e-3                          # decisions
+    assert abs(ta[:, :, 5].mean() - tb[:, :, 5].mean()) < 0.05                 # same amount of work (nfev)
+    for t in ("expected", "corrected"):
+        for si in range(2):
+            d = np.abs(a[t][si] - b[t][si])
+            ok = d <= 1e-5 * np.abs(a[t][si]) + 2e-6
+            assert ok.mean() >= 0.999, (t, si, ok.mean(), d.max())
+    for si in range(2):
+        assert np.array_equal(a["uncorrected"][si], b["uncorrected"][si]) and np.array_equal(a["bias"][si], b["bias"][si])
+
+
 def test_footprints_properties(work):
     ctx, ds, arrays = work
     _model(ctx, arrays)

@@ -192,7 +192,7 @@ def run_atacorrect(args):
     eng.set_bias(bias_obj)
     out_regions = local["output_regions"]
     out_regions.loc_sort(mine)
-    lm_exact = True          # the fit kernel is always the MINPACK-order one (--lm-exact is accepted and ignored)
+    lm_exact = bool(args.lm_exact) or args.score_mat == "PWM"
     n_out = len(out_regions)
     if n_out:
         eng.correct(out_regions, bias_obj, args.k_flank, args.window, read_shift, lm_exact)

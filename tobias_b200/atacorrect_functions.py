@@ -59,7 +59,7 @@ def bias_correction(regions_list, params, bias_obj):
     eng.set_bias(bias_obj)
     order = sorted(range(len(regions_list)), key=lambda i: (eng.index[regions_list[i].chrom], regions_list[i].start))
     regs = [regions_list[i] for i in order]
-    lm_exact = True
+    lm_exact = getattr(params, "lm_exact", params.score_mat == "PWM")
     eng.correct(regs, bias_obj, params.k_flank, params.window, tuple(params.read_shift), lm_exact)
     got = eng.tracks(split_strands=True, as_f64=True)
     offs = np.concatenate([[0], np.cumsum([r.end - r.start for r in regs])])

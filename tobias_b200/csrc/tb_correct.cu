@@ -217,7 +217,7 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
 #ifndef TB_FITG_MINBLOCKS
 #define TB_FITG_MINBLOCKS 4
 #endif
-template <bool WITH_QR>
+template <bool WITH_QR, bool FAST>
 __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
     tb_fitg_round_kernel(tb_fitg_view G, int m, const u32 *__restrict__ list, i64 n_list, double *__restrict__ fit,
                          u32 *__restrict__ nextq, u32 *__restrict__ nextt, unsigned long long *ctr) {
@@ -232,9 +232,12 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
             tb_fitg_load(G, slot, S);
             const i64 q = G.wq[slot];
             const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
-            if (WITH_QR) tb_lmt_qr(S, W, m);
+            if (WITH_QR) {
+                if (FAST) tb_lmt_qr_fast(S, W, m);
+                else tb_lmt_qr(S, W, m);
+            }
             bool accepted = false;
-            if (S.info == 0) accepted = tb_lmt_trial(S, W, m);
+            if (S.info == 0) accepted = tb_lmt_trial<FAST>(S, W, m);
             if (S.info != 0) {
                 double mode, pa, pb, pmax;
                 tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
@@ -626,13 +629,13 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
             const i64 capg = (i64)ctx->sm_count * TB_FITG_MINBLOCKS;
             if (nq > 0) {
                 i64 want = tb_div_up(nq, 128);
-                auto kq = tb_fitg_round_kernel<true>;
+                auto kq = lm_exact_order ? tb_fitg_round_kernel<true, false> : tb_fitg_round_kernel<true, true>;
                 TB_LAUNCH(ctx, kq, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lq[cur], nq, C.fit.as<double>(),
                           lq[cur ^ 1], lt[cur ^ 1], ctr);
             }
             if (nt > 0) {
                 i64 want = tb_div_up(nt, 128);
-                auto kt = tb_fitg_round_kernel<false>;
+                auto kt = lm_exact_order ? tb_fitg_round_kernel<false, false> : tb_fitg_round_kernel<false, true>;
                 TB_LAUNCH(ctx, kt, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lt[cur], nt, C.fit.as<double>(),
                           lq[cur ^ 1], lt[cur ^ 1], ctr);
             }

@@ -176,9 +176,38 @@ struct tb_jac {
     }
 };
 
+// scaled gradient norm, gtol test and the update of the scaling (end of the outer-iteration head, both forms)
+__device__ __forceinline__ void tb_lmt_qr_tail(tb_lmt &S, bool swap) {
+    const double gtol = 0.0;
+    // ---- norm of the scaled gradient
+    double gnorm = 0.0;
+    if (S.fnorm != 0.0) {
+        const double acnp0 = swap ? S.acn1 : S.acn0, acnp1 = swap ? S.acn0 : S.acn1;
+        if (acnp0 != 0.0) {
+            double s = 0.0;
+            s += S.r00 * (S.qtf0 / S.fnorm);
+            gnorm = fmax(gnorm, fabs(s / acnp0));
+        }
+        if (acnp1 != 0.0) {
+            double s = 0.0;
+            s += S.r01 * (S.qtf0 / S.fnorm);
+            s += S.r11 * (S.qtf1 / S.fnorm);
+            gnorm = fmax(gnorm, fabs(s / acnp1));
+        }
+    }
+    S.gnorm = gnorm;
+    if (gnorm <= gtol) {
+        S.info = 4;
+        return;
+    }
+    S.diag0 = fmax(S.diag0, S.acn0);
+    S.diag1 = fmax(S.diag1, S.acn1);
+}
+
+
 // fdjac2 + qrfac + Q^T fvec + scaled gradient norm (lmdif outer-loop head).  Sets S.info = 4 when gnorm <= gtol.
 __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) {
-    const double epsmch = 2.220446049250313e-16, factor = 100.0, gtol = 0.0;
+    const double epsmch = 2.220446049250313e-16, factor = 100.0;
     const double eps = sqrt(epsmch);
     tb_jac J;
     J.a = S.par0;
@@ -314,33 +343,115 @@ __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) 
         }
         S.qtf1 = w1;
     }
-    // ---- norm of the scaled gradient
-    double gnorm = 0.0;
-    if (S.fnorm != 0.0) {
-        const double acnp0 = swap ? S.acn1 : S.acn0, acnp1 = swap ? S.acn0 : S.acn1;
-        if (acnp0 != 0.0) {
-            double s = 0.0;
-            s += S.r00 * (S.qtf0 / S.fnorm);
-            gnorm = fmax(gnorm, fabs(s / acnp0));
-        }
-        if (acnp1 != 0.0) {
-            double s = 0.0;
-            s += S.r01 * (S.qtf0 / S.fnorm);
-            s += S.r11 * (S.qtf1 / S.fnorm);
-            gnorm = fmax(gnorm, fabs(s / acnp1));
-        }
+    tb_lmt_qr_tail(S, swap);
+}
+
+// ---- fast form of the outer-iteration head (lm_exact_order = 0) ----------------------------------------------------
+// Same LM iteration, same decisions, but R and Q^T fvec come from the five inner products P.P, P.Q, Q.Q, P.f, Q.f of the
+// forward-difference Jacobian columns (ONE pass over the window instead of four): with ajnorm = sign(P_0) |P|,
+//     r00 = -ajnorm,  r01 = -P.Q / ajnorm,  |r11|^2 = Q.Q - r01^2,  qtf0 = -P.f / ajnorm,  qtf1 = -(Q.f - r01 qtf0) / ajnorm1
+// (Householder algebra of qrfac written out for two columns; signs from rows 0 and 1 as MINPACK picks them).  Not bit
+// faithful to scipy: R carries a relative error ~ cond(J)^2 * 1e-16 instead of cond(J) * 1e-16, which the forward-difference
+// iteration amplifies to ~1e-8 in the fitted parameters -- the same scatter a 1e-13 change of the bias input causes in the
+// reference itself, and what the DWM-mode bias input carries anyway.  Structural rank deficiency (fewer than two rows with a
+// non-zero Jacobian row) yields r11 = 0 exactly, as in MINPACK.
+struct tb_jac_fast {
+    double a, b, ap, bp, h0inv, h1inv;
+    __device__ __forceinline__ void eval(double x, double y, double &f, double &j0, double &j1) const {
+        const double t = __dmul_rn(a, x);
+        f = tb_relu(__dadd_rn(t, b)) - y;
+        const double fa = tb_relu(__dadd_rn(__dmul_rn(ap, x), b)) - y;
+        const double fb = tb_relu(__dadd_rn(t, bp)) - y;
+        j0 = (fa - f) * h0inv;
+        j1 = (fb - f) * h1inv;
     }
-    S.gnorm = gnorm;
-    if (gnorm <= gtol) {
-        S.info = 4;
-        return;
+};
+
+__device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, int m) {
+    const double epsmch = 2.220446049250313e-16, factor = 100.0;
+    const double eps = sqrt(epsmch);
+    tb_jac_fast J;
+    J.a = S.par0;
+    J.b = S.par1;
+    {
+        double h = eps * fabs(S.par0);
+        if (h == 0.0) h = eps;
+        J.ap = S.par0 + h;
+        J.h0inv = 1.0 / h;
+        h = eps * fabs(S.par1);
+        if (h == 0.0) h = eps;
+        J.bp = S.par1 + h;
+        J.h1inv = 1.0 / h;
     }
-    S.diag0 = fmax(S.diag0, S.acn0);
-    S.diag1 = fmax(S.diag1, S.acn1);
+    S.nfev += 2;
+    double f0, a0, b0, f1, a1, b1;                      // rows 0 and 1: residual, d/da, d/db
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), f0, a0, b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), f1, a1, b1);
+    double g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
+    int nrows = 0;                                      // rows with a non-zero Jacobian row
+    TB_FOR_POINTS(W, m, i, {
+        double f, j0, j1;
+        J.eval(ex, ey, f, j0, j1);
+        g00 += j0 * j0;
+        g01 += j0 * j1;
+        g11 += j1 * j1;
+        gf0 += j0 * f;
+        gf1 += j1 * f;
+        nrows += (j0 != 0.0 || j1 != 0.0) ? 1 : 0;
+    })
+    S.acn0 = sqrt(g00);
+    S.acn1 = sqrt(g11);
+    const bool swap = S.acn1 > S.acn0;
+    S.ipvt0 = swap ? 1 : 0;
+    const double gPP = swap ? g11 : g00, gQQ = swap ? g00 : g11, gPf = swap ? gf1 : gf0, gQf = swap ? gf0 : gf1;
+    const double P0 = swap ? b0 : a0, Q0 = swap ? a0 : b0, P1 = swap ? b1 : a1, Q1 = swap ? a1 : b1;
+    double ajnorm = swap ? S.acn1 : S.acn0;
+    (void)gPP;
+    const bool have0 = ajnorm != 0.0;
+    double c11, rest2, dot2, w1;
+    if (have0) {
+        if (P0 < 0.0) ajnorm = -ajnorm;
+        const double ainv = 1.0 / ajnorm;
+        S.r01 = -g01 * ainv;
+        S.qtf0 = -gPf * ainv;
+        const double a00 = P0 * ainv + 1.0;
+        const double temp = (g01 * ainv + Q0) / a00;     // (v . Q) / v_0
+        const double c01 = P1 * ainv;
+        c11 = Q1 - temp * c01;
+        const double tq0 = -(gPf * ainv + f0) / a00;
+        w1 = f1 + c01 * tq0;
+        rest2 = gQQ - S.r01 * S.r01;
+        dot2 = gQf - S.r01 * S.qtf0;
+    } else {
+        S.r01 = Q0;
+        S.qtf0 = f0;
+        c11 = Q1;
+        w1 = f1;
+        rest2 = gQQ - Q0 * Q0;
+        dot2 = gQf - Q0 * f0;
+    }
+    S.r00 = -ajnorm;
+    double ajnorm1 = (rest2 > 0.0 && nrows >= 2) ? sqrt(rest2) : 0.0;
+    if (ajnorm1 != 0.0) {
+        if (c11 < 0.0) ajnorm1 = -ajnorm1;
+        S.qtf1 = -dot2 / ajnorm1;
+    } else {
+        S.qtf1 = w1;
+    }
+    S.r11 = -ajnorm1;
+    if (S.iter == 1) {
+        S.diag0 = S.acn0 == 0.0 ? 1.0 : S.acn0;
+        S.diag1 = S.acn1 == 0.0 ? 1.0 : S.acn1;
+        S.xnorm = tb_enorm2(S.diag0 * S.par0, S.diag1 * S.par1);
+        S.delta = factor * S.xnorm;
+        if (S.delta == 0.0) S.delta = factor;
+    }
+    tb_lmt_qr_tail(S, swap);
 }
 
 // one inner iteration of lmdif: lmpar step, trial residual, trust-region update, termination tests.
 // returns true when the step was accepted (the next round starts with tb_lmt_qr); S.info != 0 ends the fit.
+template <bool FAST>
 __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int m) {
     const double epsmch = 2.220446049250313e-16;
     const double ftol = 1.49012e-8, xtol = 1.49012e-8;
@@ -360,14 +471,24 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
     }
     double pnorm = tb_enorm2(wa3[0], wa3[1]);
     if (S.iter == 1) S.delta = fmin(S.delta, pnorm);
-    tb_enorm_acc n;
-    tb_enorm_init(n);
+    double fnorm1;
     {
         const double ta = wa2[0], tb_ = wa2[1];
-        TB_FOR_POINTS(W, m, i, { tb_enorm_add(n, tb_relu_res(ta, tb_, ex, ey), m); })
+        if (FAST) {
+            double ss = 0.0;
+            TB_FOR_POINTS(W, m, i, {
+                const double r = tb_relu_res(ta, tb_, ex, ey);
+                ss += r * r;
+            })
+            fnorm1 = sqrt(ss);
+        } else {
+            tb_enorm_acc n;
+            tb_enorm_init(n);
+            TB_FOR_POINTS(W, m, i, { tb_enorm_add(n, tb_relu_res(ta, tb_, ex, ey), m); })
+            fnorm1 = tb_enorm_result(n);
+        }
     }
     S.nfev++;
-    const double fnorm1 = tb_enorm_result(n);
     double actred = -1.0;
     if (p1 * fnorm1 < S.fnorm) {
         double t = fnorm1 / S.fnorm;
@@ -459,14 +580,16 @@ __device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref 
 }
 
 // complete fit of one window by one thread (test harness entry; the kernel interleaves the phases across lanes)
+template <bool FAST>
 __device__ __forceinline__ void tb_lm_fit_thread(const tb_win_ref W, int m, tb_lm_result &res) {
     tb_lmt S;
     double f0 = tb_lmt_fnorm0(W, m);
     tb_lmt_init(S, f0 < 0.0 ? 0.0 : f0);
     for (;;) {
-        tb_lmt_qr(S, W, m);
+        if (FAST) tb_lmt_qr_fast(S, W, m);
+        else tb_lmt_qr(S, W, m);
         if (S.info) break;
-        while (!tb_lmt_trial(S, W, m) && !S.info) {}
+        while (!tb_lmt_trial<FAST>(S, W, m) && !S.info) {}
         if (S.info) break;
     }
     double mode, pa, pb, pmax;

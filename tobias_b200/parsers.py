@@ -42,7 +42,7 @@ def add_underscore_options(parser):
 def _add_gpu_args(parser):
     g = parser.add_argument_group('B200 arguments (additions to the reference command line)')
     g.add_argument('--device', metavar="<int>", type=int, default=0, help="CUDA device of this process (default: 0, or LOCAL_RANK under torchrun)")
-    g.add_argument('--lm-exact', action="store_true", help="Accepted for compatibility: the window fits always sum in MINPACK's sequential order (bit-faithful to scipy's curve_fit on identical inputs)")
+    g.add_argument('--lm-exact', action="store_true", help="Window fits in MINPACK's own arithmetic (bit-faithful to scipy's curve_fit on identical inputs; ~3x slower fits). Default: on for --score_mat PWM (bit-identical tracks), off for DWM (one-pass outer iterations, same tolerance as the DWM bias input)")
     return parser
 
 
