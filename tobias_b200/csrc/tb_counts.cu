@@ -91,7 +91,7 @@ __global__ void tb_k2_scatter_kernel(tb_reads_view2 r, tb_k2_regions R, i64 read
 #define TB_K2_BATCH 2048         // sites per batch of a block (2 per thread); the k-mer list holds 2 per site
 #define TB_K2_PAIR_ITERS 16      // ceil(31 * 32 / 2 / 32): pair slots per lane for L <= 31
 
-// layout of the accumulators: DWM: acc[tbl][code = Sm*4+Sn][pair]   PWM: acc[tbl][S (0..4)][m]
+// layout of the accumulators: DWM: acc[tbl][code = Sm*4+Sn][pair, padded to a multiple of 32]   PWM: acc[tbl][S (0..4)][m]
 template <int IS_DWM>
 __global__ void __launch_bounds__(1024, 1)
     tb_k2_accumulate_kernel(tb_genome_view g, tb_k2_regions R, u32 *__restrict__ slab, const u64 *__restrict__ sites, i64 n_sites,
@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(1024, 1)
     TB_DYN_SMEM(smem);
     const int L = 2 * k_flank + 1;
     const int npairs = L * (L + 1) / 2;
-    const int n_acc = IS_DWM ? 4 * 16 * npairs : 4 * 5 * L;
+    const int pstride = (npairs + 31) & ~31;      // row stride = multiple of 32 words: lane l always hits bank l, whatever its code
+    const int n_acc = IS_DWM ? 4 * 16 * pstride : 4 * 5 * L;
     int *acc = (int *)smem;
     u64 *list = (u64 *)(smem + (((size_t)n_acc * 4 + 15) & ~(size_t)15));      // [2 * TB_K2_BATCH] k-mers
     uint8_t *meta = (uint8_t *)(list + 2 * TB_K2_BATCH);                       // tbl | w << 2, 0xff = no k-mer
@@ -182,13 +183,13 @@ __global__ void __launch_bounds__(1024, 1)
             if (mt == 0xff) continue;
             const u64 kmer = list[e];
             const int w = mt >> 2;
-            int *a = acc + (mt & 3) * 16 * npairs + lane;
+            int *a = acc + (mt & 3) * 16 * pstride + lane;
 #pragma unroll
             for (int it = 0; it < TB_K2_PAIR_ITERS; it++) {
                 const u32 sh = pair_sh[it];
                 if (sh != 0xffffffffu) {
                     int code = (int)(((kmer >> (sh & 255u)) & 3u) * 4 + ((kmer >> (sh >> 8)) & 3u));
-                    atomicAdd(a + code * npairs + 32 * it, w);
+                    atomicAdd(a + code * pstride + 32 * it, w);
                 }
             }
         }
@@ -229,7 +230,8 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     if (bg_shift < 0) return tb_fail(ctx, TB_ERR_ARG, "tb_bias_counts: bg_shift must be >= 0");
     const int L = 2 * k_flank + 1;
     const int npairs = L * (L + 1) / 2;
-    const size_t n_acc = is_dwm ? (size_t)4 * 16 * npairs : (size_t)4 * 5 * L;
+    const int pstride = (npairs + 31) & ~31;
+    const size_t n_acc = is_dwm ? (size_t)4 * 16 * pstride : (size_t)4 * 5 * L;
     const size_t n_out = is_dwm ? (size_t)4 * 25 * L * L : (size_t)4 * 5 * L;
     memset(counts_out, 0, n_out * sizeof(int64_t));
     memset(scalars_out, 0, 5 * sizeof(int64_t));
@@ -363,8 +365,8 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         for (int m = 0; m < L; m++)
             for (int n = m; n < L; n++) pair_of[m * L + n] = t++;
         auto T = [&](int tbl, int a, int b, int m, int n) -> int64_t {      // full symmetric forward-oriented tensor
-            if (m <= n) return (int64_t)h[((size_t)tbl * 16 + a * 4 + b) * npairs + pair_of[m * L + n]];
-            return (int64_t)h[((size_t)tbl * 16 + b * 4 + a) * npairs + pair_of[n * L + m]];
+            if (m <= n) return (int64_t)h[((size_t)tbl * 16 + a * 4 + b) * pstride + pair_of[m * L + n]];
+            return (int64_t)h[((size_t)tbl * 16 + b * 4 + a) * pstride + pair_of[n * L + m]];
         };
         for (int strand = 0; strand < 2; strand++)
             for (int which = 0; which < 2; which++) {
