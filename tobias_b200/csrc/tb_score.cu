@@ -171,29 +171,86 @@ static inline void tb_k3a2_groups(int L, int &np, int &lastbits) {
     }
 }
 
+// Tensor memory (TMEM, 256 KB per SM on sm_100) as a second home for table rows: it is read through its own datapath
+// (tcgen05.ld), so rows served from it cost no shared-memory wavefronts.  512 columns x 128 lanes x 32 bit: a warp reaches the
+// 32 lanes of its quarter (warp id mod 4), so the rows are replicated in the four quarters; lane l of a quarter holds its two
+// 16-byte chunks of a row in 8 consecutive columns -> 64 rows = the first TB_K3A2_TMEM_GROUPS = 4 dinucleotide groups.
+#define TB_K3A2_TMEM_GROUPS 4
+#ifndef TB_EMU
+__device__ __forceinline__ void tb_tmem_alloc512(u32 *smem_slot) {       // one warp; writes the base address to shared memory
+    const u32 a = (u32)__cvta_generic_to_shared(smem_slot);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(a) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tb_tmem_dealloc512(u32 taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tb_tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tb_tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tb_tmem_st8(u32 taddr, double2 a, double2 b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+                 "r"(__double2loint(a.x)), "r"(__double2hiint(a.x)), "r"(__double2loint(a.y)), "r"(__double2hiint(a.y)),
+                 "r"(__double2loint(b.x)), "r"(__double2hiint(b.x)), "r"(__double2loint(b.y)), "r"(__double2hiint(b.y))
+                 : "memory");
+}
+__device__ __forceinline__ void tb_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tb_tmem_ld8(u32 taddr, u32 (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+#endif
+
 __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     tb_score_dwm2_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ vt_fwd, const double *__restrict__ vt_rev,
-                         int L, int np, int lastbits, int strand_mask, double *__restrict__ part) {
+                         int L, int np, int lastbits, int ntm, int strand_mask, double *__restrict__ part) {
     TB_DYN_SMEM(smem);
     const unsigned FULL = 0xffffffffu;
     const int k_flank = L / 2;
-    const int rows = 16 * np + (1 << lastbits), row = 4 * L;  // doubles per row
+    const int rows = 16 * np + (1 << lastbits), row = 4 * L;  // doubles per row; the first 16 * ntm rows live in tensor memory
     const int nclass = strand_mask == 3 ? 4 : 2;
     const int cls = blockIdx.x % nclass;
     const int bpart = blockIdx.x / nclass, nparts = (gridDim.x - cls + nclass - 1) / nclass;
     const int strand = strand_mask == 3 ? (cls >> 1) : (strand_mask == 2 ? 1 : 0);
     const int model = cls & 1;
-    {
-        const double2 *src = (const double2 *)((strand ? vt_rev : vt_fwd) + (size_t)model * rows * row);
-        double2 *dst = (double2 *)smem;
-        for (int i = threadIdx.x; i < rows * row / 2; i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-    }
-    double *out = part + (size_t)(strand * 2 + model) * R.total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int nchunk = 2 * L;
     const bool hasB = 32 + lane < nchunk;
-    const double2 *V = (const double2 *)smem + lane;          // chunk c of row r at V[r * 2L + c - lane]
+    const double2 *src = (const double2 *)((strand ? vt_rev : vt_fwd) + (size_t)model * rows * row);
+#ifndef TB_EMU
+    __shared__ u32 tmem_slot;
+    u32 tq = 0;                                               // this warp's quarter of the tensor memory
+    if (ntm) {
+        if (warp == 0) tb_tmem_alloc512(&tmem_slot);
+        tb_tmem_fence_before();
+        __syncthreads();
+        tb_tmem_fence_after();
+        tq = tmem_slot + ((u32)(32 * (warp & 3)) << 16);
+        if (warp < 4) {                                       // warps 0..3 fill the four quarters
+            for (int r = 0; r < 16 * ntm; r++) {
+                const double2 a = src[(size_t)r * nchunk + lane];
+                const double2 b = hasB ? src[(size_t)r * nchunk + 32 + lane] : double2{1.0, 1.0};
+                tb_tmem_st8(tq + 8u * (u32)r, a, b);
+            }
+            tb_tmem_wait_st();
+        }
+        tb_tmem_fence_before();
+    }
+#else
+    ntm = 0;
+#endif
+    {
+        const double2 *s2 = src + (size_t)16 * ntm * nchunk;
+        double2 *dst = (double2 *)smem;
+        for (int i = threadIdx.x; i < (rows - 16 * ntm) * row / 2; i += blockDim.x) dst[i] = s2[i];
+        __syncthreads();
+    }
+#ifndef TB_EMU
+    if (ntm) tb_tmem_fence_after();
+#endif
+    double *out = part + (size_t)(strand * 2 + model) * R.total;
+    const double2 *V = (const double2 *)smem + lane - (size_t)16 * ntm * nchunk;   // chunk c of row r >= 16 ntm at V[r * 2L + c - lane]
     const int half = lane & 1;
     const int ncol = half ? 16 + (lane >> 1) : (lane >> 1);   // column this lane completes in the epilogue
     const bool colok = ncol < L;
@@ -236,7 +293,25 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                 kmer[w] = (u64)__shfl_sync(FULL, klo, it + w) | ((u64)__shfl_sync(FULL, khi, it + w) << 32);
                 a0[w] = a1[w] = b0[w] = b1[w] = 1.0;
             }
-            for (int p = 0; p < np; p++) {
+#ifndef TB_EMU
+            for (int p = 0; p < ntm; p++) {                    // rows served by tensor memory
+                u32 t[TB_K3A2_WPI][8];
+#pragma unroll
+                for (int w = 0; w < TB_K3A2_WPI; w++) {
+                    const u32 d = (u32)(kmer[w] >> (4 * p)) & 15u;
+                    tb_tmem_ld8(tq + 8u * (16u * (u32)p + d), t[w]);
+                }
+                tb_tmem_wait_ld();
+#pragma unroll
+                for (int w = 0; w < TB_K3A2_WPI; w++) {
+                    a0[w] *= __hiloint2double((int)t[w][1], (int)t[w][0]);
+                    a1[w] *= __hiloint2double((int)t[w][3], (int)t[w][2]);
+                    b0[w] *= __hiloint2double((int)t[w][5], (int)t[w][4]);
+                    b1[w] *= __hiloint2double((int)t[w][7], (int)t[w][6]);
+                }
+            }
+#endif
+            for (int p = ntm; p < np; p++) {
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
                     const int d = (int)((u32)(kmer[w] >> (4 * p)) & 15u);
@@ -322,6 +397,13 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
         if (pos0 + lane < R.total)
             out[pos0 + lane] = okl ? (log2(my_sel) - log2(my_z)) + (double)my_de : (double)NAN;
     }
+#ifndef TB_EMU
+    if (ntm) {
+        tb_tmem_fence_before();
+        __syncthreads();
+        if (warp == 0) tb_tmem_dealloc512(tmem_slot);
+    }
+#endif
 }
 
 // score = partial(bias model) - partial(background model); NaN partials mark windows without a score
@@ -464,6 +546,7 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
         const int nclass = strand_mask == 3 ? 4 : 2;
         TB_TRY(tb_reserve(ctx, ctx->scratch4, (size_t)4 * total * sizeof(double)));
         auto k = tb_score_dwm2_kernel;
+        const int ntm = (!ctx->k3a_no_tmem && k3a_np >= TB_K3A2_TMEM_GROUPS && L <= 32) ? TB_K3A2_TMEM_GROUPS : 0;
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         i64 n_units = (total + 31) >> 5;
         i64 want = tb_div_up(n_units, TB_K3A2_THREADS / 32) * nclass;
@@ -473,7 +556,7 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
         const double *vf = ctx->model[0].vtable.as<double>(), *vr = ctx->model[1].vtable.as<double>();
         if (!vf) vf = vr;
         if (!vr) vr = vf;
-        TB_LAUNCH(ctx, k, grid, TB_K3A2_THREADS, smem2, g, R, vf, vr, L, k3a_np, k3a_lastbits, strand_mask, ctx->scratch4.as<double>());
+        TB_LAUNCH(ctx, k, grid, TB_K3A2_THREADS, smem2, g, R, vf, vr, L, k3a_np, k3a_lastbits, ntm, strand_mask, ctx->scratch4.as<double>());
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_score_dwm2_kernel"));
         i64 wantc = tb_div_up(total, 256), capc = (i64)ctx->sm_count * 8;
         TB_LAUNCH(ctx, tb_score_combine_kernel, (unsigned)(wantc < capc ? wantc : capc), 256, 0,
