@@ -159,23 +159,44 @@ __device__ __forceinline__ void tb_split_exp(double v, double &mant, int &ex) { 
     mant = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(v));
 }
 
-// number of pair groups and the width (2 or 6 bits) of the last group for model length L
-static inline void tb_k3a2_groups(int L, int &np, int &lastbits) {
-    size_t rows3 = (size_t)16 * ((L - 3) / 2) + 64;
-    if (L >= 3 && rows3 * 4 * L * sizeof(double) <= (size_t)227 * 1024) {
-        np = (L - 3) / 2;
-        lastbits = 6;
-    } else {
-        np = L / 2;
-        lastbits = 2;
+#define TB_K3A2_TMEM_GROUPS 4
+// Row groups of the product-form table for model length L: np dinucleotide groups (offsets 2p, 2p+1; 16 rows each), then nt3
+// trinucleotide groups (64 rows each), then ns (0 / 1) single offsets (4 rows).  The first TB_K3A2_TMEM_GROUPS pair groups may
+// live in tensor memory; the rest must fit the shared memory of one SM.  Fewest shared-memory groups wins (= fewest row reads).
+static inline void tb_k3a2_groups(int L, bool use_tmem, int &np, int &nt3, int &ns, int &ntm) {
+    const int budget = (int)(((size_t)227 * 1024) / ((size_t)32 * L));
+    int best = 1 << 30;
+    np = L / 2; nt3 = 0; ns = L & 1; ntm = 0;
+    for (int t3 = L / 3; t3 >= 0; t3--) {
+        const int rem = L - 3 * t3, p = rem / 2, s1 = rem & 1;
+        const int tm = (use_tmem && p >= TB_K3A2_TMEM_GROUPS) ? TB_K3A2_TMEM_GROUPS : 0;
+        const int rows_smem = 16 * (p - tm) + 64 * t3 + 4 * s1;
+        const int groups = (p - tm) + t3 + s1;
+        if (rows_smem <= budget && groups < best) {
+            best = groups;
+            np = p; nt3 = t3; ns = s1; ntm = tm;
+        }
     }
+}
+static inline bool tb_k3a2_use_tmem(const tb_ctx *ctx) {
+#ifdef TB_EMU
+    (void)ctx;
+    return false;
+#else
+    return !ctx->k3a_no_tmem;
+#endif
+}
+static inline bool tb_k3a2_fits(int L, bool use_tmem) {
+    int np, nt3, ns, ntm;
+    tb_k3a2_groups(L, use_tmem, np, nt3, ns, ntm);
+    return (size_t)(16 * (np - ntm) + 64 * nt3 + 4 * ns) * 32 * L <= (size_t)227 * 1024;
 }
 
 // Tensor memory (TMEM, 256 KB per SM on sm_100) as a second home for table rows: it is read through its own datapath
 // (tcgen05.ld), so rows served from it cost no shared-memory wavefronts.  512 columns x 128 lanes x 32 bit: a warp reaches the
 // 32 lanes of its quarter (warp id mod 4), so the rows are replicated in the four quarters; lane l of a quarter holds its two
 // 16-byte chunks of a row in 8 consecutive columns -> 64 rows = the first TB_K3A2_TMEM_GROUPS = 4 dinucleotide groups.
-#define TB_K3A2_TMEM_GROUPS 4
+// Measured (chr50mb): 27.1 -> 22.3 ms with the same shared-memory grouping; the freed shared memory then takes larger groups.
 #ifndef TB_EMU
 __device__ __forceinline__ void tb_tmem_alloc512(u32 *smem_slot) {       // one warp; writes the base address to shared memory
     const u32 a = (u32)__cvta_generic_to_shared(smem_slot);
@@ -204,11 +225,11 @@ __device__ __forceinline__ void tb_tmem_wait_ld() { asm volatile("tcgen05.wait::
 
 __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     tb_score_dwm2_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ vt_fwd, const double *__restrict__ vt_rev,
-                         int L, int np, int lastbits, int ntm, int strand_mask, double *__restrict__ part) {
+                         int L, int np, int nt3, int ns, int ntm, int strand_mask, double *__restrict__ part) {
     TB_DYN_SMEM(smem);
     const unsigned FULL = 0xffffffffu;
     const int k_flank = L / 2;
-    const int rows = 16 * np + (1 << lastbits), row = 4 * L;  // doubles per row; the first 16 * ntm rows live in tensor memory
+    const int rows = 16 * np + 64 * nt3 + 4 * ns, row = 4 * L;   // doubles per row; the first 16 * ntm rows live in tensor memory
     const int nclass = strand_mask == 3 ? 4 : 2;
     const int cls = blockIdx.x % nclass;
     const int bpart = blockIdx.x / nclass, nparts = (gridDim.x - cls + nclass - 1) / nclass;
@@ -254,9 +275,7 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     const int half = lane & 1;
     const int ncol = half ? 16 + (lane >> 1) : (lane >> 1);   // column this lane completes in the epilogue
     const bool colok = ncol < L;
-    const int lastsh = 4 * np;
-    const u32 lastmask = (1u << lastbits) - 1u;
-    const double2 *Vlast = V + (size_t)(16 * np) * nchunk;
+    const int n_tail = nt3 + ns;                              // groups after the pairs: trinucleotides, then the single offset
     const i64 n_units = (R.total + 31) >> 5;
 
     for (i64 unit = (i64)bpart * wpb + warp; unit < n_units; unit += (i64)nparts * wpb) {
@@ -326,17 +345,22 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                     }
                 }
             }
+            for (int t = 0; t < n_tail; t++) {
+                const int sh = 4 * np + 6 * (t < nt3 ? t : nt3);
+                const u32 mask = t < nt3 ? 63u : 3u;
+                const double2 *Vt = V + (size_t)(16 * np + 64 * (t < nt3 ? t : nt3)) * nchunk;
 #pragma unroll
-            for (int w = 0; w < TB_K3A2_WPI; w++) {
-                const int d = (int)((u32)(kmer[w] >> lastsh) & lastmask);
-                const double2 *r = Vlast + d * nchunk;
-                double2 va = r[0];
-                a0[w] *= va.x;
-                a1[w] *= va.y;
-                if (hasB) {
-                    double2 vb = r[32];
-                    b0[w] *= vb.x;
-                    b1[w] *= vb.y;
+                for (int w = 0; w < TB_K3A2_WPI; w++) {
+                    const int d = (int)((u32)(kmer[w] >> sh) & mask);
+                    const double2 *r = Vt + d * nchunk;
+                    double2 va = r[0];
+                    a0[w] *= va.x;
+                    a1[w] *= va.y;
+                    if (hasB) {
+                        double2 vb = r[32];
+                        b0[w] *= vb.x;
+                        b1[w] *= vb.y;
+                    }
                 }
             }
             // ---- column totals.  Lane l holds half (l & 1) of columns l >> 1 (a) and 16 + (l >> 1) (b); the even lane of a pair
@@ -490,12 +514,12 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                     }
     TB_TRY(tb_h2d(ctx, M.table, U.data(), U.size() * sizeof(double)));
     // product-form table (tb_score_dwm2_kernel): V[x][row][n][a] = 2^(sum of the U rows of the group); pair group p: row 16 p + d,
-    // offsets 2p (d & 3) and 2p + 1 (d >> 2); last group: the remaining 3 offsets (64 rows) or the last offset (4 rows);
+    // offsets 2p (d & 3) and 2p + 1 (d >> 2); then the trinucleotide groups (64 rows each), then a single offset (4 rows);
     // same forward-oriented indexing as U
     {
-        int np, lastbits;
-        tb_k3a2_groups(L, np, lastbits);
-        const int rows = 16 * np + (1 << lastbits);
+        int np, nt3, ns, ntm;
+        tb_k3a2_groups(L, tb_k3a2_use_tmem(ctx), np, nt3, ns, ntm);
+        const int rows = 16 * np + 64 * nt3 + 4 * ns;
         auto u = [&](int x, int m, int s_, int n, int a) {
             return U[(((((size_t)x * L + m) * 4 + s_) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)];
         };
@@ -508,10 +532,11 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                         if (r < 16 * np) {
                             int p = r >> 4, d = r & 15;
                             t = u(x, 2 * p, d & 3, n, a) + u(x, 2 * p + 1, d >> 2, n, a);
+                        } else if (r < 16 * np + 64 * nt3) {
+                            int q = (r - 16 * np) >> 6, d = (r - 16 * np) & 63, m0 = 2 * np + 3 * q;
+                            t = (u(x, m0, d & 3, n, a) + u(x, m0 + 1, (d >> 2) & 3, n, a)) + u(x, m0 + 2, d >> 4, n, a);
                         } else {
-                            int d = r - 16 * np, m0 = 2 * np;
-                            t = u(x, m0, d & 3, n, a);
-                            if (lastbits == 6) t = (t + u(x, m0 + 1, (d >> 2) & 3, n, a)) + u(x, m0 + 2, d >> 4, n, a);
+                            t = u(x, L - 1, r - 16 * np - 64 * nt3, n, a);
                         }
                         Vt[(((size_t)x * rows + r) * L + n) * 4 + a] = exp2(t);
                     }
@@ -538,15 +563,14 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
     if (!tf) tf = tr;
     if (!tr) tr = tf;
     int L = M0.L;
-    int k3a_np, k3a_lastbits;
-    tb_k3a2_groups(L, k3a_np, k3a_lastbits);
-    const size_t smem2 = (size_t)(16 * k3a_np + (1 << k3a_lastbits)) * 4 * L * sizeof(double);
-    if (M0.is_dwm && smem2 <= (size_t)227 * 1024 && !ctx->force_sum_form) {
+    int k3a_np, k3a_nt3, k3a_ns, k3a_ntm;
+    tb_k3a2_groups(L, tb_k3a2_use_tmem(ctx), k3a_np, k3a_nt3, k3a_ns, k3a_ntm);
+    const size_t smem2 = (size_t)(16 * (k3a_np - k3a_ntm) + 64 * k3a_nt3 + 4 * k3a_ns) * 4 * L * sizeof(double);
+    if (M0.is_dwm && tb_k3a2_fits(L, tb_k3a2_use_tmem(ctx)) && !ctx->force_sum_form) {
         // product form: one (strand, model) table per block, partial scores, then bias - background
         const int nclass = strand_mask == 3 ? 4 : 2;
         TB_TRY(tb_reserve(ctx, ctx->scratch4, (size_t)4 * total * sizeof(double)));
         auto k = tb_score_dwm2_kernel;
-        const int ntm = (!ctx->k3a_no_tmem && k3a_np >= TB_K3A2_TMEM_GROUPS && L <= 32) ? TB_K3A2_TMEM_GROUPS : 0;
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         i64 n_units = (total + 31) >> 5;
         i64 want = tb_div_up(n_units, TB_K3A2_THREADS / 32) * nclass;
@@ -556,7 +580,7 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
         const double *vf = ctx->model[0].vtable.as<double>(), *vr = ctx->model[1].vtable.as<double>();
         if (!vf) vf = vr;
         if (!vr) vr = vf;
-        TB_LAUNCH(ctx, k, grid, TB_K3A2_THREADS, smem2, g, R, vf, vr, L, k3a_np, k3a_lastbits, ntm, strand_mask, ctx->scratch4.as<double>());
+        TB_LAUNCH(ctx, k, grid, TB_K3A2_THREADS, smem2, g, R, vf, vr, L, k3a_np, k3a_nt3, k3a_ns, k3a_ntm, strand_mask, ctx->scratch4.as<double>());
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_score_dwm2_kernel"));
         i64 wantc = tb_div_up(total, 256), capc = (i64)ctx->sm_count * 8;
         TB_LAUNCH(ctx, tb_score_combine_kernel, (unsigned)(wantc < capc ? wantc : capc), 256, 0,
