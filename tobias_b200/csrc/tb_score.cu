@@ -223,11 +223,16 @@ __device__ __forceinline__ void tb_tmem_ld8(u32 taddr, u32 (&v)[8]) {
 __device__ __forceinline__ void tb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 #endif
 
+// FIXED: the grouping of the default model length (L = 25: 8 pair groups, 4 of them in tensor memory, 3 trinucleotide groups)
+// as compile-time constants, so the row loops unroll and the row offsets fold into the load instructions.
+template <bool FIXED>
 __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     tb_score_dwm2_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ vt_fwd, const double *__restrict__ vt_rev,
-                         int L, int np, int nt3, int ns, int ntm, int strand_mask, double *__restrict__ part) {
+                         int L_, int np_, int nt3_, int ns_, int ntm_, int strand_mask, double *__restrict__ part) {
     TB_DYN_SMEM(smem);
     const unsigned FULL = 0xffffffffu;
+    const int L = FIXED ? 25 : L_, np = FIXED ? 8 : np_, nt3 = FIXED ? 3 : nt3_, ns = FIXED ? 0 : ns_;
+    int ntm = FIXED ? 4 : ntm_;
     const int k_flank = L / 2;
     const int rows = 16 * np + 64 * nt3 + 4 * ns, row = 4 * L;   // doubles per row; the first 16 * ntm rows live in tensor memory
     const int nclass = strand_mask == 3 ? 4 : 2;
@@ -313,7 +318,8 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                 a0[w] = a1[w] = b0[w] = b1[w] = 1.0;
             }
 #ifndef TB_EMU
-            for (int p = 0; p < ntm; p++) {                    // rows served by tensor memory
+#pragma unroll
+            for (int p = 0; p < (FIXED ? 4 : ntm); p++) {      // rows served by tensor memory
                 u32 t[TB_K3A2_WPI][8];
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
@@ -330,7 +336,8 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                 }
             }
 #endif
-            for (int p = ntm; p < np; p++) {
+#pragma unroll
+            for (int p = (FIXED ? 4 : ntm); p < (FIXED ? 8 : np); p++) {
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
                     const int d = (int)((u32)(kmer[w] >> (4 * p)) & 15u);
@@ -345,7 +352,8 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                     }
                 }
             }
-            for (int t = 0; t < n_tail; t++) {
+#pragma unroll
+            for (int t = 0; t < (FIXED ? 3 : n_tail); t++) {
                 const int sh = 4 * np + 6 * (t < nt3 ? t : nt3);
                 const u32 mask = t < nt3 ? 63u : 3u;
                 const double2 *Vt = V + (size_t)(16 * np + 64 * (t < nt3 ? t : nt3)) * nchunk;
@@ -570,7 +578,8 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
         // product form: one (strand, model) table per block, partial scores, then bias - background
         const int nclass = strand_mask == 3 ? 4 : 2;
         TB_TRY(tb_reserve(ctx, ctx->scratch4, (size_t)4 * total * sizeof(double)));
-        auto k = tb_score_dwm2_kernel;
+        const bool fixed = L == 25 && k3a_np == 8 && k3a_nt3 == 3 && k3a_ns == 0 && k3a_ntm == 4;
+        auto k = fixed ? tb_score_dwm2_kernel<true> : tb_score_dwm2_kernel<false>;
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         i64 n_units = (total + 31) >> 5;
         i64 want = tb_div_up(n_units, TB_K3A2_THREADS / 32) * nclass;
