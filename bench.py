@@ -144,7 +144,7 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
     """One pass of the hot path over this rank's shard.  Returns (AtacBias, stage_ms list)."""
     from tobias_b200.pipeline import AtacBias, STRANDS
     ctx = eng.ctx
-    trace = os.environ.get("TB_BENCH_TRACE") and not resident      # diagnostic: host wall clock per phase of an e2e step (stderr)
+    trace = os.environ.get("TB_BENCH_TRACE") and (not resident or os.environ.get("TB_BENCH_TRACE") == "2")   # diagnostic: host wall clock per phase (stderr)
     marks = [("start", time.perf_counter())]
 
     def mark(name):
@@ -162,8 +162,10 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
     # --- normalisation counters + bias-training counts, then the one exchange step of the path
     reads_peaks = ctx.count_reads(*arrays["peak_regions"], READ_SHIFT)
     reads_nonpeaks = ctx.count_reads(*arrays["nonpeak_regions"], READ_SHIFT)
+    mark("count_reads")
     counts, scalars = ctx.bias_counts(*arrays["input_regions"], K_FLANK, BG_SHIFT, READ_SHIFT, 10, True)
     k2_ms = ctx.last_kernel_ms()
+    mark("bias_counts")
     packed = np.concatenate([counts.ravel(), scalars, np.array([reads_peaks, reads_nonpeaks], dtype=np.int64)])
     allreduce_np(packed, device)
     counts = packed[:counts.size].reshape(counts.shape)
@@ -178,6 +180,7 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
         m.prepare_mat()                   # host numpy, identical on every rank
     bias.no_reads = int(scalars[0])
     bias.correction_factor = (10000000 / reads_total) * (reads_total / reads_peaks)      # atacorrect.py:298-300
+    mark("prepare_mat")
     eng.set_bias(bias)
     mark("counts+model")
     # --- correction + footprints of this rank's output regions
@@ -199,7 +202,7 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
         ctx.score_download(out=out["footprint"])
         mark("footprint_d2h")
     if trace:
-        sys.stderr.write("e2e trace (ms): " + ", ".join("%s %.1f" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])) + "\n")
+        sys.stderr.write(("e2e" if not resident else "resident") + " trace (ms): " + ", ".join("%s %.1f" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])) + "\n")
     return bias, {"K1_pileup": stage[0], "K3a_score": stage[1], "K3b_fit": stage[2], "K3c_correct": stage[3],
                   "K2_counts": k2_ms, "K4_footprint": k4_ms}
 
