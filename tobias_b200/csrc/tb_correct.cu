@@ -263,7 +263,10 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
 // centred rolling sum with the reference's accumulator: valsum is a C float, every += is a double add rounded to float
 __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w) {
     float acc = 0.0f;
-    for (int t = 0; t < w; t++) acc = (float)((double)acc + v[first + t]);
+    for (int t = 0; t < w; t++) {
+        const double x = v[first + t];
+        if (x != 0.0) acc = (float)((double)acc + x);          // adding 0.0 never changes the accumulator: skip its two conversions
+    }
     return (double)acc;
 }
 
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                     for (int t = 0; t < w; t++) {
                         double cv = cor[first + t];
                         aa = (float)((double)aa + fabs(cv));
-                        ap = (float)((double)ap + (cv < 0.0 ? 0.0 : cv));
+                        if (!(cv <= 0.0)) ap = (float)((double)ap + cv);    // the non-positive half adds 0.0: no change, no conversions
                     }
                     {   // uncorrected: only non-zero signal positions move the accumulator
                         const int fd = q - lf - d0;
