@@ -409,7 +409,7 @@ def cpu_reference(args, steps, warmup):
     params = types.SimpleNamespace(bam=npz, genome=fa, k_flank=K_FLANK, bg_shift=BG_SHIFT, read_shift=list(READ_SHIFT), score_mat="DWM",
                                    verbosity=0, log_q=None, window=WINDOW, split_strands=False, qs={}, bias_obj=None)
     out_all = [tuple(r[:3]) for r in regs["output_regions"]]
-    n_out = min(len(out_all), max(cores * 24, 48))
+    n_out = min(len(out_all), max(cores * 96, 192))          # ~10 s of correction + footprints on the box's cores per step
     rng = np.random.default_rng(1)
     out_sample = [out_all[i] for i in sorted(rng.choice(len(out_all), n_out, replace=False))]
     inp = [tuple(r[:3]) for r in regs["input_regions"]]
