@@ -357,6 +357,7 @@ __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) 
 // non-zero Jacobian row) yields r11 = 0 exactly, as in MINPACK.
 struct tb_jac_fast {
     double a, b, ap, bp, h0inv, h1inv;
+    // residuals exactly as in the exact form (unfused, as numpy evaluates the model)
     __device__ __forceinline__ void eval(double x, double y, double &f, double &j0, double &j1) const {
         const double t = __dmul_rn(a, x);
         f = tb_relu(__dadd_rn(t, b)) - y;
@@ -388,7 +389,6 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
     J.eval(W.x[0], tb_u32_to_double(W.y[0]), f0, a0, b0);
     J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), f1, a1, b1);
     double g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
-    int nrows = 0;                                      // rows with a non-zero Jacobian row
     TB_FOR_POINTS(W, m, i, {
         double f, j0, j1;
         J.eval(ex, ey, f, j0, j1);
@@ -397,7 +397,6 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
         g11 += j1 * j1;
         gf0 += j0 * f;
         gf1 += j1 * f;
-        nrows += (j0 != 0.0 || j1 != 0.0) ? 1 : 0;
     })
     S.acn0 = sqrt(g00);
     S.acn1 = sqrt(g11);
@@ -431,7 +430,18 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
         dot2 = gQf - Q0 * f0;
     }
     S.r00 = -ajnorm;
-    double ajnorm1 = (rest2 > 0.0 && nrows >= 2) ? sqrt(rest2) : 0.0;
+    // structural rank deficiency (fewer than two rows with a non-zero Jacobian row) must give r11 = 0 exactly, as in MINPACK, where
+    // the inner products leave rounding noise: count the rows, but only when the columns look (nearly) dependent
+    if (rest2 > 0.0 && !(rest2 > 1e-12 * gQQ)) {
+        int nrows = 0;
+        TB_FOR_POINTS(W, m, i, {
+            double f, j0, j1;
+            J.eval(ex, ey, f, j0, j1);
+            nrows += (j0 != 0.0 || j1 != 0.0) ? 1 : 0;
+        })
+        if (nrows < 2) rest2 = 0.0;
+    }
+    double ajnorm1 = rest2 > 0.0 ? sqrt(rest2) : 0.0;
     if (ajnorm1 != 0.0) {
         if (c11 < 0.0) ajnorm1 = -ajnorm1;
         S.qtf1 = -dot2 / ajnorm1;
