@@ -259,6 +259,41 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
     }
 }
 
+// Tail of the rounds: once few windows are left a round costs the latency of one thread's iteration plus a launch and a host
+// read-back, whatever the count.  The remaining windows are then finished in ONE launch, every thread iterating its window to the end
+// (lanes diverge, but the GPU is almost idle at that point anyway).
+template <bool FAST>
+__global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
+    tb_fitg_finish_kernel(tb_fitg_view G, int m, const u32 *__restrict__ listq, i64 nq, const u32 *__restrict__ listt, i64 nt,
+                          double *__restrict__ fit) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < nq + nt; k += stride) {
+        const u32 slot = k < nq ? listq[k] : listt[k - nq];
+        bool need_qr = k < nq;
+        tb_lmt S;
+        tb_fitg_load(G, slot, S);
+        const i64 q = G.wq[slot];
+        const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
+        for (;;) {
+            if (need_qr) {
+                if (FAST) tb_lmt_qr_fast(S, W, m);
+                else tb_lmt_qr(S, W, m);
+            }
+            if (S.info == 0) need_qr = tb_lmt_trial<FAST>(S, W, m);
+            if (S.info != 0) break;
+        }
+        double mode, pa, pb, pmax;
+        tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
+        double *rec = fit + (i64)slot * TB_FIT_REC;
+        rec[0] = mode;
+        rec[1] = pa;
+        rec[2] = pb;
+        rec[3] = pmax;
+        rec[4] = (double)S.info;
+        rec[5] = (double)S.nfev;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K3c
 // centred rolling sum with the reference's accumulator: valsum is a C float, every += is a double add rounded to float
 __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w) {
@@ -626,10 +661,18 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_TRY(tb_d2h(ctx, hc, ctr, sizeof(hc)));
         i64 nq = (i64)hc[0], nt = 0;
         int cur = 0;
+        const i64 tail_at = (i64)ctx->sm_count * 128;      // one block per SM's worth of windows: finish them in one launch
         for (int round = 0; nq + nt > 0; round++) {
             if (round > 700) return tb_fail(ctx, TB_ERR_STATE, "tb_correct_run: window fits did not terminate");
-            TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
             const i64 capg = (i64)ctx->sm_count * TB_FITG_MINBLOCKS;
+            if (nq + nt <= tail_at) {
+                i64 want = tb_div_up(nq + nt, 128);
+                auto kf = lm_exact_order ? tb_fitg_finish_kernel<false> : tb_fitg_finish_kernel<true>;
+                TB_LAUNCH(ctx, kf, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lq[cur], nq, (const u32 *)lt[cur], nt,
+                          C.fit.as<double>());
+                break;
+            }
+            TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
             if (nq > 0) {
                 i64 want = tb_div_up(nq, 128);
                 auto kq = lm_exact_order ? tb_fitg_round_kernel<true, false> : tb_fitg_round_kernel<true, true>;
