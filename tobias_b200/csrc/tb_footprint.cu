@@ -13,7 +13,9 @@
 // The reference sums sequentially in fp32; prefix differences rounded to fp32 agree with it to a few ulp (tests: rtol 1e-5).
 #include "tb_common.cuh"
 
+#include <algorithm>
 #include <cfloat>
+#include <utility>
 
 struct tb_sc_view {
     const i64 *ext_off;      // n+1 offsets of the (flank-extended) regions in the concatenated signal
@@ -468,12 +470,19 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
         // footprint scan: block size = tile size, picked to waste the fewest thread slots on these region lengths
         int bs = TB_K4_THREADS;
         if (!fos) {
+            // (most output regions have the same length: the search runs over runs of equal lengths)
+            std::vector<std::pair<i64, i64>> hist;           // (length, count)
+            for (i64 i = 0; i < S.n_regions; i++) {
+                const i64 v = S.ext_off[i + 1] - S.ext_off[i];
+                if (!hist.empty() && hist.back().first == v) hist.back().second++;
+                else hist.push_back({v, 1});
+            }
             double best_cost = -1.0;
             for (int cand = 128; cand <= TB_K4_THREADS; cand += 32) {
                 const i64 per = cand - (p->fp_max - 1);
                 if (per < 32) continue;
                 double cost = 0.0;
-                for (i64 i = 0; i < S.n_regions; i++) cost += (double)tb_div_up(S.ext_off[i + 1] - S.ext_off[i], per);
+                for (const auto &h : hist) cost += (double)tb_div_up(h.first, per) * (double)h.second;
                 cost *= (double)(cand + 2 * p->flank_max + p->fp_max);         // slots incl. the halo every tile re-scans
                 if (best_cost < 0.0 || cost < best_cost) {
                     best_cost = cost;
