@@ -143,7 +143,8 @@ extern "C" int tb_init(int device, tb_ctx **out) {
         return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
     }
     { const char *e2 = getenv("TB_K3A_SUM_FORM"); ctx->force_sum_form = (e2 && e2[0] == '1') ? 1 : 0;
-      const char *e3 = getenv("TB_K3A_NO_TMEM"); ctx->k3a_no_tmem = (e3 && e3[0] == '1') ? 1 : 0; }   // comparison runs only
+      const char *e3 = getenv("TB_K3A_NO_TMEM"); ctx->k3a_no_tmem = (e3 && e3[0] == '1') ? 1 : 0;
+      const char *e4 = getenv("TB_K3A_TMEM_GROUPS"); ctx->k3a_tmem_groups = e4 ? atoi(e4) : 0; }   // comparison runs only
     *out = ctx;
     return TB_OK;
 }

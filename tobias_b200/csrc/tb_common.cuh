@@ -123,6 +123,7 @@ struct tb_ctx {
         bool have_signal = false, have_out = false;
     } sc;
 
+    int k3a_tmem_groups = 0;    // K3a: pair groups kept in tensor memory (0 = default 5; TB_K3A_TMEM_GROUPS=1..5, comparison runs)
     int k3a_no_tmem = 0;        // K3a: 1 = all table rows from shared memory (comparison runs; TB_K3A_NO_TMEM=1)
     int force_sum_form = 0;     // K3a: 1 = first-generation sum-form kernel (comparison runs; TB_K3A_SUM_FORM=1)
     void *nccl_comm = nullptr;

@@ -160,17 +160,25 @@ __device__ __forceinline__ void tb_split_exp(double v, double &mant, int &ex) { 
     mant = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(v));
 }
 
-#define TB_K3A2_TMEM_GROUPS 4
+// ---- ratio form of the rows -----------------------------------------------------------------------------------------
+// The score of a column, 2^E[n][S_n] / sum_a 2^E[n][a], does not change when the four entries (a = 0..3) of a table row and
+// column are scaled together, so every (row, n) quadruple is stored divided by its a = 0 entry: three ratios per column, the
+// fourth is 1.  A row is L x 3 doubles (600 B for L = 25, 25 % less shared-memory traffic and one product less per column), and
+// with lane n owning column n the normaliser Z[n] = 1 + r1 + r2 + r3 and the selected term need no cross-lane work at all.
+// Row layout: (r1, r2) pairs of the L columns, then the L values r3, padded to a multiple of 16 bytes.
+#define TB_K3A2_TMEM_MAX 5                                    // pair groups in tensor memory: 6 columns per row, 16 rows per group
+__host__ __device__ static inline int tb_k3a2_rowstride(int L) { return (3 * L + 1) & ~1; }   // doubles
+
 // Row groups of the product-form table for model length L: np dinucleotide groups (offsets 2p, 2p+1; 16 rows each), then nt3
-// trinucleotide groups (64 rows each), then ns (0 / 1) single offsets (4 rows).  The first TB_K3A2_TMEM_GROUPS pair groups may
-// live in tensor memory; the rest must fit the shared memory of one SM.  Fewest shared-memory groups wins (= fewest row reads).
-static inline void tb_k3a2_groups(int L, bool use_tmem, int &np, int &nt3, int &ns, int &ntm) {
-    const int budget = (int)(((size_t)227 * 1024) / ((size_t)32 * L));
+// trinucleotide groups (64 rows each), then ns (0 / 1) single offsets (4 rows).  The first ntm pair groups live in tensor
+// memory; the rest must fit the shared memory of one SM.  Fewest shared-memory groups wins (= fewest shared-memory row reads).
+static inline void tb_k3a2_groups(int L, int tmem_groups, int &np, int &nt3, int &ns, int &ntm) {
+    const int budget = (int)(((size_t)227 * 1024) / ((size_t)tb_k3a2_rowstride(L) * sizeof(double)));
     int best = 1 << 30;
     np = L / 2; nt3 = 0; ns = L & 1; ntm = 0;
     for (int t3 = L / 3; t3 >= 0; t3--) {
         const int rem = L - 3 * t3, p = rem / 2, s1 = rem & 1;
-        const int tm = (use_tmem && p >= TB_K3A2_TMEM_GROUPS) ? TB_K3A2_TMEM_GROUPS : 0;
+        const int tm = p < tmem_groups ? p : tmem_groups;
         const int rows_smem = 16 * (p - tm) + 64 * t3 + 4 * s1;
         const int groups = (p - tm) + t3 + s1;
         if (rows_smem <= budget && groups < best) {
@@ -179,25 +187,24 @@ static inline void tb_k3a2_groups(int L, bool use_tmem, int &np, int &nt3, int &
         }
     }
 }
-static inline bool tb_k3a2_use_tmem(const tb_ctx *ctx) {
+static inline int tb_k3a2_tmem_groups(const tb_ctx *ctx) {
 #ifdef TB_EMU
     (void)ctx;
-    return false;
+    return 0;
 #else
-    return !ctx->k3a_no_tmem;
+    return ctx->k3a_no_tmem ? 0 : (ctx->k3a_tmem_groups > 0 && ctx->k3a_tmem_groups <= TB_K3A2_TMEM_MAX ? ctx->k3a_tmem_groups : TB_K3A2_TMEM_MAX);
 #endif
 }
-static inline bool tb_k3a2_fits(int L, bool use_tmem) {
+static inline bool tb_k3a2_fits(int L, int tmem_groups) {
     int np, nt3, ns, ntm;
-    tb_k3a2_groups(L, use_tmem, np, nt3, ns, ntm);
-    return (size_t)(16 * (np - ntm) + 64 * nt3 + 4 * ns) * 32 * L <= (size_t)227 * 1024;
+    tb_k3a2_groups(L, tmem_groups, np, nt3, ns, ntm);
+    return (size_t)(16 * (np - ntm) + 64 * nt3 + 4 * ns) * tb_k3a2_rowstride(L) * sizeof(double) <= (size_t)227 * 1024;
 }
 
 // Tensor memory (TMEM, 256 KB per SM on sm_100) as a second home for table rows: it is read through its own datapath
 // (tcgen05.ld), so rows served from it cost no shared-memory wavefronts.  512 columns x 128 lanes x 32 bit: a warp reaches the
-// 32 lanes of its quarter (warp id mod 4), so the rows are replicated in the four quarters; lane l of a quarter holds its two
-// 16-byte chunks of a row in 8 consecutive columns -> 64 rows = the first TB_K3A2_TMEM_GROUPS = 4 dinucleotide groups.
-// Measured (chr50mb): 27.1 -> 22.3 ms with the same shared-memory grouping; the freed shared memory then takes larger groups.
+// 32 lanes of its quarter (warp id mod 4), so the rows are replicated in the four quarters; lane n of a quarter holds the three
+// ratios of column n of a row in 6 consecutive columns -> 80 rows = the first five dinucleotide groups.
 #ifndef TB_EMU
 __device__ __forceinline__ void tb_tmem_alloc512(u32 *smem_slot) {       // one warp; writes the base address to shared memory
     const u32 a = (u32)__cvta_generic_to_shared(smem_slot);
@@ -209,14 +216,16 @@ __device__ __forceinline__ void tb_tmem_dealloc512(u32 taddr) {
 }
 __device__ __forceinline__ void tb_tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tb_tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tb_tmem_st8(u32 taddr, double2 a, double2 b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
-                 "r"(__double2loint(a.x)), "r"(__double2hiint(a.x)), "r"(__double2loint(a.y)), "r"(__double2hiint(a.y)),
-                 "r"(__double2loint(b.x)), "r"(__double2hiint(b.x)), "r"(__double2loint(b.y)), "r"(__double2hiint(b.y))
+__device__ __forceinline__ void tb_tmem_st6(u32 taddr, double r1, double r2, double r3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(__double2loint(r1)),
+                 "r"(__double2hiint(r1)), "r"(__double2loint(r2)), "r"(__double2hiint(r2))
+                 : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(taddr + 4u), "r"(__double2loint(r3)),
+                 "r"(__double2hiint(r3))
                  : "memory");
 }
 __device__ __forceinline__ void tb_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void tb_tmem_ld8(u32 taddr, u32 (&v)[8]) {
+__device__ __forceinline__ void tb_tmem_ld8(u32 taddr, u32 (&v)[8]) {      // 6 columns of this row + 2 of the next (ignored)
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
@@ -224,27 +233,26 @@ __device__ __forceinline__ void tb_tmem_ld8(u32 taddr, u32 (&v)[8]) {
 __device__ __forceinline__ void tb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 #endif
 
-// FIXED: the grouping of the default model length (L = 25: 8 pair groups, 4 of them in tensor memory, 3 trinucleotide groups)
-// as compile-time constants, so the row loops unroll and the row offsets fold into the load instructions.
+// FIXED: the grouping of the default model length (L = 25: 5 pair groups in tensor memory, 5 trinucleotide groups in shared
+// memory) as compile-time constants, so the row loops unroll and the row offsets fold into the load instructions.
 template <bool FIXED>
 __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     tb_score_dwm2_kernel(tb_genome_view g, tb_score_regions_view R, const double *__restrict__ vt_fwd, const double *__restrict__ vt_rev,
                          int L_, int np_, int nt3_, int ns_, int ntm_, int strand_mask, double *__restrict__ part) {
     TB_DYN_SMEM(smem);
     const unsigned FULL = 0xffffffffu;
-    const int L = FIXED ? 25 : L_, np = FIXED ? 8 : np_, nt3 = FIXED ? 3 : nt3_, ns = FIXED ? 0 : ns_;
-    int ntm = FIXED ? 4 : ntm_;
+    const int L = FIXED ? 25 : L_, np = FIXED ? 5 : np_, nt3 = FIXED ? 5 : nt3_, ns = FIXED ? 0 : ns_;
+    int ntm = FIXED ? 5 : ntm_;
     const int k_flank = L / 2;
-    const int rows = 16 * np + 64 * nt3 + 4 * ns, row = 4 * L;   // doubles per row; the first 16 * ntm rows live in tensor memory
+    const int rows = 16 * np + 64 * nt3 + 4 * ns, rs = tb_k3a2_rowstride(L);   // row stride in doubles; the first 16 ntm rows live in tensor memory
     const int nclass = strand_mask == 3 ? 4 : 2;
     const int cls = blockIdx.x % nclass;
     const int bpart = blockIdx.x / nclass, nparts = (gridDim.x - cls + nclass - 1) / nclass;
     const int strand = strand_mask == 3 ? (cls >> 1) : (strand_mask == 2 ? 1 : 0);
     const int model = cls & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int nchunk = 2 * L;
-    const bool hasB = 32 + lane < nchunk;
-    const double2 *src = (const double2 *)((strand ? vt_rev : vt_fwd) + (size_t)model * rows * row);
+    const bool col = lane < L;                                // lane n owns column n
+    const double *src = (strand ? vt_rev : vt_fwd) + (size_t)model * rows * rs;
 #ifndef TB_EMU
     __shared__ u32 tmem_slot;
     u32 tq = 0;                                               // this warp's quarter of the tensor memory
@@ -256,9 +264,9 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
         tq = tmem_slot + ((u32)(32 * (warp & 3)) << 16);
         if (warp < 4) {                                       // warps 0..3 fill the four quarters
             for (int r = 0; r < 16 * ntm; r++) {
-                const double2 a = src[(size_t)r * nchunk + lane];
-                const double2 b = hasB ? src[(size_t)r * nchunk + 32 + lane] : double2{1.0, 1.0};
-                tb_tmem_st8(tq + 8u * (u32)r, a, b);
+                const double *rp = src + (size_t)r * rs;
+                const double r1 = col ? rp[2 * lane] : 1.0, r2 = col ? rp[2 * lane + 1] : 1.0, r3 = col ? rp[2 * L + lane] : 1.0;
+                tb_tmem_st6(tq + 6u * (u32)r, r1, r2, r3);
             }
             tb_tmem_wait_st();
         }
@@ -268,19 +276,19 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     ntm = 0;
 #endif
     {
-        const double2 *s2 = src + (size_t)16 * ntm * nchunk;
+        const double2 *s2 = (const double2 *)(src + (size_t)16 * ntm * rs);
         double2 *dst = (double2 *)smem;
-        for (int i = threadIdx.x; i < (rows - 16 * ntm) * row / 2; i += blockDim.x) dst[i] = s2[i];
+        for (int i = threadIdx.x; i < (rows - 16 * ntm) * rs / 2; i += blockDim.x) dst[i] = s2[i];
         __syncthreads();
     }
 #ifndef TB_EMU
     if (ntm) tb_tmem_fence_after();
 #endif
     double *out = part + (size_t)(strand * 2 + model) * R.total;
-    const double2 *V = (const double2 *)smem + lane - (size_t)16 * ntm * nchunk;   // chunk c of row r >= 16 ntm at V[r * 2L + c - lane]
-    const int half = lane & 1;
-    const int ncol = half ? 16 + (lane >> 1) : (lane >> 1);   // column this lane completes in the epilogue
-    const bool colok = ncol < L;
+    // row r >= 16 ntm: (r1, r2) of this lane's column at V12[r * rs], r3 at V3[r * rs]
+    const int cl = col ? lane : 0;
+    const double *V12 = (const double *)smem + 2 * cl - (size_t)16 * ntm * rs;
+    const double *V3 = (const double *)smem + 2 * L + cl - (size_t)16 * ntm * rs;
     const int n_tail = nt3 + ns;                              // groups after the pairs: trinucleotides, then the single offset
     const i64 n_units = (R.total + 31) >> 5;
 
@@ -312,82 +320,73 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
         for (int it = 0; it < 32; it += TB_K3A2_WPI) {
             if (((okmask >> it) & ((1u << TB_K3A2_WPI) - 1u)) == 0u) continue;       // warp-uniform
             u64 kmer[TB_K3A2_WPI];
-            double a0[TB_K3A2_WPI], a1[TB_K3A2_WPI], b0[TB_K3A2_WPI], b1[TB_K3A2_WPI];
+            double a1[TB_K3A2_WPI], a2[TB_K3A2_WPI], a3[TB_K3A2_WPI];               // products of the ratios of column `lane`
 #pragma unroll
             for (int w = 0; w < TB_K3A2_WPI; w++) {
                 kmer[w] = (u64)__shfl_sync(FULL, klo, it + w) | ((u64)__shfl_sync(FULL, khi, it + w) << 32);
-                a0[w] = a1[w] = b0[w] = b1[w] = 1.0;
+                a1[w] = a2[w] = a3[w] = 1.0;
             }
 #ifndef TB_EMU
 #pragma unroll
-            for (int p = 0; p < (FIXED ? 4 : ntm); p++) {      // rows served by tensor memory
+            for (int p = 0; p < (FIXED ? 5 : ntm); p++) {      // rows served by tensor memory
                 u32 t[TB_K3A2_WPI][8];
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
                     const u32 d = (u32)(kmer[w] >> (4 * p)) & 15u;
-                    tb_tmem_ld8(tq + 8u * (16u * (u32)p + d), t[w]);
+                    tb_tmem_ld8(tq + 6u * (16u * (u32)p + d), t[w]);
                 }
                 tb_tmem_wait_ld();
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
-                    a0[w] *= __hiloint2double((int)t[w][1], (int)t[w][0]);
-                    a1[w] *= __hiloint2double((int)t[w][3], (int)t[w][2]);
-                    b0[w] *= __hiloint2double((int)t[w][5], (int)t[w][4]);
-                    b1[w] *= __hiloint2double((int)t[w][7], (int)t[w][6]);
+                    a1[w] *= __hiloint2double((int)t[w][1], (int)t[w][0]);
+                    a2[w] *= __hiloint2double((int)t[w][3], (int)t[w][2]);
+                    a3[w] *= __hiloint2double((int)t[w][5], (int)t[w][4]);
                 }
             }
 #endif
 #pragma unroll
-            for (int p = (FIXED ? 4 : ntm); p < (FIXED ? 8 : np); p++) {
+            for (int p = (FIXED ? 5 : ntm); p < (FIXED ? 5 : np); p++) {
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
                     const int d = (int)((u32)(kmer[w] >> (4 * p)) & 15u);
-                    const double2 *r = V + (p * 16 + d) * nchunk;
-                    double2 va = r[0];
-                    a0[w] *= va.x;
-                    a1[w] *= va.y;
-                    if (hasB) {
-                        double2 vb = r[32];
-                        b0[w] *= vb.x;
-                        b1[w] *= vb.y;
+                    const int ro = (p * 16 + d) * rs;
+                    if (col) {
+                        const double2 v = *(const double2 *)(V12 + ro);
+                        a1[w] *= v.x;
+                        a2[w] *= v.y;
+                        a3[w] *= V3[ro];
                     }
                 }
             }
 #pragma unroll
-            for (int t = 0; t < (FIXED ? 3 : n_tail); t++) {
+            for (int t = 0; t < (FIXED ? 5 : n_tail); t++) {
                 const int sh = 4 * np + 6 * (t < nt3 ? t : nt3);
                 const u32 mask = t < nt3 ? 63u : 3u;
-                const double2 *Vt = V + (size_t)(16 * np + 64 * (t < nt3 ? t : nt3)) * nchunk;
+                const int rb = 16 * np + 64 * (t < nt3 ? t : nt3);
 #pragma unroll
                 for (int w = 0; w < TB_K3A2_WPI; w++) {
                     const int d = (int)((u32)(kmer[w] >> sh) & mask);
-                    const double2 *r = Vt + d * nchunk;
-                    double2 va = r[0];
-                    a0[w] *= va.x;
-                    a1[w] *= va.y;
-                    if (hasB) {
-                        double2 vb = r[32];
-                        b0[w] *= vb.x;
-                        b1[w] *= vb.y;
+                    const int ro = (rb + d) * rs;
+                    if (col) {
+                        const double2 v = *(const double2 *)(V12 + ro);
+                        a1[w] *= v.x;
+                        a2[w] *= v.y;
+                        a3[w] *= V3[ro];
                     }
                 }
             }
-            // ---- column totals.  Lane l holds half (l & 1) of columns l >> 1 (a) and 16 + (l >> 1) (b); the even lane of a pair
-            // completes column a, the odd lane column b: Z = sum_a 2^E[n][a] and the selected term 2^E[n][S_n]
+            // ---- column totals in the owning lane: Z = 1 + r1 + r2 + r3 (the a = 0 term is the unit), selected term by S_n
             double msel[TB_K3A2_WPI], mz[TB_K3A2_WPI];
             int de[TB_K3A2_WPI];
 #pragma unroll
             for (int w = 0; w < TB_K3A2_WPI; w++) {
-                const int sA = (int)((u32)(kmer[w] >> (2 * (lane >> 1))) & 3u), sB = (int)((u32)(kmer[w] >> (2 * (16 + (lane >> 1)))) & 3u);
-                const double zA = a0[w] + a1[w], zB = b0[w] + b1[w];
-                const double selA = (sA >> 1) == half ? ((sA & 1) ? a1[w] : a0[w]) : 0.0;
-                const double selB = (sB >> 1) == half ? ((sB & 1) ? b1[w] : b0[w]) : 0.0;
-                double z = (half ? zB : zA) + __shfl_xor_sync(FULL, half ? zA : zB, 1);
-                double sel = (half ? selB : selA) + __shfl_xor_sync(FULL, half ? selA : selB, 1);
+                const int sn = (int)((u32)(kmer[w] >> (2 * cl)) & 3u);
+                const double z = ((1.0 + a1[w]) + a2[w]) + a3[w];
+                const double sel = sn == 0 ? 1.0 : (sn == 1 ? a1[w] : (sn == 2 ? a2[w] : a3[w]));
                 int es = 0, ez = 0;
                 msel[w] = 1.0;
                 mz[w] = 1.0;
-                if (colok) {
+                if (col) {
                     tb_split_exp(sel, msel[w], es);
                     tb_split_exp(z, mz[w], ez);
                 }
@@ -407,19 +406,19 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                 pz[h] = kz * __shfl_xor_sync(FULL, up16 ? mz[wk] : mz[ws], 16);
                 pe[h] = ke + __shfl_xor_sync(FULL, up16 ? de[wk] : de[ws], 16);
             }
-            double rs = (up8 ? ps[1] : ps[0]) * __shfl_xor_sync(FULL, up8 ? ps[0] : ps[1], 8);
+            double rs_ = (up8 ? ps[1] : ps[0]) * __shfl_xor_sync(FULL, up8 ? ps[0] : ps[1], 8);
             double rz = (up8 ? pz[1] : pz[0]) * __shfl_xor_sync(FULL, up8 ? pz[0] : pz[1], 8);
             int re = (up8 ? pe[1] : pe[0]) + __shfl_xor_sync(FULL, up8 ? pe[0] : pe[1], 8);
 #pragma unroll
             for (int dlt = 4; dlt > 0; dlt >>= 1) {
-                rs *= __shfl_xor_sync(FULL, rs, dlt);
+                rs_ *= __shfl_xor_sync(FULL, rs_, dlt);
                 rz *= __shfl_xor_sync(FULL, rz, dlt);
                 re += __shfl_xor_sync(FULL, re, dlt);
             }
             // lanes with (bit 4, bit 3) = (b4, b3) now hold window it + b4 + 2 * b3; hand the results to lanes it .. it + 3
             const int k = (lane - it) & 3;
             const int srcl = ((k & 1) << 4) | ((k >> 1) << 3);
-            const double gs = __shfl_sync(FULL, rs, srcl), gz = __shfl_sync(FULL, rz, srcl);
+            const double gs = __shfl_sync(FULL, rs_, srcl), gz = __shfl_sync(FULL, rz, srcl);
             const int ge = __shfl_sync(FULL, re, srcl);
             if (lane >= it && lane < it + TB_K3A2_WPI) {
                 my_sel = gs;
@@ -522,33 +521,38 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                         U[(((((size_t)x * L + m) * 4 + s) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)] = v;
                     }
     TB_TRY(tb_h2d(ctx, M.table, U.data(), U.size() * sizeof(double)));
-    // product-form table (tb_score_dwm2_kernel): V[x][row][n][a] = 2^(sum of the U rows of the group); pair group p: row 16 p + d,
-    // offsets 2p (d & 3) and 2p + 1 (d >> 2); then the trinucleotide groups (64 rows each), then a single offset (4 rows);
-    // same forward-oriented indexing as U
+    // product-form table (tb_score_dwm2_kernel), ratio form: with T[x][row][n][a] = the summed U rows of the group (pair group p: row
+    // 16 p + d, offsets 2p (d & 3) and 2p + 1 (d >> 2); then the trinucleotide groups, 64 rows each; then a single offset, 4 rows),
+    // a row stores 2^(T[a] - T[0]) for a = 1..3: (r1, r2) pairs of the L columns, then the L values r3; same forward-oriented
+    // indexing as U
     {
         int np, nt3, ns, ntm;
-        tb_k3a2_groups(L, tb_k3a2_use_tmem(ctx), np, nt3, ns, ntm);
-        const int rows = 16 * np + 64 * nt3 + 4 * ns;
+        tb_k3a2_groups(L, tb_k3a2_tmem_groups(ctx), np, nt3, ns, ntm);
+        const int rows = 16 * np + 64 * nt3 + 4 * ns, rs = tb_k3a2_rowstride(L);
         auto u = [&](int x, int m, int s_, int n, int a) {
             return U[(((((size_t)x * L + m) * 4 + s_) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)];
         };
-        std::vector<double> Vt((size_t)2 * rows * L * 4);
+        std::vector<double> Vt((size_t)2 * rows * rs, 1.0);
         for (int x = 0; x < 2; x++)
             for (int r = 0; r < rows; r++)
-                for (int n = 0; n < L; n++)
+                for (int n = 0; n < L; n++) {
+                    double t[4];
                     for (int a = 0; a < 4; a++) {
-                        double t;
                         if (r < 16 * np) {
                             int p = r >> 4, d = r & 15;
-                            t = u(x, 2 * p, d & 3, n, a) + u(x, 2 * p + 1, d >> 2, n, a);
+                            t[a] = u(x, 2 * p, d & 3, n, a) + u(x, 2 * p + 1, d >> 2, n, a);
                         } else if (r < 16 * np + 64 * nt3) {
                             int q = (r - 16 * np) >> 6, d = (r - 16 * np) & 63, m0 = 2 * np + 3 * q;
-                            t = (u(x, m0, d & 3, n, a) + u(x, m0 + 1, (d >> 2) & 3, n, a)) + u(x, m0 + 2, d >> 4, n, a);
+                            t[a] = (u(x, m0, d & 3, n, a) + u(x, m0 + 1, (d >> 2) & 3, n, a)) + u(x, m0 + 2, d >> 4, n, a);
                         } else {
-                            t = u(x, L - 1, r - 16 * np - 64 * nt3, n, a);
+                            t[a] = u(x, L - 1, r - 16 * np - 64 * nt3, n, a);
                         }
-                        Vt[(((size_t)x * rows + r) * L + n) * 4 + a] = exp2(t);
                     }
+                    double *rp = Vt.data() + ((size_t)x * rows + r) * rs;
+                    rp[2 * n] = exp2(t[1] - t[0]);
+                    rp[2 * n + 1] = exp2(t[2] - t[0]);
+                    rp[2 * L + n] = exp2(t[3] - t[0]);
+                }
         TB_TRY(tb_h2d(ctx, M.vtable, Vt.data(), Vt.size() * sizeof(double)));
     }
     return tb_sync(ctx, "tb_set_bias_model");
@@ -573,13 +577,13 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
     if (!tr) tr = tf;
     int L = M0.L;
     int k3a_np, k3a_nt3, k3a_ns, k3a_ntm;
-    tb_k3a2_groups(L, tb_k3a2_use_tmem(ctx), k3a_np, k3a_nt3, k3a_ns, k3a_ntm);
-    const size_t smem2 = (size_t)(16 * (k3a_np - k3a_ntm) + 64 * k3a_nt3 + 4 * k3a_ns) * 4 * L * sizeof(double);
-    if (M0.is_dwm && tb_k3a2_fits(L, tb_k3a2_use_tmem(ctx)) && !ctx->force_sum_form) {
+    tb_k3a2_groups(L, tb_k3a2_tmem_groups(ctx), k3a_np, k3a_nt3, k3a_ns, k3a_ntm);
+    const size_t smem2 = (size_t)(16 * (k3a_np - k3a_ntm) + 64 * k3a_nt3 + 4 * k3a_ns) * tb_k3a2_rowstride(L) * sizeof(double);
+    if (M0.is_dwm && tb_k3a2_fits(L, tb_k3a2_tmem_groups(ctx)) && !ctx->force_sum_form) {
         // product form: one (strand, model) table per block, partial scores, then bias - background
         const int nclass = strand_mask == 3 ? 4 : 2;
         TB_TRY(tb_reserve(ctx, ctx->scratch4, (size_t)4 * total * sizeof(double)));
-        const bool fixed = L == 25 && k3a_np == 8 && k3a_nt3 == 3 && k3a_ns == 0 && k3a_ntm == 4;
+        const bool fixed = L == 25 && k3a_np == 5 && k3a_nt3 == 5 && k3a_ns == 0 && k3a_ntm == 5;
         auto k = fixed ? tb_score_dwm2_kernel<true> : tb_score_dwm2_kernel<false>;
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         i64 n_units = (total + 31) >> 5;
