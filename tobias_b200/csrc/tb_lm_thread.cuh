@@ -64,6 +64,27 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
         }                                                                      \
     }
 #define TB_FOR_POINTS(W, m, i, ...) TB_FOR_POINTS_FROM(W, m, 0, i, __VA_ARGS__)
+// all points in storage order (plane by plane: v = 0..9, then u): for sums whose order is free (the one-pass form).  No index
+// arithmetic per point -- consecutive points of a plane are consecutive slots.
+#define TB_FOR_POINTS_ANY_ORDER(W, m, ...)                                     \
+    for (int _v = 0; _v < 10; _v++) {                                          \
+        const int _n = ((m) - _v + 9) / 10;                                    \
+        if (_n <= 0) break;                                                    \
+        const double *_px = (W).x + (i64)_v * (W).stride;                      \
+        const u32 *_py = (W).y + (i64)_v * (W).stride;                         \
+        double _nx = _px[0];                                                   \
+        u32 _ny = _py[0];                                                      \
+        for (int _u = 0; _u < _n; _u++) {                                      \
+            const double ex = _nx;                                             \
+            const u32 eyi = _ny;                                               \
+            if (_u + 1 < _n) {                                                 \
+                _nx = _px[_u + 1];                                             \
+                _ny = _py[_u + 1];                                             \
+            }                                                                  \
+            const double ey = tb_u32_to_double(eyi);                           \
+            __VA_ARGS__                                                        \
+        }                                                                      \
+    }
 
 // a / d with dinv = 1.0 / d (correctly rounded, see header)
 __device__ __forceinline__ double tb_div_inv(double a, double d, double dinv) {
@@ -389,7 +410,7 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
     J.eval(W.x[0], tb_u32_to_double(W.y[0]), f0, a0, b0);
     J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), f1, a1, b1);
     double g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
-    TB_FOR_POINTS(W, m, i, {
+    TB_FOR_POINTS_ANY_ORDER(W, m, {
         double f, j0, j1;
         J.eval(ex, ey, f, j0, j1);
         g00 += j0 * j0;
@@ -434,7 +455,7 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
     // the inner products leave rounding noise: count the rows, but only when the columns look (nearly) dependent
     if (rest2 > 0.0 && !(rest2 > 1e-12 * gQQ)) {
         int nrows = 0;
-        TB_FOR_POINTS(W, m, i, {
+        TB_FOR_POINTS_ANY_ORDER(W, m, {
             double f, j0, j1;
             J.eval(ex, ey, f, j0, j1);
             nrows += (j0 != 0.0 || j1 != 0.0) ? 1 : 0;
@@ -486,7 +507,7 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
         const double ta = wa2[0], tb_ = wa2[1];
         if (FAST) {
             double ss = 0.0;
-            TB_FOR_POINTS(W, m, i, {
+            TB_FOR_POINTS_ANY_ORDER(W, m, {
                 const double r = tb_relu_res(ta, tb_, ex, ey);
                 ss += r * r;
             })
