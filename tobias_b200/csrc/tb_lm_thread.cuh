@@ -66,6 +66,9 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
 #define TB_FOR_POINTS(W, m, i, ...) TB_FOR_POINTS_FROM(W, m, 0, i, __VA_ARGS__)
 // all points in storage order (plane by plane: v = 0..9, then u): for sums whose order is free (the one-pass form).  No index
 // arithmetic per point -- consecutive points of a plane are consecutive slots.
+#ifndef TB_FIT_UNROLL_ANY
+#define TB_FIT_UNROLL_ANY 2
+#endif
 #define TB_FOR_POINTS_ANY_ORDER(W, m, ...)                                     \
     for (int _v = 0; _v < 10; _v++) {                                          \
         const int _n = ((m) - _v + 9) / 10;                                    \
@@ -74,6 +77,7 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
         const u32 *_py = (W).y + (i64)_v * (W).stride;                         \
         double _nx = _px[0];                                                   \
         u32 _ny = _py[0];                                                      \
+        TB_PRAGMA(unroll TB_FIT_UNROLL_ANY)                                    \
         for (int _u = 0; _u < _n; _u++) {                                      \
             const double ex = _nx;                                             \
             const u32 eyi = _ny;                                               \
