@@ -138,19 +138,19 @@ __global__ void __launch_bounds__(768, 1) tb_score_dwm_kernel(tb_genome_view g, 
 // 100 exp2 + 25 log2 per model and window.  Second formulation, same mathematics:
 //   * rows are grouped: PAIRS of window offsets, T[p][d] = U[2p][d & 3] + U[2p+1][d >> 2] for the 16 dinucleotides d, then
 //     TRIPLES (64 trinucleotide rows each), then at most one single offset (4 rows); tb_k3a2_groups picks the grouping with
-//     the fewest shared-memory groups that fits the SM: 8 pair + 3 triple groups = 11 row reads instead of 25 for L = 25;
-//   * the first four pair groups are served from tensor memory (below), the rest from shared memory;
-//   * the table holds V = 2^T, so 2^E[n][a] = prod_groups V[g][d_g][n][a] is a product of 11 table entries -- no exp2 at
-//     all -- and the per-model score  sum_n (E[n][S_n] - log2 sum_a 2^E[n][a])  =  log2 prod_n (2^E[n][S_n] / Z[n])  needs
-//     two log2 per window (of the products of the 25 selected terms and of the 25 normalisers, exponents carried apart).
+//     the fewest shared-memory groups that fits the SM: 5 pair + 5 triple groups = 10 row reads instead of 25 for L = 25;
+//   * the table holds powers of two, so 2^E[n][a] is a product of 10 table entries -- no exp2 at all -- and the per-model
+//     score  sum_n (E[n][S_n] - log2 sum_a 2^E[n][a])  =  log2 prod_n (2^E[n][S_n] / Z[n])  needs two log2 per window (of the
+//     products of the 25 selected terms and of the 25 normalisers, exponents carried apart);
+//   * ratio form (below): three values per column instead of four, lane n owns column n;
+//   * the pair groups are served from tensor memory (below), the triples from shared memory.
 // One model of one strand is resident per block; the four (strand, model) classes of blocks write partial scores that
 // tb_score_combine_kernel subtracts (bias - background).  A warp owns 32 consecutive positions: lane w prepares window
 // w (region lookup, N test, packed k-mer) and finishes it (log2, one coalesced store of the 32 results); in between the
-// warp walks the windows four at a time, lane l multiplying the 16-byte chunks l and 32 + l of each row ([n][a] order:
-// chunk c = (n, a >> 1)), i.e. a row costs 7 shared-memory wavefronts (6.25 ideal).  The cross-lane products of the four
-// windows are reduced together (each butterfly level halves the number of windows a lane still carries), 12.75 shuffles
-// per window instead of 28.  Relative error of a product of 11 correctly rounded factors ~ 2e-15, i.e. ~1e-14 absolute
-// on the score -- the same order as the sum form's difference to the reference's libm.
+// warp walks the windows four at a time.  The cross-lane products of the four windows are reduced together (each butterfly
+// level halves the number of windows a lane still carries), 8.75 shuffles per window.  Relative error of a product of 10
+// correctly rounded factors ~ 2e-15, i.e. ~1e-14 absolute on the score -- the same order as the sum form's difference to
+// the reference's libm.
 #define TB_K3A2_THREADS 768
 #define TB_K3A2_WPI 4
 
