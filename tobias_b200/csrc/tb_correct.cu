@@ -318,7 +318,7 @@ __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w)
     return (double)acc;
 }
 
-#define TB_K3C_TILE 512
+#define TB_K3C_TILE_MAX 1024     // positions per tile (chosen per launch from the region lengths, a multiple of 64 up to this)
 #define TB_K3C_THREADS 256
 
 // Persistent blocks walk the (region, 512-bp tile) list.  Per tile and strand:
@@ -334,14 +334,14 @@ __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w)
 //      base) accumulators -- no atomics in the loop (first version: 25 x 3 shared-memory fp64 atomics = CAS loops per position)
 __global__ void __launch_bounds__(TB_K3C_THREADS)
     tb_correct_kernel(tb_genome_view g, tb_cor_view V, const int32_t *__restrict__ tile_region,
-                      const int32_t *__restrict__ tile_start, i64 n_tiles, const u32 *__restrict__ pile,
+                      const int32_t *__restrict__ tile_start, i64 n_tiles, int tile_len, const u32 *__restrict__ pile,
                       const double *__restrict__ biasraw, const double *__restrict__ fit, double cf,
                       double *__restrict__ tracks, double *__restrict__ prepost) {
     TB_DYN_SMEM(smem);
     const int w = V.window, k = V.k_flank, L = V.L;
     const int lf = w / 2;
     const int overlaps = w / TB_STEP;
-    const int cap = TB_K3C_TILE + 4 * w;
+    const int cap = tile_len + 4 * w;
     double *sig = (double *)smem;              // [d0, d1)  signal;            phase 4: pre weights of [t0, t1)
     double *bp = sig + cap;                    // [d0, d1)  mean prediction;   phase 4: post(+) weights
     double *unc = bp + cap;                    // [c0, c1)  signal * cf
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
     u32 *pcnt = psum + cap + 1;                // [cap + 1] prefix counts of its non-zero positions
     u32 *wsum = pcnt + cap + 1;                // [2][32] warp totals of the block scan
     unsigned short *nzpos = (unsigned short *)(wsum + 64);      // [cap] non-zero positions (relative to d0)
-    uint8_t *bases = (uint8_t *)(nzpos + cap);                  // [TB_K3C_TILE + L] base codes of [t0 - k, t1 + k)
+    uint8_t *bases = (uint8_t *)(nzpos + cap);                  // [tile_len + L] base codes of [t0 - k, t1 + k)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
         const int t0 = tile_start[tile];
         const int Lr = (int)(V.ext_off[j + 1] - V.ext_off[j]);
         const int nwin = tb_n_windows(Lr, k, w);
-        const int t1 = min(Lr, t0 + TB_K3C_TILE);                 // tile = [t0, t1)
+        const int t1 = min(Lr, t0 + tile_len);                    // tile = [t0, t1)
         const int c0 = max(0, t0 - w), c1 = min(Lr, t1 + w);      // domain of the raw corrected signal
         const int d0 = max(0, c0 - w), d1 = min(Lr, c1 + w);      // domain of signal / bias prediction
         const int nd = d1 - d0;
@@ -611,7 +611,35 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         C.ext_off[i + 1] = C.ext_off[i] + reg_len;
         C.out_off[i + 1] = C.out_off[i] + (le[i] - ls[i]);
         C.win_off[i + 1] = C.win_off[i] + nw;
-        for (i64 t = 0; t < reg_len; t += TB_K3C_TILE) {
+    }
+    // K3c tile length: every tile recomputes a halo of 2 * window positions on each side, so the tile that covers most regions in
+    // one piece wins (hg38 peaks: 824-bp regions -> one 832-position tile each instead of two 512-position tiles with halos)
+    int tile_len = 512;
+    {
+        std::vector<std::pair<i64, i64>> hist;               // runs of equal region lengths
+        for (i64 i = 0; i < n_regions; i++) {
+            const i64 v = C.ext_off[i + 1] - C.ext_off[i];
+            if (!hist.empty() && hist.back().first == v) hist.back().second++;
+            else hist.push_back({v, 1});
+        }
+        double best = -1.0;
+        for (int cand = 256; cand <= TB_K3C_TILE_MAX; cand += 64) {
+            double cost = 0.0;
+            for (const auto &h : hist) {
+                const i64 nt = tb_div_up(h.first, cand);
+                const i64 halo = nt > 1 ? 4 * (i64)window * (nt - 1) : 0;       // positions computed twice for the interior borders
+                cost += (double)(h.first + halo + 32 * nt) * (double)h.second;  // + a per-tile constant (barriers, scans)
+            }
+            cost *= 1.0 + 0.15 * (double)cand / TB_K3C_TILE_MAX;                // larger tiles: fewer resident blocks
+            if (best < 0.0 || cost < best) {
+                best = cost;
+                tile_len = cand;
+            }
+        }
+    }
+    for (i64 i = 0; i < n_regions; i++) {
+        const i64 reg_len = C.ext_off[i + 1] - C.ext_off[i];
+        for (i64 t = 0; t < reg_len; t += tile_len) {
             tile_region.push_back((int32_t)i);
             tile_start.push_back((int32_t)t);
         }
@@ -726,8 +754,8 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     tb_mark(ctx, 3);
     {
         tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
-        const size_t capk = TB_K3C_TILE + 4 * window;
-        size_t smem = ((size_t)5 * capk + 2 * 3 * 4 * L) * sizeof(double) + (2 * (capk + 1) + 64) * sizeof(u32) + capk * 2 + TB_K3C_TILE + L + 16;
+        const size_t capk = (size_t)tile_len + 4 * window;
+        size_t smem = ((size_t)5 * capk + 2 * 3 * 4 * L) * sizeof(double) + (2 * (capk + 1) + 64) * sizeof(u32) + capk * 2 + tile_len + L + 16;
         auto kc = tb_correct_kernel;
         TB_CUDA(ctx, cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const i64 n_tiles = (i64)tile_region.size();
@@ -736,7 +764,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         if (per_sm > 8) per_sm = 8;
         const i64 capg = (i64)ctx->sm_count * per_sm;
         TB_LAUNCH(ctx, kc, (unsigned)(n_tiles < capg ? n_tiles : capg), TB_K3C_THREADS, smem, g, V, (const int32_t *)ctx->reg_a.as<int32_t>(),
-                  (const int32_t *)ctx->reg_b.as<int32_t>(), n_tiles, (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),
+                  (const int32_t *)ctx->reg_b.as<int32_t>(), n_tiles, tile_len, (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),
                   (const double *)C.fit.as<double>(), correction_factor, C.tracks.as<double>(), C.prepost.as<double>());
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_correct_kernel"));
     }
