@@ -99,6 +99,28 @@ def test_bias_counts_in_several_slab_chunks(loaded_ctx, golden, monkeypatch):
     assert np.array_equal(counts, counts3) and np.array_equal(scalars, scalars3)
 
 
+def test_bias_counts_histogram_forms(loaded_ctx, golden, monkeypatch):
+    """DWM counts come from joint chunk histograms (one atomic per k-mer and chunk pair) folded into position pairs; every
+    chunking -- including a last chunk of one base, two chunks only, and the shared-memory-atomic kernel that serves models of a
+    single chunk / TB_K2_NO_HIST=1 -- gives the same integers as the reference."""
+    regs = [tuple(int(x) for x in r) for r in golden.atac["nonpeak"]]
+    emu = loaded_ctx.device_info()["is_emulator"]
+    for k_flank, chunkings in ((12, (3, 4) if emu else (3, 4, 5)), (5, (1, 2, 5)), (2, (3, 4, 5))):
+        kw = dict(k_flank=k_flank, bg_shift=37, cap=3)
+        ref = restate.bias_estimation(golden.reads, golden.genome, regs, golden.lengths, **kw)
+        monkeypatch.setenv("TB_K2_NO_HIST", "1")
+        base, base_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
+        monkeypatch.delenv("TB_K2_NO_HIST")
+        for si, st in enumerate(("forward", "reverse")):
+            assert np.array_equal(base[si, 0], ref.bias[st].counts) and np.array_equal(base[si, 1], ref.bias[st].bg_counts)
+        assert base_sc[0] == ref.no_reads
+        for ch in chunkings:
+            monkeypatch.setenv("TB_K2_CHUNK", str(ch))
+            got, got_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
+            monkeypatch.delenv("TB_K2_CHUNK")
+            assert np.array_equal(got, base) and np.array_equal(got_sc, base_sc), (k_flank, ch)
+
+
 def _set_model(ctx, g, mode):
     for si, st in enumerate(("forward", "reverse")):
         if mode == "DWM":

@@ -159,7 +159,7 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     tb_dbuf *bufs[] = {&ctx->seq2, &ctx->nmask, &ctx->d_contig_off, &ctx->r_start, &ctx->r_len, &ctx->r_clip, &ctx->r_flags,
                        &ctx->reg_a, &ctx->reg_b, &ctx->reg_c, &ctx->reg_d, &ctx->reg_e, &ctx->scratch0, &ctx->scratch1,
                        &ctx->scratch2, &ctx->scratch3, &ctx->scratch4, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
-                       &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_slab, &ctx->k2_sites,
+                       &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_slab, &ctx->k2_sites, &ctx->k2_hist,
                        &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
                        &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.fitg_x, &ctx->cor.fitg_y, &ctx->cor.fitg_st,
                        &ctx->cor.fitg_sti, &ctx->cor.fitg_wq, &ctx->cor.fitg_lists, &ctx->cor.tracks, &ctx->cor.prepost,

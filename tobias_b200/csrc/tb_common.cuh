@@ -82,6 +82,7 @@ struct tb_ctx {
     bool reads_sorted = false;        // records sorted by (contig, start): lets K2 narrow the record range of a region chunk
     i64 max_read_len = 0;             // longest reference span of a record (bounds the records a region chunk can see)
     tb_dbuf k2_slab, k2_sites;        // K2: multiplicity slab (kept all-zero between calls) and site list
+    tb_dbuf k2_hist;                  // K2: joint chunk histograms (u32 [4 tensors][chunk pairs][4^ch][4^ch])
 
     // scratch / per-call device tables
     tb_dbuf reg_a, reg_b, reg_c, reg_d, reg_e;

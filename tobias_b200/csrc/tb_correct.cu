@@ -308,14 +308,29 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
 }
 
 // ------------------------------------------------------------------------------------------------ K3c
-// centred rolling sum with the reference's accumulator: valsum is a C float, every += is a double add rounded to float
+// centred rolling sum with the reference's accumulator: valsum is a C float, every += is a double add rounded to float.
+// The accumulator is kept as a double that always holds a float value; the rounding to float after each add is done in the
+// fp64 pipe instead of two trips through the conversion unit: with E the exponent of s (at least -126: below that the float
+// grid is the fixed denormal grid 2^-149), adding and subtracting c = 1.5 * 2^(E + 29) rounds s to a multiple of 2^(E - 23)
+// = the float grid at s, to nearest / ties to even by the hardware's own rounding of s + c (c is a multiple of 2^(E + 28),
+// so evenness on the grid is preserved).  NaN and infinity pass through; sums here never approach the float overflow.
+__device__ __forceinline__ double tb_round_f32(double s) {
+#ifdef TB_K3C_CVT                                  // comparison build: through the conversion unit
+    return (double)(float)s;
+#endif
+    int e = __double2hiint(s) & 0x7ff00000;
+    e = max(e, (1023 - 126) << 20);
+    const double c = __hiloint2double(e + ((29 << 20) | 0x00080000), 0);
+    return __dadd_rn(__dadd_rn(s, c), -c);
+}
+
 __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w) {
-    float acc = 0.0f;
+    double acc = 0.0;
     for (int t = 0; t < w; t++) {
         const double x = v[first + t];
-        if (x != 0.0) acc = (float)((double)acc + x);          // adding 0.0 never changes the accumulator: skip its two conversions
+        if (x != 0.0) acc = tb_round_f32(__dadd_rn(acc, x));   // adding 0.0 never changes the accumulator
     }
-    return (double)acc;
+    return acc;
 }
 
 #define TB_K3C_TILE_MAX 1024     // positions per tile (chosen per launch from the region lengths, a multiple of 64 up to this)
@@ -488,15 +503,15 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                 double scale = 1.0;
                 if (q >= lf && q - lf + w <= Lr) {
                     int first = q - lf - c0;
-                    float au = 0.0f, aa = 0.0f, ap = 0.0f;
+                    double au = 0.0, aa = 0.0, ap = 0.0;            // float-valued accumulators (tb_round_f32)
                     for (int t = 0; t < w; t++) {
                         double cv = cor[first + t];
-                        aa = (float)((double)aa + fabs(cv));
-                        if (!(cv <= 0.0)) ap = (float)((double)ap + cv);    // the non-positive half adds 0.0: no change, no conversions
+                        aa = tb_round_f32(__dadd_rn(aa, fabs(cv)));
+                        if (!(cv <= 0.0)) ap = tb_round_f32(__dadd_rn(ap, cv));     // the non-positive half adds 0.0: no change
                     }
                     {   // uncorrected: only non-zero signal positions move the accumulator
                         const int fd = q - lf - d0;
-                        for (u32 z = pcnt[fd]; z < pcnt[fd + w]; z++) au = (float)((double)au + unc[(int)nzpos[z] + d0 - c0]);
+                        for (u32 z = pcnt[fd]; z < pcnt[fd + w]; z++) au = tb_round_f32(__dadd_rn(au, unc[(int)nzpos[z] + d0 - c0]));
                     }
                     double usum = au, asum = aa, psum_ = ap;
                     double nsum = asum - psum_;

@@ -210,6 +210,186 @@ __global__ void __launch_bounds__(1024, 1)
     if (tid < 5 && sc[tid]) atomicAdd(&g_scalars[tid], (u64)(i64)sc[tid]);
 }
 
+// ------------------------------------------------------------------------------------------------ K2, joint-histogram form (DWM)
+// The accumulate kernel above spends L(L+1)/2 = 325 shared-memory atomics on every k-mer.  The count tensor is a sum of
+// per-position-pair dinucleotide counts, and a position pair (m, n) only needs the JOINT distribution of the two chunks of
+// the k-mer that hold m and n.  So the k-mer is cut into chunks of `ch` bases (six chunks of 4 and one of 1 for L = 25), and for every pair
+// of chunks the weighted joint histogram H[v_row][v_col] (4^ch x 4^ch bins, u32, L2 resident: 10 tables x 4 MB per tensor)
+// receives ONE integer atomic per k-mer: 21 atomics instead of 325.  A second, tiny kernel folds every table into the
+// position-pair counts (marginals over the other bases of each chunk) -- cross-chunk pairs from the table of the two
+// chunks, pairs inside a chunk from the row marginal of one table in which that chunk is the row chunk (the pair {0, last}
+// is stored as (last, 0) so that every chunk is a row chunk somewhere).  Integers throughout: bit-exact in any order.
+#define TB_K2H_MAXT 64           // chunk pairs: L <= 31 -> 8 chunks of 4 (28 pairs) on the GPU, 11 chunks of 3 (55 pairs) in the test emulator
+
+struct tb_k2h_desc {
+    int L, ch, nc, nt, pstride;
+    unsigned char row[TB_K2H_MAXT], col[TB_K2H_MAXT], within[TB_K2H_MAXT];
+};
+
+static inline bool tb_k2h_plan(int L, int ch, int pstride, tb_k2h_desc &D) {
+    D.L = L; D.ch = ch; D.pstride = pstride;
+    D.nc = (L + ch - 1) / ch;
+    D.nt = 0;
+    if (D.nc < 2) return false;
+    for (int i = 0; i < D.nc; i++)
+        for (int j = i + 1; j < D.nc; j++) {
+            if (D.nt >= TB_K2H_MAXT) return false;
+            const bool flip = (i == 0 && j == D.nc - 1 && D.nc > 2);
+            D.row[D.nt] = (unsigned char)(flip ? j : i);
+            D.col[D.nt] = (unsigned char)(flip ? i : j);
+            D.within[D.nt] = 0;
+            D.nt++;
+        }
+    if (D.nc == 2) {             // chunk 1 is never a row chunk: one more table, used for its row marginal only (within = 2)
+        D.row[D.nt] = 1; D.col[D.nt] = 0; D.within[D.nt] = 2;
+        D.nt++;
+    }
+    for (int c = 0; c < D.nc; c++)
+        for (int t = 0; t < D.nt; t++)
+            if (D.row[t] == c) {
+                D.within[t] |= 1;
+                break;
+            }
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+    tb_k2_hist_kernel(tb_genome_view g, tb_k2_regions R, u32 *__restrict__ slab, const u64 *__restrict__ sites, i64 n_sites, int k_flank,
+                      int bg_shift, int cap, tb_k2h_desc D, u32 *__restrict__ H, u64 *__restrict__ g_scalars) {
+    __shared__ int sc[5];            // no_reads, no_bias_f, no_bg_f, no_bias_r, no_bg_r
+    if (threadIdx.x < 5) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const int L = D.L, ch = D.ch, nt = D.nt;
+    const u32 vmask = (1u << (2 * ch)) - 1u;
+    const int vbits = 2 * ch;
+    int mine[5] = {0, 0, 0, 0, 0};       // indexed by compile-time constants only (registers)
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_sites; k += stride) {
+        const u64 site = sites[k];
+        const i64 j = (i64)(site >> 32), x = (i64)(site & 0x7fffffffu);
+        const int strand = (int)((site >> 31) & 1u);
+        u32 *slot = slab + (i64)strand * R.slab_len + x;
+        const u32 cnt = *slot;
+        *slot = 0u;                                                      // the slab is all-zero again after this kernel
+        const int w = (int)(cnt < (u32)cap ? cnt : (u32)cap);
+        const i64 es = R.es[j], ee = R.ee[j];
+        const i64 gp = es + (x - R.soff[j]);
+        mine[0] += w;
+#pragma unroll
+        for (int which = 0; which < 2; which++) {                        // 0: bias k-mer, 1: background k-mer
+            const i64 c = which == 0 ? gp : (strand ? gp + bg_shift : gp - bg_shift);
+            if (!((c > es + k_flank) && (c <= ee - k_flank - 1))) continue;              // OneRead.get_kmer, ngs.pyx:115
+            if (tb_nflags(g, c - k_flank, L) != 0) continue;
+            const u64 kmer = tb_bases(g, c - k_flank, L);
+            const int tbl = strand * 2 + which;
+            mine[1 + which] += strand ? 0 : w;
+            mine[3 + which] += strand ? w : 0;
+            u32 *Ht = H + (((size_t)tbl * nt) << (2 * vbits));
+            for (int t = 0; t < nt; t++) {
+                const u32 vr = (u32)(kmer >> (vbits * D.row[t])) & vmask, vc = (u32)(kmer >> (vbits * D.col[t])) & vmask;
+                atomicAdd(Ht + (((size_t)t << vbits | vr) << vbits | vc), (u32)w);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        int v = mine[i];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sc[i], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && sc[threadIdx.x]) atomicAdd(&g_scalars[threadIdx.x], (u64)(i64)sc[threadIdx.x]);
+}
+
+// Folds the joint histograms into g_acc[tbl][code = Sm*4+Sn][pair (m <= n)].  grid = (row slabs, 4 * nt); a warp per table row.
+#define TB_K2H_MAXCH 5
+__global__ void __launch_bounds__(256) tb_k2_fold_kernel(tb_k2h_desc D, const u32 *__restrict__ H, u64 *__restrict__ g_acc) {
+    __shared__ u64 cross[TB_K2H_MAXCH * 4 * TB_K2H_MAXCH * 4];           // [(m, a)][(n, b)]
+    __shared__ u64 inner[TB_K2H_MAXCH * (TB_K2H_MAXCH + 1) / 2 * 16];    // [pair inside the row chunk][code]
+    __shared__ u32 wsum[8][TB_K2H_MAXCH * 4];
+    const int L = D.L, ch = D.ch, vbits = 2 * ch, V = 1 << vbits;
+    const int tt = blockIdx.y, tbl = tt / D.nt, t = tt % D.nt;
+    const int rc = D.row[t], cc = D.col[t], flags = D.within[t];
+    const int len_r = min(ch, L - rc * ch), len_c = min(ch, L - cc * ch);
+    const bool do_cross = !(flags & 2), do_inner = (flags & 1) != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < TB_K2H_MAXCH * 4 * TB_K2H_MAXCH * 4; i += blockDim.x) cross[i] = 0;
+    for (int i = threadIdx.x; i < TB_K2H_MAXCH * (TB_K2H_MAXCH + 1) / 2 * 16; i += blockDim.x) inner[i] = 0;
+    __syncthreads();
+    const u32 *Ht = H + ((size_t)tt << (2 * vbits));
+    const int rows_per_block = (V + gridDim.x - 1) / gridDim.x;
+    const int r_lo = blockIdx.x * rows_per_block, r_hi = min(V, r_lo + rows_per_block);
+    // lane's pair inside the row chunk (m <= n), for the inner counts
+    int im = -1, in_ = -1;
+    {
+        int q = 0;
+        for (int m = 0; m < len_r; m++)
+            for (int n = m; n < len_r; n++, q++)
+                if (q == lane) { im = m; in_ = n; }
+    }
+    for (int vr = r_lo + warp; vr < r_hi; vr += nwarps) {
+        u32 Rs[TB_K2H_MAXCH][4];
+#pragma unroll
+        for (int n = 0; n < TB_K2H_MAXCH; n++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) Rs[n][b] = 0u;
+        const u32 *row = Ht + ((size_t)vr << vbits);
+        for (int vc = lane; vc < V; vc += 32) {
+            const u32 h = row[vc];
+            if (h == 0u) continue;
+#pragma unroll
+            for (int n = 0; n < TB_K2H_MAXCH; n++) {
+                const int b = (vc >> (2 * n)) & 3;
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++) Rs[n][bb] += b == bb ? h : 0u;
+            }
+        }
+        // warp totals through shared memory: lane n * 4 + b ends up with R[n][b]
+        u32 *ws = wsum[warp];
+        if (lane < TB_K2H_MAXCH * 4) ws[lane] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < TB_K2H_MAXCH; n++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (Rs[n][b]) atomicAdd(&ws[n * 4 + b], Rs[n][b]);
+        __syncwarp();
+        const u32 rowsum = ws[0] + ws[1] + ws[2] + ws[3];
+        const u32 my = lane < TB_K2H_MAXCH * 4 ? ws[lane] : 0u;
+        __syncwarp();
+        if (rowsum == 0u) continue;                                      // warp-uniform
+        if (do_cross && lane < 4 * len_c && my)
+            for (int m = 0; m < len_r; m++) {
+                const int a = (vr >> (2 * m)) & 3;
+                atomicAdd(&cross[(m * 4 + a) * (TB_K2H_MAXCH * 4) + lane], (u64)my);
+            }
+        if (do_inner && im >= 0) {
+            const int code = ((vr >> (2 * im)) & 3) * 4 + ((vr >> (2 * in_)) & 3);
+            atomicAdd(&inner[lane * 16 + code], (u64)rowsum);
+        }
+    }
+    __syncthreads();
+    u64 *ga = g_acc + (size_t)tbl * 16 * D.pstride;
+    if (do_cross)
+        for (int i = threadIdx.x; i < len_r * 4 * TB_K2H_MAXCH * 4; i += blockDim.x) {
+            const u64 v = cross[i];
+            const int ma = i / (TB_K2H_MAXCH * 4), nb = i % (TB_K2H_MAXCH * 4);
+            if (!v || nb >= 4 * len_c) continue;
+            int M = rc * ch + ma / 4, a = ma & 3, N = cc * ch + nb / 4, b = nb & 3;
+            if (M > N) { int s = M; M = N; N = s; s = a; a = b; b = s; }
+            atomicAdd(&ga[(size_t)(a * 4 + b) * D.pstride + (M * L - M * (M - 1) / 2 + (N - M))], v);
+        }
+    if (do_inner)
+        for (int i = threadIdx.x; i < len_r * (len_r + 1) / 2 * 16; i += blockDim.x) {
+            const u64 v = inner[i];
+            if (!v) continue;
+            int q = i / 16, code = i & 15, m = 0;
+            while (q >= len_r - m) { q -= len_r - m; m++; }
+            const int M = rc * ch + m, N = M + q;
+            atomicAdd(&ga[(size_t)code * D.pstride + (M * L - M * (M - 1) / 2 + (N - M))], v);
+        }
+}
+
 // first record index with lstart >= v (records are sorted by linear start)
 __global__ void tb_k2_read_bound_kernel(const i64 *__restrict__ lstart, i64 n, i64 v, i64 *__restrict__ out) {
     if (threadIdx.x || blockIdx.x) return;
@@ -283,6 +463,21 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         if (ev && atoll(ev) > 0) site_cap = atoll(ev);
     }
 
+    // DWM: joint-histogram form unless the model is a single chunk (TB_K2_NO_HIST=1 / TB_K2_CHUNK=n: comparison runs and tests)
+    tb_k2h_desc HD;
+    bool use_hist = false;
+    if (is_dwm) {
+#ifdef TB_EMU
+        int ch = 3;              // the test emulator folds 64 x 64 tables (same code, fewer bins)
+#else
+        int ch = 4;              // 4^8 bins x 21 chunk pairs x 4 tensors = 22 MB: L2 resident (chunks of 5: 168 MB, measured slower)
+#endif
+        const char *ev = getenv("TB_K2_CHUNK");
+        if (ev && atoi(ev) >= 1 && atoi(ev) <= TB_K2H_MAXCH) ch = atoi(ev);
+        const char *nh = getenv("TB_K2_NO_HIST");
+        use_hist = !(nh && atoi(nh) > 0) && tb_k2h_plan(L, ch, pstride, HD);
+    }
+
     tb_timer_start(ctx);
     i64 j0 = 0;
     std::vector<i64> soff;
@@ -335,7 +530,18 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
                 site_cap = n_sites + n_sites / 8 + 1024;
                 continue;
             }
-            if (n_sites > 0) {
+            if (n_sites > 0 && use_hist && (double)n_sites * cap < 4.0e9) {
+                // joint-histogram form: one atomic per (k-mer, chunk pair) into L2-resident tables, then the fold
+                const size_t hbytes = ((size_t)4 * HD.nt << (4 * HD.ch)) * sizeof(u32);
+                TB_TRY(tb_reserve(ctx, ctx->k2_hist, hbytes));
+                TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_hist.p, 0, hbytes, ctx->stream));
+                i64 want = tb_div_up(n_sites, 256), capg = (i64)ctx->sm_count * 8;
+                TB_LAUNCH(ctx, tb_k2_hist_kernel, (unsigned)(want < capg ? want : capg), 256, 0, g, R, ctx->k2_slab.as<u32>(),
+                          (const u64 *)ctx->k2_sites.as<u64>(), n_sites, k_flank, bg_shift, cap, HD, ctx->k2_hist.as<u32>(), d_sc);
+                const int V = 1 << (2 * HD.ch);
+                const int slabs = V >= 64 ? V / 64 : 1;              // 64 table rows per block: 8 per warp
+                TB_LAUNCH(ctx, tb_k2_fold_kernel, dim3((unsigned)slabs, (unsigned)(4 * HD.nt)), 256, 0, HD, (const u32 *)ctx->k2_hist.as<u32>(), d_acc);
+            } else if (n_sites > 0) {
                 i64 n_batches = tb_div_up(n_sites, TB_K2_BATCH);
                 unsigned grid = (unsigned)(n_batches < ctx->sm_count ? n_batches : ctx->sm_count);
                 if (is_dwm) {
