@@ -72,6 +72,12 @@ int tb_launch_count(tb_ctx *ctx, int64_t *n);
 int tb_genome_create(tb_ctx *ctx, int n_contigs, const int64_t *lengths);
 /* upload ASCII bases [offset, offset+n) of one contig; offset must be a multiple of 32 */
 int tb_genome_upload(tb_ctx *ctx, int contig, int64_t offset, const uint8_t *ascii, int64_t n);
+/* asynchronous form of tb_genome_upload: copies and packing are enqueued on the context's copy stream and the call returns;
+ * `ascii` (page-locked: tb_host_alloc) must stay untouched until tb_genome_wait.  Every entry point that reads the genome waits on
+ * the device for the contigs it needs, so tb_count_reads / tb_bias_counts on the first contigs overlap with the transfer of the rest */
+int tb_genome_upload_async(tb_ctx *ctx, int contig, int64_t offset, const uint8_t *ascii, int64_t n);
+/* blocks the host until every asynchronous upload has completed */
+int tb_genome_wait(tb_ctx *ctx);
 /* debugging / tests: nucleotide codes (0..4) of contig[start, start+n) */
 int tb_genome_fetch(tb_ctx *ctx, int contig, int64_t start, int64_t n, uint8_t *codes_out);
 

@@ -100,12 +100,13 @@ def test_bias_counts_in_several_slab_chunks(loaded_ctx, golden, monkeypatch):
 
 
 def test_bias_counts_histogram_forms(loaded_ctx, golden, monkeypatch):
-    """DWM counts come from joint chunk histograms (one atomic per k-mer and chunk pair) folded into position pairs; every
-    chunking -- including a last chunk of one base, two chunks only, and the shared-memory-atomic kernel that serves models of a
-    single chunk / TB_K2_NO_HIST=1 -- gives the same integers as the reference."""
+    """DWM counts come from joint chunk histograms (one atomic per k-mer and chunk pair) folded into position pairs: the
+    shared-memory form (chunks of 2 bases, the default; also chunks of 1), the L2 form (every chunking -- including a last chunk
+    of one base and two chunks only) and the shared-memory-atomic kernel (TB_K2_NO_HIST=1, models of a single chunk) give the
+    same integers as the reference."""
     regs = [tuple(int(x) for x in r) for r in golden.atac["nonpeak"]]
     emu = loaded_ctx.device_info()["is_emulator"]
-    for k_flank, chunkings in ((12, (3, 4) if emu else (3, 4, 5)), (5, (1, 2, 5)), (2, (3, 4, 5))):
+    for k_flank, chunkings, smem_chunks in ((12, (3, 4) if emu else (3, 4, 5), (2,)), (5, (1, 2, 5), (1, 2)), (2, (3, 4, 5), (1, 2)), (1, (2,), (2,))):
         kw = dict(k_flank=k_flank, bg_shift=37, cap=3)
         ref = restate.bias_estimation(golden.reads, golden.genome, regs, golden.lengths, **kw)
         monkeypatch.setenv("TB_K2_NO_HIST", "1")
@@ -114,11 +115,42 @@ def test_bias_counts_histogram_forms(loaded_ctx, golden, monkeypatch):
         for si, st in enumerate(("forward", "reverse")):
             assert np.array_equal(base[si, 0], ref.bias[st].counts) and np.array_equal(base[si, 1], ref.bias[st].bg_counts)
         assert base_sc[0] == ref.no_reads
+        for ch in smem_chunks:
+            monkeypatch.setenv("TB_K2_SMEM_CHUNK", str(ch))
+            got, got_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
+            monkeypatch.delenv("TB_K2_SMEM_CHUNK")
+            assert np.array_equal(got, base) and np.array_equal(got_sc, base_sc), ("smem", k_flank, ch)
+        monkeypatch.setenv("TB_K2_NO_SMEM_HIST", "1")
         for ch in chunkings:
             monkeypatch.setenv("TB_K2_CHUNK", str(ch))
             got, got_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
             monkeypatch.delenv("TB_K2_CHUNK")
-            assert np.array_equal(got, base) and np.array_equal(got_sc, base_sc), (k_flank, ch)
+            assert np.array_equal(got, base) and np.array_equal(got_sc, base_sc), ("l2", k_flank, ch)
+        monkeypatch.delenv("TB_K2_NO_SMEM_HIST")
+
+
+def test_asynchronous_genome_upload(loaded_ctx, golden):
+    """tb_genome_upload_async + device-side fences: counts taken while the genome is still in flight (per-chunk waits in
+    tb_bias_counts, several chunks) equal the counts over the synchronously loaded genome; the host buffers are released by
+    genome_wait.  The fixture's genome is restored afterwards."""
+    kw = dict(k_flank=12, bg_shift=100, cap=10)
+    base, base_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
+    codes = [loaded_ctx.genome_fetch(i, 0, n) for i, n in enumerate(golden.lengths)]
+    try:
+        loaded_ctx.genome_create(golden.lengths)
+        bufs = []
+        for i, g in enumerate(golden.genome):
+            b = loaded_ctx.pinned_empty(g.shape, np.uint8)
+            b[...] = g
+            bufs.append(b)
+            loaded_ctx.genome_upload_async(i, b)
+        got, got_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
+        loaded_ctx.genome_wait()
+        assert np.array_equal(got, base) and np.array_equal(got_sc, base_sc)
+        for i, n in enumerate(golden.lengths):
+            assert np.array_equal(loaded_ctx.genome_fetch(i, 0, n), codes[i])
+    finally:
+        loaded_ctx.genome_load(golden.genome)
 
 
 def _set_model(ctx, g, mode):

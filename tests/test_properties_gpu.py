@@ -183,3 +183,38 @@ def test_footprints_properties(work):
     assert np.array_equal(part, fp[:n])
     zero = ctx.score_regions(np.zeros(5000, dtype=np.float32), [5000], ctx.score_params("footprint", flank=30, as_f64=False))
     assert not zero.any()
+
+
+def test_whole_contig_footprint_scan_matches_the_oracle_on_slices():
+    """BASELINE.json configs[3]: ScoreBigwig footprint scan, fp widths 20-50, flank 100, over a whole-contig corrected track
+    (one region of 120 Mb: ~300k tiles; dense float32 track, ~70 % exact zeros).  The score of a position depends on the
+    signal within flank_max + fp_max of it only, so random slices (incl. both contig ends) are checked against the oracle's
+    restatement of tobias_footprint_array run on the slice + halo; plus: an all-zero stretch scores zero."""
+    from oracle import restate
+    from tobias_b200 import lib
+    n = 120_000_000
+    rng = np.random.default_rng(77)
+    sig = np.zeros(n, dtype=np.float32)
+    nz = rng.random(n) >= 0.7
+    sig[nz] = np.round(rng.normal(0.0, 0.5, size=int(nz.sum())), 5).astype(np.float32)
+    sig[50_000_000:50_100_000] = 0.0
+    args = (100, 100, 20, 50)
+    halo = args[1] + args[3]
+    with lib.Context(0) as ctx:
+        p = ctx.score_params("footprint", flank=0, flank_min=args[0], flank_max=args[1], fp_min=args[2], fp_max=args[3], as_f64=False)
+        got = ctx.score_regions(sig, [n], p)
+        ms = ctx.last_kernel_ms()
+    assert got.shape == (n,) and np.all(np.isfinite(got)) and np.all(got >= 0)
+    assert not got[50_000_000 + halo:50_100_000 - halo].any()
+    starts = [0, n - 3000] + [int(x) for x in rng.integers(halo, n - 3000 - halo, size=10)] + [50_000_000 - 1500]
+    for a in starts:
+        lo, hi = max(0, a - 2 * halo), min(n, a + 3000 + 2 * halo)
+        ref = restate.tobias_footprint_array(sig[lo:hi].astype(np.float64), *args)
+        # positions whose windows all lie inside the slice (or at a true contig end) are complete in the slice's result
+        a0 = a if lo > 0 else 0
+        b0 = a + 3000 if hi < n else n
+        r, g = ref[a0 - lo:b0 - lo], got[a0:b0].astype(np.float64)
+        assert np.array_equal(g == 0, r == 0), a
+        m = r != 0
+        assert np.all(np.abs(g[m] - r[m]) <= 1e-5 * np.abs(r[m])), a
+    print("whole-contig footprint scan: %.1f ms for %d bp (%.3g bp/s)" % (ms, n, n / (ms * 1e-3)))

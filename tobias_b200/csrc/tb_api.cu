@@ -159,7 +159,7 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     tb_dbuf *bufs[] = {&ctx->seq2, &ctx->nmask, &ctx->d_contig_off, &ctx->r_start, &ctx->r_len, &ctx->r_clip, &ctx->r_flags,
                        &ctx->reg_a, &ctx->reg_b, &ctx->reg_c, &ctx->reg_d, &ctx->reg_e, &ctx->scratch0, &ctx->scratch1,
                        &ctx->scratch2, &ctx->scratch3, &ctx->scratch4, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
-                       &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_slab, &ctx->k2_sites, &ctx->k2_hist,
+                       &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_slab, &ctx->k2_sites, &ctx->k2_hist, &ctx->k2_wts, &ctx->staging_up,
                        &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
                        &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.fitg_x, &ctx->cor.fitg_y, &ctx->cor.fitg_st,
                        &ctx->cor.fitg_sti, &ctx->cor.fitg_wq, &ctx->cor.fitg_lists, &ctx->cor.tracks, &ctx->cor.prepost,
@@ -172,6 +172,8 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_copy);
+    for (cudaEvent_t e : ctx->contig_ready)
+        if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -291,6 +293,8 @@ static const i64 TB_CONTIG_PAD = 1024;     // >= this many N bases between conti
 extern "C" int tb_genome_create(tb_ctx *ctx, int n_contigs, const int64_t *lengths) {
     if (!ctx) return TB_ERR_ARG;
     if (n_contigs <= 0 || !lengths) return tb_fail(ctx, TB_ERR_ARG, "tb_genome_create: need at least one contig");
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));           // asynchronous uploads into the previous genome
+    ctx->contig_pending.assign(n_contigs, 0);
     ctx->contig_len.assign(lengths, lengths + n_contigs);
     ctx->contig_off.resize(n_contigs + 1);
     i64 off = TB_CONTIG_PAD;
@@ -320,6 +324,7 @@ extern "C" int tb_genome_upload(tb_ctx *ctx, int contig, int64_t offset, const u
     if (offset < 0 || (offset & 31) || n < 0 || offset + n > ctx->contig_len[contig])
         return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload: bad range offset=%lld n=%lld (offset must be a multiple of 32)",
                        (i64)offset, (i64)n);
+    TB_TRY(tb_genome_fence(ctx, contig, contig));                    // after an asynchronous upload of the same contig
     const i64 CHUNK = (i64)64 << 20;
     for (i64 done = 0; done < n; done += CHUNK) {
         i64 m = n - done < CHUNK ? n - done : CHUNK;
@@ -334,11 +339,60 @@ extern "C" int tb_genome_upload(tb_ctx *ctx, int contig, int64_t offset, const u
     return tb_check(ctx, cudaGetLastError(), "tb_pack_kernel");
 }
 
+// Asynchronous form: the copies and the packing kernels are enqueued on the copy stream and the call returns; `ascii` (page-locked,
+// tb_host_alloc, for a truly asynchronous copy) must stay untouched until tb_genome_wait.  Everything that reads the genome waits on
+// the device for the contigs it needs, so e.g. tb_bias_counts works on the first contigs while the later ones are still in flight.
+extern "C" int tb_genome_upload_async(tb_ctx *ctx, int contig, int64_t offset, const uint8_t *ascii, int64_t n) {
+    if (!ctx) return TB_ERR_ARG;
+    if (ctx->n_contigs == 0) return tb_fail(ctx, TB_ERR_STATE, "tb_genome_upload_async: call tb_genome_create first");
+    if (contig < 0 || contig >= ctx->n_contigs) return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload_async: contig %d out of range", contig);
+    if (offset < 0 || (offset & 31) || n < 0 || offset + n > ctx->contig_len[contig])
+        return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload_async: bad range offset=%lld n=%lld (offset must be a multiple of 32)",
+                       (i64)offset, (i64)n);
+    const i64 CHUNK = (i64)64 << 20;
+    if (ctx->staging_up.cap < (size_t)CHUNK + 64) {
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));       // nothing in flight may still read the old buffer
+        TB_TRY(tb_reserve(ctx, ctx->staging_up, (size_t)CHUNK + 64));
+    }
+    if ((int)ctx->contig_ready.size() < ctx->n_contigs) {
+        size_t have = ctx->contig_ready.size();
+        ctx->contig_ready.resize(ctx->n_contigs, nullptr);
+        for (size_t c = have; c < ctx->contig_ready.size(); c++)
+            TB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->contig_ready[c], cudaEventDisableTiming));
+    }
+    ctx->contig_pending.resize(ctx->n_contigs, 0);
+    for (i64 done = 0; done < n; done += CHUNK) {                    // one stream, one staging buffer: in order, no hazards
+        i64 m = n - done < CHUNK ? n - done : CHUNK;
+        TB_CUDA(ctx, cudaMemcpyAsync(ctx->staging_up.p, ascii + done, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TB_LAUNCH_ON(ctx, ctx->copy_stream, tb_pack_kernel, (unsigned)tb_div_up(tb_div_up(m, 32), 256), 256, 0, ctx->staging_up.as<uint8_t>(), m,
+                     ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->contig_off[contig] + offset + done);
+    }
+    TB_CUDA(ctx, cudaEventRecord(ctx->contig_ready[contig], ctx->copy_stream));
+    ctx->contig_pending[contig] = 1;
+    return tb_check(ctx, cudaGetLastError(), "tb_genome_upload_async");
+}
+
+// Host-side completion of every asynchronous upload (the host buffers may be reused afterwards).
+extern "C" int tb_genome_wait(tb_ctx *ctx) {
+    if (!ctx) return TB_ERR_ARG;
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    ctx->contig_pending.assign(ctx->contig_pending.size(), 0);
+    return tb_check(ctx, cudaGetLastError(), "tb_genome_wait");
+}
+
+int tb_genome_fence(tb_ctx *ctx, int c_lo, int c_hi) {
+    const int n = (int)ctx->contig_pending.size();
+    for (int c = c_lo < 0 ? 0 : c_lo; c <= c_hi && c < n; c++)
+        if (ctx->contig_pending[c]) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->contig_ready[c], 0));
+    return TB_OK;
+}
+
 extern "C" int tb_genome_fetch(tb_ctx *ctx, int contig, int64_t start, int64_t n, uint8_t *codes_out) {
     if (!ctx) return TB_ERR_ARG;
     if (contig < 0 || contig >= ctx->n_contigs || start < 0 || n < 0 || start + n > ctx->contig_len[contig])
         return tb_fail(ctx, TB_ERR_ARG, "tb_genome_fetch: bad range");
     if (n == 0) return TB_OK;
+    TB_TRY(tb_genome_fence(ctx, contig, contig));
     TB_TRY(tb_reserve(ctx, ctx->scratch0, (size_t)n));
     tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
     TB_LAUNCH(ctx, tb_fetch_codes_kernel, (unsigned)tb_div_up(n, 256), 256, 0, g, ctx->contig_off[contig] + start, (i64)n,

@@ -83,6 +83,12 @@ struct tb_ctx {
     i64 max_read_len = 0;             // longest reference span of a record (bounds the records a region chunk can see)
     tb_dbuf k2_slab, k2_sites;        // K2: multiplicity slab (kept all-zero between calls) and site list
     tb_dbuf k2_hist;                  // K2: joint chunk histograms (u32 [4 tensors][chunk pairs][4^ch][4^ch])
+    tb_dbuf k2_wts;                   // K2: capped multiplicity of every site (shared-memory histogram form)
+    // asynchronous genome uploads (tb_genome_upload_async): copies + packing run on copy_stream; consumers on `stream` wait for the
+    // events of the contigs they read (tb_genome_fence), so work on the first contigs overlaps with the transfer of the later ones
+    tb_dbuf staging_up;
+    std::vector<cudaEvent_t> contig_ready;
+    std::vector<char> contig_pending;
 
     // scratch / per-call device tables
     tb_dbuf reg_a, reg_b, reg_c, reg_d, reg_e;
@@ -133,6 +139,7 @@ struct tb_ctx {
 
 int tb_fail(tb_ctx *ctx, int code, const char *fmt, ...);
 int tb_reserve(tb_ctx *ctx, tb_dbuf &b, size_t bytes);
+int tb_genome_fence(tb_ctx *ctx, int c_lo, int c_hi);      // `stream` waits for pending asynchronous uploads of contigs [c_lo, c_hi]
 void tb_release(tb_dbuf &b);
 int tb_pinned(tb_ctx *ctx, size_t bytes);
 int tb_check(tb_ctx *ctx, cudaError_t e, const char *what);

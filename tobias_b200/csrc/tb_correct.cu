@@ -345,12 +345,12 @@ __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w)
 //   3. rescale factor and outputs.  sum of uncorrected = signal * cf: adding 0.0 never changes the accumulator, so only
 //      the non-zero signal positions are accumulated, in order; |corrected| and corrected+ sums: sequential
 //   4. verification counts: pre / post(+) / post(-) weights of every valid position are left in shared memory; lane m of
-//      a warp then owns k-mer offset m and adds the weights of the warp's strip of positions into 12 private (weight kind,
+//      a warp then owns k-mer offset m and adds the non-zero weights of the warp's strip of positions into 12 private (weight kind,
 //      base) accumulators -- no atomics in the loop (first version: 25 x 3 shared-memory fp64 atomics = CAS loops per position)
 __global__ void __launch_bounds__(TB_K3C_THREADS)
     tb_correct_kernel(tb_genome_view g, tb_cor_view V, const int32_t *__restrict__ tile_region,
                       const int32_t *__restrict__ tile_start, i64 n_tiles, int tile_len, const u32 *__restrict__ pile,
-                      const double *__restrict__ biasraw, const double *__restrict__ fit, double cf,
+                      const double *__restrict__ biasraw, const double *__restrict__ fit, double cf, int frec_off,
                       double *__restrict__ tracks, double *__restrict__ prepost) {
     TB_DYN_SMEM(smem);
     const int w = V.window, k = V.k_flank, L = V.L;
@@ -358,16 +358,18 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
     const int overlaps = w / TB_STEP;
     const int cap = tile_len + 4 * w;
     double *sig = (double *)smem;              // [d0, d1)  signal;            phase 4: pre weights of [t0, t1)
-    double *bp = sig + cap;                    // [d0, d1)  mean prediction;   phase 4: post(+) weights
+    double *bp = sig + cap;                    // [d0, d1)  mean prediction;   phase 4: post weights (sign picks counts / neg_counts)
     double *unc = bp + cap;                    // [c0, c1)  signal * cf
     double *cor = unc + cap;                   // [c0, c1)  uncorrected - expected
-    double *expd = cor + cap;                  // [t0, t1)  expected;          phase 4: post(-) weights
+    double *expd = cor + cap;                  // [t0, t1)  expected
     double *ver = expd + cap;                  // [2 strands][3][4][L] verification accumulators of this block
     u32 *psum = (u32 *)(ver + 2 * 3 * 4 * L);  // [cap + 1] prefix sums of the signal over [d0, d1)
     u32 *pcnt = psum + cap + 1;                // [cap + 1] prefix counts of its non-zero positions
     u32 *wsum = pcnt + cap + 1;                // [2][32] warp totals of the block scan
     unsigned short *nzpos = (unsigned short *)(wsum + 64);      // [cap] non-zero positions (relative to d0)
     uint8_t *bases = (uint8_t *)(nzpos + cap);                  // [tile_len + L] base codes of [t0 - k, t1 + k)
+    const int cap_w = (cap + w) / TB_STEP + 3;
+    double *frec = (double *)(smem + frec_off);                 // [cap_w][4] mode, a, b, max(prediction) of the windows over [d0, d1)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
@@ -397,6 +399,12 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
             const double *ft = fit + ((i64)strand * V.n_windows + V.win_off[j]) * TB_FIT_REC;
             // ---- 1. signal, bias_prediction = nanmean over the `overlaps` rows (:279-309), prefix sums
             const int per = (nd + nt - 1) / nt;                   // consecutive positions per thread in the scan
+            const int jw_lo = max(0, (d0 - k - w) / TB_STEP);     // windows that can cover a position of [d0, d1)
+            {
+                const int jw_hi = min(nwin - 1, max(0, d1 - 1 - k) / TB_STEP);
+                const int nrec = min(cap_w, jw_hi - jw_lo + 1);
+                for (int i = tid; i < nrec * 4; i += nt) frec[i] = ft[(i64)(jw_lo + (i >> 2)) * TB_FIT_REC + (i & 3)];   // read after the scan's barrier
+            }
             {
                 u32 s_loc = 0, c_loc = 0;
                 for (int e = 0; e < per; e++) {
@@ -445,14 +453,17 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                 int cnt = 0;
                 int jmax = q >= k ? (q - k) / TB_STEP : -1;
                 if (jmax > nwin - 1) jmax = nwin - 1;
+                const int r0 = jmax >= 0 ? jmax % overlaps : 0;
                 for (int r = 0; r < overlaps; r++) {
                     double val = 0.0;
                     bool have = false;
                     if (jmax >= r) {
-                        int jw = jmax - ((jmax - r) % overlaps);       // last window of row r starting at or before q
+                        int back = r0 - r;                              // (jmax - r) mod overlaps
+                        if (back < 0) back += overlaps;
+                        const int jw = jmax - back;                     // last window of row r starting at or before q
                         if (k + TB_STEP * jw + w > q) {
                             have = true;
-                            const double *f = ft + (i64)jw * TB_FIT_REC;
+                            const double *f = frec + (jw - jw_lo) * 4;
                             double mode = f[0], mx = f[3];
                             if (mode == 0.0) {
                                 double t = __dadd_rn(__dmul_rn(f[1], x), f[2]);
@@ -531,10 +542,9 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                 }
                 bool valid = q > k && q < Lr - k - 1 && (u != 0.0 || c != 0.0);
                 if (valid) valid = tb_nflags(g, gstart + q - k, L) == 0;
-                // sig / bp are not read in this phase and expd[q - t0] only by this thread: they now carry the weights of phase 4
+                // sig / bp are not read in this phase: they now carry the weights of phase 4
                 sig[q - t0] = (valid && u > 0.0) ? u : 0.0;       // pre_bias counts
-                bp[q - t0] = (valid && c > 0.0) ? c : 0.0;        // post_bias counts
-                expd[q - t0] = (valid && !(c > 0.0)) ? c : 0.0;   // post_bias neg_counts
+                bp[q - t0] = valid ? c : 0.0;                     // post_bias counts (c > 0) / neg_counts (c < 0)
             }
             __syncthreads();
             // ---- 4. verification counts: lane m owns offset m of the k-mer around every position of the warp's strip
@@ -549,16 +559,23 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                     for (int s = 0; s < 4; s++) acc[a][s] = 0.0;
                 if (lane < L) {
                     for (int q = qa; q < qb; q++) {
-                        const double v0 = sig[q], v1 = bp[q], v2 = expd[q];
-                        if (v0 == 0.0 && v1 == 0.0 && v2 == 0.0) continue;            // warp-uniform
+                        const double v0 = sig[q], v1 = bp[q];
+                        if (v0 == 0.0 && v1 == 0.0) continue;                         // every branch here is warp-uniform
                         const int s = bases[q + lane];
+                        if (v0 != 0.0) {
 #pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            if (s == b) {
-                                acc[0][b] += v0;
-                                acc[1][b] += v1;
-                                acc[2][b] += v2;
-                            }
+                            for (int b = 0; b < 4; b++)
+                                if (s == b) acc[0][b] += v0;
+                        }
+                        if (v1 > 0.0) {
+#pragma unroll
+                            for (int b = 0; b < 4; b++)
+                                if (s == b) acc[1][b] += v1;
+                        } else if (v1 != 0.0) {
+#pragma unroll
+                            for (int b = 0; b < 4; b++)
+                                if (s == b) acc[2][b] += v1;
+                        }
                     }
                     const int mm = strand ? L - 1 - lane : lane;
 #pragma unroll
@@ -768,9 +785,13 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     }
     tb_mark(ctx, 3);
     {
+        TB_TRY(tb_genome_fence(ctx, 0, ctx->n_contigs - 1));
         tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
         const size_t capk = (size_t)tile_len + 4 * window;
         size_t smem = ((size_t)5 * capk + 2 * 3 * 4 * L) * sizeof(double) + (2 * (capk + 1) + 64) * sizeof(u32) + capk * 2 + tile_len + L + 16;
+        smem = (smem + 15) & ~(size_t)15;
+        const int frec_off = (int)smem;                                 // fit records of the tile's windows
+        smem += ((capk + window) / TB_STEP + 3) * 4 * sizeof(double);
         auto kc = tb_correct_kernel;
         TB_CUDA(ctx, cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const i64 n_tiles = (i64)tile_region.size();
@@ -780,7 +801,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         const i64 capg = (i64)ctx->sm_count * per_sm;
         TB_LAUNCH(ctx, kc, (unsigned)(n_tiles < capg ? n_tiles : capg), TB_K3C_THREADS, smem, g, V, (const int32_t *)ctx->reg_a.as<int32_t>(),
                   (const int32_t *)ctx->reg_b.as<int32_t>(), n_tiles, tile_len, (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),
-                  (const double *)C.fit.as<double>(), correction_factor, C.tracks.as<double>(), C.prepost.as<double>());
+                  (const double *)C.fit.as<double>(), correction_factor, frec_off, C.tracks.as<double>(), C.prepost.as<double>());
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_correct_kernel"));
     }
     tb_mark(ctx, 4);

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(1024, 1)
 // position-pair counts (marginals over the other bases of each chunk) -- cross-chunk pairs from the table of the two
 // chunks, pairs inside a chunk from the row marginal of one table in which that chunk is the row chunk (the pair {0, last}
 // is stored as (last, 0) so that every chunk is a row chunk somewhere).  Integers throughout: bit-exact in any order.
-#define TB_K2H_MAXT 64           // chunk pairs: L <= 31 -> 8 chunks of 4 (28 pairs) on the GPU, 11 chunks of 3 (55 pairs) in the test emulator
+#define TB_K2H_MAXT 128          // chunk pairs: L <= 31 -> 16 chunks of 2 (120 pairs, shared-memory form), 8 chunks of 4 (28 pairs, L2 form)
 
 struct tb_k2h_desc {
     int L, ch, nc, nt, pstride;
@@ -299,6 +299,125 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     if (threadIdx.x < 5 && sc[threadIdx.x]) atomicAdd(&g_scalars[threadIdx.x], (u64)(i64)sc[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ K2, joint histograms in shared memory
+// Same decomposition with chunks of TWO bases: a table has 16 x 16 bins, so the tables of every chunk pair (78 for L = 25) of both
+// strands of ONE k-mer kind (bias or background) fit in the shared memory of a block: 2 x 78 x 1 KB = 156 KB.  Even blocks take the
+// bias k-mer of every site, odd blocks the background k-mer; 78 shared-memory atomics per k-mer instead of 21 L2 atomics (the L2
+// form above is bound by the L2 atomic rate, ~55 G/s) or 325 shared-memory atomics (accumulate kernel).  The blocks add their tables
+// into the same global layout the L2 form uses and the same fold kernel finishes.  Both kinds of block need a site's capped
+// multiplicity while the slab is being cleaned, so a first small kernel moves it into a per-site array.
+__global__ void __launch_bounds__(256)
+    tb_k2_weights_kernel(tb_k2_regions R, u32 *__restrict__ slab, const u64 *__restrict__ sites, i64 n_sites, int cap, u32 *__restrict__ wts,
+                         u64 *__restrict__ g_scalars) {
+    __shared__ int sc;
+    if (threadIdx.x == 0) sc = 0;
+    __syncthreads();
+    int mine = 0;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_sites; k += stride) {
+        const u64 site = sites[k];
+        u32 *slot = slab + (i64)((site >> 31) & 1u) * R.slab_len + (i64)(site & 0x7fffffffu);
+        const u32 cnt = *slot;
+        *slot = 0u;                                                      // the slab is all-zero again after this kernel
+        const u32 w = cnt < (u32)cap ? cnt : (u32)cap;
+        wts[k] = w;
+        mine += (int)w;
+    }
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sc, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && sc) atomicAdd(&g_scalars[0], (u64)(i64)sc);      // no_reads
+}
+
+// NC > 0: number of chunks known at compile time (chunk values in registers, table offsets immediate); NC = 0: any plan
+template <int NC>
+__global__ void __launch_bounds__(1024, 1)
+    tb_k2_hist_smem_kernel(tb_genome_view g, tb_k2_regions R, const u32 *__restrict__ wts, const u64 *__restrict__ sites, i64 n_sites,
+                           int k_flank, int bg_shift, int cap, tb_k2h_desc D, u32 *__restrict__ H, u64 *__restrict__ g_scalars) {
+    TB_DYN_SMEM(smem);
+    u32 *T = (u32 *)smem;                                                // [strand][table][row value][column value]
+    __shared__ int sc[2];                                                // weighted k-mers of this kind, forward / reverse
+    const int which = blockIdx.x & 1;                                    // 0: bias k-mer, 1: background k-mer
+    const int L = D.L, nt = D.nt, vbits = 2 * D.ch;
+    const u32 vmask = (1u << vbits) - 1u;
+    const int n_bins = (2 * nt) << (2 * vbits);
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) T[i] = 0u;
+    if (threadIdx.x < 2) sc[threadIdx.x] = 0;
+    __syncthreads();
+    int mine_f = 0, mine_r = 0;
+    const i64 stride = (i64)(gridDim.x >> 1) * blockDim.x;
+    const i64 flush_every = ((i64)1 << 31) / ((i64)(cap > 0 ? cap : 1) * blockDim.x);      // per-thread k-mers before a bin could wrap
+    i64 since = 0;
+    for (i64 k0 = (i64)(blockIdx.x >> 1) * blockDim.x; k0 < n_sites; k0 += stride) {       // block-uniform trip count (barrier below)
+        const i64 k = k0 + threadIdx.x;
+        if (k < n_sites) {
+            const u64 site = sites[k];
+            const i64 j = (i64)(site >> 32), x = (i64)(site & 0x7fffffffu);
+            const int strand = (int)((site >> 31) & 1u);
+            const u32 w = wts[k];
+            const i64 es = R.es[j], ee = R.ee[j];
+            const i64 gp = es + (x - R.soff[j]);
+            const i64 c = which == 0 ? gp : (strand ? gp + bg_shift : gp - bg_shift);
+            if ((c > es + k_flank) && (c <= ee - k_flank - 1) && tb_nflags(g, c - k_flank, L) == 0) {     // OneRead.get_kmer, ngs.pyx:115
+                const u64 kmer = tb_bases(g, c - k_flank, L);
+                mine_f += strand ? 0 : (int)w;
+                mine_r += strand ? (int)w : 0;
+                u32 *Tt = T + ((size_t)(strand * nt) << (2 * vbits));
+                if (NC > 0) {
+                    u32 v[NC > 0 ? NC : 1];
+#pragma unroll
+                    for (int i = 0; i < NC; i++) v[i] = (u32)(kmer >> (vbits * i)) & vmask;
+                    int t = 0;
+#pragma unroll
+                    for (int i = 0; i < NC; i++)
+#pragma unroll
+                        for (int jj = i + 1; jj < NC; jj++, t++) {
+                            const bool flip = (i == 0 && jj == NC - 1 && NC > 2);            // as tb_k2h_plan
+                            const u32 vr = flip ? v[jj] : v[i], vc = flip ? v[i] : v[jj];
+                            atomicAdd(Tt + (((size_t)t << vbits | vr) << vbits | vc), w);
+                        }
+                } else {
+                    for (int t = 0; t < nt; t++) {
+                        const u32 vr = (u32)(kmer >> (vbits * D.row[t])) & vmask, vc = (u32)(kmer >> (vbits * D.col[t])) & vmask;
+                        atomicAdd(Tt + (((size_t)t << vbits | vr) << vbits | vc), w);
+                    }
+                }
+            }
+        }
+        if (++since >= flush_every) {                                    // block-uniform
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_bins; i += blockDim.x) {
+                const u32 v = T[i];
+                if (v) {
+                    const int per = nt << (2 * vbits), st = i / per;
+                    atomicAdd(&H[(size_t)(st * 2 + which) * per + (i - st * per)], v);
+                    T[i] = 0u;
+                }
+            }
+            since = 0;
+            __syncthreads();
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mine_f += __shfl_xor_sync(0xffffffffu, mine_f, d);
+        mine_r += __shfl_xor_sync(0xffffffffu, mine_r, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mine_f) atomicAdd(&sc[0], mine_f);
+        if (mine_r) atomicAdd(&sc[1], mine_r);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) {
+        const u32 v = T[i];
+        if (v) {
+            const int per = nt << (2 * vbits), st = i / per;
+            atomicAdd(&H[(size_t)(st * 2 + which) * per + (i - st * per)], v);
+        }
+    }
+    // scalars: [1] no_bias_f, [2] no_bg_f, [3] no_bias_r, [4] no_bg_r
+    if (threadIdx.x < 2 && sc[threadIdx.x]) atomicAdd(&g_scalars[1 + 2 * threadIdx.x + which], (u64)(i64)sc[threadIdx.x]);
 }
 
 // Folds the joint histograms into g_acc[tbl][code = Sm*4+Sn][pair (m <= n)].  grid = (row slabs, 4 * nt); a warp per table row.
@@ -446,6 +565,10 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         SLAB_BUDGET = (i64)(free_b / 4 / (2 * sizeof(u32)));
         if (SLAB_BUDGET < ((i64)1 << 22)) SLAB_BUDGET = (i64)1 << 22;
         if (SLAB_BUDGET > (((i64)1 << 31) - 1)) SLAB_BUDGET = ((i64)1 << 31) - 1;
+        // genome still arriving (tb_genome_upload_async): smaller chunks, each waiting only for its own contigs
+        bool pending = false;
+        for (char c : ctx->contig_pending) pending = pending || c;
+        if (pending && SLAB_BUDGET > ((i64)3 << 27)) SLAB_BUDGET = (i64)3 << 27;
         const char *ev = getenv("TB_K2_SLAB_BUDGET");            // tests: force several chunks
         if (ev && atoll(ev) > 0) SLAB_BUDGET = atoll(ev);
     }
@@ -476,6 +599,29 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         if (ev && atoi(ev) >= 1 && atoi(ev) <= TB_K2H_MAXCH) ch = atoi(ev);
         const char *nh = getenv("TB_K2_NO_HIST");
         use_hist = !(nh && atoi(nh) > 0) && tb_k2h_plan(L, ch, pstride, HD);
+    }
+    // ... and its shared-memory form (chunks of two bases) when the tables of both strands fit in one block (L <= 29)
+    tb_k2h_desc SD;
+    bool use_smem_hist = false;
+    size_t sh_bytes = 0;
+    if (is_dwm) {
+        int ch = 2;
+        const char *ev = getenv("TB_K2_SMEM_CHUNK");              // tests: 1 (more tables) or 2
+        if (ev && atoi(ev) >= 1 && atoi(ev) <= 2) ch = atoi(ev);
+        const char *nh = getenv("TB_K2_NO_HIST"), *ns = getenv("TB_K2_NO_SMEM_HIST");
+        if (!(nh && atoi(nh) > 0) && !(ns && atoi(ns) > 0) && tb_k2h_plan(L, ch, pstride, SD)) {
+            sh_bytes = ((size_t)2 * SD.nt << (4 * SD.ch)) * sizeof(u32);
+            use_smem_hist = sh_bytes <= (size_t)200 * 1024;
+        }
+        if (use_smem_hist) {
+            if (SD.nc == 13 && ch == 2) {
+                auto k = tb_k2_hist_smem_kernel<13>;
+                TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
+            } else {
+                auto k = tb_k2_hist_smem_kernel<0>;
+                TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
+            }
+        }
     }
 
     tb_timer_start(ctx);
@@ -525,12 +671,43 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
             unsigned long long hc[2];
             TB_TRY(tb_d2h(ctx, hc, d_ctr, sizeof(hc)));
             i64 n_sites = (i64)hc[0];
+            {   // the k-mer kernels read the genome of this chunk's contigs
+                int c_lo = contig[j0], c_hi = contig[j0];
+                for (i64 j = j0; j < j1; j++) {
+                    c_lo = contig[j] < c_lo ? contig[j] : c_lo;
+                    c_hi = contig[j] > c_hi ? contig[j] : c_hi;
+                }
+                TB_TRY(tb_genome_fence(ctx, c_lo, c_hi));
+            }
             if (hc[1]) {       // site list too small (records spanning many tiny regions): clean the slab, grow, redo the chunk
                 TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_slab.p, 0, ctx->k2_slab.cap, ctx->stream));
                 site_cap = n_sites + n_sites / 8 + 1024;
                 continue;
             }
-            if (n_sites > 0 && use_hist && (double)n_sites * cap < 4.0e9) {
+            if (n_sites > 0 && use_smem_hist && (double)n_sites * cap < 4.0e9) {
+                // joint histograms of 2-base chunks in shared memory (even blocks: bias k-mers, odd blocks: background k-mers), then the fold
+                const size_t hbytes = ((size_t)4 * SD.nt << (4 * SD.ch)) * sizeof(u32);
+                TB_TRY(tb_reserve(ctx, ctx->k2_hist, hbytes));
+                TB_TRY(tb_reserve(ctx, ctx->k2_wts, (size_t)n_sites * sizeof(u32)));
+                TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_hist.p, 0, hbytes, ctx->stream));
+                i64 want = tb_div_up(n_sites, 256), capg = (i64)ctx->sm_count * 8;
+                TB_LAUNCH(ctx, tb_k2_weights_kernel, (unsigned)(want < capg ? want : capg), 256, 0, R, ctx->k2_slab.as<u32>(),
+                          (const u64 *)ctx->k2_sites.as<u64>(), n_sites, cap, ctx->k2_wts.as<u32>(), d_sc);
+                i64 pairs = tb_div_up(n_sites, 1024), capp = (ctx->sm_count + 1) / 2;          // one block per SM
+                if (pairs > capp) pairs = capp;
+                if (SD.nc == 13 && SD.ch == 2) {
+                    auto k = tb_k2_hist_smem_kernel<13>;
+                    TB_LAUNCH(ctx, k, (unsigned)(2 * pairs), 1024, sh_bytes, g, R, (const u32 *)ctx->k2_wts.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(),
+                              n_sites, k_flank, bg_shift, cap, SD, ctx->k2_hist.as<u32>(), d_sc);
+                } else {
+                    auto k = tb_k2_hist_smem_kernel<0>;
+                    TB_LAUNCH(ctx, k, (unsigned)(2 * pairs), 1024, sh_bytes, g, R, (const u32 *)ctx->k2_wts.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(),
+                              n_sites, k_flank, bg_shift, cap, SD, ctx->k2_hist.as<u32>(), d_sc);
+                }
+                const int V = 1 << (2 * SD.ch);
+                const int slabs = V >= 64 ? V / 64 : 1;
+                TB_LAUNCH(ctx, tb_k2_fold_kernel, dim3((unsigned)slabs, (unsigned)(4 * SD.nt)), 256, 0, SD, (const u32 *)ctx->k2_hist.as<u32>(), d_acc);
+            } else if (n_sites > 0 && use_hist && (double)n_sites * cap < 4.0e9) {
                 // joint-histogram form: one atomic per (k-mer, chunk pair) into L2-resident tables, then the fold
                 const size_t hbytes = ((size_t)4 * HD.nt << (4 * HD.ch)) * sizeof(u32);
                 TB_TRY(tb_reserve(ctx, ctx->k2_hist, hbytes));

@@ -570,6 +570,7 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
                 return tb_fail(ctx, TB_ERR_STATE, "forward and reverse bias models differ in type or length");
         }
     if (total == 0) return TB_OK;
+    TB_TRY(tb_genome_fence(ctx, 0, ctx->n_contigs - 1));
     tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
     tb_score_regions_view R{d_ext_start, d_ext_off, n_regions, total};
     const double *tf = ctx->model[0].table.as<double>(), *tr = ctx->model[1].table.as<double>();

@@ -46,6 +46,8 @@ _PROTOS = {
     "tb_host_free": (_i, [_vp, _vp]),
     "tb_genome_create": (_i, [_vp, _i, _vp]),
     "tb_genome_upload": (_i, [_vp, _i, _i64, _vp, _i64]),
+    "tb_genome_upload_async": (_i, [_vp, _i, _i64, _vp, _i64]),
+    "tb_genome_wait": (_i, [_vp]),
     "tb_genome_fetch": (_i, [_vp, _i, _i64, _i64, _vp]),
     "tb_reads_upload": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tb_count_reads": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, C.POINTER(_i64)]),
@@ -195,6 +197,17 @@ class Context:
     def genome_upload(self, contig, ascii_arr, offset=0):
         a = _arr(ascii_arr, np.uint8)
         self._ck(self._lib.tb_genome_upload(self._h, int(contig), int(offset), _ptr(a), int(a.shape[0])))
+
+    def genome_upload_async(self, contig, ascii_arr, offset=0):
+        """Enqueues the upload and returns; `ascii_arr` (ideally from pinned_empty) must stay alive and untouched until genome_wait()."""
+        a = _arr(ascii_arr, np.uint8)
+        self._pending_uploads = getattr(self, "_pending_uploads", [])
+        self._pending_uploads.append(a)
+        self._ck(self._lib.tb_genome_upload_async(self._h, int(contig), int(offset), _ptr(a), int(a.shape[0])))
+
+    def genome_wait(self):
+        self._ck(self._lib.tb_genome_wait(self._h))
+        self._pending_uploads = []
 
     def genome_load(self, contigs):
         """contigs: list of uint8 ASCII arrays, one per contig, in contig-id order."""
