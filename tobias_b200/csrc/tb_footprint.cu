@@ -130,9 +130,9 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
     double *P = (double *)smem;                                 // n_in + 1
     double *N = P + (n_in + 1);                                 // n_in + 1
     double *aux = N + (n_in + 1);                               // 2 * S
-    float *W0 = (float *)(aux + 2 * S);                         // n_in, two buffers
-    float *W1 = W0 + n_in;
-    float *A = W1 + n_in;                                       // S
+    float *W0 = (float *)(aux + 2 * S);                         // n_in + 32 (the width loop reads a full batch of 32), two buffers
+    float *W1 = W0 + n_in + TB_K4_NPW;
+    float *A = W1 + n_in + TB_K4_NPW;                           // S
     float *B = A + S;                                           // S
     const float *sg = signal + V.ext_off[j];
 
@@ -160,16 +160,16 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
         for (int fw = fmin_; fw <= fmax_; fw++) {
             float *W = wbuf ? W1 : W0;
             wbuf ^= 1;
-            for (int i = tid; i + fw <= n_in; i += S) W[i] = (float)(P[i + fw] - P[i]);
+            // flank sums already divided by 2 * fw (once per element instead of once per element and footprint width)
+            const float inv = 1.0f / (2.0f * (float)fw);
+            for (int i = tid; i + fw <= n_in; i += S) W[i] = (float)(P[i + fw] - P[i]) * inv;
             __syncthreads();                                    // the other buffer is rewritten only after the next barrier
             const i64 i0 = s - fw;
             if (i0 >= 0 && i0 < limit) {
                 const float l = W[si - fw];
-                const float inv = 1.0f / (2.0f * (float)fw);
                 const float *wr = W + si + pw0;
 #pragma unroll
-                for (int c = 0; c < TB_K4_NPW; c++)
-                    if (c < npw) acc[c] = fmaxf(acc[c], (l + wr[c]) * inv);
+                for (int c = 0; c < TB_K4_NPW; c++) acc[c] = fmaxf(acc[c], l + wr[c]);      // c >= npw: padding, dropped below
             }
         }
         // acc[c] -> score of (s, pw0 + c)
@@ -494,7 +494,7 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
         TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles));
         tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
         const int n_in = fos ? bs + 2 * (p->flank_max + p->fp_max) : bs + 2 * p->flank_max + p->fp_max;
-        size_t smem = (size_t)(2 * (n_in + 1) + 2 * bs) * sizeof(double) + (size_t)(2 * n_in + 2 * bs) * sizeof(float);
+        size_t smem = (size_t)(2 * (n_in + 1) + 2 * bs) * sizeof(double) + (size_t)(2 * (n_in + TB_K4_NPW) + 2 * bs) * sizeof(float);
         if (smem > (size_t)220 * 1024) return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: flank/footprint widths too large for one tile");
 #define TB_FP_CASE(KERNEL, OM)                                                                                              \
     {                                                                                                                       \
