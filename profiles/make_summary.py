@@ -71,7 +71,10 @@ def stage_of(kernel):
 HISTORY = """History of the same line this round (ms per step, hg38, 1 GPU): 1377 (warp-per-window fits with tree sums, sum-form DWM scoring)
 -> 1082 (thread-per-window exact fits) -> 883 (product-form scoring) -> 754 (K2 site list) -> 614 (K3c without fp64 shared atomics, K3a trinucleotide
 group + butterfly reduction) -> 604 (K4) -> 478 (one-pass outer iterations for DWM fits) -> 444 (K3a rows from tensor memory) -> 427 (K3a compile-time
-grouping) -> 367 (K3a ratio form, lane = column) -> 338 (plane-major traversal in the one-pass fits).  e2e: 1496 -> ~430 ms.
+grouping) -> 367 (K3a ratio form, lane = column) -> 338 (plane-major traversal in the one-pass fits) -> 317 (K3c one tile per region, K2 joint histograms
+in L2) -> 309 (K3c rounding in the fp64 pipe, fit records in shared memory) -> 291 (K2 joint histograms of 2-base chunks in shared memory) -> 288 (K4
+pre-scaled flank sums, unconditional width loop).  e2e: 1496 -> ~430 -> 396 -> 355 ms (genome upload on the copy stream, overlapped with the read
+counts and the training counts).
 """
 
 READINGS = """## 4. Readings: which unit binds each kernel
@@ -81,11 +84,11 @@ DRAM traffic of every kernel is within ~2x of its algorithmic bytes and none of 
 | kernel | binding unit | what was done about it this round | what is left |
 |---|---|---|---|
 | K1 `tb_pileup_kernel` | L2 atomics / integer issue (scatter), 1.1 ms for 49M records + 124M positions | -- (0.3 % of the step) | -- |
-| K2 `tb_k2_scatter` + `tb_k2_accumulate` | integer issue + shared-memory atomics | site list instead of a slab scan; warp-per-k-mer atomics without return value; conflict-free accumulator rows (174 -> 40 ms) | 325 atomics per k-mer are the work itself |
+| K2 `tb_k2_scatter` + `tb_k2_weights` + `tb_k2_hist_smem` + `tb_k2_fold` | scatter / weights: DRAM latency of sector-sized read-modify-writes on the 24 GB multiplicity slab (12.6 of the 16 ms); histogram: shared-memory atomics | site list instead of a slab scan (174 -> 40 ms); joint histograms of chunk pairs instead of one atomic per position pair: 21 L2 atomics per k-mer (32 ms, bound by the L2 atomic rate), then 78 shared-memory atomics per k-mer on 16 x 16 tables (histogram kernel 25 -> 3.2 ms, K2 16 ms) | the slab passes: a sort-based dedup of (region, strand, cut site) would avoid the 24 GB slab |
 | K3a `tb_score_dwm2_kernel` | **instruction issue**, then shared-memory bandwidth | product form (no exp2), pair / trinucleotide row groups (25 -> 10 rows), ratio form (3 values per column, lane = column), 5 groups read from **tensor memory** through tcgen05.ld, butterfly reduction, compile-time grouping (446 -> 98 ms) | epilogue instructions (exponent split, butterfly selects) |
 | K3b `tb_fitg_round_kernel` | **instruction issue + L1 miss latency** (thread-sequential LM arithmetic; fp64 and integer instructions issue at half rate) | one thread per window, rounds over compacted lists, exact MINPACK order without m-vector storage (2854 -> 227 ms exact); one-pass outer iterations, plane-major traversal, tail finished in one launch for DWM (-> ~80 ms) | compulsory L1 misses of the window data every round |
-| K3c `tb_correct_kernel` | **conversion unit (XU)**: the reference's float accumulator = 2 conversions per term of the rolling sums | no fp64 shared atomics, integer prefix / sparse sums where exact, zero addends skipped (103 -> 68 ms); integer / fp64 emulations of the conversions were measured and are slower | three dense rolling sums (bias prediction, abs(corrected), corrected+) -- the semantics are the reference's |
-| K4 `tb_footprint_kernel` | issue (fp32 + shared loads), 651 width combinations per position | fitted block size, half the barriers, suffix-maximum spreading (49 -> 30 ms) | -- |
+| K3c `tb_correct_kernel` | instruction issue, spread over four phases (was: conversion unit, two conversions per term of the float-accumulator rolling sums) | no fp64 shared atomics, integer prefix / sparse sums where exact, zero addends skipped (103 -> 68 ms); one tile per 824-bp region (-> 57); float rounding in the fp64 pipe by adding and subtracting 1.5 * 2^(E+29) -- exact, no conversions (-> 56); fit records staged in shared memory, no per-row modulo, sign-split verification adds (-> 52.5) | three dense sequential rolling sums of 100 terms per position -- the semantics are the reference's |
+| K4 `tb_footprint_kernel` | issue (fp32 + shared loads), 651 width combinations per position | fitted block size, half the barriers, suffix-maximum spreading (49 -> 30 ms); flank sums divided by 2 x width once per element and an unconditional, padded width loop: LDS + FADD + FMNMX per combination instead of five instructions (-> 26 ms) | two footprint starts per thread with 64-bit shared loads |
 
 Bytes-based roofline fractions (algorithmic bytes of SURVEY 8d / measured time / 6554.9 GB/s measured copy bandwidth) are therefore small for
 K2-K4 (0.1 - 0.6 %) and are reported in every bench line (`stages[*].alg_GBps`, `roofline`) because the contract asks for them; K1 reaches 16 %.
@@ -115,19 +118,19 @@ def main():
          "## 1. Bench line the profiles belong to (not under a profiler)\n",
          "`python bench.py --steps 3 --warmup 3 --no-cpu-baseline` (hg38 workload: 3.1 Gb, 150k peaks, 49.3M records, 105.1 Mb of output regions), 1 GPU:\n",
          "| quantity | value |\n|---|---|",
-         "| `value` (inputs resident) | %.4g bp/s, %.1f ms per step (kernels %.1f ms; the rest is host work between launches, 14 - 40 ms from run to run) |"
+         "| `value` (inputs resident) | %.4g bp/s, %.1f ms per step (the six stages %.1f ms; the rest: read-count kernels 3.3 ms, footprint input 3.5 ms, host work between launches; one run in five shows 30 ms more of it) |"
          % (bench["value"], ms, ssum),
-         "| `e2e` (host buffers, H2D 3.94 GB + D2H 2.10 GB per step inside the timed region) | %.4g bp/s, %.1f ms per step |"
+         "| `e2e` (host buffers, H2D 3.94 GB + D2H 2.10 GB per step inside the timed region; 76 ms of H2D at 52 GB/s is the floor under it) | %.4g bp/s, %.1f ms per step |"
          % (bench["e2e"]["value"], bench["e2e"]["ms_per_step"]),
          "| `gpu_launches` in the timed region (3 steps) | %d |" % bench["gpu_launches"],
          "| clocks during the timed region | %s MHz of %s MHz, throttle reasons %s |"
          % (bench["clocks"]["sm_mhz"], bench["clocks"]["sm_max_mhz"], bench["clocks"]["reasons"]),
-         "| reference on the box's 16 host cores (`--impl reference`) | 1.0e5 bp/s |",
+         "| reference on the box's 16 host cores (`--impl reference`; `cpu_baseline` of the default bench line) | 1.0e5 - 1.1e5 bp/s |",
          "\nStage times (CUDA events on the library stream, mean over the timed steps; DWM default = one-pass outer iterations in the window fits):\n",
          "| stage | ms | share of the kernels | algorithmic GB/s (SURVEY 8d bytes / time) |\n|---|---|---|---|"]
     for k, v in st.items():
         L.append("| %s | %.2f | %.1f%% | %s |" % (k, v["ms"], 100 * v["ms"] / ssum, v["alg_GBps"]))
-    L.append("\nWith `--lm-exact` (MINPACK-exact window fits, the PWM default): K3b ~215 ms.\n")
+    L.append("\nWith `--lm-exact` (MINPACK-exact window fits, the PWM default): K3b ~215 ms.  Whole-contig footprint scan of BASELINE configs[3] (fp 20-50, flank 100, one 120 Mb region, `tests/test_properties_gpu.py`): 14.1 ms = 8.5e9 bp/s.\n")
     L.append(HISTORY)
     L.append("## 2. ncu launch list of the bench command\n")
     L.append("`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tb_ -c 3000 --csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline`\n"
@@ -165,11 +168,25 @@ def main():
         return {"bound": bound, "bound_util_pct": d.get(key), "dram_MB_per_launch_chr50mb": round(d.get("dram_read_MB", 0) + d.get("dram_write_MB", 0), 1)}
     roofs = {"_source": "profiles/r01_summary.md section 3-4 (ncu --set full, one launch per kernel, chr50mb workload, B200)",
              "K1_pileup": roof("tb_pileup_kernel<0>", "L2 atomics / integer issue", "alu_pipe_pct"),
-             "K2_counts": roof("tb_k2_accumulate", "integer issue + shared-memory atomics", "alu_pipe_pct"),
+             "K2_counts": roof("tb_k2_scatter", "DRAM latency of the slab read-modify-writes (scatter, weights); shared-memory atomics (histogram)", "sm_throughput_pct"),
              "K3a_score": roof("tb_score_dwm2", "instruction issue, then shared-memory bandwidth (+ tensor-memory reads)", "issue_active_pct"),
              "K3b_fit": roof("tb_fitg_round_kernel<1, 1>", "instruction issue (thread-sequential LM arithmetic) + L1 miss latency", "issue_active_pct"),
-             "K3c_correct": roof("tb_correct_kernel", "conversion unit (float-accumulator rolling sums)", "xu_pipe_pct"),
+             "K3c_correct": roof("tb_correct_kernel", "instruction issue (sequential float-accumulator rolling sums, 10-row mean, verification counts)", "issue_active_pct"),
              "K4_footprint": roof("tb_footprint_kernel", "instruction issue (fp32 + shared loads)", "issue_active_pct")}
+    # DRAM traffic of the dominant kernel at the bench's own size: one --set full launch of tb_score_dwm2_kernel in the hg38 bench
+    # (gpurun_out/r01_full_hg38.ncu-rep; the kernel has not changed since that capture)
+    rep = os.path.join(OUT, "r01_full_hg38.ncu-rep")
+    if os.path.exists(rep):
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rws = list(csv.reader(io.StringIO(txt)))
+        h, u = rws[0], rws[1]
+        for v in rws[2:]:
+            if "tb_score_dwm2" in v[h.index("Kernel Name")]:
+                rd = float(v[h.index("dram__bytes_read.sum")]) * SCALE[u[h.index("dram__bytes_read.sum")]] * 1e6
+                wr = float(v[h.index("dram__bytes_write.sum")]) * SCALE[u[h.index("dram__bytes_write.sum")]] * 1e6
+                roofs["K3a_score"]["dram_bytes_per_launch_hg38"] = rd + wr
+                roofs["K3a_score"]["dram_note"] = ("read %.3g + write %.3g bytes; the write side is twice the 16 B per position of the final scores because the "
+                                                   "four (strand, model) block classes write partial scores that a 2 ms kernel combines" % (rd, wr))
     json.dump(roofs, open(os.path.join(PROF, "r01_roofs.json"), "w"), indent=1)
 
 

@@ -91,6 +91,21 @@ def test_slab_chunking_is_invisible(work, monkeypatch):
     assert np.array_equal(counts, chunked) and np.array_equal(scalars, scalars2)
 
 
+def test_count_kernels_agree(work, monkeypatch):
+    """The three DWM count kernels -- joint histograms in shared memory (default), joint histograms in L2, one shared-memory atomic
+    per position pair -- produce the same integers on the benchmark-shaped workload (1.2M records, cap path included)."""
+    ctx, ds, arrays = work
+    regs = arrays["input_regions"]
+    counts, scalars = ctx.bias_counts(*regs, is_dwm=True)
+    monkeypatch.setenv("TB_K2_NO_SMEM_HIST", "1")
+    l2, l2_sc = ctx.bias_counts(*regs, is_dwm=True)
+    monkeypatch.setenv("TB_K2_NO_HIST", "1")
+    pairs, pairs_sc = ctx.bias_counts(*regs, is_dwm=True)
+    assert np.array_equal(counts, l2) and np.array_equal(scalars, l2_sc)
+    assert np.array_equal(counts, pairs) and np.array_equal(scalars, pairs_sc)
+    assert scalars[0] > 100000
+
+
 def _model(ctx, arrays):
     from tobias_b200.pipeline import AtacBias, STRANDS
     counts, scalars = ctx.bias_counts(*arrays["input_regions"], is_dwm=True)
