@@ -147,11 +147,11 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
     trace = os.environ.get("TB_BENCH_TRACE") and (not resident or os.environ.get("TB_BENCH_TRACE") == "2")   # diagnostic: host wall clock per phase (stderr)
     marks = [("start", time.perf_counter())]
 
-    def mark(name):
+    def mark(name):                       # resident passes: every library call below returns synchronised, so the host clock is enough
         if trace:
             import torch
             torch.cuda.synchronize()
-            marks.append((name, time.perf_counter()))
+        marks.append((name, time.perf_counter()))
     if not resident:                      # e2e: inputs come from (pinned) host buffers every step
         ctx.genome_create(host["lengths"])
         ctx.reads_upload(*host["reads"])
@@ -207,8 +207,9 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
         mark("footprint_d2h")
     if trace:
         sys.stderr.write(("e2e" if not resident else "resident") + " trace (ms): " + ", ".join("%s %.1f" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])) + "\n")
+    phases = {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}
     return bias, {"K1_pileup": stage[0], "K3a_score": stage[1], "K3b_fit": stage[2], "K3c_correct": stage[3],
-                  "K2_counts": k2_ms, "K4_footprint": k4_ms}
+                  "K2_counts": k2_ms, "K4_footprint": k4_ms}, phases
 
 
 def bench_b200(args):
@@ -257,31 +258,33 @@ def bench_b200(args):
     def timed(resident, n_warm, n_steps):
         stages, last = None, None
         for _ in range(n_warm):
-            last, stages = run_step(eng, arrays, device, resident, host, out)
+            last, stages, _ = run_step(eng, arrays, device, resident, host, out)
         barrier()
         launches0 = ctx.launch_count()
         ctx.timer_begin()
         t0 = time.perf_counter()
-        acc = {}
+        acc, pacc = {}, {}
         for _ in range(n_steps):
-            last, stages = run_step(eng, arrays, device, resident, host, out)
+            last, stages, phases = run_step(eng, arrays, device, resident, host, out)
             for k, v in stages.items():
                 acc[k] = acc.get(k, 0.0) + v
+            for k, v in phases.items():
+                pacc.setdefault(k, []).append(round(v, 2))
         ms = ctx.timer_end()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
         t = torch.tensor([ms, wall], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), {k: v / n_steps for k, v in acc.items()}, ctx.launch_count() - launches0, last
+        return float(t[0]), float(t[1]), {k: v / n_steps for k, v in acc.items()}, ctx.launch_count() - launches0, last, pacc
 
     # resident inputs for `value`
     run_step(eng, arrays, device, False, host, out)
     sampler = ClockSampler(local)
     sampler.start()
-    ms_res, wall_res, stages, launches, bias = timed(True, args.warmup, args.steps)
+    ms_res, wall_res, stages, launches, bias, phases_res = timed(True, args.warmup, args.steps)
     clocks = sampler.stop()
-    ms_e2e, wall_e2e, _, _, _ = timed(False, max(1, min(args.warmup, 2)), args.steps)
+    ms_e2e, wall_e2e, _, _, _, phases_e2e = timed(False, max(1, min(args.warmup, 2)), args.steps)
 
     tot_bp = torch.tensor([out_bp, int((arrays["output_regions"][2] - arrays["output_regions"][1] + 124).sum())], dtype=torch.float64, device=device)
     if world > 1:
@@ -331,6 +334,9 @@ def bench_b200(args):
                              "HBM bound -- the unit that binds each kernel and its ncu utilisation are in `stages` (profiles/r01_summary.md); "
                              "traffic: no --set full capture of this exact launch (chr50mb capture in profiles/r01_roofs.json)"},
         "stages": per_stage, "wall_ms_per_step": wall_res / args.steps, "setup_s": round(setup_s, 1),
+        # host clock around every library call of the timed steps (one entry per step; resident: each call returns synchronised, so these
+        # add up to ms_per_step and show where host work sits between the kernels; e2e: calls overlap with the copy stream)
+        "host_phases_ms": {"resident": phases_res, "e2e": phases_e2e},
         "correction_factor": bias.correction_factor,
     }
     if world == 1 and rank == 0 and not args.no_cpu_baseline:

@@ -347,7 +347,7 @@ __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w)
 //   4. verification counts: pre / post(+) / post(-) weights of every valid position are left in shared memory; lane m of
 //      a warp then owns k-mer offset m and adds the non-zero weights of the warp's strip of positions into 12 private (weight kind,
 //      base) accumulators -- no atomics in the loop (first version: 25 x 3 shared-memory fp64 atomics = CAS loops per position)
-__global__ void __launch_bounds__(TB_K3C_THREADS)
+__global__ void __launch_bounds__(TB_K3C_THREADS, 3)
     tb_correct_kernel(tb_genome_view g, tb_cor_view V, const int32_t *__restrict__ tile_region,
                       const int32_t *__restrict__ tile_start, i64 n_tiles, int tile_len, const u32 *__restrict__ pile,
                       const double *__restrict__ biasraw, const double *__restrict__ fit, double cf, int frec_off,
@@ -358,16 +358,17 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
     const int overlaps = w / TB_STEP;
     const int cap = tile_len + 4 * w;
     double *sig = (double *)smem;              // [d0, d1)  signal;            phase 4: pre weights of [t0, t1)
-    double *bp = sig + cap;                    // [d0, d1)  mean prediction;   phase 4: post weights (sign picks counts / neg_counts)
-    double *unc = bp + cap;                    // [c0, c1)  signal * cf
+    double *bp = sig + cap;                    // [d0, d1)  mean prediction;   phase 4: post(-) weights, padded by L zeros
+    double *unc = bp + cap;                    // [c0, c1)  signal * cf;       phase 4: positions by base
     double *cor = unc + cap;                   // [c0, c1)  uncorrected - expected
-    double *expd = cor + cap;                  // [t0, t1)  expected
+    double *expd = cor + cap;                  // [t0, t1)  expected;          phase 4: post(+) weights
     double *ver = expd + cap;                  // [2 strands][3][4][L] verification accumulators of this block
     u32 *psum = (u32 *)(ver + 2 * 3 * 4 * L);  // [cap + 1] prefix sums of the signal over [d0, d1)
     u32 *pcnt = psum + cap + 1;                // [cap + 1] prefix counts of its non-zero positions
     u32 *wsum = pcnt + cap + 1;                // [2][32] warp totals of the block scan
     unsigned short *nzpos = (unsigned short *)(wsum + 64);      // [cap] non-zero positions (relative to d0)
     uint8_t *bases = (uint8_t *)(nzpos + cap);                  // [tile_len + L] base codes of [t0 - k, t1 + k)
+    __shared__ int bcnt[4];                                     // positions per base in the tile (+- k_flank)
     const int cap_w = (cap + w) / TB_STEP + 3;
     double *frec = (double *)(smem + frec_off);                 // [cap_w][4] mode, a, b, max(prediction) of the windows over [d0, d1)
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -518,7 +519,11 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                     for (int t = 0; t < w; t++) {
                         double cv = cor[first + t];
                         aa = tb_round_f32(__dadd_rn(aa, fabs(cv)));
+#ifdef TB_K3C_MIX                                       // comparison build: this sum through the conversion unit, the other in the fp64 pipe
+                        if (!(cv <= 0.0)) ap = (double)(float)__dadd_rn(ap, cv);
+#else
                         if (!(cv <= 0.0)) ap = tb_round_f32(__dadd_rn(ap, cv));     // the non-positive half adds 0.0: no change
+#endif
                     }
                     {   // uncorrected: only non-zero signal positions move the accumulator
                         const int fd = q - lf - d0;
@@ -543,11 +548,36 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                 bool valid = q > k && q < Lr - k - 1 && (u != 0.0 || c != 0.0);
                 if (valid) valid = tb_nflags(g, gstart + q - k, L) == 0;
                 // sig / bp are not read in this phase: they now carry the weights of phase 4
-                sig[q - t0] = (valid && u > 0.0) ? u : 0.0;       // pre_bias counts
-                bp[q - t0] = valid ? c : 0.0;                     // post_bias counts (c > 0) / neg_counts (c < 0)
+                sig[q - t0] = (valid && u > 0.0) ? u : 0.0;               // pre_bias counts
+                expd[q - t0] = (valid && c > 0.0) ? c : 0.0;              // post_bias counts
+                bp[L + q - t0] = (valid && !(c > 0.0)) ? c : 0.0;         // post_bias neg_counts, L zeros on either side
+            }
+            {
+                const int n_pos = t1 - t0;
+                if (tid < L) bp[tid] = 0.0;
+                else if (tid < 2 * L) bp[n_pos + tid] = 0.0;
+                // positions of [t0 - k, t1 + k) by base, increasing (in the memory of `unc`, which the phase above does not read ... but
+                // other threads may still be in it: the lists are written after the barrier)
             }
             __syncthreads();
-            // ---- 4. verification counts: lane m owns offset m of the k-mer around every position of the warp's strip
+            unsigned short *blist = (unsigned short *)unc;               // [4][tile_len + L]
+            const int bl_cap = tile_len + L;
+            if (warp < 4) {
+                const int nb = t1 - t0 + 2 * k;
+                int cnt = 0;
+                for (int i = 0; i < nb; i += 32) {
+                    const bool mine = i + lane < nb && bases[i + lane] == warp;
+                    const unsigned m = __ballot_sync(0xffffffffu, mine);
+                    if (mine) blist[warp * bl_cap + cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(i + lane);
+                    cnt += __popc(m);
+                }
+                if (lane == 0) bcnt[warp] = cnt;
+            }
+            __syncthreads();
+            // ---- 4. verification counts: lane m owns offset m of the k-mer.  pre / post(+) weights are sparse: the positions of the warp's
+            //         strip that carry one are broadcast and added under the base of the lane's k-mer position.  post(-) weights are dense
+            //         (every covered position without reads): per base, the lane walks the list of positions holding that base and adds the
+            //         weight of the k-mer centre that puts its offset there -- one load and one add per (position, offset), no predication
             {
                 const int n_pos = t1 - t0;
                 const int strip = (n_pos + nwarps - 1) / nwarps;
@@ -559,7 +589,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                     for (int s = 0; s < 4; s++) acc[a][s] = 0.0;
                 if (lane < L) {
                     for (int q = qa; q < qb; q++) {
-                        const double v0 = sig[q], v1 = bp[q];
+                        const double v0 = sig[q], v1 = expd[q];
                         if (v0 == 0.0 && v1 == 0.0) continue;                         // every branch here is warp-uniform
                         const int s = bases[q + lane];
                         if (v0 != 0.0) {
@@ -567,15 +597,22 @@ __global__ void __launch_bounds__(TB_K3C_THREADS)
                             for (int b = 0; b < 4; b++)
                                 if (s == b) acc[0][b] += v0;
                         }
-                        if (v1 > 0.0) {
+                        if (v1 != 0.0) {
 #pragma unroll
                             for (int b = 0; b < 4; b++)
                                 if (s == b) acc[1][b] += v1;
-                        } else if (v1 != 0.0) {
-#pragma unroll
-                            for (int b = 0; b < 4; b++)
-                                if (s == b) acc[2][b] += v1;
                         }
+                    }
+                    const double *negw = bp + L - lane;                               // negw[p] = weight of centre p - lane (0 outside the tile)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int nb = bcnt[b];
+                        const int per = (nb + nwarps - 1) / nwarps;
+                        const int ia = warp * per, ib = min(nb, ia + per);
+                        const unsigned short *lst = blist + b * bl_cap;
+                        double a2 = 0.0;
+                        for (int i = ia; i < ib; i++) a2 += negw[lst[i]];
+                        acc[2][b] = a2;
                     }
                     const int mm = strand ? L - 1 - lane : lane;
 #pragma unroll
