@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- runs tb_lm_fit_warp (tobias_b200/csrc/tb_lm.cuh) inside the kernel emulator (one warp =
 // 32 fibers) on windows read from a text file, so that tests/test_lm_exact.py can compare it with scipy.optimize.curve_fit.
-// usage: lm_harness <file> <seq 0|1|2>   (0 warp-tree sums, 1 warp with MINPACK-order sums, 2 thread-per-window exact, 4 thread-per-window fast)     file: repeated blocks, a line "W <m>" followed by m lines "<x> <y>"
+// usage: lm_harness <file> <seq 0|1|2>   (0 warp-tree sums, 1 warp with MINPACK-order sums, 2 thread-per-window exact, 4 thread-per-window one-pass form, 5 the same with the fused trial + next head)     file: repeated blocks, a line "W <m>" followed by m lines "<x> <y>"
 // prints one line per window: a b info nfev usable   (%.17g)
 #define TB_EMU 1
 #include "tb_common.cuh"
@@ -16,14 +16,14 @@ static double gtx[10 * TB_FIT_Q];
 static unsigned gty[10 * TB_FIT_Q];
 void kern() {
     int lane = threadIdx.x & 31;
-    if (g_seq == 2 || g_seq == 4) {                    // thread-per-window form (tb_lm_thread.cuh): lane 0 fits the window alone
+    if (g_seq == 2 || g_seq == 4 || g_seq == 5) {                    // thread-per-window form (tb_lm_thread.cuh): lane 0 fits the window alone
         if (lane == 0) {
             for (int i = 0; i < gm; i++) {
                 gtx[(i % 10) * TB_FIT_Q + i / 10] = gx[i];
                 gty[(i % 10) * TB_FIT_Q + i / 10] = (unsigned)gy[i];
             }
             tb_win_ref W{gtx, gty, TB_FIT_Q};
-            if (g_seq == 2) tb_lm_fit_thread<false>(W, gm, gres); else tb_lm_fit_thread<true>(W, gm, gres);
+            if (g_seq == 2) tb_lm_fit_thread<false>(W, gm, gres); else if (g_seq == 4) tb_lm_fit_thread<true>(W, gm, gres); else tb_lm_fit_thread<true, true>(W, gm, gres);
         }
         return;
     }

@@ -118,6 +118,15 @@ def test_fast_forms_follow_the_same_fit(harness, tmp_path, form):
             assert np.allclose(pred, pred_ref, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(pred_ref).max()))
 
 
+def test_fused_trial_and_head_is_bit_identical(harness, tmp_path):
+    """form 5 = form 4 with the Jacobian inner products of the next outer iteration formed in the trial pass (what the round kernels
+    run): the same arithmetic in the same order, so every window ends with the same bits, info and nfev."""
+    windows = _windows(480, seed=9)
+    a = _run(harness, windows, 4, str(tmp_path))
+    b = _run(harness, windows, 5, str(tmp_path))
+    assert a == b
+
+
 def test_reference_sensitivity():
     """scipy's own answer moves by ~1e-9..1e-6 (relative) when its input moves by 1e-13: forward-difference Jacobians."""
     rng = np.random.default_rng(2)

@@ -217,6 +217,9 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
 #ifndef TB_FITG_MINBLOCKS
 #define TB_FITG_MINBLOCKS 4
 #endif
+#ifndef TB_FITG_FUSE
+#define TB_FITG_FUSE 1      // 0: separate Jacobian and trial passes in the one-pass form (comparison builds)
+#endif
 template <bool WITH_QR, bool FAST>
 __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
     tb_fitg_round_kernel(tb_fitg_view G, int m, const u32 *__restrict__ list, i64 n_list, double *__restrict__ fit,
@@ -249,8 +252,9 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
                 if (FAST) tb_lmt_qr_fast(S, W, m);
                 else tb_lmt_qr(S, W, m);
             }
+            // one-pass form: fused trial + next head, so every surviving window continues on the trial-only list
             bool accepted = false;
-            if (S.info == 0) accepted = tb_lmt_trial<FAST>(S, W, m);
+            if (S.info == 0) accepted = tb_lmt_trial<FAST, FAST && TB_FITG_FUSE>(S, W, m);
             if (S.info != 0) {
                 double mode, pa, pb, pmax;
                 tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
                 rec[5] = (double)S.nfev;
             } else {
                 tb_fitg_store(G, slot, S);
-                to_q = accepted;
-                to_t = !accepted;
+                to_q = accepted && !(FAST && TB_FITG_FUSE);
+                to_t = !to_q;
             }
         }
         tb_fitg_append(to_q, slot, nextq, ctr);

@@ -559,12 +559,23 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     // 24 GB for both strands -> one or two chunks on a 180 GB B200), at most 2^31 - 1 (site records hold 31 bits)
     i64 SLAB_BUDGET;
     {
-        size_t free_b = 0, total_b = 0;
-        TB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-        free_b += ctx->k2_slab.cap;
-        SLAB_BUDGET = (i64)(free_b / 4 / (2 * sizeof(u32)));
+        const i64 LIM = ((i64)1 << 31) - 1;
+        i64 need = 0;
+        for (i64 i = 0; i < n_regions; i++) need += ee[i] - es[i];
+        if (ctx->k2_budget > 0 && need <= ctx->k2_budget_need) {
+            // same or smaller region space than an earlier call: its budget (a quarter of the memory that was free then) still holds.  No
+            // driver query on the steady path: cudaMemGetInfo was seen to stall for 10 - 40 ms now and then while nvidia-smi samples clocks
+            SLAB_BUDGET = ctx->k2_budget;
+        } else {
+            size_t free_b = 0, total_b = 0;
+            TB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+            free_b += ctx->k2_slab.cap;
+            SLAB_BUDGET = (i64)(free_b / 4 / (2 * sizeof(u32)));
+            ctx->k2_budget = SLAB_BUDGET;
+            ctx->k2_budget_need = need;
+        }
         if (SLAB_BUDGET < ((i64)1 << 22)) SLAB_BUDGET = (i64)1 << 22;
-        if (SLAB_BUDGET > (((i64)1 << 31) - 1)) SLAB_BUDGET = ((i64)1 << 31) - 1;
+        if (SLAB_BUDGET > LIM) SLAB_BUDGET = LIM;
         // genome still arriving (tb_genome_upload_async): smaller chunks, each waiting only for its own contigs
         bool pending = false;
         for (char c : ctx->contig_pending) pending = pending || c;

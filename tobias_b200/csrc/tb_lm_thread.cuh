@@ -393,26 +393,34 @@ struct tb_jac_fast {
     }
 };
 
-__device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, int m) {
-    const double epsmch = 2.220446049250313e-16, factor = 100.0;
+// inner products of the forward-difference Jacobian columns and the residual at one parameter point, plus rows 0 and 1
+struct tb_gram {
+    double g00, g01, g11, gf0, gf1;
+    double f0, a0, b0, f1, a1, b1;                      // rows 0 and 1: residual, d/da, d/db
+};
+__device__ __forceinline__ tb_jac_fast tb_jac_fast_at(double par0, double par1) {
+    const double epsmch = 2.220446049250313e-16;
     const double eps = sqrt(epsmch);
     tb_jac_fast J;
-    J.a = S.par0;
-    J.b = S.par1;
-    {
-        double h = eps * fabs(S.par0);
-        if (h == 0.0) h = eps;
-        J.ap = S.par0 + h;
-        J.h0inv = 1.0 / h;
-        h = eps * fabs(S.par1);
-        if (h == 0.0) h = eps;
-        J.bp = S.par1 + h;
-        J.h1inv = 1.0 / h;
-    }
-    S.nfev += 2;
-    double f0, a0, b0, f1, a1, b1;                      // rows 0 and 1: residual, d/da, d/db
-    J.eval(W.x[0], tb_u32_to_double(W.y[0]), f0, a0, b0);
-    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), f1, a1, b1);
+    J.a = par0;
+    J.b = par1;
+    double h = eps * fabs(par0);
+    if (h == 0.0) h = eps;
+    J.ap = par0 + h;
+    J.h0inv = 1.0 / h;
+    h = eps * fabs(par1);
+    if (h == 0.0) h = eps;
+    J.bp = par1 + h;
+    J.h1inv = 1.0 / h;
+    return J;
+}
+__device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref W, int m, const tb_jac_fast &J, const tb_gram &Gm);
+
+__device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, int m) {
+    const tb_jac_fast J = tb_jac_fast_at(S.par0, S.par1);
+    tb_gram Gm;
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
     double g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
     TB_FOR_POINTS_ANY_ORDER(W, m, {
         double f, j0, j1;
@@ -423,6 +431,17 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
         gf0 += j0 * f;
         gf1 += j1 * f;
     })
+    Gm.g00 = g00; Gm.g01 = g01; Gm.g11 = g11; Gm.gf0 = gf0; Gm.gf1 = gf1;
+    tb_lmt_qr_from_gram(S, W, m, J, Gm);
+}
+
+// R, Q^T fvec, column norms and the outer-iteration bookkeeping from the inner products (no pass over the window unless the columns look
+// dependent); counts the two function evaluations of the forward differences
+__device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref W, int m, const tb_jac_fast &J, const tb_gram &Gm) {
+    const double factor = 100.0;
+    S.nfev += 2;
+    const double g00 = Gm.g00, g01 = Gm.g01, g11 = Gm.g11, gf0 = Gm.gf0, gf1 = Gm.gf1;
+    const double f0 = Gm.f0, a0 = Gm.a0, b0 = Gm.b0, f1 = Gm.f1, a1 = Gm.a1, b1 = Gm.b1;
     S.acn0 = sqrt(g00);
     S.acn1 = sqrt(g11);
     const bool swap = S.acn1 > S.acn0;
@@ -486,7 +505,11 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
 
 // one inner iteration of lmdif: lmpar step, trial residual, trust-region update, termination tests.
 // returns true when the step was accepted (the next round starts with tb_lmt_qr); S.info != 0 ends the fit.
-template <bool FAST>
+// FUSE (one-pass form only): the pass that forms the trial residual norm also forms the inner products of the Jacobian columns AT THE
+// TRIAL POINT, and when the step is accepted the head of the next outer iteration (tb_lmt_qr_from_gram) follows at once -- an accepted
+// step then costs one pass over the window instead of two, and the next round needs no Jacobian pass.  Same arithmetic in the same
+// order as the separate passes: the fits are bit-identical.  A rejected step wastes the two extra model evaluations per point.
+template <bool FAST, bool FUSE = false>
 __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int m) {
     const double epsmch = 2.220446049250313e-16;
     const double ftol = 1.49012e-8, xtol = 1.49012e-8;
@@ -507,9 +530,28 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
     double pnorm = tb_enorm2(wa3[0], wa3[1]);
     if (S.iter == 1) S.delta = fmin(S.delta, pnorm);
     double fnorm1;
+    tb_jac_fast J;
+    tb_gram Gm;
     {
         const double ta = wa2[0], tb_ = wa2[1];
-        if (FAST) {
+        if (FAST && FUSE) {
+            J = tb_jac_fast_at(ta, tb_);
+            J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+            J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
+            double ss = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
+            TB_FOR_POINTS_ANY_ORDER(W, m, {
+                double f, j0, j1;
+                J.eval(ex, ey, f, j0, j1);
+                ss += f * f;
+                g00 += j0 * j0;
+                g01 += j0 * j1;
+                g11 += j1 * j1;
+                gf0 += j0 * f;
+                gf1 += j1 * f;
+            })
+            Gm.g00 = g00; Gm.g01 = g01; Gm.g11 = g11; Gm.gf0 = gf0; Gm.gf1 = gf1;
+            fnorm1 = sqrt(ss);
+        } else if (FAST) {
             double ss = 0.0;
             TB_FOR_POINTS_ANY_ORDER(W, m, {
                 const double r = tb_relu_res(ta, tb_, ex, ey);
@@ -573,6 +615,7 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
         if (S.gnorm <= epsmch) info = 8;
     }
     S.info = info;
+    if (FAST && FUSE && accepted && info == 0) tb_lmt_qr_from_gram(S, W, m, J, Gm);      // head of the next outer iteration (may set S.info)
     return accepted;
 }
 
@@ -615,17 +658,21 @@ __device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref 
 }
 
 // complete fit of one window by one thread (test harness entry; the kernel interleaves the phases across lanes)
-template <bool FAST>
+template <bool FAST, bool FUSE = false>
 __device__ __forceinline__ void tb_lm_fit_thread(const tb_win_ref W, int m, tb_lm_result &res) {
     tb_lmt S;
     double f0 = tb_lmt_fnorm0(W, m);
     tb_lmt_init(S, f0 < 0.0 ? 0.0 : f0);
+    bool need_qr = true;
     for (;;) {
-        if (FAST) tb_lmt_qr_fast(S, W, m);
-        else tb_lmt_qr(S, W, m);
+        if (need_qr) {
+            if (FAST) tb_lmt_qr_fast(S, W, m);
+            else tb_lmt_qr(S, W, m);
+            if (S.info) break;
+        }
+        const bool accepted = tb_lmt_trial<FAST, FAST && FUSE>(S, W, m);
         if (S.info) break;
-        while (!tb_lmt_trial<FAST>(S, W, m) && !S.info) {}
-        if (S.info) break;
+        need_qr = accepted && !(FAST && FUSE);          // fused: the head of the next outer iteration ran inside the trial
     }
     double mode, pa, pb, pmax;
     tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
