@@ -202,6 +202,25 @@ __device__ __forceinline__ u32 tb_nflags(const tb_genome_view &g, i64 k, int nb)
     if (nb < 32) r &= ((1u << nb) - 1u);
     return r;
 }
+// the same for a value shared by the 32 lanes of a warp (all of them must call it): every round probes 32 pivots at once, so the
+// chain of dependent loads is log33(n) long instead of log2(n) (4 rounds instead of 18 for 150k regions)
+__device__ __forceinline__ i64 tb_upper_bound_warp(const i64 *a, i64 n, i64 v) {
+    const int lane = threadIdx.x & 31;
+    i64 lo = 0, hi = n;                                   // a[i] <= v below lo, a[i] > v from hi on
+    while (lo < hi) {
+        const i64 step = (hi - lo + 32) / 33;
+        const i64 idx = lo + (i64)(lane + 1) * step - 1;
+        const bool gt = idx < hi ? a[idx] > v : true;
+        const unsigned m = __ballot_sync(0xffffffffu, gt);
+        const int first = m ? __ffs((int)m) - 1 : 32;
+        const i64 nlo = first == 0 ? lo : lo + (i64)first * step;
+        i64 nhi = lo + (i64)(first + 1) * step - 1;
+        if (first == 32 || nhi > hi) nhi = hi;
+        lo = nlo;
+        hi = nhi;
+    }
+    return lo;
+}
 // first index i in [0, n) with a[i] > v  (a ascending)
 __device__ __forceinline__ i64 tb_upper_bound(const i64 *a, i64 n, i64 v) {
     i64 lo = 0, hi = n;

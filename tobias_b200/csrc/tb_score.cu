@@ -299,8 +299,9 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
         bool okl = false;
         {
             const i64 pos = pos0 + lane;
+            i64 j = tb_upper_bound_warp(R.ext_off, R.n + 1, pos0) - 1;     // region of the unit's first position, found by the whole warp
             if (pos < R.total) {
-                i64 j = tb_upper_bound(R.ext_off, R.n + 1, pos) - 1;
+                while (pos >= R.ext_off[j + 1]) j++;                       // the lane's own region: the same or one of the next few
                 i64 local = pos - R.ext_off[j];
                 i64 len = R.ext_off[j + 1] - R.ext_off[j];
                 if (local >= k_flank && local < len - k_flank) {
