@@ -197,11 +197,16 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
             const i64 j = tb_upper_bound(V.win_off, V.n_regions + 1, wg) - 1;
             const i64 q = (i64)strand * qs + wg + (i64)(qm - 1) * j;
             G.wq[slot] = (u32)q;
-            const double f0 = tb_lmt_fnorm0(tb_win_ref{G.gx + q, G.gy + q, G.qtot}, V.window);
+            tb_win_stats st;
+            const double f0 = tb_lmt_fnorm0_stats(tb_win_ref{G.gx + q, G.gy + q, G.qtot}, V.window, st);
             if (f0 >= 0.0) {                                           // signalmax > 0 (:290)
                 tb_lmt S;
                 tb_lmt_init(S, f0);
                 tb_fitg_store(G, slot, S);
+                double *rec = fit + slot * TB_FIT_REC;                 // parked in the window's record until its fit ends
+                rec[1] = st.xmax;
+                rec[2] = st.xmin;
+                rec[3] = st.bmin;
                 live = true;
             } else {
                 double *rec = fit + slot * TB_FIT_REC;
@@ -257,8 +262,9 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
             if (S.info == 0) accepted = tb_lmt_trial<FAST, FAST && TB_FITG_FUSE>(S, W, m);
             if (S.info != 0) {
                 double mode, pa, pb, pmax;
-                tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
                 double *rec = fit + (i64)slot * TB_FIT_REC;
+                const tb_win_stats st{rec[1], rec[2], rec[3]};         // left there by tb_fitg_init_kernel
+                tb_lmt_finish_stats(S, st, mode, pa, pb, pmax);
                 rec[0] = mode;
                 rec[1] = pa;
                 rec[2] = pb;
@@ -300,8 +306,9 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
             if (S.info != 0) break;
         }
         double mode, pa, pb, pmax;
-        tb_lmt_finish(S, W, m, mode, pa, pb, pmax);
         double *rec = fit + (i64)slot * TB_FIT_REC;
+        const tb_win_stats st{rec[1], rec[2], rec[3]};
+        tb_lmt_finish_stats(S, st, mode, pa, pb, pmax);
         rec[0] = mode;
         rec[1] = pa;
         rec[2] = pb;

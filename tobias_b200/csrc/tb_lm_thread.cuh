@@ -162,6 +162,30 @@ __device__ __forceinline__ double tb_relu_res(double a, double b, double x, doub
     return tb_relu(__dadd_rn(__dmul_rn(a, x), b)) - y;          // np.maximum(0.0, a*x + b) - ydata
 }
 
+// the window statistics the end of a fit needs (tb_lmt_finish_stats): max / min of the bias and the smallest bias under a non-zero signal.
+// They depend on the window only, so the pass that forms the first residual norm takes them along and no fit pays a pass for them at its
+// end (in the round kernels that pass ran with only the finishing lanes of a warp active -- a third of the instructions of a round).
+struct tb_win_stats {
+    double xmax, xmin, bmin;
+};
+__device__ __forceinline__ double tb_lmt_fnorm0_stats(const tb_win_ref W, int m, tb_win_stats &st) {
+    tb_enorm_acc n;
+    tb_enorm_init(n);
+    u32 ymax = 0;
+    double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
+    TB_FOR_POINTS(W, m, i, {
+        ymax = eyi > ymax ? eyi : ymax;
+        xmax = fmax(xmax, ex);
+        xmin = fmin(xmin, ex);
+        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
+        tb_enorm_add(n, tb_relu_res(1.0, 1.0, ex, ey), m);
+    })
+    st.xmax = xmax;
+    st.xmin = xmin;
+    st.bmin = bmin;
+    return ymax > 0 ? tb_enorm_result(n) : -1.0;
+}
+
 // residual norm at the start point p0 = (1, 1) and max(signal) of one window; returns -1 when the window holds no signal
 __device__ __forceinline__ double tb_lmt_fnorm0(const tb_win_ref W, int m) {
     tb_enorm_acc n;
@@ -622,8 +646,7 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
 // scipy's post-conditions (ier in {1,2,3,4}; inv(R) exists and the covariance holds no NaN) and the window record:
 // mode 0: usable fit (a, b), mode 1: the reference's fallback (atacorrect_functions.py:296-299); pmax = max(prediction).
 // The prediction max(0, a*x + b) is monotonic in x (rounding is monotonic), so its maximum sits at max(x) or min(x).
-__device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref W, int m, double &mode, double &pa, double &pb,
-                                              double &pmax) {
+__device__ __forceinline__ void tb_lmt_finish_stats(const tb_lmt &S, const tb_win_stats &st, double &mode, double &pa, double &pb, double &pmax) {
     int usable = (S.info >= 1 && S.info <= 4) ? 1 : 0;
     if (usable) {
         if (S.r00 == 0.0 || S.r11 == 0.0) usable = 0;
@@ -634,13 +657,7 @@ __device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref 
             if (c00 != c00 || c01 != c01 || c11 != c11) usable = 0;
         }
     }
-    double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
-    TB_FOR_POINTS(W, m, i, {
-        xmax = fmax(xmax, ex);
-        xmin = fmin(xmin, ex);
-        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
-        (void)ey;
-    })
+    const double xmax = st.xmax, xmin = st.xmin, bmin = st.bmin;
     if (usable) {
         const double a = S.par0, b = S.par1;
         mode = 0.0;
@@ -655,6 +672,17 @@ __device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref 
         double t = xmax - bmin;                                 // max_i max(0, x_i - bmin)
         pmax = t < 0.0 ? 0.0 : t;
     }
+}
+__device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref W, int m, double &mode, double &pa, double &pb,
+                                              double &pmax) {
+    tb_win_stats st{-INFINITY, INFINITY, INFINITY};
+    TB_FOR_POINTS(W, m, i, {
+        st.xmax = fmax(st.xmax, ex);
+        st.xmin = fmin(st.xmin, ex);
+        if (eyi != 0u) st.bmin = fmin(st.bmin, ex);             // ~isclose(signal, 0)
+        (void)ey;
+    })
+    tb_lmt_finish_stats(S, st, mode, pa, pb, pmax);
 }
 
 // complete fit of one window by one thread (test harness entry; the kernel interleaves the phases across lanes)
