@@ -66,28 +66,59 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
 #define TB_FOR_POINTS(W, m, i, ...) TB_FOR_POINTS_FROM(W, m, 0, i, __VA_ARGS__)
 // all points in storage order (plane by plane: v = 0..9, then u): for sums whose order is free (the one-pass form).  No index
 // arithmetic per point -- consecutive points of a plane are consecutive slots.
-#ifndef TB_FIT_UNROLL_ANY
-#define TB_FIT_UNROLL_ANY 2
+// One flat loop over the m points (plane by plane) with the loads running TB_FIT_AHEAD points ahead of the arithmetic, across plane
+// boundaries.  Measured on hg38 (K3b): 2 ahead 59.8 ms, 3: 63.9, 4: 66.9, 6: 67.4 (register pressure: the round kernels sit at the
+// 128-register limit of four blocks per SM); the per-plane loop with one point ahead it replaces: 61.0.
+#ifndef TB_FIT_AHEAD
+#define TB_FIT_AHEAD 2
 #endif
-#define TB_FOR_POINTS_ANY_ORDER(W, m, ...)                                     \
-    for (int _v = 0; _v < 10; _v++) {                                          \
-        const int _n = ((m) - _v + 9) / 10;                                    \
-        if (_n <= 0) break;                                                    \
-        const double *_px = (W).x + (i64)_v * (W).stride;                      \
-        const u32 *_py = (W).y + (i64)_v * (W).stride;                         \
-        double _nx = _px[0];                                                   \
-        u32 _ny = _py[0];                                                      \
-        TB_PRAGMA(unroll TB_FIT_UNROLL_ANY)                                    \
-        for (int _u = 0; _u < _n; _u++) {                                      \
-            const double ex = _nx;                                             \
-            const u32 eyi = _ny;                                               \
-            if (_u + 1 < _n) {                                                 \
-                _nx = _px[_u + 1];                                             \
-                _ny = _py[_u + 1];                                             \
-            }                                                                  \
-            const double ey = tb_u32_to_double(eyi);                           \
-            __VA_ARGS__                                                        \
-        }                                                                      \
+#define TB_FOR_POINTS_ANY_ORDER(W, m, ...)                                                                  \
+    {                                                                                                       \
+        const double *_px = (W).x;                                                                          \
+        const u32 *_py = (W).y;                                                                             \
+        int _v = 0, _left = ((m) + 9) / 10;            /* points of plane 0 still to load */                \
+        double _qx[TB_FIT_AHEAD];                                                                           \
+        u32 _qy[TB_FIT_AHEAD];                                                                              \
+        _Pragma("unroll") for (int _k = 0; _k < TB_FIT_AHEAD; _k++) {                                       \
+            _qx[_k] = 0.0;                                                                                  \
+            _qy[_k] = 0u;                                                                                   \
+            if (_k < (m)) {                                                                                 \
+                _qx[_k] = *_px;                                                                             \
+                _qy[_k] = *_py;                                                                             \
+                if (--_left == 0) {                                                                         \
+                    _v++;                                                                                   \
+                    _left = ((m) - _v + 9) / 10;                                                            \
+                    _px = (W).x + (i64)_v * (W).stride;                                                     \
+                    _py = (W).y + (i64)_v * (W).stride;                                                     \
+                } else {                                                                                    \
+                    _px++;                                                                                  \
+                    _py++;                                                                                  \
+                }                                                                                           \
+            }                                                                                               \
+        }                                                                                                   \
+        for (int _i0 = 0; _i0 < (m); _i0 += TB_FIT_AHEAD) {                                                 \
+            _Pragma("unroll") for (int _k = 0; _k < TB_FIT_AHEAD; _k++) {                                   \
+                if (_i0 + _k < (m)) {                                                                       \
+                    const double ex = _qx[_k];                                                              \
+                    const u32 eyi = _qy[_k];                                                                \
+                    if (_i0 + _k + TB_FIT_AHEAD < (m)) {                                                    \
+                        _qx[_k] = *_px;                                                                     \
+                        _qy[_k] = *_py;                                                                     \
+                        if (--_left == 0) {                                                                 \
+                            _v++;                                                                           \
+                            _left = ((m) - _v + 9) / 10;                                                    \
+                            _px = (W).x + (i64)_v * (W).stride;                                             \
+                            _py = (W).y + (i64)_v * (W).stride;                                             \
+                        } else {                                                                            \
+                            _px++;                                                                          \
+                            _py++;                                                                          \
+                        }                                                                                   \
+                    }                                                                                       \
+                    const double ey = tb_u32_to_double(eyi);                                                \
+                    __VA_ARGS__                                                                             \
+                }                                                                                           \
+            }                                                                                               \
+        }                                                                                                   \
     }
 
 // a / d with dinv = 1.0 / d (correctly rounded, see header)
