@@ -53,6 +53,7 @@ struct tb_model {
     tb_dbuf table;       // DWM: U[2 models][L][4][L][4] doubles; PWM: pssm[5][L]
     tb_dbuf vtable;      // DWM: V[2 models][16 * (L / 2) + 4 rows][L][4] doubles = 2^(pair / single rows of U), see tb_score.cu
     std::vector<double> host_raw[4];
+    int product_ok = 1;  // DWM: every product of table rows stays below 2^480 in magnitude (the product-form kernel multiplies two of them unsplit)
 };
 
 struct tb_ctx {

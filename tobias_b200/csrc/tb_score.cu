@@ -290,6 +290,10 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
     const double *V12 = (const double *)smem + 2 * cl - (size_t)16 * ntm * rs;
     const double *V3 = (const double *)smem + 2 * L + cl - (size_t)16 * ntm * rs;
     const int n_tail = nt3 + ns;                              // groups after the pairs: trinucleotides, then the single offset
+    const int shcl = 2 * cl;
+    const u32 snmask = col ? 3u : 0u;
+    const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+    const int myw = 4 * (lane & 7) + ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1);
     const i64 n_units = (R.total + 31) >> 5;
 
     for (i64 unit = (i64)bpart * wpb + warp; unit < n_units; unit += (i64)nparts * wpb) {
@@ -376,36 +380,36 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                     }
                 }
             }
-            // ---- column totals in the owning lane: Z = 1 + r1 + r2 + r3 (the a = 0 term is the unit), selected term by S_n
-            double msel[TB_K3A2_WPI], mz[TB_K3A2_WPI];
-            int de[TB_K3A2_WPI];
+            // ---- column totals in the owning lane: Z = 1 + r1 + r2 + r3 (the a = 0 term is the unit), selected term by S_n.
+            // Lanes >= L carry a1 = a2 = a3 = 1 and select the unit (snmask = 0): sel = 1, Z = 4 exactly, i.e. every idle lane
+            // adds -2 to the exponent balance of a window and nothing to the mantissas; the +2 (32 - L) goes back in at the end.
+            double sel[TB_K3A2_WPI], zz[TB_K3A2_WPI];
 #pragma unroll
             for (int w = 0; w < TB_K3A2_WPI; w++) {
-                const int sn = (int)((u32)(kmer[w] >> (2 * cl)) & 3u);
-                const double z = ((1.0 + a1[w]) + a2[w]) + a3[w];
-                const double sel = sn == 0 ? 1.0 : (sn == 1 ? a1[w] : (sn == 2 ? a2[w] : a3[w]));
-                int es = 0, ez = 0;
-                msel[w] = 1.0;
-                mz[w] = 1.0;
-                if (col) {
-                    tb_split_exp(sel, msel[w], es);
-                    tb_split_exp(z, mz[w], ez);
-                }
-                de[w] = es - ez;
+                const u32 sn = (u32)(kmer[w] >> shcl) & snmask;
+                zz[w] = ((1.0 + a1[w]) + a2[w]) + a3[w];
+                // (1, a1, a2, a3)[S_n] word by word with selects: a branch here diverges four ways inside every warp
+                const bool b0 = (sn & 1u) != 0u, b1 = (sn & 2u) != 0u;
+                const int lo_h = b0 ? __double2hiint(a1[w]) : 0x3ff00000, lo_l = b0 ? __double2loint(a1[w]) : 0;
+                const int hi_h = b0 ? __double2hiint(a3[w]) : __double2hiint(a2[w]), hi_l = b0 ? __double2loint(a3[w]) : __double2loint(a2[w]);
+                sel[w] = __hiloint2double(b1 ? hi_h : lo_h, b1 ? hi_l : lo_l);
             }
-            // ---- products over the 32 lanes, four windows at once: after level 16 a lane carries two windows, after level 8 one
+            // ---- products over the 32 lanes, four windows at once: after level 16 a lane carries two windows, after level 8 one.
+            // Level 16 multiplies the raw terms (two factors of magnitude < 2^480 each, tb_set_bias_model checks the table for
+            // that); the products are then split into mantissa in [1, 2) and integer exponent and only mantissas are multiplied.
             static_assert(TB_K3A2_WPI == 4, "the reduction below is written for four windows in flight");
-            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
             double ps[2], pz[2];
             int pe[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {          // windows (0,1) -> ps[0], windows (2,3) -> ps[1]
                 const int wk = 2 * h, ws = 2 * h + 1;
-                double ks = up16 ? msel[ws] : msel[wk], kz = up16 ? mz[ws] : mz[wk];
-                int ke = up16 ? de[ws] : de[wk];
-                ps[h] = ks * __shfl_xor_sync(FULL, up16 ? msel[wk] : msel[ws], 16);
-                pz[h] = kz * __shfl_xor_sync(FULL, up16 ? mz[wk] : mz[ws], 16);
-                pe[h] = ke + __shfl_xor_sync(FULL, up16 ? de[wk] : de[ws], 16);
+                const double ks = up16 ? sel[ws] : sel[wk], kz = up16 ? zz[ws] : zz[wk];
+                const double s2 = ks * __shfl_xor_sync(FULL, up16 ? sel[wk] : sel[ws], 16);
+                const double z2 = kz * __shfl_xor_sync(FULL, up16 ? zz[wk] : zz[ws], 16);
+                int es, ez;
+                tb_split_exp(s2, ps[h], es);
+                tb_split_exp(z2, pz[h], ez);
+                pe[h] = es - ez;
             }
             double rs_ = (up8 ? ps[1] : ps[0]) * __shfl_xor_sync(FULL, up8 ? ps[0] : ps[1], 8);
             double rz = (up8 ? pz[1] : pz[0]) * __shfl_xor_sync(FULL, up8 ? pz[0] : pz[1], 8);
@@ -416,19 +420,16 @@ __global__ void __launch_bounds__(TB_K3A2_THREADS, 1)
                 rz *= __shfl_xor_sync(FULL, rz, dlt);
                 re += __shfl_xor_sync(FULL, re, dlt);
             }
-            // lanes with (bit 4, bit 3) = (b4, b3) now hold window it + b4 + 2 * b3; hand the results to lanes it .. it + 3
-            const int k = (lane - it) & 3;
-            const int srcl = ((k & 1) << 4) | ((k >> 1) << 3);
-            const double gs = __shfl_sync(FULL, rs_, srcl), gz = __shfl_sync(FULL, rz, srcl);
-            const int ge = __shfl_sync(FULL, re, srcl);
-            if (lane >= it && lane < it + TB_K3A2_WPI) {
-                my_sel = gs;
-                my_z = gz;
-                my_de = ge;
+            // the 8 lanes with (bit 4, bit 3) = (b4, b3) now all hold window it + b4 + 2 * b3: lane it / 4 of each group keeps it
+            if ((lane & 7) == (it >> 2)) {
+                my_sel = rs_;
+                my_z = rz;
+                my_de = re;
             }
         }
-        if (pos0 + lane < R.total)
-            out[pos0 + lane] = okl ? (log2(my_sel) - log2(my_z)) + (double)my_de : (double)NAN;
+        // lane (b4, b3, j) finishes window 4 j + b4 + 2 b3 of the unit
+        if (pos0 + myw < R.total)
+            out[pos0 + myw] = ((okmask >> myw) & 1u) ? (log2(my_sel) - log2(my_z)) + (double)(my_de + 2 * (32 - L)) : (double)NAN;
     }
 #ifndef TB_EMU
     if (ntm) {
@@ -534,6 +535,9 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
             return U[(((((size_t)x * L + m) * 4 + s_) * 2 + (a >> 1)) * L + n) * 2 + (a & 1)];
         };
         std::vector<double> Vt((size_t)2 * rows * rs, 1.0);
+        // range of a column product: sum over the groups of the largest |T[a] - T[0]| of the group (log2 units)
+        const int ngroups = np + nt3 + ns;
+        std::vector<double> span((size_t)2 * L * 3 * ngroups, 0.0);
         for (int x = 0; x < 2; x++)
             for (int r = 0; r < rows; r++)
                 for (int n = 0; n < L; n++) {
@@ -553,7 +557,19 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
                     rp[2 * n] = exp2(t[1] - t[0]);
                     rp[2 * n + 1] = exp2(t[2] - t[0]);
                     rp[2 * L + n] = exp2(t[3] - t[0]);
+                    const int grp = r < 16 * np ? r >> 4 : (r < 16 * np + 64 * nt3 ? np + ((r - 16 * np) >> 6) : np + nt3);
+                    for (int a = 1; a < 4; a++) {
+                        double &sp = span[(((size_t)x * L + n) * 3 + (a - 1)) * ngroups + grp];
+                        const double d = fabs(t[a] - t[0]);
+                        if (!(d <= sp)) sp = d;              // NaN / inf end up in the span as well
+                    }
                 }
+        M.product_ok = 1;
+        for (size_t c = 0; c < (size_t)2 * L * 3; c++) {
+            double tot = 0.0;
+            for (int q = 0; q < ngroups; q++) tot += span[c * ngroups + q];
+            if (!(tot < 480.0)) M.product_ok = 0;           // tb_score_device falls back to the sum form (exp2 / log2 per column)
+        }
         TB_TRY(tb_h2d(ctx, M.vtable, Vt.data(), Vt.size() * sizeof(double)));
     }
     return tb_sync(ctx, "tb_set_bias_model");
@@ -581,7 +597,7 @@ int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i
     int k3a_np, k3a_nt3, k3a_ns, k3a_ntm;
     tb_k3a2_groups(L, tb_k3a2_tmem_groups(ctx), k3a_np, k3a_nt3, k3a_ns, k3a_ntm);
     const size_t smem2 = (size_t)(16 * (k3a_np - k3a_ntm) + 64 * k3a_nt3 + 4 * k3a_ns) * tb_k3a2_rowstride(L) * sizeof(double);
-    if (M0.is_dwm && tb_k3a2_fits(L, tb_k3a2_tmem_groups(ctx)) && !ctx->force_sum_form) {
+    if (M0.is_dwm && tb_k3a2_fits(L, tb_k3a2_tmem_groups(ctx)) && !ctx->force_sum_form && ctx->model[0].product_ok && ctx->model[1].product_ok) {
         // product form: one (strand, model) table per block, partial scores, then bias - background
         const int nclass = strand_mask == 3 ? 4 : 2;
         TB_TRY(tb_reserve(ctx, ctx->scratch4, (size_t)4 * total * sizeof(double)));
