@@ -316,6 +316,8 @@ def bench_b200(args):
                 per_stage[k]["bound_util_pct_ncu"] = roofs[k]["bound_util_pct"]
     except Exception:
         roofs = {}
+    # DRAM traffic of the dominant kernel from the committed --set full capture of this workload on one GPU (profiles/collect.sh, step 4)
+    traffic = roofs.get(dom, {}).get("dram_bytes_per_launch_hg38") if (args.workload == "hg38" and world == 1) else None
     result = {
         "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -328,11 +330,12 @@ def bench_b200(args):
         "e2e": {"value": e2e_value, "unit": "bp/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "algorithmic_bytes_per_launch": alg[dom], "peak_source": peak_src,
                      "binding_unit": roofs.get(dom, {}).get("bound"), "binding_unit_util_pct_ncu": roofs.get(dom, {}).get("bound_util_pct"),
                      "note": "achieved = algorithmic bytes of the stage (SURVEY 8d) / its CUDA-event time (all launches of the stage); none of K2-K4 is "
                              "HBM bound -- the unit that binds each kernel and its ncu utilisation are in `stages` (profiles/r01_summary.md); "
-                             "traffic: no --set full capture of this exact launch (chr50mb capture in profiles/r01_roofs.json)"},
+                             "traffic: the ncu --set full capture of this kernel in this workload committed under profiles/ (null for other workloads / ranks)"},
         "stages": per_stage, "wall_ms_per_step": wall_res / args.steps, "setup_s": round(setup_s, 1),
         # host clock around every library call of the timed steps (one entry per step; resident: each call returns synchronised, so these
         # add up to ms_per_step and show where host work sits between the kernels; e2e: calls overlap with the copy stream)

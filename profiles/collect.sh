@@ -17,4 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:tb_fitg_round_ke
     -f -o $O/${R}_full_b python bench.py --workload chr50mb --steps 1 --warmup 0 --no-cpu-baseline > $O/${R}_full_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tb_fitg_round_kernel -c 2 \
     -f -o $O/${R}_full_c python bench.py --workload chr50mb --steps 1 --warmup 0 --no-cpu-baseline --lm-exact > $O/${R}_full_c.log 2>&1
+# 4. the dominant kernel at the bench's own size (DRAM traffic per launch for the bench line's roofline.traffic)
+ncu --set full --clock-control none --import-source on -k regex:tb_score_dwm2 -c 1 \
+    -f -o $O/${R}_full_hg38 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $O/${R}_full_hg38.log 2>&1
 ls -la $O/${R}_full_*.ncu-rep $O/${R}_launches_hg38.csv

@@ -73,8 +73,12 @@ HISTORY = """History of the same line this round (ms per step, hg38, 1 GPU): 137
 group + butterfly reduction) -> 604 (K4) -> 478 (one-pass outer iterations for DWM fits) -> 444 (K3a rows from tensor memory) -> 427 (K3a compile-time
 grouping) -> 367 (K3a ratio form, lane = column) -> 338 (plane-major traversal in the one-pass fits) -> 317 (K3c one tile per region, K2 joint histograms
 in L2) -> 309 (K3c rounding in the fp64 pipe, fit records in shared memory) -> 291 (K2 joint histograms of 2-base chunks in shared memory) -> 288 (K4
-pre-scaled flank sums, unconditional width loop).  e2e: 1496 -> ~430 -> 396 -> 355 ms (genome upload on the copy stream, overlapped with the read
-counts and the training counts).
+pre-scaled flank sums, unconditional width loop) -> 283 (K3c verification weights through per-base position lists) -> 276 (K3b one pass per
+accepted step) -> 261 (K3b window statistics taken in the init pass, no divergent finish pass) -> 259 (K3b loads two points ahead) -> 253 (K3a
+epilogue: branch-free column selection, half the exponent splits, no gather shuffles).  e2e: 1496 -> ~430 -> 396 -> 355 (genome upload on the copy
+stream, overlapped with the read counts and the training counts) -> 321 ms; with 3.94 GB of H2D (76 ms at 52 GB/s, only ~20 ms of kernels can
+overlap it because the model needs the counts of the whole genome) and 2.10 GB of D2H (40 ms, hidden behind the footprint kernels except for the
+last 10 ms) the e2e line sits ~5 ms above what the PCIe link allows for these kernel times.
 """
 
 READINGS = """## 4. Readings: which unit binds each kernel
@@ -85,7 +89,7 @@ DRAM traffic of every kernel is within ~2x of its algorithmic bytes and none of 
 |---|---|---|---|
 | K1 `tb_pileup_kernel` | L2 atomics / integer issue (scatter), 1.1 ms for 49M records + 124M positions | -- (0.3 % of the step) | -- |
 | K2 `tb_k2_scatter` + `tb_k2_weights` + `tb_k2_hist_smem` + `tb_k2_fold` | scatter / weights: DRAM latency of sector-sized read-modify-writes on the 24 GB multiplicity slab (12.6 of the 16 ms); histogram: shared-memory atomics | site list instead of a slab scan (174 -> 40 ms); joint histograms of chunk pairs instead of one atomic per position pair: 21 L2 atomics per k-mer (32 ms, bound by the L2 atomic rate), then 78 shared-memory atomics per k-mer on 16 x 16 tables (histogram kernel 25 -> 3.2 ms, K2 16 ms) | the slab passes: a sort-based dedup of (region, strand, cut site) would avoid the 24 GB slab |
-| K3a `tb_score_dwm2_kernel` | **instruction issue**, then shared-memory bandwidth | product form (no exp2), pair / trinucleotide row groups (25 -> 10 rows), ratio form (3 values per column, lane = column), 5 groups read from **tensor memory** through tcgen05.ld, butterfly reduction, compile-time grouping (446 -> 98 ms) | epilogue instructions (exponent split, butterfly selects) |
+| K3a `tb_score_dwm2_kernel` | **shared-memory data pipe (76 %: table rows 30 + shuffles 10 wavefronts per window) and instruction issue (70 %)** together | product form (no exp2), pair / trinucleotide row groups (25 -> 10 rows), ratio form (3 values per column, lane = column), 5 groups read from **tensor memory** through tcgen05.ld, butterfly reduction, compile-time grouping (446 -> 98 ms); branch-free column selection, raw level-16 products split afterwards, idle lanes as exact constants, no gather shuffles: 631 -> 527 instructions per four windows (-> 91 ms) | both pipes are near their limit with fp64 at 33 %: fewer shared-memory rows (a fourth table store does not exist on the SM), k-mers from uniform loads instead of 2 shuffles per window |
 | K3b `tb_fitg_round_kernel` | **instruction issue + L1 miss latency** (thread-sequential LM arithmetic; fp64 and integer instructions issue at half rate) | one thread per window, rounds over compacted lists, exact MINPACK order without m-vector storage (2854 -> 227 ms exact); one-pass outer iterations, plane-major traversal, tail finished in one launch for DWM (-> ~80 ms) | compulsory L1 misses of the window data every round |
 | K3c `tb_correct_kernel` | instruction issue, spread over four phases (was: conversion unit, two conversions per term of the float-accumulator rolling sums) | no fp64 shared atomics, integer prefix / sparse sums where exact, zero addends skipped (103 -> 68 ms); one tile per 824-bp region (-> 57); float rounding in the fp64 pipe by adding and subtracting 1.5 * 2^(E+29) -- exact, no conversions (-> 56); fit records staged in shared memory, no per-row modulo, sign-split verification adds (-> 52.5) | three dense sequential rolling sums of 100 terms per position -- the semantics are the reference's |
 | K4 `tb_footprint_kernel` | issue (fp32 + shared loads), 651 width combinations per position | fitted block size, half the barriers, suffix-maximum spreading (49 -> 30 ms); flank sums divided by 2 x width once per element and an unconditional, padded width loop: LDS + FADD + FMNMX per combination instead of five instructions (-> 26 ms) | two footprint starts per thread with 64-bit shared loads |
@@ -169,12 +173,12 @@ def main():
     roofs = {"_source": "profiles/r01_summary.md section 3-4 (ncu --set full, one launch per kernel, chr50mb workload, B200)",
              "K1_pileup": roof("tb_pileup_kernel<0>", "L2 atomics / integer issue", "alu_pipe_pct"),
              "K2_counts": roof("tb_k2_scatter", "DRAM latency of the slab read-modify-writes (scatter, weights); shared-memory atomics (histogram)", "sm_throughput_pct"),
-             "K3a_score": roof("tb_score_dwm2", "instruction issue, then shared-memory bandwidth (+ tensor-memory reads)", "issue_active_pct"),
+             "K3a_score": roof("tb_score_dwm2", "shared-memory data pipe (table rows + shuffles) together with instruction issue (~70 %); half of the rows come from tensor memory", "smem_pipe_pct"),
              "K3b_fit": roof("tb_fitg_round_kernel<1, 1>", "instruction issue (thread-sequential LM arithmetic) + L1 miss latency", "issue_active_pct"),
              "K3c_correct": roof("tb_correct_kernel", "instruction issue (sequential float-accumulator rolling sums, 10-row mean, verification counts)", "issue_active_pct"),
              "K4_footprint": roof("tb_footprint_kernel", "instruction issue (fp32 + shared loads)", "issue_active_pct")}
     # DRAM traffic of the dominant kernel at the bench's own size: one --set full launch of tb_score_dwm2_kernel in the hg38 bench
-    # (gpurun_out/r01_full_hg38.ncu-rep; the kernel has not changed since that capture)
+    # (gpurun_out/r01_full_hg38.ncu-rep, step 4 of profiles/collect.sh)
     rep = os.path.join(OUT, "r01_full_hg38.ncu-rep")
     if os.path.exists(rep):
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

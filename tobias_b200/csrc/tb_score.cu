@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(768, 1) tb_score_dwm_kernel(tb_genome_view g, 
 // level halves the number of windows a lane still carries), 8.75 shuffles per window.  Relative error of a product of 10
 // correctly rounded factors ~ 2e-15, i.e. ~1e-14 absolute on the score -- the same order as the sum form's difference to
 // the reference's libm.
+#ifndef TB_K3A2_THREADS
 #define TB_K3A2_THREADS 768
+#endif
 #define TB_K3A2_WPI 4
 
 __device__ __forceinline__ void tb_split_exp(double v, double &mant, int &ex) {      // v = mant * 2^ex, mant in [1, 2)  (v > 0, normal)
