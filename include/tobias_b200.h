@@ -128,6 +128,11 @@ int tb_allreduce_f64(tb_ctx *ctx, double *buf, int64_t n);
 int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, const double *bias_pwm_log,
                       const double *bg_pwm_log, const double *bias_dwm_log, const double *bg_dwm_log);
 
+/* What tb_set_bias_model stored for a strand: *is_dwm (-1: no model yet), *L, and *product_form = 1 when DWM scoring
+ * (sequences.pyx:263-342) runs as products of powers of two of the table rows, 0 when the tables are so wide (a column
+ * product could pass 2^480) that the kernel evaluating exp2 / log2 per column is used instead.  Any pointer may be NULL. */
+int tb_bias_model_info(tb_ctx *ctx, int strand, int *is_dwm, int *L, int *product_form);
+
 /* SequenceMatrix.score_sequence (sequences.pyx:123-151,263-342) of one strand over contig[start, end),
  * with the reference's conventions: NaN in the first/last L//2 positions and for windows holding N; the
  * reverse strand is the score of the reverse complement, reversed (atacorrect_functions.py:258-260). */

@@ -189,6 +189,37 @@ def test_score_sequence(loaded_ctx, golden, mode):
                 assert np.all(np.abs(ref[v] - got[v]) <= 1e-9 * np.maximum(1.0, np.abs(ref[v])))
 
 
+@pytest.mark.parametrize("spread", [4.0, 12.0])
+def test_score_sequence_table_range(loaded_ctx, golden, spread):
+    """Product-form DWM scoring multiplies powers of two of the table rows.  spread 4: column products up to ~2^200, still
+    the product form; spread 12: the bound on a column product passes the 2^480 the kernel allows, tb_set_bias_model must route the model to the sum form
+    (sequences.pyx:263-342 evaluated with exp2 / log2 per column).  Both agree with the oracle."""
+    g = golden.atac
+    rng = np.random.default_rng(int(spread))
+    tabs = {}
+    for st in ("forward", "reverse"):
+        for k in ("bias_pwm_log", "bg_pwm_log", "bias_dwm_log", "bg_dwm_log"):
+            base = np.array(g["DWM_%s_%s" % (st, k)], dtype=np.float64)
+            tabs[(st, k)] = base + rng.uniform(-spread, spread, size=base.shape)
+    for si, st in enumerate(("forward", "reverse")):
+        loaded_ctx.set_bias_model(si, True, 25, tabs[(st, "bias_pwm_log")], tabs[(st, "bg_pwm_log")], tabs[(st, "bias_dwm_log")],
+                                  tabs[(st, "bg_dwm_log")])
+        assert loaded_ctx.bias_model_info(si) == (1, 25, 1 if spread < 10 else 0)
+    c, a, b = 0, 700, 1500
+    codes = restate.encode(golden.genome[c][a:b])
+    for si, st in enumerate(("forward", "reverse")):
+        m = restate.Matrix(25, "DWM")
+        for k in ("bias_pwm_log", "bg_pwm_log", "bias_dwm_log", "bg_dwm_log"):
+            setattr(m, k, tabs[(st, k)])
+        ref = m.score_sequence(codes) if si == 0 else m.score_sequence(restate.revcomp(codes))[::-1]
+        got = loaded_ctx.score_sequence(si, c, a, b)
+        assert np.array_equal(np.isnan(ref), np.isnan(got))
+        v = np.isfinite(ref)
+        assert v.sum() > 500
+        assert np.all(np.abs(ref[v] - got[v]) <= 1e-9 * np.maximum(1.0, np.abs(ref[v])))
+    _set_model(loaded_ctx, g, "DWM")          # leave the session context as the other tests expect it
+
+
 @pytest.mark.parametrize("mode", ["PWM", "DWM"])
 def test_bias_correction_tracks(loaded_ctx, golden, mode):
     g = golden.atac

@@ -577,6 +577,17 @@ extern "C" int tb_set_bias_model(tb_ctx *ctx, int strand, int is_dwm, int L, con
     return tb_sync(ctx, "tb_set_bias_model");
 }
 
+extern "C" int tb_bias_model_info(tb_ctx *ctx, int strand, int *is_dwm, int *L, int *product_form) {
+    if (!ctx) return TB_ERR_ARG;
+    if (strand < 0 || strand > 1) return tb_fail(ctx, TB_ERR_ARG, "tb_bias_model_info: strand must be 0 or 1");
+    const tb_model &M = ctx->model[strand];
+    if (is_dwm) *is_dwm = M.is_dwm;
+    if (L) *L = M.L;
+    if (product_form)
+        *product_form = M.is_dwm == 1 && M.product_ok && !ctx->force_sum_form && tb_k3a2_fits(M.L, tb_k3a2_tmem_groups(ctx)) ? 1 : 0;
+    return TB_OK;
+}
+
 // scores both strands (mask 3) or one; d_out_* are device arrays over the concatenated position space
 int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i64 n_regions, i64 total, int strand_mask,
                     int nan_invalid, double *d_out_fwd, double *d_out_rev) {

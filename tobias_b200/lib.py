@@ -58,6 +58,7 @@ _PROTOS = {
     "tb_allreduce_i64": (_i, [_vp, _vp, _i64]),
     "tb_allreduce_f64": (_i, [_vp, _vp, _i64]),
     "tb_set_bias_model": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tb_bias_model_info": (_i, [_vp, _i, _vp, _vp, _vp]),
     "tb_score_sequence": (_i, [_vp, _i, _i, _i64, _i64, _vp]),
     "tb_correct_run": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _d, _i, _i, _i]),
     "tb_stage_ms": (_i, [_vp, C.POINTER(C.c_float), _i]),
@@ -293,6 +294,12 @@ class Context:
         t = [None if x is None else _arr(x, np.float64) for x in (bias_pwm_log, bg_pwm_log, bias_dwm_log, bg_dwm_log)]
         self._ck(self._lib.tb_set_bias_model(self._h, int(strand), int(bool(is_dwm)), int(L), _ptr(t[0]), _ptr(t[1]),
                                              _ptr(t[2]), _ptr(t[3])))
+
+    def bias_model_info(self, strand):
+        """(is_dwm, L, product_form) of the model tb_set_bias_model stored for a strand."""
+        a, b, c = C.c_int(-1), C.c_int(0), C.c_int(0)
+        self._ck(self._lib.tb_bias_model_info(self._h, int(strand), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def score_sequence(self, strand, contig, start, end):
         out = np.empty(int(end - start), dtype=np.float64)
