@@ -270,6 +270,7 @@ inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline float __fadd_rn(float a, float b) { return a + b; }

@@ -10,6 +10,7 @@
 //                              expected / corrected / rescale (:323-350), verification k-mer counts (:358-373),
 //                              trimmed per-strand tracks (:381-383)
 #include "tb_common.cuh"
+#include <chrono>
 #include "tb_lm.cuh"
 #include "tb_lm_thread.cuh"
 
@@ -225,8 +226,9 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
 #ifndef TB_FITG_FUSE
 #define TB_FITG_FUSE 1      // 0: separate Jacobian and trial passes in the one-pass form (comparison builds)
 #endif
+// One-pass form: five blocks per SM (96 registers) measured 58.2 ms on hg38 against 59.8 with four (128) and 59.5 with six (80).
 template <bool WITH_QR, bool FAST>
-__global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
+__global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MINBLOCKS)
     tb_fitg_round_kernel(tb_fitg_view G, int m, const u32 *__restrict__ list, i64 n_list, double *__restrict__ fit,
                          u32 *__restrict__ nextq, u32 *__restrict__ nextt, unsigned long long *ctr) {
     const i64 n_round = ((n_list + 31) / 32) * 32;
@@ -657,6 +659,12 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
                               int k_flank, int window, double correction_factor, int shift_fwd, int shift_rev,
                               int lm_exact_order) {
     if (!ctx) return TB_ERR_ARG;
+    const bool trace = getenv("TB_HOST_TRACE") != nullptr;       // host clock at the phase borders of this call, to stderr
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto tr = [&](const char *what) {
+        if (trace) fprintf(stderr, "[tb_correct_run] %-28s %9.3f ms\n", what,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
+    };
     ctx->cor.valid = false;
     if (window < TB_STEP || window > 512) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: window must be in [10, 512]");
     if (ctx->model[0].is_dwm < 0 || ctx->model[1].is_dwm < 0)
@@ -731,6 +739,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         C.valid = true;
         return TB_OK;
     }
+    tr("host tables built");
     TB_TRY(tb_h2d(ctx, C.d_ext_start, C.ext_start.data(), sizeof(i64) * n_regions));
     TB_TRY(tb_h2d(ctx, C.d_ext_end, ext_end.data(), sizeof(i64) * n_regions));
     TB_TRY(tb_h2d(ctx, C.d_ext_off, C.ext_off.data(), sizeof(i64) * (n_regions + 1)));
@@ -745,6 +754,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     TB_TRY(tb_reserve(ctx, C.prepost, (size_t)2 * 3 * 5 * L * sizeof(double)));
     TB_CUDA(ctx, cudaMemsetAsync(C.prepost.p, 0, (size_t)2 * 3 * 5 * L * sizeof(double), ctx->stream));
 
+    tr("tables uploaded, buffers");
     tb_timer_start(ctx);
     tb_mark(ctx, 0);
     TB_TRY(tb_pileup_device(ctx, n_regions, C.d_ext_start.as<i64>(), C.d_ext_end.as<i64>(), C.d_ext_off.as<i64>(), C.ext_total,
@@ -753,6 +763,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     TB_TRY(tb_score_device(ctx, C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), n_regions, C.ext_total, 3, 0,
                            C.biasraw.as<double>(), C.biasraw.as<double>() + C.ext_total));
     tb_mark(ctx, 2);
+    tr("K1 + K3a enqueued");
     tb_cor_view V{C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), C.d_out_off.as<i64>(), C.d_win_off.as<i64>(),
                   n_regions, C.ext_total, C.out_total, C.n_windows, k_flank, window, L, f_extend};
     if (lm_exact_order < 2) {
@@ -832,6 +843,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_fit_kernel"));
     }
     tb_mark(ctx, 3);
+    tr("K3b rounds done (host)");
     {
         TB_TRY(tb_genome_fence(ctx, 0, ctx->n_contigs - 1));
         tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
@@ -853,9 +865,12 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_correct_kernel"));
     }
     tb_mark(ctx, 4);
+    tr("K3c enqueued");
     tb_timer_stop(ctx);
+    tr("timer stop (GPU drained)");
     tb_marks_collect(ctx, 5);      // stage_ms: [0] K1 pileup, [1] K3a score, [2] K3b fit, [3] K3c correct
     TB_TRY(tb_sync(ctx, "tb_correct_run"));
+    tr("return");
     C.valid = true;
     return TB_OK;
 }
