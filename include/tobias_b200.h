@@ -188,6 +188,11 @@ typedef struct tb_score_params {
 int tb_signal_upload(tb_ctx *ctx, const float *signal, int64_t n_regions, const int64_t *ext_len);
 int tb_score_run(tb_ctx *ctx, const tb_score_params *p);
 int tb_score_download(tb_ctx *ctx, void *out);
+/* Scores of the last tb_score_run at `n` positions of its concatenated output space (region offsets = prefix sums of the
+ * trimmed region lengths), as doubles, without downloading the track: the reads BINDetect's scan_and_score makes from the
+ * footprint bigWig -- the middle of every TFBS and the random background positions of every region
+ * (tobias/tools/bindetect_functions.py:296-330).  An index outside the track is an error (TB_ERR_ARG). */
+int tb_score_gather(tb_ctx *ctx, int64_t n, const int64_t *index, double *out);
 int tb_score_regions(tb_ctx *ctx, const float *signal, int64_t n_regions, const int64_t *ext_len,
                      const tb_score_params *p, void *out);
 /* Chain ATACorrect -> ScoreBigwig on the device: use the corrected track of the last tb_correct_run (rounded to

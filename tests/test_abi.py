@@ -22,7 +22,7 @@ def test_header_declares_the_documented_entry_points():
     names = declared_functions()
     for must in ("tb_init", "tb_destroy", "tb_last_error", "tb_genome_create", "tb_genome_upload", "tb_reads_upload", "tb_count_reads",
                  "tb_pileup", "tb_bias_counts", "tb_allreduce_i64", "tb_set_bias_model", "tb_bias_model_info", "tb_score_sequence", "tb_correct_run",
-                 "tb_correct_download", "tb_score_regions", "tb_rolling"):
+                 "tb_correct_download", "tb_score_regions", "tb_score_gather", "tb_rolling"):
         assert must in names
 
 

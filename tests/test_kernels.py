@@ -362,6 +362,47 @@ def test_footprint_width_ranges_and_tile_sizes(ctx):
             off += x.shape[0]
 
 
+def test_bindetect_site_and_background_scores(ctx):
+    """The per-base step of BINDetect's scan_and_score (bindetect_functions.py:294-331): footprint scores at the middle of every
+    site and at the region-length-seeded random background positions, gathered on the device from the track of the last
+    score_run -- against indexing the oracle's track the way the reference indexes the bigWig values."""
+    import random
+    from tobias_b200 import bindetect_functions as bf
+    rng = np.random.default_rng(21)
+    lens = [460, 1300, 260, 5000]                          # extended by flank 30 on both sides
+    starts = [10_000, 20_000, 30_000, 40_000]              # genomic start of every trimmed region
+    sig = [np.where(rng.random(n) < 0.5, 0, rng.standard_t(3, size=n)).astype(np.float32) for n in lens]
+    p = ctx.score_params("footprint", flank=30)
+    ctx.signal_upload(np.concatenate(sig), lens)
+    ctx.score_run(p)
+    track = [restate.calculate_scores_region(x, 30, "footprint") for x in sig]
+    sites = []
+    for r, n in enumerate(lens):
+        for _ in range(40):
+            width = int(rng.integers(6, 25))
+            a = starts[r] + int(rng.integers(0, n - 60 - width))
+            sites.append((r, a, a + width))
+    got_sites, got_bg, bg_off = bf.gather_scores(ctx, [n - 60 for n in lens], starts, sites)
+    full = ctx.score_download()                            # float32 track the bigWig would hold
+    off = np.concatenate([[0], np.cumsum([n - 60 for n in lens])])
+    for i, (r, a, b) in enumerate(sites):
+        pos = a - starts[r] + int((b - a) / 2.0)           # :323-324
+        assert got_sites[i] == float(full[off[r] + pos])
+        assert abs(got_sites[i] - track[r][pos]) <= 1e-5 * max(1.0, abs(track[r][pos]))
+    k = 0
+    for r, n in enumerate(lens):
+        reglen = n - 60
+        random.seed(reglen)                                # :295-296
+        want = random.sample(range(reglen), max(1, int(reglen / 200)))
+        assert bg_off[r] == want
+        for pos in want:
+            assert got_bg[k] == float(full[off[r] + pos])
+            k += 1
+    assert k == got_bg.shape[0]
+    with pytest.raises(Exception):
+        ctx.score_gather([int(off[-1])])                   # one past the end of the track
+
+
 def test_calculate_scores_against_golden(ctx, golden):
     sc, g = golden.score, golden.atac
     sig = sc["signal"]

@@ -536,6 +536,51 @@ extern "C" int tb_score_download(tb_ctx *ctx, void *out) {
     return tb_d2h(ctx, out, S.out.p, (size_t)S.out_total * (S.out_f64 ? 8 : 4));
 }
 
+// Scores of the last tb_score_run at chosen positions of the concatenated output space, without bringing the track to the host:
+// what BINDetect's scan_and_score reads from the footprint bigWig (tobias/tools/bindetect_functions.py:296-330: the score at the
+// middle of every TFBS and at the random background positions of every region).
+template <class T>
+__global__ void tb_score_gather_kernel(const T *__restrict__ track, i64 total, const i64 *__restrict__ index, i64 n, double *__restrict__ out,
+                                       int *__restrict__ bad) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const i64 q = index[i];
+        if (q < 0 || q >= total) {
+            out[i] = (double)NAN;
+            *bad = 1;
+        } else {
+            out[i] = (double)track[q];
+        }
+    }
+}
+
+extern "C" int tb_score_gather(tb_ctx *ctx, int64_t n, const int64_t *index, double *out) {
+    if (!ctx || n < 0 || (n > 0 && (!index || !out))) return TB_ERR_ARG;
+    auto &S = ctx->sc;
+    if (!S.have_out) return tb_fail(ctx, TB_ERR_STATE, "tb_score_gather: no completed tb_score_run");
+    if (n == 0) return TB_OK;
+    TB_TRY(tb_h2d(ctx, ctx->reg_a, index, sizeof(i64) * (size_t)n));
+    TB_TRY(tb_reserve(ctx, ctx->scratch0, sizeof(double) * (size_t)n + 16));
+    double *d_out = ctx->scratch0.as<double>();
+    int *d_bad = (int *)(d_out + n);
+    TB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    const i64 want = tb_div_up(n, 256), capg = (i64)ctx->sm_count * 16;
+    const unsigned grid = (unsigned)(want < capg ? want : capg);
+    if (S.out_f64) {
+        auto kg = tb_score_gather_kernel<double>;
+        TB_LAUNCH(ctx, kg, grid, 256, 0, (const double *)S.out.as<double>(), S.out_total, (const i64 *)ctx->reg_a.as<i64>(), (i64)n, d_out, d_bad);
+    } else {
+        auto kg = tb_score_gather_kernel<float>;
+        TB_LAUNCH(ctx, kg, grid, 256, 0, (const float *)S.out.as<float>(), S.out_total, (const i64 *)ctx->reg_a.as<i64>(), (i64)n, d_out, d_bad);
+    }
+    TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_score_gather_kernel"));
+    TB_TRY(tb_d2h(ctx, out, d_out, sizeof(double) * (size_t)n));
+    int bad = 0;
+    TB_TRY(tb_d2h(ctx, &bad, d_bad, sizeof(int)));
+    if (bad) return tb_fail(ctx, TB_ERR_ARG, "tb_score_gather: an index lies outside [0, %lld)", (long long)S.out_total);
+    return TB_OK;
+}
+
 extern "C" int tb_score_regions(tb_ctx *ctx, const float *signal, int64_t n_regions, const int64_t *ext_len, const tb_score_params *p,
                                 void *out) {
     TB_TRY(tb_signal_upload(ctx, signal, n_regions, ext_len));

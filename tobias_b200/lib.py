@@ -69,6 +69,7 @@ _PROTOS = {
     "tb_signal_upload": (_i, [_vp, _vp, _i64, _vp]),
     "tb_score_run": (_i, [_vp, C.POINTER(ScoreParams)]),
     "tb_score_download": (_i, [_vp, _vp]),
+    "tb_score_gather": (_i, [_vp, _i64, _vp, _vp]),
     "tb_score_regions": (_i, [_vp, _vp, _i64, _vp, C.POINTER(ScoreParams), _vp]),
     "tb_signal_from_corrected": (_i, [_vp, _i]),
     "tb_rolling": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
@@ -391,6 +392,13 @@ class Context:
         assert out.dtype == dt and out.size >= total and out.flags.c_contiguous
         out = out[:total]
         self._ck(self._lib.tb_score_download(self._h, _ptr(out)))
+        return out
+
+    def score_gather(self, index):
+        """Scores of the last score_run at positions of its concatenated output space (float64), gathered on the device."""
+        idx = _arr(index, np.int64)
+        out = np.empty(idx.shape[0], dtype=np.float64)
+        self._ck(self._lib.tb_score_gather(self._h, int(idx.shape[0]), _ptr(idx), _ptr(out)))
         return out
 
     def score_regions(self, signal, ext_len, params):
