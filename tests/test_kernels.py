@@ -189,6 +189,33 @@ def test_score_sequence(loaded_ctx, golden, mode):
                 assert np.all(np.abs(ref[v] - got[v]) <= 1e-9 * np.maximum(1.0, np.abs(ref[v])))
 
 
+@pytest.mark.parametrize("L", [5, 21, 31])
+def test_score_sequence_other_model_lengths(loaded_ctx, golden, L):
+    """--k_flank other than the default 12: the product-form kernel picks another row grouping (run-time loop bounds instead of the
+    unrolled L = 25 form; for L = 31 every lane owns a column).  Models built by the oracle's prepare_mat from random k-mer counts."""
+    g = golden.atac
+    rng = np.random.default_rng(L)
+    models = []
+    for si in range(2):
+        m = restate.Matrix(L, "DWM")
+        for _ in range(400):
+            m.add_sequence(rng.integers(0, 4, size=L), float(rng.integers(1, 11)))
+            m.add_background(rng.integers(0, 4, size=L), float(rng.integers(1, 11)))
+        m.prepare_mat()
+        models.append(m)
+        loaded_ctx.set_bias_model(si, True, L, m.bias_pwm_log, m.bg_pwm_log, m.bias_dwm_log, m.bg_dwm_log)
+        assert loaded_ctx.bias_model_info(si) == (1, L, 1)
+    for (c, a, b) in ((0, 700, 1500), (1, 12000, 12300), (0, 0, 70)):
+        codes = restate.encode(golden.genome[c][a:b])
+        for si, m in enumerate(models):
+            ref = m.score_sequence(codes) if si == 0 else m.score_sequence(restate.revcomp(codes))[::-1]
+            got = loaded_ctx.score_sequence(si, c, a, b)
+            assert np.array_equal(np.isnan(ref), np.isnan(got))
+            v = ~np.isnan(ref)
+            assert np.all(np.abs(ref[v] - got[v]) <= 1e-9 * np.maximum(1.0, np.abs(ref[v])))
+    _set_model(loaded_ctx, g, "DWM")
+
+
 @pytest.mark.parametrize("spread", [4.0, 12.0])
 def test_score_sequence_table_range(loaded_ctx, golden, spread):
     """Product-form DWM scoring multiplies powers of two of the table rows.  spread 4: column products up to ~2^200, still

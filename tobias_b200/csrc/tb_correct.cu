@@ -796,7 +796,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         const i64 tail_at = (i64)ctx->sm_count * 128;      // one block per SM's worth of windows: finish them in one launch
         for (int round = 0; nq + nt > 0; round++) {
             if (round > 700) return tb_fail(ctx, TB_ERR_STATE, "tb_correct_run: window fits did not terminate");
-            const i64 capg = (i64)ctx->sm_count * TB_FITG_MINBLOCKS;
+            const i64 capg = (i64)ctx->sm_count * (lm_exact_order ? TB_FITG_MINBLOCKS : TB_FITG_MINBLOCKS + 1);      // resident blocks (launch bounds of the round kernels)
             if (nq + nt <= tail_at) {
                 i64 want = tb_div_up(nq + nt, 128);
                 auto kf = lm_exact_order ? tb_fitg_finish_kernel<false> : tb_fitg_finish_kernel<true>;
