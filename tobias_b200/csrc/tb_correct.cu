@@ -348,6 +348,7 @@ __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w)
 
 #define TB_K3C_TILE_MAX 1024     // positions per tile (chosen per launch from the region lengths, a multiple of 64 up to this)
 #define TB_K3C_THREADS 256
+#define TB_K3C_FREC 6            // doubles per staged fit record: mode, max(prediction), a, b, 1 / max, pad (16-byte aligned pairs)
 
 // Persistent blocks walk the (region, 512-bp tile) list.  Per tile and strand:
 //   1. signal + bias prediction (mean of the 10 window predictions) over the tile widened by 2 * window; integer prefix
@@ -382,12 +383,14 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
     unsigned short *nzpos = (unsigned short *)(wsum + 64);      // [cap] non-zero positions (relative to d0)
     uint8_t *bases = (uint8_t *)(nzpos + cap);                  // [tile_len + L] base codes of [t0 - k, t1 + k)
     __shared__ int bcnt[4];                                     // positions per base in the tile (+- k_flank)
+    __shared__ double rcnt[512 / TB_STEP + 2];                  // 1 / n for the row counts of the mean (n <= window / 10)
     const int cap_w = (cap + w) / TB_STEP + 3;
-    double *frec = (double *)(smem + frec_off);                 // [cap_w][4] mode, a, b, max(prediction) of the windows over [d0, d1)
+    double *frec = (double *)(smem + frec_off);                 // [cap_w][6] mode, max(prediction), a, b, 1 / max of the windows over [d0, d1)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
     for (int i = tid; i < 2 * 3 * 4 * L; i += nt) ver[i] = 0.0;
+    for (int i = tid; i <= overlaps; i += nt) rcnt[i] = i > 0 ? 1.0 / (double)i : 0.0;
     __syncthreads();
 
     for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -417,7 +420,13 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
             {
                 const int jw_hi = min(nwin - 1, max(0, d1 - 1 - k) / TB_STEP);
                 const int nrec = min(cap_w, jw_hi - jw_lo + 1);
-                for (int i = tid; i < nrec * 4; i += nt) frec[i] = ft[(i64)(jw_lo + (i >> 2)) * TB_FIT_REC + (i & 3)];   // read after the scan's barrier
+                for (int i = tid; i < nrec * 4; i += nt) {                           // read after the scan's barrier
+                    const double v = ft[(i64)(jw_lo + (i >> 2)) * TB_FIT_REC + (i & 3)];         // mode, a, b, max(prediction)
+                    double *fr = frec + (i >> 2) * TB_K3C_FREC;
+                    const int c = i & 3;
+                    fr[c == 0 ? 0 : (c == 3 ? 1 : c + 1)] = v;                       // -> mode, max, a, b
+                    if (c == 3) fr[4] = v > 0.0 ? 1.0 / v : 0.0;                     // one division per window instead of one per covered position
+                }
             }
             {
                 u32 s_loc = 0, c_loc = 0;
@@ -477,16 +486,16 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                         const int jw = jmax - back;                     // last window of row r starting at or before q
                         if (k + TB_STEP * jw + w > q) {
                             have = true;
-                            const double *f = frec + (jw - jw_lo) * 4;
-                            double mode = f[0], mx = f[3];
+                            const double *f = frec + (jw - jw_lo) * TB_K3C_FREC;
+                            const double mode = f[0], mx = f[1], minv = f[4];
                             if (mode == 0.0) {
-                                double t = __dadd_rn(__dmul_rn(f[1], x), f[2]);
+                                double t = __dadd_rn(__dmul_rn(f[2], x), f[3]);
                                 val = t > 0.0 ? t : 0.0;
-                                if (mx > 0.0) val = val / mx;
+                                if (mx > 0.0) val = tb_div_inv(val, mx, minv);      // = val / mx, correctly rounded (tb_lm_thread.cuh)
                             } else if (mode == 1.0) {
-                                double t = x - f[2];
+                                double t = x - f[3];
                                 val = t < 0.0 ? 0.0 : t;
-                                if (mx > 0.0) val = val / mx;
+                                if (mx > 0.0) val = tb_div_inv(val, mx, minv);
                             }
                         }
                     }
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                         cnt++;
                     }
                 }
-                bp[q - d0] = cnt > 0 ? sum / (double)cnt : (double)NAN;
+                bp[q - d0] = cnt > 0 ? tb_div_inv(sum, (double)cnt, rcnt[cnt]) : (double)NAN;     // = sum / cnt
             }
             __syncthreads();
             // ---- 2. expected and raw corrected signal on [c0, c1) (:314-328)
@@ -851,11 +860,11 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         size_t smem = ((size_t)5 * capk + 2 * 3 * 4 * L) * sizeof(double) + (2 * (capk + 1) + 64) * sizeof(u32) + capk * 2 + tile_len + L + 16;
         smem = (smem + 15) & ~(size_t)15;
         const int frec_off = (int)smem;                                 // fit records of the tile's windows
-        smem += ((capk + window) / TB_STEP + 3) * 4 * sizeof(double);
+        smem += ((capk + window) / TB_STEP + 3) * TB_K3C_FREC * sizeof(double);
         auto kc = tb_correct_kernel;
         TB_CUDA(ctx, cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const i64 n_tiles = (i64)tile_region.size();
-        i64 per_sm = (i64)(220 * 1024) / (i64)(smem + 1024);
+        i64 per_sm = (i64)(227 * 1024) / (i64)(smem + 1024);            // 227 KB usable per SM, 1 KB reserved per block
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 8) per_sm = 8;
         const i64 capg = (i64)ctx->sm_count * per_sm;
