@@ -75,7 +75,7 @@ grouping) -> 367 (K3a ratio form, lane = column) -> 338 (plane-major traversal i
 in L2) -> 309 (K3c rounding in the fp64 pipe, fit records in shared memory) -> 291 (K2 joint histograms of 2-base chunks in shared memory) -> 288 (K4
 pre-scaled flank sums, unconditional width loop) -> 283 (K3c verification weights through per-base position lists) -> 276 (K3b one pass per
 accepted step) -> 261 (K3b window statistics taken in the init pass, no divergent finish pass) -> 259 (K3b loads two points ahead) -> 254 (K3a
-epilogue: branch-free column selection, half the exponent splits, no gather shuffles) -> 252.7 (K3b one-pass rounds at five blocks per SM).  e2e: 1496 -> ~430 -> 396 -> 355 (genome upload on the copy
+epilogue: branch-free column selection, half the exponent splits, no gather shuffles) -> 252.7 (K3b one-pass rounds at five blocks per SM) -> 247.9 (K3c: quotients of the 10-row mean through per-window reciprocals, correctly rounded).  e2e: 1496 -> ~430 -> 396 -> 355 (genome upload on the copy
 stream, overlapped with the read counts and the training counts) -> 321 ms; with 3.94 GB of H2D (76 ms at 52 GB/s, only ~20 ms of kernels can
 overlap it because the model needs the counts of the whole genome) and 2.10 GB of D2H (40 ms, hidden behind the footprint kernels except for the
 last 10 ms) the e2e line sits ~5 ms above what the PCIe link allows for these kernel times.
@@ -91,7 +91,7 @@ DRAM traffic of every kernel is within ~2x of its algorithmic bytes and none of 
 | K2 `tb_k2_scatter` + `tb_k2_weights` + `tb_k2_hist_smem` + `tb_k2_fold` | scatter / weights: DRAM latency of sector-sized read-modify-writes on the 24 GB multiplicity slab (12.6 of the 16 ms); histogram: shared-memory atomics | site list instead of a slab scan (174 -> 40 ms); joint histograms of chunk pairs instead of one atomic per position pair: 21 L2 atomics per k-mer (32 ms, bound by the L2 atomic rate), then 78 shared-memory atomics per k-mer on 16 x 16 tables (histogram kernel 25 -> 3.2 ms, K2 16 ms) | the slab passes: a sort-based dedup of (region, strand, cut site) would avoid the 24 GB slab |
 | K3a `tb_score_dwm2_kernel` | **shared-memory data pipe (76 %: table rows 30 + shuffles 10 wavefronts per window) and instruction issue (70 %)** together | product form (no exp2), pair / trinucleotide row groups (25 -> 10 rows), ratio form (3 values per column, lane = column), 5 groups read from **tensor memory** through tcgen05.ld, butterfly reduction, compile-time grouping (446 -> 98 ms); branch-free column selection, raw level-16 products split afterwards, idle lanes as exact constants, no gather shuffles: 631 -> 527 instructions per four windows (-> 91 ms) | both pipes are near their limit with fp64 at 33 %: fewer shared-memory rows (a fourth table store does not exist on the SM), k-mers from uniform loads instead of 2 shuffles per window |
 | K3b `tb_fitg_round_kernel` | **instruction issue + L1 miss latency** (thread-sequential LM arithmetic; fp64 and integer instructions issue at half rate) | one thread per window, rounds over compacted lists, exact MINPACK order without m-vector storage (2854 -> 227 ms exact); one-pass outer iterations, plane-major traversal, tail finished in one launch for DWM (-> ~80 ms) | compulsory L1 misses of the window data every round |
-| K3c `tb_correct_kernel` | instruction issue, spread over four phases (was: conversion unit, two conversions per term of the float-accumulator rolling sums) | no fp64 shared atomics, integer prefix / sparse sums where exact, zero addends skipped (103 -> 68 ms); one tile per 824-bp region (-> 57); float rounding in the fp64 pipe by adding and subtracting 1.5 * 2^(E+29) -- exact, no conversions (-> 56); fit records staged in shared memory, no per-row modulo, sign-split verification adds (-> 52.5) | three dense sequential rolling sums of 100 terms per position -- the semantics are the reference's |
+| K3c `tb_correct_kernel` | instruction issue, spread over four phases (was: conversion unit, two conversions per term of the float-accumulator rolling sums) | no fp64 shared atomics, integer prefix / sparse sums where exact, zero addends skipped (103 -> 68 ms); one tile per 824-bp region (-> 57); float rounding in the fp64 pipe by adding and subtracting 1.5 * 2^(E+29) -- exact, no conversions (-> 56); fit records staged in shared memory, no per-row modulo, sign-split verification adds (-> 52.5); verification weights through per-base position lists (-> 47.4); quotients of the 10-row mean through per-window reciprocals + two fused corrections, correctly rounded (-> 43.3) | three dense sequential rolling sums of 100 terms per position -- the semantics are the reference's |
 | K4 `tb_footprint_kernel` | issue (fp32 + shared loads), 651 width combinations per position | fitted block size, half the barriers, suffix-maximum spreading (49 -> 30 ms); flank sums divided by 2 x width once per element and an unconditional, padded width loop: LDS + FADD + FMNMX per combination instead of five instructions (-> 26 ms) | two footprint starts per thread with 64-bit shared loads (tried: 128-bit loads of the 32 values from four shifted copies of the flank sums -- 33.7 ms instead of 26.1: the 32 result registers in flight next to the 32 accumulators leave no room at 64 registers per thread) |
 
 Bytes-based roofline fractions (algorithmic bytes of SURVEY 8d / measured time / 6554.9 GB/s measured copy bandwidth) are therefore small for
