@@ -301,6 +301,41 @@ def test_bias_correction_other_fit_kernels(loaded_ctx, golden, lm_mode):
                 assert np.array_equal(got[t][si], ref)
 
 
+def test_bias_correction_edge_regions(loaded_ctx, golden):
+    """Regions the golden set does not hold, against the oracle region by region (PWM mode: every track bit-identical): a region whose
+    extension starts at position 0 of a contig and lies in an N block without reads, one whose extension ends at the contig end, a
+    one-base region, a region of another contig; and an empty region list."""
+    g = golden.atac
+    _set_model(loaded_ctx, g, "PWM")
+    bias = restate.AtacBias(25, "PWM")
+    for st in ("forward", "reverse"):
+        bias.bias[st].pssm = g["PWM_%s_pssm" % st]
+    bias.correction_factor = 0.75
+    regs = [(0, 162, 700), (0, 5000, 5001), (0, 20000, 20350), (0, 41200, 41838), (1, 15000, 15900), (2, 400, 1400)]
+    c, s, e = _cols(np.array(regs))
+    loaded_ctx.correct_run(c, s, e, correction_factor=0.75, lm_exact_order=True)
+    got = loaded_ctx.correct_download(split_strands=True, as_f64=True)
+    off = 0
+    pre_sum = np.zeros((2, 5, 25))
+    for (ci, a, b) in regs:
+        out, pre, post = restate.bias_correction_region(golden.reads, golden.genome, ci, a, b, bias)
+        n = b - a
+        for t in TRACKS:
+            for si, st in enumerate(("forward", "reverse")):
+                assert np.array_equal(got[t][si][off:off + n], out[t][st]), (ci, a, b, t, st)
+        for si, st in enumerate(("forward", "reverse")):
+            pre_sum[si] += pre[st].counts
+        off += n
+    assert off == got["corrected"][0].shape[0]
+    assert np.allclose(got["prepost"][:, 0, :4, :], pre_sum[:, :4, :], rtol=1e-12, atol=1e-9)
+    # no regions at all: a valid, empty result
+    z = np.zeros(0, dtype=np.int64)
+    loaded_ctx.correct_run(z.astype(np.int32), z, z, correction_factor=1.0)
+    empty = loaded_ctx.correct_download(split_strands=False, as_f64=False)
+    assert all(empty[t].shape == (0,) for t in TRACKS)
+    assert loaded_ctx.count_reads(z.astype(np.int32), z, z) == 0
+
+
 def test_fit_trace_matches_scipy_exactly_in_pwm_mode(loaded_ctx, golden):
     g = golden.atac
     _set_model(loaded_ctx, g, "PWM")
