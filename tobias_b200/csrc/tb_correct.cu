@@ -223,6 +223,9 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
 #ifndef TB_FITG_MINBLOCKS
 #define TB_FITG_MINBLOCKS 4
 #endif
+#ifndef TB_FITG_PREFETCH_FAST
+#define TB_FITG_PREFETCH_FAST 0      // 1: one-pass form prefetches both ends of the warp's span in every plane at the start of a round (measured: 58.3 -> 64.5 ms, off)
+#endif
 #ifndef TB_FITG_FUSE
 #define TB_FITG_FUSE 1      // 0: separate Jacobian and trial passes in the one-pass form (comparison builds)
 #endif
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
             const i64 q = G.wq[slot];
             const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
 #ifndef TB_EMU
-            if (!FAST) {   // (measured: -5 % on the exact form, nothing on the one-pass form)
+            if (!FAST || TB_FITG_PREFETCH_FAST) {   // (measured: -5 % on the exact form)
                 // The lanes of a warp read consecutive slots q .. q + 31 of a plane and move up by one slot every ten points, so the top
                 // of the warp's span enters the cache one sector at a time, each time as a miss the pass loop has to wait for.  Ask for
                 // the last slot every lane will need in every plane now: the whole span of the round is then in flight at once.
@@ -252,6 +255,10 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
                 for (int v = 0; v < 10; v++) {
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(W.x + (i64)v * W.stride + top));
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(W.y + (i64)v * W.stride + top));
+                    if (FAST) {        // plane-major traversal: the first touch of every plane would otherwise be a miss two points ahead of its use
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(W.x + (i64)v * W.stride));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(W.y + (i64)v * W.stride));
+                    }
                 }
             }
 #endif
