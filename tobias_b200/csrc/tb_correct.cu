@@ -186,6 +186,8 @@ __global__ void tb_fitg_transpose_kernel(tb_cor_view V, const u32 *__restrict__ 
 }
 
 // per window: tile slot, residual norm at p0, empty-window record, initial state, first Q list
+// FAST_HEAD (one-pass form): the same pass also runs the first outer-iteration head, the window goes to the trial-only list
+template <bool FAST_HEAD>
 __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int qm, double *__restrict__ fit, u32 *__restrict__ listq,
                                     unsigned long long *ctr) {
     const i64 n_round = ((G.n_slots + 31) / 32) * 32;
@@ -199,10 +201,11 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
             const i64 q = (i64)strand * qs + wg + (i64)(qm - 1) * j;
             G.wq[slot] = (u32)q;
             tb_win_stats st;
-            const double f0 = tb_lmt_fnorm0_stats(tb_win_ref{G.gx + q, G.gy + q, G.qtot}, V.window, st);
+            tb_lmt S;
+            const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
+            const double f0 = FAST_HEAD ? tb_lmt_start_fast(S, W, V.window, st) : tb_lmt_fnorm0_stats(W, V.window, st);
             if (f0 >= 0.0) {                                           // signalmax > 0 (:290)
-                tb_lmt S;
-                tb_lmt_init(S, f0);
+                if (!FAST_HEAD) tb_lmt_init(S, f0);
                 tb_fitg_store(G, slot, S);
                 double *rec = fit + slot * TB_FIT_REC;                 // parked in the window's record until its fit ends
                 rec[1] = st.xmax;
@@ -803,11 +806,15 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
         {
             i64 want = tb_div_up(n_slots, 128), capg = (i64)ctx->sm_count * 16;
-            TB_LAUNCH(ctx, tb_fitg_init_kernel, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lq[0], ctr);
+            if (lm_exact_order) {
+                TB_LAUNCH(ctx, tb_fitg_init_kernel<false>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lq[0], ctr);
+            } else {      // one-pass form: the first head ran in the init pass, every window starts on the trial-only list
+                TB_LAUNCH(ctx, tb_fitg_init_kernel<true>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lt[0], ctr + 1);
+            }
         }
         unsigned long long hc[2] = {0, 0};
         TB_TRY(tb_d2h(ctx, hc, ctr, sizeof(hc)));
-        i64 nq = (i64)hc[0], nt = 0;
+        i64 nq = (i64)hc[0], nt = (i64)hc[1];
         int cur = 0;
         const i64 tail_at = (i64)ctx->sm_count * 128;      // one block per SM's worth of windows: finish them in one launch
         for (int round = 0; nq + nt > 0; round++) {

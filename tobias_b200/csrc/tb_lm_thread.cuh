@@ -490,6 +490,42 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
     tb_lmt_qr_from_gram(S, W, m, J, Gm);
 }
 
+// One-pass form, start of a fit: the pass that forms the residual norm at p0 = (1, 1) and the window statistics also forms the inner
+// products of the first Jacobian (the start point is the same for every window), so the first outer-iteration head costs no pass of its
+// own.  Returns -1 for a window without signal (no fit), else the state after the head (S.info may already be non-zero).
+__device__ __forceinline__ double tb_lmt_start_fast(tb_lmt &S, const tb_win_ref W, int m, tb_win_stats &st) {
+    const tb_jac_fast J = tb_jac_fast_at(1.0, 1.0);
+    tb_gram Gm;
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
+    u32 ymax = 0;
+    double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
+    double ss = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
+    TB_FOR_POINTS_ANY_ORDER(W, m, {
+        ymax = eyi > ymax ? eyi : ymax;
+        xmax = fmax(xmax, ex);
+        xmin = fmin(xmin, ex);
+        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
+        double f, j0, j1;
+        J.eval(ex, ey, f, j0, j1);
+        ss += f * f;
+        g00 += j0 * j0;
+        g01 += j0 * j1;
+        g11 += j1 * j1;
+        gf0 += j0 * f;
+        gf1 += j1 * f;
+    })
+    st.xmax = xmax;
+    st.xmin = xmin;
+    st.bmin = bmin;
+    if (ymax == 0u) return -1.0;
+    Gm.g00 = g00; Gm.g01 = g01; Gm.g11 = g11; Gm.gf0 = gf0; Gm.gf1 = gf1;
+    const double f0 = sqrt(ss);
+    tb_lmt_init(S, f0);
+    tb_lmt_qr_from_gram(S, W, m, J, Gm);
+    return f0;
+}
+
 // R, Q^T fvec, column norms and the outer-iteration bookkeeping from the inner products (no pass over the window unless the columns look
 // dependent); counts the two function evaluations of the forward differences
 __device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref W, int m, const tb_jac_fast &J, const tb_gram &Gm) {
