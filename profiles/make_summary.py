@@ -75,7 +75,7 @@ grouping) -> 367 (K3a ratio form, lane = column) -> 338 (plane-major traversal i
 in L2) -> 309 (K3c rounding in the fp64 pipe, fit records in shared memory) -> 291 (K2 joint histograms of 2-base chunks in shared memory) -> 288 (K4
 pre-scaled flank sums, unconditional width loop) -> 283 (K3c verification weights through per-base position lists) -> 276 (K3b one pass per
 accepted step) -> 261 (K3b window statistics taken in the init pass, no divergent finish pass) -> 259 (K3b loads two points ahead) -> 254 (K3a
-epilogue: branch-free column selection, half the exponent splits, no gather shuffles) -> 252.7 (K3b one-pass rounds at five blocks per SM) -> 247.9 (K3c: quotients of the 10-row mean through per-window reciprocals, correctly rounded).  e2e: 1496 -> ~430 -> 396 -> 355 (genome upload on the copy
+epilogue: branch-free column selection, half the exponent splits, no gather shuffles) -> 252.7 (K3b one-pass rounds at five blocks per SM) -> 247.9 (K3c: quotients of the 10-row mean through per-window reciprocals, correctly rounded) -> 243.8 (K3b: first outer-iteration head inside the init pass).  e2e: 1496 -> ~430 -> 396 -> 355 (genome upload on the copy
 stream, overlapped with the read counts and the training counts) -> 321 ms; with 3.94 GB of H2D (76 ms at 52 GB/s, only ~20 ms of kernels can
 overlap it because the model needs the counts of the whole genome) and 2.10 GB of D2H (40 ms, hidden behind the footprint kernels except for the
 last 10 ms) the e2e line sits ~5 ms above what the PCIe link allows for these kernel times.
@@ -90,7 +90,7 @@ DRAM traffic of every kernel is within ~2x of its algorithmic bytes and none of 
 | K1 `tb_pileup_kernel` | L2 atomics / integer issue (scatter), 1.1 ms for 49M records + 124M positions | -- (0.3 % of the step) | -- |
 | K2 `tb_k2_scatter` + `tb_k2_weights` + `tb_k2_hist_smem` + `tb_k2_fold` | scatter / weights: DRAM latency of sector-sized read-modify-writes on the 24 GB multiplicity slab (12.6 of the 16 ms); histogram: shared-memory atomics | site list instead of a slab scan (174 -> 40 ms); joint histograms of chunk pairs instead of one atomic per position pair: 21 L2 atomics per k-mer (32 ms, bound by the L2 atomic rate), then 78 shared-memory atomics per k-mer on 16 x 16 tables (histogram kernel 25 -> 3.2 ms, K2 16 ms) | the slab passes: a sort-based dedup of (region, strand, cut site) would avoid the 24 GB slab |
 | K3a `tb_score_dwm2_kernel` | **shared-memory data pipe (76 %: table rows 30 + shuffles 10 wavefronts per window) and instruction issue (70 %)** together | product form (no exp2), pair / trinucleotide row groups (25 -> 10 rows), ratio form (3 values per column, lane = column), 5 groups read from **tensor memory** through tcgen05.ld, butterfly reduction, compile-time grouping (446 -> 98 ms); branch-free column selection, raw level-16 products split afterwards, idle lanes as exact constants, no gather shuffles: 631 -> 527 instructions per four windows (-> 91 ms) | both pipes are near their limit with fp64 at 33 %: fewer shared-memory rows (a fourth table store does not exist on the SM), k-mers from uniform loads instead of 2 shuffles per window |
-| K3b `tb_fitg_round_kernel` | **instruction issue + L1 miss latency** (thread-sequential LM arithmetic; fp64 and integer instructions issue at half rate) | one thread per window, rounds over compacted lists, exact MINPACK order without m-vector storage (2854 -> 227 ms exact); one-pass outer iterations, plane-major traversal, tail finished in one launch for DWM (-> ~80 ms) | compulsory L1 misses of the window data every round |
+| K3b `tb_fitg_round_kernel` | **instruction issue + L1 miss latency** (thread-sequential LM arithmetic; fp64 and integer instructions issue at half rate) | one thread per window, rounds over compacted lists, exact MINPACK order without m-vector storage (2854 -> 227 ms exact); one-pass outer iterations, plane-major traversal, tail finished in one launch for DWM (-> ~80 ms); one pass per accepted step, window statistics in the init pass, loads two points ahead (-> 59.8); five resident blocks per SM (-> 58.2); first outer-iteration head inside the init pass (-> 54.0) | a quarter of the stall samples sit on the first use of the look-ahead loads; software prefetch measured slower both ways tried (64.5 / 61.2 ms) |
 | K3c `tb_correct_kernel` | instruction issue, spread over four phases (was: conversion unit, two conversions per term of the float-accumulator rolling sums) | no fp64 shared atomics, integer prefix / sparse sums where exact, zero addends skipped (103 -> 68 ms); one tile per 824-bp region (-> 57); float rounding in the fp64 pipe by adding and subtracting 1.5 * 2^(E+29) -- exact, no conversions (-> 56); fit records staged in shared memory, no per-row modulo, sign-split verification adds (-> 52.5); verification weights through per-base position lists (-> 47.4); quotients of the 10-row mean through per-window reciprocals + two fused corrections, correctly rounded (-> 43.3) | three dense sequential rolling sums of 100 terms per position -- the semantics are the reference's |
 | K4 `tb_footprint_kernel` | issue (fp32 + shared loads), 651 width combinations per position | fitted block size, half the barriers, suffix-maximum spreading (49 -> 30 ms); flank sums divided by 2 x width once per element and an unconditional, padded width loop: LDS + FADD + FMNMX per combination instead of five instructions (-> 26 ms) | two footprint starts per thread with 64-bit shared loads (tried: 128-bit loads of the 32 values from four shifted copies of the flank sums -- 33.7 ms instead of 26.1: the 32 result registers in flight next to the 32 accumulators leave no room at 64 registers per thread) |
 
@@ -150,6 +150,9 @@ def main():
     L.append("\nShares per stage (of the six stages), launch list vs bench (CUDA events): "
              + "; ".join("%s %.1f%% vs %.1f%%" % (k, 100 * g[k] / gt, 100 * st[k]["ms"] / ssum) for k in st) + ".\n")
     L.append("## 3. `ncu --set full --clock-control none --import-source on` (one launch per kernel, chr50mb workload: 16.4M extended positions, 4.9M records)\n")
+    L.append("(Captured one commit before the last K3b change: `tb_fitg_round_kernel<1, 1>` is the first-round kernel of that commit; since the init pass "
+             "runs the first outer-iteration head, the DWM default launches only `tb_fitg_init_kernel<1>` and `tb_fitg_round_kernel<0, 1>` -- the launch list "
+             "of section 2 and the bench line of section 1 are of the final commit.)\n")
     L.append("| kernel | ms | grid x block | regs | DRAM read / write MB | SM thr % | issue % | fp64 pipe % | ALU pipe % | XU pipe % | shared pipe % | lanes / inst | warps active % |\n"
              "|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for k, d in full.items():
@@ -174,7 +177,7 @@ def main():
              "K1_pileup": roof("tb_pileup_kernel<0>", "L2 atomics / integer issue", "alu_pipe_pct"),
              "K2_counts": roof("tb_k2_scatter", "DRAM latency of the slab read-modify-writes (scatter, weights); shared-memory atomics (histogram)", "sm_throughput_pct"),
              "K3a_score": roof("tb_score_dwm2", "shared-memory data pipe (table rows + shuffles) together with instruction issue (~70 %); half of the rows come from tensor memory", "smem_pipe_pct"),
-             "K3b_fit": roof("tb_fitg_round_kernel<1, 1>", "instruction issue (thread-sequential LM arithmetic) + L1 miss latency", "issue_active_pct"),
+             "K3b_fit": roof("tb_fitg_round_kernel<0, 1>", "instruction issue (thread-sequential LM arithmetic) + L1 miss latency", "issue_active_pct"),
              "K3c_correct": roof("tb_correct_kernel", "instruction issue (sequential float-accumulator rolling sums, 10-row mean, verification counts)", "issue_active_pct"),
              "K4_footprint": roof("tb_footprint_kernel", "instruction issue (fp32 + shared loads)", "issue_active_pct")}
     # DRAM traffic of the dominant kernel at the bench's own size: one --set full launch of tb_score_dwm2_kernel in the hg38 bench
