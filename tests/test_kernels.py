@@ -247,12 +247,13 @@ def test_score_sequence_table_range(loaded_ctx, golden, spread):
     _set_model(loaded_ctx, g, "DWM")          # leave the session context as the other tests expect it
 
 
-@pytest.mark.parametrize("mode", ["PWM", "DWM"])
-def test_bias_correction_tracks(loaded_ctx, golden, mode):
+@pytest.mark.parametrize("mode,lm", [("PWM", 1), ("DWM", 1), ("DWM", 0)])
+def test_bias_correction_tracks(loaded_ctx, golden, mode, lm):
+    """lm = 1: MINPACK-exact window fits (PWM default, --lm-exact); lm = 0: the one-pass form, the DWM default and the benchmarked one."""
     g = golden.atac
     _set_model(loaded_ctx, g, mode)
     c, s, e = _cols(g["outreg"])
-    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=True)
+    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=lm)
     got = loaded_ctx.correct_download(split_strands=True, as_f64=True)
     for t in TRACKS:
         for si, st in enumerate(("forward", "reverse")):

@@ -140,11 +140,13 @@ def run_atacorrect(args):
     local = {k: RegionList([r for r in rd[k] if owner[r.chrom] == comm.rank]) for k in
              ("input_regions", "output_regions", "peak_regions", "nonpeak_regions")}
     device = int(os.environ.get("LOCAL_RANK", args.device))
-    eng = Engine(device)
-    eng.load_genome_fasta(fasta, mine)
-    name_to_old = {n: i for i, n in enumerate(reads.references)}
-    sel = np.isin(reads.chrom_id, [name_to_old[c] for c in mine])
-    eng.load_reads(reads.select(sel))
+    eng = None
+    if mine:              # a rank without contigs (more ranks than kept contigs) holds no data: it adds zeros to the all-reduces, nothing to the gathers
+        eng = Engine(device)
+        eng.load_genome_fasta(fasta, mine)
+        name_to_old = {n: i for i, n in enumerate(reads.references)}
+        sel = np.isin(reads.chrom_id, [name_to_old[c] for c in mine])
+        eng.load_reads(reads.select(sel))
     read_shift = tuple(args.read_shift)
 
     logger.comment("")
@@ -152,7 +154,8 @@ def run_atacorrect(args):
     if not args.norm_off:
         logger.info("Counting reads in peak regions")
         logger.info("Counting reads in nonpeak regions")
-        cnt = np.array([eng.count_reads(local["peak_regions"], read_shift), eng.count_reads(local["nonpeak_regions"], read_shift)], dtype=np.int64)
+        cnt = np.array([eng.count_reads(local["peak_regions"], read_shift), eng.count_reads(local["nonpeak_regions"], read_shift)] if eng else [0, 0],
+                       dtype=np.int64)
         comm.allreduce_sum(cnt)
         reads_peaks, reads_nonpeaks = int(cnt[0]), int(cnt[1])
         reads_total = reads_peaks + reads_nonpeaks
@@ -172,7 +175,8 @@ def run_atacorrect(args):
     logger.comment("")
     if args.bias_pkl is None:
         logger.info("Started estimation of sequence bias...")
-        bias_obj = eng.estimate_bias(local["input_regions"], args.k_flank, args.bg_shift, read_shift, args.score_mat)
+        bias_obj = (eng.estimate_bias(local["input_regions"], args.k_flank, args.bg_shift, read_shift, args.score_mat) if eng
+                    else AtacBias(2 * args.k_flank + 1, args.score_mat))
         packed = bias_obj.pack_counts()
         comm.allreduce_sum(packed)
         bias_obj.unpack_counts(packed)
@@ -189,7 +193,8 @@ def run_atacorrect(args):
 
     logger.comment("")
     logger.info("----- Correcting reads from .bam within output regions -----")
-    eng.set_bias(bias_obj)
+    if eng:
+        eng.set_bias(bias_obj)
     out_regions = local["output_regions"]
     out_regions.loc_sort(mine)
     lm_exact = bool(args.lm_exact) or args.score_mat == "PWM"
@@ -240,7 +245,8 @@ def run_atacorrect(args):
         import matplotlib  # noqa: F401
     except ImportError:
         logger.warning("matplotlib is not available: {0} was not written".format(figures_f))
-    eng.close()
+    if eng:
+        eng.close()
     fasta.close()
     logger.end()
     return {"correction_factor": correct_factor, "bias": bias_obj, "pre_bias": pre_bias, "post_bias": post_bias}

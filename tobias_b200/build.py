@@ -52,12 +52,12 @@ def build(force=False, verbose=False, ptxas_info=False, extra_flags=(), out=None
         objs.append(obj)
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
             failed = True
-            sys.stderr.write("nvcc failed on %s:\n%s\n" % (src, out))
-        elif (verbose or ptxas_info) and out.strip():
-            print(out)
+            sys.stderr.write("nvcc failed on %s:\n%s\n" % (src, log))
+        elif (verbose or ptxas_info) and log.strip():
+            print(log)
     if failed:
         raise RuntimeError("nvcc compilation failed")
     cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs + ["-lcudart", "-ldl"]

@@ -42,6 +42,7 @@ class FastaFile:
     def _build_index(self):
         buf = self._buf
         gt = np.flatnonzero(buf == ord(">"))
+        gt = gt[(gt == 0) | (buf[np.maximum(gt, 1) - 1] == ord("\n"))]      # a header starts a line; '>' inside a description is text
         nl = np.flatnonzero(buf == ord("\n"))
         total = buf.shape[0]
         for k, h in enumerate(gt):

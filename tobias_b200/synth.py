@@ -92,13 +92,18 @@ def _outside_blocks(pos, width, blocks, margin=0):
     return ok
 
 
-def make_peaks(seed, lengths, nblocks, n_peaks, width=500, skip=("chrM",)):
+def make_peaks(seed, lengths, nblocks, n_peaks, width=500, skip=("chrM",), universe=None):
     """Sorted list of (chrom, start, end): non-overlapping `width`-bp intervals outside the large N blocks,
-    plus a few book-ended and overlapping pairs (exercise RegionList.merge, regions.py:343-373)."""
+    plus a few book-ended and overlapping pairs (exercise RegionList.merge, regions.py:343-373).
+    universe: the whole workload's name -> length when `lengths` is a shard of it (seeds and shares per contig then do not
+    depend on the shard)."""
+    universe = universe if universe is not None else lengths
+    unames = [n for n in universe if n not in skip]
     names = [n for n in lengths if n not in skip]
-    tot = float(sum(lengths[n] for n in names))
+    tot = float(sum(universe[n] for n in unames))
     peaks = []
-    for k, name in enumerate(names):
+    for name in names:
+        k = unames.index(name)
         rng = np.random.default_rng([seed, 2, k])
         ln = lengths[name]
         n = max(1, int(round(n_peaks * ln / tot)))

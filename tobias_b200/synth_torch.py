@@ -156,16 +156,22 @@ def make_reads_contig(seed, k, codes, blocks, pk, n_frag, pwm, device, read_len=
 class TorchDataset:
     """names, genome (list of uint8 ASCII numpy arrays), peaks [(name, s, e)], reads (ReadColumns)."""
 
-    def __init__(self, seed, lengths, n_peaks, n_records, device=None, skip=("chrM",), pin=False):
+    def __init__(self, seed, lengths, n_peaks, n_records, device=None, skip=("chrM",), pin=False, universe=None):
+        """universe: name -> length of the WHOLE workload when `lengths` is one rank's shard of it.  Every contig is then seeded by its
+        index in the universe and receives its share of the universe's peaks / records, so a contig holds the same bases, peaks and
+        records whichever rank builds it (n_peaks / n_records are the universe's totals in that case)."""
         device = device or ("cuda" if torch.cuda.is_available() else "cpu")
         self.names = list(lengths.keys())
         self.lengths = [int(lengths[n]) for n in self.names]
+        universe = dict(universe) if universe is not None else dict(lengths)
+        key = {n: i for i, n in enumerate(universe)}
         ascii_lut = torch.tensor(list(b"ATCGN"), dtype=torch.uint8, device=device)
         pwm = synth.planted_pwm(np.random.default_rng([seed, 3]))
-        tot = float(sum(ln for n, ln in zip(self.names, self.lengths) if n not in skip))
+        tot = float(sum(ln for n, ln in universe.items() if n not in skip))
         codes_dev, nblocks = {}, {}
         self.genome = []
-        for k, (name, ln) in enumerate(zip(self.names, self.lengths)):
+        for name, ln in zip(self.names, self.lengths):
+            k = key[name]
             codes, blocks = make_contig(seed, k, ln, device)
             nblocks[name] = blocks
             codes_dev[name] = codes
@@ -173,12 +179,13 @@ class TorchDataset:
             host.copy_(ascii_lut[codes.long()] if device == "cpu" else torch.take(ascii_lut, codes.long()))
             self.genome.append(host.numpy())
         self.nblocks = nblocks
-        self.peaks = synth.make_peaks(seed, dict(zip(self.names, self.lengths)), nblocks, n_peaks, skip=skip)
+        self.peaks = synth.make_peaks(seed, dict(zip(self.names, self.lengths)), nblocks, n_peaks, skip=skip, universe=universe)
         by_chrom = {}
         for c, s, e in self.peaks:
             by_chrom.setdefault(c, []).append((s, e))
         parts = []
-        for k, (name, ln) in enumerate(zip(self.names, self.lengths)):
+        for ki, (name, ln) in enumerate(zip(self.names, self.lengths)):
+            k = key[name]
             if ln < 2000:
                 continue
             n_frag = int(round(n_records * (ln / tot) / 2.0)) if name not in skip else max(50, int(n_records * 1e-4))
@@ -186,7 +193,7 @@ class TorchDataset:
                 continue
             cols = make_reads_contig(seed, k, codes_dev[name], nblocks[name], by_chrom.get(name, []), n_frag, pwm, device)
             n = cols["ref_start"].shape[0]
-            parts.append(ReadColumns(self.names, self.lengths, chrom_id=np.full(n, k, dtype=np.int32),
+            parts.append(ReadColumns(self.names, self.lengths, chrom_id=np.full(n, ki, dtype=np.int32),
                                      **{f: v.cpu().numpy() for f, v in cols.items()}))
             del codes_dev[name]
         self.reads = ReadColumns.concat(parts)
