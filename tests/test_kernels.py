@@ -85,48 +85,48 @@ def test_bias_counts_in_several_slab_chunks(loaded_ctx, golden, monkeypatch):
     """The multiplicity slab is processed in chunks of regions when it does not fit the memory budget; a tiny budget forces
     many chunks (each with its own record range) and the site-list growth path -- same integers."""
     g = golden.atac
-    monkeypatch.setenv("TB_K2_SLAB_BUDGET", "20000")
+    loaded_ctx.set_option("k2_slab_budget", 20000)
     counts, scalars = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)
-    monkeypatch.delenv("TB_K2_SLAB_BUDGET")
+    loaded_ctx.set_option("k2_slab_budget", -1)
     assert scalars[0] == int(g["DWM_no_reads"])
     for si, st in enumerate(("forward", "reverse")):
         assert np.array_equal(counts[si, 0], g["DWM_%s_counts" % st]) and np.array_equal(counts[si, 1], g["DWM_%s_bg_counts" % st])
     counts2, scalars2 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)           # slab left clean by the chunked run
     assert np.array_equal(counts, counts2) and np.array_equal(scalars, scalars2)
-    monkeypatch.setenv("TB_K2_SITE_CAP", "100")                                            # site list too small: regrown, chunk redone
+    loaded_ctx.set_option("k2_site_cap", 100)                                            # site list too small: regrown, chunk redone
     counts3, scalars3 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)
-    monkeypatch.delenv("TB_K2_SITE_CAP")
+    loaded_ctx.set_option("k2_site_cap", -1)
     assert np.array_equal(counts, counts3) and np.array_equal(scalars, scalars3)
 
 
 def test_bias_counts_histogram_forms(loaded_ctx, golden, monkeypatch):
     """DWM counts come from joint chunk histograms (one atomic per k-mer and chunk pair) folded into position pairs: the
     shared-memory form (chunks of 2 bases, the default; also chunks of 1), the L2 form (every chunking -- including a last chunk
-    of one base and two chunks only) and the shared-memory-atomic kernel (TB_K2_NO_HIST=1, models of a single chunk) give the
+    of one base and two chunks only) and the shared-memory-atomic kernel (option k2_no_hist, models of a single chunk) give the
     same integers as the reference."""
     regs = [tuple(int(x) for x in r) for r in golden.atac["nonpeak"]]
     emu = loaded_ctx.device_info()["is_emulator"]
     for k_flank, chunkings, smem_chunks in ((12, (3, 4) if emu else (3, 4, 5), (2,)), (5, (1, 2, 5), (1, 2)), (2, (3, 4, 5), (1, 2)), (1, (2,), (2,))):
         kw = dict(k_flank=k_flank, bg_shift=37, cap=3)
         ref = restate.bias_estimation(golden.reads, golden.genome, regs, golden.lengths, **kw)
-        monkeypatch.setenv("TB_K2_NO_HIST", "1")
+        loaded_ctx.set_option("k2_no_hist", 1)
         base, base_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
-        monkeypatch.delenv("TB_K2_NO_HIST")
+        loaded_ctx.set_option("k2_no_hist", -1)
         for si, st in enumerate(("forward", "reverse")):
             assert np.array_equal(base[si, 0], ref.bias[st].counts) and np.array_equal(base[si, 1], ref.bias[st].bg_counts)
         assert base_sc[0] == ref.no_reads
         for ch in smem_chunks:
-            monkeypatch.setenv("TB_K2_SMEM_CHUNK", str(ch))
+            loaded_ctx.set_option("k2_smem_chunk", ch)
             got, got_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
-            monkeypatch.delenv("TB_K2_SMEM_CHUNK")
+            loaded_ctx.set_option("k2_smem_chunk", -1)
             assert np.array_equal(got, base) and np.array_equal(got_sc, base_sc), ("smem", k_flank, ch)
-        monkeypatch.setenv("TB_K2_NO_SMEM_HIST", "1")
+        loaded_ctx.set_option("k2_no_smem_hist", 1)
         for ch in chunkings:
-            monkeypatch.setenv("TB_K2_CHUNK", str(ch))
+            loaded_ctx.set_option("k2_chunk", ch)
             got, got_sc = loaded_ctx.bias_counts(*_cols(golden.atac["nonpeak"]), **kw)
-            monkeypatch.delenv("TB_K2_CHUNK")
+            loaded_ctx.set_option("k2_chunk", -1)
             assert np.array_equal(got, base) and np.array_equal(got_sc, base_sc), ("l2", k_flank, ch)
-        monkeypatch.delenv("TB_K2_NO_SMEM_HIST")
+        loaded_ctx.set_option("k2_no_smem_hist", -1)
 
 
 def test_asynchronous_genome_upload(loaded_ctx, golden):

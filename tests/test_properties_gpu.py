@@ -86,8 +86,9 @@ def test_slab_chunking_is_invisible(work, monkeypatch):
     ctx, ds, arrays = work
     regs = arrays["input_regions"]
     counts, scalars = ctx.bias_counts(*regs, is_dwm=True)
-    monkeypatch.setenv("TB_K2_SLAB_BUDGET", "1500000")
+    ctx.set_option("k2_slab_budget", 1500000)
     chunked, scalars2 = ctx.bias_counts(*regs, is_dwm=True)
+    ctx.set_option("k2_slab_budget", -1)
     assert np.array_equal(counts, chunked) and np.array_equal(scalars, scalars2)
 
 
@@ -97,10 +98,12 @@ def test_count_kernels_agree(work, monkeypatch):
     ctx, ds, arrays = work
     regs = arrays["input_regions"]
     counts, scalars = ctx.bias_counts(*regs, is_dwm=True)
-    monkeypatch.setenv("TB_K2_NO_SMEM_HIST", "1")
+    ctx.set_option("k2_no_smem_hist", 1)
     l2, l2_sc = ctx.bias_counts(*regs, is_dwm=True)
-    monkeypatch.setenv("TB_K2_NO_HIST", "1")
+    ctx.set_option("k2_no_hist", 1)
     pairs, pairs_sc = ctx.bias_counts(*regs, is_dwm=True)
+    ctx.set_option("k2_no_smem_hist", -1)
+    ctx.set_option("k2_no_hist", -1)
     assert np.array_equal(counts, l2) and np.array_equal(scalars, l2_sc)
     assert np.array_equal(counts, pairs) and np.array_equal(scalars, pairs_sc)
     assert scalars[0] > 100000

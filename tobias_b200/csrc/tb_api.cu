@@ -142,10 +142,23 @@ extern "C" int tb_init(int device, tb_ctx **out) {
         delete ctx;
         return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
     }
-    { const char *e2 = getenv("TB_K3A_SUM_FORM"); ctx->force_sum_form = (e2 && e2[0] == '1') ? 1 : 0;
-      const char *e3 = getenv("TB_K3A_NO_TMEM"); ctx->k3a_no_tmem = (e3 && e3[0] == '1') ? 1 : 0;
-      const char *e4 = getenv("TB_K3A_TMEM_GROUPS"); ctx->k3a_tmem_groups = e4 ? atoi(e4) : 0; }   // comparison runs only
     *out = ctx;
+    return TB_OK;
+}
+
+// Switches between kernel variants / chunk sizes that produce the same results (comparison runs and tests; never needed in production).
+extern "C" int tb_set_option(tb_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return TB_ERR_ARG;
+    static const char *known[] = {"k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_slab_budget", "k2_site_cap", "k2_chunk",
+                                  "k2_no_hist", "k2_smem_chunk", "k2_no_smem_hist", "k2_region_blocks", "k3b_persistent", "host_trace", nullptr};
+    bool ok = false;
+    for (int i = 0; known[i]; i++) ok = ok || strcmp(known[i], key) == 0;
+    if (!ok) return tb_fail(ctx, TB_ERR_ARG, "tb_set_option: unknown option '%s'", key);
+    if (value < 0) ctx->opts.erase(key);          // negative: back to the default
+    else ctx->opts[key] = value;
+    ctx->force_sum_form = (int)tb_opt(ctx, "k3a_sum_form", 0);
+    ctx->k3a_no_tmem = (int)tb_opt(ctx, "k3a_no_tmem", 0);
+    ctx->k3a_tmem_groups = (int)tb_opt(ctx, "k3a_tmem_groups", 0);
     return TB_OK;
 }
 

@@ -31,6 +31,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "../../include/tobias_b200.h"
@@ -132,12 +134,18 @@ struct tb_ctx {
         bool have_signal = false, have_out = false;
     } sc;
 
-    int k3a_tmem_groups = 0;    // K3a: pair groups kept in tensor memory (0 = default 5; TB_K3A_TMEM_GROUPS=1..5, comparison runs)
-    int k3a_no_tmem = 0;        // K3a: 1 = all table rows from shared memory (comparison runs; TB_K3A_NO_TMEM=1)
-    int force_sum_form = 0;     // K3a: 1 = first-generation sum-form kernel (comparison runs; TB_K3A_SUM_FORM=1)
+    int k3a_tmem_groups = 0;    // K3a: pair groups kept in tensor memory (0 = default 5; option "k3a_tmem_groups" = 1..5, comparison runs)
+    int k3a_no_tmem = 0;        // K3a: 1 = all table rows from shared memory (comparison runs; option "k3a_no_tmem")
+    int force_sum_form = 0;     // K3a: 1 = first-generation sum-form kernel (comparison runs; option "k3a_sum_form")
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    std::map<std::string, long long> opts;      // tb_set_option: kernel-variant / chunking switches for comparison runs and tests
 };
+
+static inline long long tb_opt(const tb_ctx *ctx, const char *key, long long dflt) {
+    auto it = ctx->opts.find(key);
+    return it == ctx->opts.end() ? dflt : it->second;
+}
 
 int tb_fail(tb_ctx *ctx, int code, const char *fmt, ...);
 int tb_reserve(tb_ctx *ctx, tb_dbuf &b, size_t bytes);
@@ -222,6 +230,49 @@ __device__ __forceinline__ i64 tb_upper_bound_warp(const i64 *a, i64 n, i64 v) {
     }
     return lo;
 }
+// Exclusive block-wide prefix sums of two fp64 sequences held in shared memory, in place: a[i] = sum of the inputs below i, a[n] / b[n]
+// receive the totals.  Every thread of the block must call it; wtot: 64 doubles of shared scratch.  Ends with a barrier.
+__device__ __forceinline__ void tb_block_scan2w(double *a, double *b, int n, double *wtot) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + nt - 1) / nt;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    double sa = 0.0, sb = 0.0;
+    for (int i = lo; i < hi; i++) {
+        sa += a[i];
+        sb += b[i];
+    }
+    double ia = sa, ib = sb;                                      // inclusive scan over the lanes
+    for (int d = 1; d < 32; d <<= 1) {
+        const double oa = __shfl_up_sync(0xffffffffu, ia, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= d) {
+            ia += oa;
+            ib += ob;
+        }
+    }
+    if (lane == 31) {
+        wtot[warp] = ia;
+        wtot[32 + warp] = ib;
+    }
+    __syncthreads();
+    double ra = ia - sa, rb = ib - sb;
+    for (int ww = 0; ww < warp; ww++) {
+        ra += wtot[ww];
+        rb += wtot[32 + ww];
+    }
+    for (int i = lo; i < hi; i++) {
+        const double va = a[i], vb = b[i];
+        a[i] = ra;
+        b[i] = rb;
+        ra += va;
+        rb += vb;
+    }
+    if ((hi == n && lo < n) || (n == 0 && tid == 0)) {
+        a[n] = ra;
+        b[n] = rb;
+    }
+    __syncthreads();
+}
+
 // first index i in [0, n) with a[i] > v  (a ascending)
 __device__ __forceinline__ i64 tb_upper_bound(const i64 *a, i64 n, i64 v) {
     i64 lo = 0, hi = n;

@@ -371,31 +371,73 @@ __device__ __forceinline__ double tb_roll_f32(const double *v, int first, int w)
 //   4. verification counts: pre / post(+) / post(-) weights of every valid position are left in shared memory; lane m of
 //      a warp then owns k-mer offset m and adds the non-zero weights of the warp's strip of positions into 12 private (weight kind,
 //      base) accumulators -- no atomics in the loop (first version: 25 x 3 shared-memory fp64 atomics = CAS loops per position)
+// FAST (lm_exact_order = 0, the DWM default: a tolerance path anyway): the three float-accumulator rolling sums of a position (bias
+// prediction, |corrected|, corrected+) are differences of block-wide fp64 prefix sums, rounded to float once (the reference's 100
+// sequential float roundings scatter ~3e-7 around that value); the uncorrected sum is cf * (integer prefix difference).  O(1) per position
+// and sum instead of 100 dependent add + round steps.  Shared-memory layout per mode: tb_k3c_layout.
+struct tb_k3c_layout {
+    int capd;        // doubles per position array (cap + 1: room for the total of a prefix sum)
+    int off_ver, off_psum, off_pcnt, off_wsum, off_nzpos, off_wpre, off_bases, off_frec, total;     // byte offsets
+};
+static inline tb_k3c_layout tb_k3c_make_layout(int tile_len, int w, int L, bool fast) {
+    tb_k3c_layout y;
+    const int cap = tile_len + 4 * w;
+    y.capd = cap + 1;
+    size_t o = (size_t)5 * y.capd * sizeof(double);
+    y.off_ver = (int)o;
+    o += (size_t)2 * 3 * 4 * L * sizeof(double);
+    y.off_psum = (int)o;
+    o += (size_t)(cap + 1) * sizeof(u32);
+    y.off_wsum = (int)o;
+    o += 64 * sizeof(u32);
+    o = (o + 7) & ~(size_t)7;
+    y.off_pcnt = y.off_nzpos = y.off_wpre = (int)o;
+    if (fast) {
+        o += (size_t)tile_len * sizeof(double);                     // pre weights of phase 4 (the exact form keeps them in `sig`)
+    } else {
+        o += (size_t)(cap + 1) * sizeof(u32);
+        y.off_nzpos = (int)o;
+        o += (size_t)cap * sizeof(unsigned short);
+    }
+    y.off_bases = (int)o;
+    o += (size_t)tile_len + L + 16;
+    o = (o + 15) & ~(size_t)15;
+    y.off_frec = (int)o;
+    o += (size_t)((cap + w) / TB_STEP + 3) * TB_K3C_FREC * sizeof(double);
+    y.total = (int)o;
+    return y;
+}
+
+// FAST = 2: all sums O(1); FAST = 1: the rolling sum of the bias prediction keeps the literal float accumulator (it is the denominator of
+// `expected`, whose ~3e-7 scatter the subtraction uncorrected - expected can amplify), the rescaling sums are O(1); FAST = 0: all literal.
+template <int FAST>
 __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
     tb_correct_kernel(tb_genome_view g, tb_cor_view V, const int32_t *__restrict__ tile_region,
                       const int32_t *__restrict__ tile_start, i64 n_tiles, int tile_len, const u32 *__restrict__ pile,
-                      const double *__restrict__ biasraw, const double *__restrict__ fit, double cf, int frec_off,
+                      const double *__restrict__ biasraw, const double *__restrict__ fit, double cf, tb_k3c_layout Y,
                       double *__restrict__ tracks, double *__restrict__ prepost) {
     TB_DYN_SMEM(smem);
     const int w = V.window, k = V.k_flank, L = V.L;
     const int lf = w / 2;
     const int overlaps = w / TB_STEP;
     const int cap = tile_len + 4 * w;
-    double *sig = (double *)smem;              // [d0, d1)  signal;            phase 4: pre weights of [t0, t1)
-    double *bp = sig + cap;                    // [d0, d1)  mean prediction;   phase 4: post(-) weights, padded by L zeros
-    double *unc = bp + cap;                    // [c0, c1)  signal * cf;       phase 4: positions by base
-    double *cor = unc + cap;                   // [c0, c1)  uncorrected - expected
-    double *expd = cor + cap;                  // [t0, t1)  expected;          phase 4: post(+) weights
-    double *ver = expd + cap;                  // [2 strands][3][4][L] verification accumulators of this block
-    u32 *psum = (u32 *)(ver + 2 * 3 * 4 * L);  // [cap + 1] prefix sums of the signal over [d0, d1)
-    u32 *pcnt = psum + cap + 1;                // [cap + 1] prefix counts of its non-zero positions
-    u32 *wsum = pcnt + cap + 1;                // [2][32] warp totals of the block scan
-    unsigned short *nzpos = (unsigned short *)(wsum + 64);      // [cap] non-zero positions (relative to d0)
-    uint8_t *bases = (uint8_t *)(nzpos + cap);                  // [tile_len + L] base codes of [t0 - k, t1 + k)
+    double *sig = (double *)smem;              // [d0, d1)  signal;            phase 4: pre weights of [t0, t1).  FAST: prefix sums of bp, then of corrected+
+    double *bp = sig + Y.capd;                 // [d0, d1)  mean prediction;   phase 4: post(-) weights, padded by L zeros
+    double *unc = bp + Y.capd;                 // [c0, c1)  signal * cf;       phase 4: positions by base.  FAST: prefix sums of |corrected|
+    double *cor = unc + Y.capd;                // [c0, c1)  uncorrected - expected
+    double *expd = cor + Y.capd;               // [t0, t1)  expected;          phase 4: post(+) weights
+    double *ver = (double *)(smem + Y.off_ver);        // [2 strands][3][4][L] verification accumulators of this block
+    u32 *psum = (u32 *)(smem + Y.off_psum);            // [cap + 1] prefix sums of the signal over [d0, d1)
+    u32 *pcnt = (u32 *)(smem + Y.off_pcnt);            // [cap + 1] prefix counts of its non-zero positions (exact form)
+    u32 *wsum = (u32 *)(smem + Y.off_wsum);            // [2][32] warp totals of the block scan
+    unsigned short *nzpos = (unsigned short *)(smem + Y.off_nzpos);     // [cap] non-zero positions (relative to d0; exact form)
+    double *wpre = FAST ? (double *)(smem + Y.off_wpre) : sig;          // [tile_len] pre weights of phase 4
+    uint8_t *bases = (uint8_t *)(smem + Y.off_bases);                   // [tile_len + L] base codes of [t0 - k, t1 + k)
     __shared__ int bcnt[4];                                     // positions per base in the tile (+- k_flank)
     __shared__ double rcnt[512 / TB_STEP + 2];                  // 1 / n for the row counts of the mean (n <= window / 10)
+    __shared__ double wtot[64];                                 // FAST: warp totals of the fp64 block scans
     const int cap_w = (cap + w) / TB_STEP + 3;
-    double *frec = (double *)(smem + frec_off);                 // [cap_w][6] mode, max(prediction), a, b, 1 / max of the windows over [d0, d1)
+    double *frec = (double *)(smem + Y.off_frec);               // [cap_w][6] mode, max(prediction), a, b, 1 / max of the windows over [d0, d1)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
@@ -466,17 +508,22 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                     s_off += wsum[ww];
                     c_off += wsum[32 + ww];
                 }
-                if (tid == 0) psum[0] = pcnt[0] = 0;
+                if (tid == 0) {
+                    psum[0] = 0;
+                    if (!FAST) pcnt[0] = 0;
+                }
                 for (int e = 0; e < per; e++) {
                     int i = tid * per + e;
                     if (i < nd) {
                         u32 v = ps[d0 + i];
-                        if (v != 0u) nzpos[c_off] = (unsigned short)i;
                         s_off += v;
-                        c_off += v != 0u;
                         psum[i + 1] = s_off;
-                        pcnt[i + 1] = c_off;
-                        sig[i] = (double)v;
+                        if (!FAST) {
+                            if (v != 0u) nzpos[c_off] = (unsigned short)i;
+                            c_off += v != 0u;
+                            pcnt[i + 1] = c_off;
+                            sig[i] = (double)v;
+                        }
                     }
                 }
             }
@@ -515,17 +562,32 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                         cnt++;
                     }
                 }
-                bp[q - d0] = cnt > 0 ? tb_div_inv(sum, (double)cnt, rcnt[cnt]) : (double)NAN;     // = sum / cnt
+                const double m = cnt > 0 ? tb_div_inv(sum, (double)cnt, rcnt[cnt]) : (double)NAN;  // = sum / cnt
+                bp[q - d0] = m;
+                if (FAST == 2) {
+                    sig[q - d0] = m;
+                    unc[q - d0] = 0.0;
+                }
             }
             __syncthreads();
+            if (FAST == 2) tb_block_scan2w(sig, unc, nd, wtot);    // sig := prefix sums of the bias prediction (unc rides along, rewritten below)
             // ---- 2. expected and raw corrected signal on [c0, c1) (:314-328)
             for (int q = c0 + tid; q < c1; q += nt) {
                 double ssum = 0.0, bsum = 1.0, probas = 0.0;
                 if (q >= lf && q - lf + w <= Lr) {
                     const int first = q - lf - d0;
                     const u32 isum = psum[first + w] - psum[first];
-                    ssum = isum < (1u << 24) ? (double)isum : tb_roll_f32(sig, first, w);
-                    double b = tb_roll_f32(bp, first, w);
+                    double b;
+                    if (FAST == 2) {
+                        ssum = isum < (1u << 24) ? (double)isum : tb_round_f32((double)isum);
+                        b = tb_round_f32(sig[first + w] - sig[first]);
+                    } else if (FAST == 1) {
+                        ssum = isum < (1u << 24) ? (double)isum : tb_round_f32((double)isum);
+                        b = tb_roll_f32(bp, first, w);
+                    } else {
+                        ssum = isum < (1u << 24) ? (double)isum : tb_roll_f32(sig, first, w);
+                        b = tb_roll_f32(bp, first, w);
+                    }
                     bool null = !(fabs(b) > 1e-8);                 // isclose(bias_sum, 0) or NaN
                     if (!null) {
                         bsum = b;
@@ -533,33 +595,50 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                     }
                 }
                 double e = ssum * probas;
-                double u = sig[q - d0] * cf;
+                double u = (FAST ? (double)(psum[q - d0 + 1] - psum[q - d0]) : sig[q - d0]) * cf;
                 e = e * cf;
-                unc[q - c0] = u;
+                if (!FAST) unc[q - c0] = u;
                 cor[q - c0] = u - e;
                 if (q >= t0 && q < t1) expd[q - t0] = e;
             }
             __syncthreads();
+            if (FAST) {      // prefix sums of |corrected| (in unc) and of its positive part (in sig: the prefix sums of bp are no longer read)
+                const int nc = c1 - c0;
+                for (int i = tid; i < nc; i += nt) {
+                    const double cv = cor[i];
+                    unc[i] = fabs(cv);
+                    sig[i] = cv > 0.0 ? cv : 0.0;
+                }
+                __syncthreads();
+                tb_block_scan2w(unc, sig, nc, wtot);
+            }
             // ---- 3. rescale (:331-350), outputs, verification weights (:358-373)
             for (int q = t0 + tid; q < t1; q += nt) {
                 double c = cor[q - c0];
-                double u = unc[q - c0];
+                double u = FAST ? (double)(psum[q - d0 + 1] - psum[q - d0]) * cf : unc[q - c0];
                 double scale = 1.0;
                 if (q >= lf && q - lf + w <= Lr) {
                     int first = q - lf - c0;
                     double au = 0.0, aa = 0.0, ap = 0.0;            // float-valued accumulators (tb_round_f32)
-                    for (int t = 0; t < w; t++) {
-                        double cv = cor[first + t];
-                        aa = tb_round_f32(__dadd_rn(aa, fabs(cv)));
-#ifdef TB_K3C_MIX                                       // comparison build: this sum through the conversion unit, the other in the fp64 pipe
-                        if (!(cv <= 0.0)) ap = (double)(float)__dadd_rn(ap, cv);
-#else
-                        if (!(cv <= 0.0)) ap = tb_round_f32(__dadd_rn(ap, cv));     // the non-positive half adds 0.0: no change
-#endif
-                    }
-                    {   // uncorrected: only non-zero signal positions move the accumulator
+                    if (FAST) {
                         const int fd = q - lf - d0;
-                        for (u32 z = pcnt[fd]; z < pcnt[fd + w]; z++) au = tb_round_f32(__dadd_rn(au, unc[(int)nzpos[z] + d0 - c0]));
+                        aa = tb_round_f32(unc[first + w] - unc[first]);
+                        ap = tb_round_f32(sig[first + w] - sig[first]);
+                        au = tb_round_f32((double)(psum[fd + w] - psum[fd]) * cf);
+                    } else {
+                        for (int t = 0; t < w; t++) {
+                            double cv = cor[first + t];
+                            aa = tb_round_f32(__dadd_rn(aa, fabs(cv)));
+#ifdef TB_K3C_MIX                                       // comparison build: this sum through the conversion unit, the other in the fp64 pipe
+                            if (!(cv <= 0.0)) ap = (double)(float)__dadd_rn(ap, cv);
+#else
+                            if (!(cv <= 0.0)) ap = tb_round_f32(__dadd_rn(ap, cv));     // the non-positive half adds 0.0: no change
+#endif
+                        }
+                        {   // uncorrected: only non-zero signal positions move the accumulator
+                            const int fd = q - lf - d0;
+                            for (u32 z = pcnt[fd]; z < pcnt[fd + w]; z++) au = tb_round_f32(__dadd_rn(au, unc[(int)nzpos[z] + d0 - c0]));
+                        }
                     }
                     double usum = au, asum = aa, psum_ = ap;
                     double nsum = asum - psum_;
@@ -579,8 +658,8 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                 }
                 bool valid = q > k && q < Lr - k - 1 && (u != 0.0 || c != 0.0);
                 if (valid) valid = tb_nflags(g, gstart + q - k, L) == 0;
-                // sig / bp are not read in this phase: they now carry the weights of phase 4
-                sig[q - t0] = (valid && u > 0.0) ? u : 0.0;               // pre_bias counts
+                // wpre (exact form: sig) / bp are not read in this phase: they now carry the weights of phase 4
+                wpre[q - t0] = (valid && u > 0.0) ? u : 0.0;              // pre_bias counts
                 expd[q - t0] = (valid && c > 0.0) ? c : 0.0;              // post_bias counts
                 bp[L + q - t0] = (valid && !(c > 0.0)) ? c : 0.0;         // post_bias neg_counts, L zeros on either side
             }
@@ -621,7 +700,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                     for (int s = 0; s < 4; s++) acc[a][s] = 0.0;
                 if (lane < L) {
                     for (int q = qa; q < qb; q++) {
-                        const double v0 = sig[q], v1 = expd[q];
+                        const double v0 = wpre[q], v1 = expd[q];
                         if (v0 == 0.0 && v1 == 0.0) continue;                         // every branch here is warp-uniform
                         const int s = bases[q + lane];
                         if (v0 != 0.0) {
@@ -678,7 +757,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
                               int k_flank, int window, double correction_factor, int shift_fwd, int shift_rev,
                               int lm_exact_order) {
     if (!ctx) return TB_ERR_ARG;
-    const bool trace = getenv("TB_HOST_TRACE") != nullptr;       // host clock at the phase borders of this call, to stderr
+    const bool trace = tb_opt(ctx, "host_trace", 0) != 0;        // host clock at the phase borders of this call, to stderr
     const auto t_entry = std::chrono::steady_clock::now();
     auto tr = [&](const char *what) {
         if (trace) fprintf(stderr, "[tb_correct_run] %-28s %9.3f ms\n", what,
@@ -870,12 +949,12 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     {
         TB_TRY(tb_genome_fence(ctx, 0, ctx->n_contigs - 1));
         tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
-        const size_t capk = (size_t)tile_len + 4 * window;
-        size_t smem = ((size_t)5 * capk + 2 * 3 * 4 * L) * sizeof(double) + (2 * (capk + 1) + 64) * sizeof(u32) + capk * 2 + tile_len + L + 16;
-        smem = (smem + 15) & ~(size_t)15;
-        const int frec_off = (int)smem;                                 // fit records of the tile's windows
-        smem += ((capk + window) / TB_STEP + 3) * TB_K3C_FREC * sizeof(double);
-        auto kc = tb_correct_kernel;
+        // the O(1) rolling sums need every row of the 10-row mean to count everywhere (k_flank >= window / 10: no NaN in the bias prediction)
+        int fast = (lm_exact_order == 0 && k_flank >= window / TB_STEP) ? 2 : 0;
+        if (fast) fast = (int)tb_opt(ctx, "k3c_fast", fast);      // comparison runs: 0 literal, 1 literal bias-prediction sum only
+        const tb_k3c_layout Y = tb_k3c_make_layout(tile_len, window, L, fast != 0);
+        const size_t smem = (size_t)Y.total;
+        auto kc = fast == 2 ? tb_correct_kernel<2> : (fast == 1 ? tb_correct_kernel<1> : tb_correct_kernel<0>);
         TB_CUDA(ctx, cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const i64 n_tiles = (i64)tile_region.size();
         i64 per_sm = (i64)(227 * 1024) / (i64)(smem + 1024);            // 227 KB usable per SM, 1 KB reserved per block
@@ -884,7 +963,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         const i64 capg = (i64)ctx->sm_count * per_sm;
         TB_LAUNCH(ctx, kc, (unsigned)(n_tiles < capg ? n_tiles : capg), TB_K3C_THREADS, smem, g, V, (const int32_t *)ctx->reg_a.as<int32_t>(),
                   (const int32_t *)ctx->reg_b.as<int32_t>(), n_tiles, tile_len, (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),
-                  (const double *)C.fit.as<double>(), correction_factor, frec_off, C.tracks.as<double>(), C.prepost.as<double>());
+                  (const double *)C.fit.as<double>(), correction_factor, Y, C.tracks.as<double>(), C.prepost.as<double>());
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_correct_kernel"));
     }
     tb_mark(ctx, 4);

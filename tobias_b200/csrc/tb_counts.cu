@@ -580,8 +580,7 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         bool pending = false;
         for (char c : ctx->contig_pending) pending = pending || c;
         if (pending && SLAB_BUDGET > ((i64)3 << 27)) SLAB_BUDGET = (i64)3 << 27;
-        const char *ev = getenv("TB_K2_SLAB_BUDGET");            // tests: force several chunks
-        if (ev && atoll(ev) > 0) SLAB_BUDGET = atoll(ev);
+        if (tb_opt(ctx, "k2_slab_budget", 0) > 0) SLAB_BUDGET = tb_opt(ctx, "k2_slab_budget", 0);     // tests: force several chunks
     }
     size_t smem = ((n_acc * 4 + 15) & ~(size_t)15) + (size_t)2 * TB_K2_BATCH * 9;
     if (is_dwm) {
@@ -593,8 +592,7 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     }
     i64 site_cap = ctx->n_reads + ctx->n_reads / 4 + 1024;       // one site per (record, overlapped region) at most; grown on overflow
     {
-        const char *ev = getenv("TB_K2_SITE_CAP");                // tests: force the overflow / regrow path
-        if (ev && atoll(ev) > 0) site_cap = atoll(ev);
+        if (tb_opt(ctx, "k2_site_cap", 0) > 0) site_cap = tb_opt(ctx, "k2_site_cap", 0);             // tests: force the overflow / regrow path
     }
 
     // DWM: joint-histogram form unless the model is a single chunk (TB_K2_NO_HIST=1 / TB_K2_CHUNK=n: comparison runs and tests)
@@ -606,10 +604,9 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
 #else
         int ch = 4;              // 4^8 bins x 21 chunk pairs x 4 tensors = 22 MB: L2 resident (chunks of 5: 168 MB, measured slower)
 #endif
-        const char *ev = getenv("TB_K2_CHUNK");
-        if (ev && atoi(ev) >= 1 && atoi(ev) <= TB_K2H_MAXCH) ch = atoi(ev);
-        const char *nh = getenv("TB_K2_NO_HIST");
-        use_hist = !(nh && atoi(nh) > 0) && tb_k2h_plan(L, ch, pstride, HD);
+        const int ev = (int)tb_opt(ctx, "k2_chunk", 0);
+        if (ev >= 1 && ev <= TB_K2H_MAXCH) ch = ev;
+        use_hist = tb_opt(ctx, "k2_no_hist", 0) == 0 && tb_k2h_plan(L, ch, pstride, HD);
     }
     // ... and its shared-memory form (chunks of two bases) when the tables of both strands fit in one block (L <= 29)
     tb_k2h_desc SD;
@@ -617,10 +614,9 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     size_t sh_bytes = 0;
     if (is_dwm) {
         int ch = 2;
-        const char *ev = getenv("TB_K2_SMEM_CHUNK");              // tests: 1 (more tables) or 2
-        if (ev && atoi(ev) >= 1 && atoi(ev) <= 2) ch = atoi(ev);
-        const char *nh = getenv("TB_K2_NO_HIST"), *ns = getenv("TB_K2_NO_SMEM_HIST");
-        if (!(nh && atoi(nh) > 0) && !(ns && atoi(ns) > 0) && tb_k2h_plan(L, ch, pstride, SD)) {
+        const int ev = (int)tb_opt(ctx, "k2_smem_chunk", 0);      // tests: 1 (more tables) or 2
+        if (ev >= 1 && ev <= 2) ch = ev;
+        if (tb_opt(ctx, "k2_no_hist", 0) == 0 && tb_opt(ctx, "k2_no_smem_hist", 0) == 0 && tb_k2h_plan(L, ch, pstride, SD)) {
             sh_bytes = ((size_t)2 * SD.nt << (4 * SD.ch)) * sizeof(u32);
             use_smem_hist = sh_bytes <= (size_t)200 * 1024;
         }

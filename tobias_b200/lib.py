@@ -40,6 +40,7 @@ _PROTOS = {
     "tb_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i)]),
     "tb_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "tb_launch_count": (_i, [_vp, C.POINTER(_i64)]),
+    "tb_set_option": (_i, [_vp, C.c_char_p, _i64]),
     "tb_timer_begin": (_i, [_vp]),
     "tb_timer_end": (_i, [_vp, C.POINTER(C.c_float)]),
     "tb_host_alloc": (_i, [_vp, _i64, C.POINTER(_vp)]),
@@ -169,6 +170,10 @@ class Context:
         n = _i64()
         self._ck(self._lib.tb_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def set_option(self, key, value):
+        """Kernel-variant / chunk-size switch (comparison runs and tests); value < 0 restores the default."""
+        self._ck(self._lib.tb_set_option(self._h, key.encode(), int(value)))
 
     def timer_begin(self):
         self._ck(self._lib.tb_timer_begin(self._h))
