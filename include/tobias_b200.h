@@ -66,7 +66,7 @@ int tb_host_free(tb_ctx *ctx, void *p);
 /* number of kernel launches issued by this context so far */
 int tb_launch_count(tb_ctx *ctx, int64_t *n);
 /* Kernel-variant / chunk-size switches for comparison runs and tests (every setting yields the same results; production code never
- * calls this): "k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_slab_budget", "k2_site_cap", "k2_chunk", "k2_no_hist",
+ * calls this): "k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_tile", "k2_site_cap", "k2_chunk", "k2_no_hist",
  * "k2_smem_chunk", "k2_no_smem_hist", "k2_region_blocks", "k3b_persistent", "host_trace".  value < 0 restores the default.  (These
  * replace the environment variables the library read in its first version.) */
 int tb_set_option(tb_ctx *ctx, const char *key, int64_t value);

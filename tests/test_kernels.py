@@ -81,17 +81,17 @@ def test_bias_counts_other_parameters(loaded_ctx, golden):
     assert scalars[0] == ref.no_reads
 
 
-def test_bias_counts_in_several_slab_chunks(loaded_ctx, golden, monkeypatch):
-    """The multiplicity slab is processed in chunks of regions when it does not fit the memory budget; a tiny budget forces
-    many chunks (each with its own record range) and the site-list growth path -- same integers."""
+def test_bias_counts_in_several_slab_tiles(loaded_ctx, golden, monkeypatch):
+    """A region longer than the shared-memory multiplicity slab is walked tile by tile; a tiny tile forces many tiles per region (and,
+    with more distinct sites than the block's list holds, the dense-scan path) and a tiny site list the growth path -- same integers."""
     g = golden.atac
-    loaded_ctx.set_option("k2_slab_budget", 20000)
+    loaded_ctx.set_option("k2_tile", 1024)
     counts, scalars = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)
-    loaded_ctx.set_option("k2_slab_budget", -1)
+    loaded_ctx.set_option("k2_tile", -1)
     assert scalars[0] == int(g["DWM_no_reads"])
     for si, st in enumerate(("forward", "reverse")):
         assert np.array_equal(counts[si, 0], g["DWM_%s_counts" % st]) and np.array_equal(counts[si, 1], g["DWM_%s_bg_counts" % st])
-    counts2, scalars2 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)           # slab left clean by the chunked run
+    counts2, scalars2 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)           # slab left clean by the tiled run
     assert np.array_equal(counts, counts2) and np.array_equal(scalars, scalars2)
     loaded_ctx.set_option("k2_site_cap", 100)                                            # site list too small: regrown, chunk redone
     counts3, scalars3 = loaded_ctx.bias_counts(*_cols(g["nonpeak"]), is_dwm=True)

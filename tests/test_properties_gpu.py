@@ -86,9 +86,9 @@ def test_slab_chunking_is_invisible(work, monkeypatch):
     ctx, ds, arrays = work
     regs = arrays["input_regions"]
     counts, scalars = ctx.bias_counts(*regs, is_dwm=True)
-    ctx.set_option("k2_slab_budget", 1500000)
+    ctx.set_option("k2_tile", 4096)
     chunked, scalars2 = ctx.bias_counts(*regs, is_dwm=True)
-    ctx.set_option("k2_slab_budget", -1)
+    ctx.set_option("k2_tile", -1)
     assert np.array_equal(counts, chunked) and np.array_equal(scalars, scalars2)
 
 

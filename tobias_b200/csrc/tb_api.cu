@@ -149,7 +149,7 @@ extern "C" int tb_init(int device, tb_ctx **out) {
 // Switches between kernel variants / chunk sizes that produce the same results (comparison runs and tests; never needed in production).
 extern "C" int tb_set_option(tb_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return TB_ERR_ARG;
-    static const char *known[] = {"k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_slab_budget", "k2_site_cap", "k2_chunk",
+    static const char *known[] = {"k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_tile", "k2_site_cap", "k2_chunk",
                                   "k2_no_hist", "k2_smem_chunk", "k2_no_smem_hist", "k2_region_blocks", "k3b_persistent", "host_trace", nullptr};
     bool ok = false;
     for (int i = 0; known[i]; i++) ok = ok || strcmp(known[i], key) == 0;
@@ -172,7 +172,7 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     tb_dbuf *bufs[] = {&ctx->seq2, &ctx->nmask, &ctx->d_contig_off, &ctx->r_start, &ctx->r_len, &ctx->r_clip, &ctx->r_flags,
                        &ctx->reg_a, &ctx->reg_b, &ctx->reg_c, &ctx->reg_d, &ctx->reg_e, &ctx->scratch0, &ctx->scratch1,
                        &ctx->scratch2, &ctx->scratch3, &ctx->scratch4, &ctx->staging, &ctx->model[0].table, &ctx->model[1].table,
-                       &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_slab, &ctx->k2_sites, &ctx->k2_hist, &ctx->k2_wts, &ctx->staging_up,
+                       &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_sites, &ctx->k2_hist, &ctx->k2_wts, &ctx->staging_up,
                        &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
                        &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.fitg_x, &ctx->cor.fitg_y, &ctx->cor.fitg_st,
                        &ctx->cor.fitg_sti, &ctx->cor.fitg_wq, &ctx->cor.fitg_lists, &ctx->cor.tracks, &ctx->cor.prepost,

@@ -84,10 +84,9 @@ struct tb_ctx {
     tb_dbuf r_flags;
     bool reads_sorted = false;        // records sorted by (contig, start): lets K2 narrow the record range of a region chunk
     i64 max_read_len = 0;             // longest reference span of a record (bounds the records a region chunk can see)
-    tb_dbuf k2_slab, k2_sites;        // K2: multiplicity slab (kept all-zero between calls) and site list
+    tb_dbuf k2_sites;                 // K2: site list (region, strand, offset of the cut site)
     tb_dbuf k2_hist;                  // K2: joint chunk histograms (u32 [4 tensors][chunk pairs][4^ch][4^ch])
-    tb_dbuf k2_wts;                   // K2: capped multiplicity of every site (shared-memory histogram form)
-    i64 k2_budget = 0, k2_budget_need = 0;   // K2: slab positions per chunk decided from the free memory at an earlier call, and the region space it was decided for
+    tb_dbuf k2_wts;                   // K2: capped multiplicity of every site
     // asynchronous genome uploads (tb_genome_upload_async): copies + packing run on copy_stream; consumers on `stream` wait for the
     // events of the contigs they read (tb_genome_fence), so work on the first contigs overlaps with the transfer of the later ones
     tb_dbuf staging_up;

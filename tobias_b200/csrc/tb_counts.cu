@@ -9,16 +9,16 @@
 //     k_flank + bg_shift and clipped to the contig (:142-143)  -- reference quirk, kept
 //   * bias k-mer at the cut site, background k-mer bg_shift upstream of the read (:170-175)
 //
-// Two kernels over a per-(region, strand) multiplicity slab (u32 per position of every extended region, both strands).
-// (1) scatter: one thread per record, an integer atomic per (record, overlapped region); the thread that finds the
-// slot at zero appends the site (region, strand, slab slot) to a global site list (warp-aggregated append), so the
-// slab is never scanned -- it is touched only where reads fall.  (2) accumulate: persistent blocks take batches of
-// sites: phase A, one thread per site, reads the final multiplicity (and zeroes the slot again: the slab cleans itself),
-// forms the bias / background k-mers into a shared-memory list; phase B, one WARP per k-mer, lanes spread over the
-// L(L+1)/2 position pairs (m <= n; the tensor is symmetric), one shared-memory integer atomic per pair -- the atomics
-// return nothing, so the loop runs at the issue / shared-atomic rate (first version: one thread per pair walking the
-// list as a read-modify-write chain, 844 cycles per k-mer).  The reverse strand is accumulated in forward orientation
-// and reverse-complemented by an index permutation on the host.  Everything is integer: bit-exact in any order.
+// (1) sites: one block per (input region, tile of <= TB_K2_TILE positions) with the region's multiplicity slab IN SHARED MEMORY (u16 counters of
+// both strands, 197 KB).  The records are sorted by position, so the records of a region are a contiguous range of the columns (found by a
+// small search kernel).  A thread per record adds 1 to the slot of its cut site with a shared-memory atomic; the thread that finds the slot at
+// zero appends the slot to a list in shared memory, so only touched slots are visited afterwards: final count -> capped weight, (region, strand,
+// offset) + weight appended to the global site list, slot zeroed again (the slab is cleared once per block, not per region).  A region with
+// more distinct sites than the list holds falls back to a dense scan of its slab.  (First version: a 24 GB slab in HBM for the hg38 non-peak
+// space, random sector-sized read-modify-writes: 12.6 of the 16 ms of K2.)
+// (2) counts from the site list: joint histograms of 2-base chunks in shared memory (default), joint histograms in L2, or one shared-memory
+// atomic per position pair (PWM counts, single-chunk models) -- see below.  The reverse strand is accumulated in forward orientation and
+// reverse-complemented by an index permutation on the host.  Everything is integer: bit-exact in any order.
 #include "tb_common.cuh"
 
 struct tb_reads_view2 {
@@ -32,60 +32,139 @@ struct tb_reads_view2 {
 struct tb_k2_regions {
     const i64 *s, *e;      // original bounds (linear)
     const i64 *es, *ee;    // extended + clipped bounds (linear)
-    const i64 *soff;       // slab offset of each region (relative to the chunk), n+1 entries
-    i64 n;                 // regions in this chunk
-    i64 slab_len;          // entries per strand in this chunk (< 2^31)
+    i64 n;
 };
 
-// site record: region (chunk-local) in the high word, strand in bit 31, slab slot (per strand) in bits 0..30
+// site record: region in the high word, strand in bit 31, offset of the cut site from the extended region start in bits 0..30
 __device__ __forceinline__ u64 tb_k2_site(i64 j, int rev, i64 x) { return ((u64)j << 32) | ((u64)rev << 31) | (u64)x; }
 
-// ctr[0] = number of sites appended, ctr[1] = overflow flag (list capacity exceeded)
-__global__ void tb_k2_scatter_kernel(tb_reads_view2 r, tb_k2_regions R, i64 read_lo, i64 read_hi, int shift_fwd, int shift_rev,
-                                     u32 *__restrict__ slab, u64 *__restrict__ sites, i64 site_cap, unsigned long long *__restrict__ ctr) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+// record range of every region: records whose alignment can overlap [s, e) start in [s - longest alignment, e)
+__global__ void tb_k2_ranges_kernel(const i64 *__restrict__ lstart, i64 n_reads, tb_k2_regions R, i64 max_read_len, int sorted,
+                                    i64 *__restrict__ rng) {
     const i64 stride = (i64)gridDim.x * blockDim.x;
-    const i64 n_round = read_lo + ((read_hi - read_lo + 31) / 32) * 32;         // whole warps iterate together
-    for (i64 i = read_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool live = i < read_hi;
-        i64 rs = 0, re = 0, p = 0, j = R.n;
-        int rev = 0;
-        if (live) {
-            uint8_t f = r.flags[i];
-            live = !(f & TB_READ_SKIP) && (f & TB_READ_5P_MATCH);
-            if (live) {
-                rev = (f & TB_READ_REVERSE) ? 1 : 0;
-                rs = r.lstart[i];
-                re = rs + r.rlen[i];
-                p = rev ? re + r.clip[i] + shift_rev : rs - r.clip[i] + shift_fwd;
-                j = tb_upper_bound(R.e, R.n, rs);
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < R.n; j += stride) {
+        i64 lo = 0, hi = n_reads;
+        if (sorted) {
+            const i64 v0 = R.s[j] - max_read_len, v1 = R.e[j];
+            i64 a = 0, b = n_reads;
+            while (a < b) {                                   // first record with lstart >= v0
+                const i64 mid = (a + b) >> 1;
+                if (lstart[mid] >= v0) b = mid; else a = mid + 1;
+            }
+            lo = a;
+            b = n_reads;
+            while (a < b) {                                   // first record with lstart >= v1
+                const i64 mid = (a + b) >> 1;
+                if (lstart[mid] >= v1) b = mid; else a = mid + 1;
+            }
+            hi = a;
+        }
+        rng[2 * j] = lo;
+        rng[2 * j + 1] = hi;
+    }
+}
+
+#define TB_K2_TILE 50432         // slab positions per block: a 50-kb split piece (atacorrect.py:233) + 2 x (k_flank + bg_shift) in one tile
+#define TB_K2_LIST 6144          // touched slots a block can list before it falls back to the dense scan
+
+// ctr[0] = number of sites appended, ctr[1] = overflow flag (global list capacity exceeded)
+__global__ void __launch_bounds__(1024, 1)
+    tb_k2_sites_kernel(tb_reads_view2 r, tb_k2_regions R, const i64 *__restrict__ rng, const int32_t *__restrict__ unit_region,
+                       const int32_t *__restrict__ unit_tile, i64 n_units, int tile, int shift_fwd, int shift_rev, int cap,
+                       u64 *__restrict__ sites, u32 *__restrict__ wts, i64 site_cap, unsigned long long *__restrict__ ctr,
+                       u64 *__restrict__ g_scalars) {
+    TB_DYN_SMEM(smem);
+    const int words = tile / 2;                                // u32 words per strand (two u16 counters each)
+    u32 *slab = (u32 *)smem;                                   // [2 strands][words]
+    u32 *list = slab + 2 * words;                              // [TB_K2_LIST] strand << 31 | slot
+    __shared__ u32 nlist;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    for (int i = tid; i < 2 * words; i += nt) slab[i] = 0u;
+    if (tid == 0) nlist = 0u;
+    __syncthreads();
+    long long wsum = 0;                                        // sum of the capped multiplicities this thread emitted (no_reads, :177)
+    for (i64 unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const i64 j = unit_region[unit];
+        const i64 es = R.es[j], ee = R.ee[j], s0 = R.s[j], e0 = R.e[j];
+        const i64 t0 = (i64)unit_tile[unit] * tile;             // first slab position of this tile, relative to es
+        const i64 lo = rng[2 * j], hi = rng[2 * j + 1];
+        for (i64 i = lo + tid; i < hi; i += nt) {
+            const uint8_t f = r.flags[i];
+            if ((f & TB_READ_SKIP) || !(f & TB_READ_5P_MATCH)) continue;
+            const int rev = (f & TB_READ_REVERSE) ? 1 : 0;
+            const i64 rs = r.lstart[i], re = rs + r.rlen[i];
+            if (!(rs < e0 && re > s0)) continue;                // fetch: the alignment overlaps the region (:134)
+            const i64 p = rev ? re + r.clip[i] + shift_rev : rs - r.clip[i] + shift_fwd;
+            if (!(p >= es && p <= ee - 2)) continue;            // start < cutsite < end on the extended region (:166)
+            const i64 x = p - es - t0;
+            if (x < 0 || x >= tile) continue;                   // another tile of this region
+            u32 *wp = slab + rev * words + (int)(x >> 1);
+            const int sh = 16 * (int)(x & 1);
+            const u32 old = (atomicAdd(wp, 1u << sh) >> sh) & 0xffffu;
+            if (old == 0u) {
+                const u32 k = atomicAdd(&nlist, 1u);
+                if (k < TB_K2_LIST) list[k] = ((u32)rev << 31) | (u32)x;
+            } else if (old >= 0x7fffu) {
+                atomicAdd(wp, 0u - (1u << sh));                     // saturate far above any cap, far below a carry into the neighbour
             }
         }
-        for (;;) {                                          // regions the alignment overlaps (usually one)
-            const bool more = live && j < R.n && R.s[j] < re;
-            if (!__any_sync(FULL, more)) break;
-            bool fresh = false;
-            i64 x = 0;
-            if (more && p >= R.es[j] && p <= R.ee[j] - 2) { // start < cutsite < end on the extended region
-                x = R.soff[j] + (p - R.es[j]);
-                fresh = atomicAdd(&slab[(i64)rev * R.slab_len + x], 1u) == 0u;
-            }
-            const unsigned nz = __ballot_sync(FULL, fresh);
-            if (nz) {
-                const int leader = __ffs((int)nz) - 1;
+        __syncthreads();
+        const u32 n = nlist;
+        if (n <= TB_K2_LIST) {
+            const u32 n_round = (n + 31u) & ~31u;
+            for (u32 k = tid; k < n_round; k += nt) {
+                const bool have = k < n;
+                u32 ent = 0, w = 0;
+                if (have) {
+                    ent = list[k];
+                    unsigned short *cp = (unsigned short *)slab + (size_t)(ent >> 31) * (2 * words) + (ent & 0x7fffffffu);
+                    const u32 cnt = *cp;
+                    *cp = 0;
+                    w = cnt < (u32)cap ? cnt : (u32)cap;
+                    wsum += w;
+                }
+                const unsigned m = __ballot_sync(FULL, have);
                 unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(&ctr[0], (unsigned long long)__popc(nz));
+                const int leader = __ffs((int)m) - 1;
+                if (lane == leader) base = atomicAdd(&ctr[0], (unsigned long long)__popc(m));
                 base = __shfl_sync(FULL, base, leader);
-                if (fresh) {
-                    const i64 slot = (i64)base + __popc(nz & ((1u << lane) - 1u));
-                    if (slot < site_cap) sites[slot] = tb_k2_site(j, rev, x);
-                    else ctr[1] = 1ull;
+                if (have) {
+                    const i64 slot = (i64)base + __popc(m & ((1u << lane) - 1u));
+                    if (slot < site_cap) {
+                        sites[slot] = tb_k2_site(j, (int)(ent >> 31), t0 + (i64)(ent & 0x7fffffffu));
+                        wts[slot] = w;
+                    } else ctr[1] = 1ull;
                 }
             }
-            if (more) j++;
+        } else {                                               // more distinct sites than the list holds: dense scan of the tile
+            const i64 span = ee - es - t0;
+            const int used = (int)(((span < tile ? span : tile) + 1) / 2);
+            for (int i = tid; i < 2 * words; i += nt) {
+                const int strand = i >= words ? 1 : 0, wi = i - strand * words;
+                if (wi >= used) continue;
+                const u32 v = slab[i];
+                if (v == 0u) continue;
+                slab[i] = 0u;
+                for (int h = 0; h < 2; h++) {
+                    const u32 cnt = (v >> (16 * h)) & 0xffffu;
+                    if (cnt == 0u) continue;
+                    const u32 w = cnt < (u32)cap ? cnt : (u32)cap;
+                    wsum += w;
+                    const i64 slot = (i64)atomicAdd(&ctr[0], 1ull);
+                    if (slot < site_cap) {
+                        sites[slot] = tb_k2_site(j, strand, t0 + 2 * (i64)wi + h);
+                        wts[slot] = w;
+                    } else ctr[1] = 1ull;
+                }
+            }
         }
+        __syncthreads();
+        if (tid == 0) nlist = 0u;
+        __syncthreads();
     }
+    for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(FULL, wsum, d);
+    if (lane == 0 && wsum) atomicAdd((unsigned long long *)&g_scalars[0], (unsigned long long)wsum);
 }
 
 #define TB_K2_BATCH 2048         // sites per batch of a block (2 per thread); the k-mer list holds 2 per site
@@ -94,7 +173,7 @@ __global__ void tb_k2_scatter_kernel(tb_reads_view2 r, tb_k2_regions R, i64 read
 // layout of the accumulators: DWM: acc[tbl][code = Sm*4+Sn][pair, padded to a multiple of 32]   PWM: acc[tbl][S (0..4)][m]
 template <int IS_DWM>
 __global__ void __launch_bounds__(1024, 1)
-    tb_k2_accumulate_kernel(tb_genome_view g, tb_k2_regions R, u32 *__restrict__ slab, const u64 *__restrict__ sites, i64 n_sites,
+    tb_k2_accumulate_kernel(tb_genome_view g, tb_k2_regions R, const u32 *__restrict__ wts, const u64 *__restrict__ sites, i64 n_sites,
                             int k_flank, int bg_shift, int cap, u64 *__restrict__ g_acc, u64 *__restrict__ g_scalars) {
     TB_DYN_SMEM(smem);
     const int L = 2 * k_flank + 1;
@@ -104,7 +183,7 @@ __global__ void __launch_bounds__(1024, 1)
     int *acc = (int *)smem;
     u64 *list = (u64 *)(smem + (((size_t)n_acc * 4 + 15) & ~(size_t)15));      // [2 * TB_K2_BATCH] k-mers
     uint8_t *meta = (uint8_t *)(list + 2 * TB_K2_BATCH);                       // tbl | w << 2, 0xff = no k-mer
-    __shared__ int sc[5];            // no_reads, no_bias_f, no_bg_f, no_bias_r, no_bg_r
+    __shared__ int sc[5];            // (no_reads: counted by the sites kernel), no_bias_f, no_bg_f, no_bias_r, no_bg_r
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
@@ -135,13 +214,9 @@ __global__ void __launch_bounds__(1024, 1)
             const u64 site = sites[b0 + k];
             const i64 j = (i64)(site >> 32), x = (i64)(site & 0x7fffffffu);
             const int strand = (int)((site >> 31) & 1u);
-            u32 *slot = slab + (i64)strand * R.slab_len + x;
-            const u32 cnt = *slot;
-            *slot = 0u;                                                  // the slab is all-zero again after this kernel
-            const int w = (int)(cnt < (u32)cap ? cnt : (u32)cap);
+            const int w = (int)wts[b0 + k];
             const i64 es = R.es[j], ee = R.ee[j];
-            const i64 gp = es + (x - R.soff[j]);
-            atomicAdd(&sc[0], w);
+            const i64 gp = es + x;
             for (int which = 0; which < 2; which++) {                    // 0: bias k-mer, 1: background k-mer
                 i64 c = which == 0 ? gp : (strand ? gp + bg_shift : gp - bg_shift);
                 bool valid = (c > es + k_flank) && (c <= ee - k_flank - 1);          // OneRead.get_kmer, ngs.pyx:115
@@ -254,7 +329,7 @@ static inline bool tb_k2h_plan(int L, int ch, int pstride, tb_k2h_desc &D) {
 }
 
 __global__ void __launch_bounds__(256)
-    tb_k2_hist_kernel(tb_genome_view g, tb_k2_regions R, u32 *__restrict__ slab, const u64 *__restrict__ sites, i64 n_sites, int k_flank,
+    tb_k2_hist_kernel(tb_genome_view g, tb_k2_regions R, const u32 *__restrict__ wts, const u64 *__restrict__ sites, i64 n_sites, int k_flank,
                       int bg_shift, int cap, tb_k2h_desc D, u32 *__restrict__ H, u64 *__restrict__ g_scalars) {
     __shared__ int sc[5];            // no_reads, no_bias_f, no_bg_f, no_bias_r, no_bg_r
     if (threadIdx.x < 5) sc[threadIdx.x] = 0;
@@ -268,13 +343,9 @@ __global__ void __launch_bounds__(256)
         const u64 site = sites[k];
         const i64 j = (i64)(site >> 32), x = (i64)(site & 0x7fffffffu);
         const int strand = (int)((site >> 31) & 1u);
-        u32 *slot = slab + (i64)strand * R.slab_len + x;
-        const u32 cnt = *slot;
-        *slot = 0u;                                                      // the slab is all-zero again after this kernel
-        const int w = (int)(cnt < (u32)cap ? cnt : (u32)cap);
+        const int w = (int)wts[k];
         const i64 es = R.es[j], ee = R.ee[j];
-        const i64 gp = es + (x - R.soff[j]);
-        mine[0] += w;
+        const i64 gp = es + x;
 #pragma unroll
         for (int which = 0; which < 2; which++) {                        // 0: bias k-mer, 1: background k-mer
             const i64 c = which == 0 ? gp : (strand ? gp + bg_shift : gp - bg_shift);
@@ -306,31 +377,7 @@ __global__ void __launch_bounds__(256)
 // strands of ONE k-mer kind (bias or background) fit in the shared memory of a block: 2 x 78 x 1 KB = 156 KB.  Even blocks take the
 // bias k-mer of every site, odd blocks the background k-mer; 78 shared-memory atomics per k-mer instead of 21 L2 atomics (the L2
 // form above is bound by the L2 atomic rate, ~55 G/s) or 325 shared-memory atomics (accumulate kernel).  The blocks add their tables
-// into the same global layout the L2 form uses and the same fold kernel finishes.  Both kinds of block need a site's capped
-// multiplicity while the slab is being cleaned, so a first small kernel moves it into a per-site array.
-__global__ void __launch_bounds__(256)
-    tb_k2_weights_kernel(tb_k2_regions R, u32 *__restrict__ slab, const u64 *__restrict__ sites, i64 n_sites, int cap, u32 *__restrict__ wts,
-                         u64 *__restrict__ g_scalars) {
-    __shared__ int sc;
-    if (threadIdx.x == 0) sc = 0;
-    __syncthreads();
-    int mine = 0;
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_sites; k += stride) {
-        const u64 site = sites[k];
-        u32 *slot = slab + (i64)((site >> 31) & 1u) * R.slab_len + (i64)(site & 0x7fffffffu);
-        const u32 cnt = *slot;
-        *slot = 0u;                                                      // the slab is all-zero again after this kernel
-        const u32 w = cnt < (u32)cap ? cnt : (u32)cap;
-        wts[k] = w;
-        mine += (int)w;
-    }
-    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sc, mine);
-    __syncthreads();
-    if (threadIdx.x == 0 && sc) atomicAdd(&g_scalars[0], (u64)(i64)sc);      // no_reads
-}
-
+// into the same global layout the L2 form uses and the same fold kernel finishes.
 // NC > 0: number of chunks known at compile time (chunk values in registers, table offsets immediate); NC = 0: any plan
 template <int NC>
 __global__ void __launch_bounds__(1024, 1)
@@ -358,7 +405,7 @@ __global__ void __launch_bounds__(1024, 1)
             const int strand = (int)((site >> 31) & 1u);
             const u32 w = wts[k];
             const i64 es = R.es[j], ee = R.ee[j];
-            const i64 gp = es + (x - R.soff[j]);
+            const i64 gp = es + x;
             const i64 c = which == 0 ? gp : (strand ? gp + bg_shift : gp - bg_shift);
             if ((c > es + k_flank) && (c <= ee - k_flank - 1) && tb_nflags(g, c - k_flank, L) == 0) {     // OneRead.get_kmer, ngs.pyx:115
                 const u64 kmer = tb_bases(g, c - k_flank, L);
@@ -509,17 +556,6 @@ __global__ void __launch_bounds__(256) tb_k2_fold_kernel(tb_k2h_desc D, const u3
         }
 }
 
-// first record index with lstart >= v (records are sorted by linear start)
-__global__ void tb_k2_read_bound_kernel(const i64 *__restrict__ lstart, i64 n, i64 v, i64 *__restrict__ out) {
-    if (threadIdx.x || blockIdx.x) return;
-    i64 lo = 0, hi = n;
-    while (lo < hi) {
-        i64 mid = (lo + hi) >> 1;
-        if (lstart[mid] >= v) hi = mid; else lo = mid + 1;
-    }
-    *out = lo;
-}
-
 extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end,
                               int k_flank, int bg_shift, int shift_fwd, int shift_rev, int cap, int is_dwm, int64_t *counts_out,
                               int64_t *scalars_out) {
@@ -555,33 +591,6 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     tb_reads_view2 rv{ctx->r_start.as<i64>(), ctx->r_len.as<int32_t>(), ctx->r_clip.as<int32_t>(), ctx->r_flags.as<uint8_t>(),
                       ctx->n_reads};
     tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
-    // slab entries per strand per chunk: as much as a quarter of the free memory allows (hg38 non-peak space: 3.0e9 positions,
-    // 24 GB for both strands -> one or two chunks on a 180 GB B200), at most 2^31 - 1 (site records hold 31 bits)
-    i64 SLAB_BUDGET;
-    {
-        const i64 LIM = ((i64)1 << 31) - 1;
-        i64 need = 0;
-        for (i64 i = 0; i < n_regions; i++) need += ee[i] - es[i];
-        if (ctx->k2_budget > 0 && need <= ctx->k2_budget_need) {
-            // same or smaller region space than an earlier call: its budget (a quarter of the memory that was free then) still holds.  No
-            // driver query on the steady path: cudaMemGetInfo was seen to stall for 10 - 40 ms now and then while nvidia-smi samples clocks
-            SLAB_BUDGET = ctx->k2_budget;
-        } else {
-            size_t free_b = 0, total_b = 0;
-            TB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-            free_b += ctx->k2_slab.cap;
-            SLAB_BUDGET = (i64)(free_b / 4 / (2 * sizeof(u32)));
-            ctx->k2_budget = SLAB_BUDGET;
-            ctx->k2_budget_need = need;
-        }
-        if (SLAB_BUDGET < ((i64)1 << 22)) SLAB_BUDGET = (i64)1 << 22;
-        if (SLAB_BUDGET > LIM) SLAB_BUDGET = LIM;
-        // genome still arriving (tb_genome_upload_async): smaller chunks, each waiting only for its own contigs
-        bool pending = false;
-        for (char c : ctx->contig_pending) pending = pending || c;
-        if (pending && SLAB_BUDGET > ((i64)3 << 27)) SLAB_BUDGET = (i64)3 << 27;
-        if (tb_opt(ctx, "k2_slab_budget", 0) > 0) SLAB_BUDGET = tb_opt(ctx, "k2_slab_budget", 0);     // tests: force several chunks
-    }
     size_t smem = ((n_acc * 4 + 15) & ~(size_t)15) + (size_t)2 * TB_K2_BATCH * 9;
     if (is_dwm) {
         auto k = tb_k2_accumulate_kernel<1>;
@@ -591,11 +600,11 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     i64 site_cap = ctx->n_reads + ctx->n_reads / 4 + 1024;       // one site per (record, overlapped region) at most; grown on overflow
-    {
-        if (tb_opt(ctx, "k2_site_cap", 0) > 0) site_cap = tb_opt(ctx, "k2_site_cap", 0);             // tests: force the overflow / regrow path
-    }
+    if (tb_opt(ctx, "k2_site_cap", 0) > 0) site_cap = tb_opt(ctx, "k2_site_cap", 0);                 // tests: force the overflow / regrow path
+    if (!ctx->reads_sorted && (double)ctx->n_reads * (double)n_regions > 4.0e9)
+        return tb_fail(ctx, TB_ERR_STATE, "tb_bias_counts: the records must be sorted by (contig, start) for this many regions");
 
-    // DWM: joint-histogram form unless the model is a single chunk (TB_K2_NO_HIST=1 / TB_K2_CHUNK=n: comparison runs and tests)
+    // DWM: joint-histogram form unless the model is a single chunk (options k2_no_hist / k2_chunk: comparison runs and tests)
     tb_k2h_desc HD;
     bool use_hist = false;
     if (is_dwm) {
@@ -631,119 +640,109 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         }
     }
 
-    tb_timer_start(ctx);
-    i64 j0 = 0;
-    std::vector<i64> soff;
-    while (j0 < n_regions) {
-        i64 j1 = j0, len = 0;
-        soff.assign(1, 0);
-        while (j1 < n_regions && (j1 == j0 || len + (ee[j1] - es[j1]) <= SLAB_BUDGET)) {
-            len += ee[j1] - es[j1];
-            soff.push_back(len);
-            j1++;
+    // units of the sites kernel: (region, tile); a region longer than one tile (not produced by the ATACorrect driver: split pieces are
+    // <= 50 kb) is walked tile by tile, every tile scanning the region's record range
+    int tile = TB_K2_TILE;
+    if (tb_opt(ctx, "k2_tile", 0) >= 64) tile = (int)(tb_opt(ctx, "k2_tile", 0) & ~63LL);             // tests: force several tiles per region
+    if (tile > TB_K2_TILE) tile = TB_K2_TILE;
+    std::vector<int32_t> unit_region, unit_tile;
+    unit_region.reserve(n_regions);
+    unit_tile.reserve(n_regions);
+    for (i64 i = 0; i < n_regions; i++) {
+        const i64 len = ee[i] - es[i];
+        if (len >= ((i64)1 << 31)) return tb_fail(ctx, TB_ERR_ARG, "tb_bias_counts: region %lld longer than 2^31", i);
+        for (i64 t = 0; t * tile < len; t++) {
+            unit_region.push_back((int32_t)i);
+            unit_tile.push_back((int32_t)t);
         }
-        if (len > (((i64)1 << 31) - 1)) return tb_fail(ctx, TB_ERR_ARG, "tb_bias_counts: region %lld longer than 2^31", j0);
-        i64 nr = j1 - j0;
-        TB_TRY(tb_h2d(ctx, ctx->reg_a, ls.data() + j0, sizeof(i64) * nr));
-        TB_TRY(tb_h2d(ctx, ctx->reg_b, le.data() + j0, sizeof(i64) * nr));
-        TB_TRY(tb_h2d(ctx, ctx->reg_c, es.data() + j0, sizeof(i64) * nr));
-        TB_TRY(tb_h2d(ctx, ctx->reg_d, ee.data() + j0, sizeof(i64) * nr));
-        TB_TRY(tb_h2d(ctx, ctx->reg_e, soff.data(), sizeof(i64) * (nr + 1)));
-        {   // the slab is kept all-zero between uses (the accumulate kernel zeroes what the scatter touched)
-            void *before = ctx->k2_slab.p;
-            TB_TRY(tb_reserve(ctx, ctx->k2_slab, (size_t)len * 2 * sizeof(u32)));
-            if (ctx->k2_slab.p != before) TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_slab.p, 0, ctx->k2_slab.cap, ctx->stream));
-        }
-        tb_k2_regions R{ctx->reg_a.as<i64>(), ctx->reg_b.as<i64>(), ctx->reg_c.as<i64>(), ctx->reg_d.as<i64>(),
-                        ctx->reg_e.as<i64>(), nr, len};
-        // records that can overlap this chunk: start in [first region start - longest alignment, last region end)
-        i64 read_lo = 0, read_hi = rv.n;
-        if ((j0 > 0 || j1 < n_regions) && ctx->reads_sorted) {
-            i64 bounds[2];
-            TB_LAUNCH(ctx, tb_k2_read_bound_kernel, 1, 32, 0, rv.lstart, rv.n, ls[j0] - ctx->max_read_len, (i64 *)(d_ctr + 2));
-            TB_LAUNCH(ctx, tb_k2_read_bound_kernel, 1, 32, 0, rv.lstart, rv.n, le[j1 - 1], (i64 *)(d_ctr + 3));
-            TB_TRY(tb_d2h(ctx, bounds, d_ctr + 2, sizeof(bounds)));
-            read_lo = bounds[0];
-            read_hi = bounds[1];
-        }
-        for (;;) {
-            TB_TRY(tb_reserve(ctx, ctx->k2_sites, (size_t)site_cap * sizeof(u64)));
-            TB_CUDA(ctx, cudaMemsetAsync(d_ctr, 0, 2 * sizeof(u64), ctx->stream));
-            i64 n_rd = read_hi - read_lo;
-            if (n_rd > 0) {
-                i64 want = tb_div_up(n_rd, 256), capg = (i64)ctx->sm_count * 16;
-                TB_LAUNCH(ctx, tb_k2_scatter_kernel, (unsigned)(want < capg ? want : capg), 256, 0, rv, R, read_lo, read_hi, shift_fwd,
-                          shift_rev, ctx->k2_slab.as<u32>(), ctx->k2_sites.as<u64>(), site_cap, d_ctr);
-            }
-            unsigned long long hc[2];
-            TB_TRY(tb_d2h(ctx, hc, d_ctr, sizeof(hc)));
-            i64 n_sites = (i64)hc[0];
-            {   // the k-mer kernels read the genome of this chunk's contigs
-                int c_lo = contig[j0], c_hi = contig[j0];
-                for (i64 j = j0; j < j1; j++) {
-                    c_lo = contig[j] < c_lo ? contig[j] : c_lo;
-                    c_hi = contig[j] > c_hi ? contig[j] : c_hi;
-                }
-                TB_TRY(tb_genome_fence(ctx, c_lo, c_hi));
-            }
-            if (hc[1]) {       // site list too small (records spanning many tiny regions): clean the slab, grow, redo the chunk
-                TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_slab.p, 0, ctx->k2_slab.cap, ctx->stream));
-                site_cap = n_sites + n_sites / 8 + 1024;
-                continue;
-            }
-            if (n_sites > 0 && use_smem_hist && (double)n_sites * cap < 4.0e9) {
-                // joint histograms of 2-base chunks in shared memory (even blocks: bias k-mers, odd blocks: background k-mers), then the fold
-                const size_t hbytes = ((size_t)4 * SD.nt << (4 * SD.ch)) * sizeof(u32);
-                TB_TRY(tb_reserve(ctx, ctx->k2_hist, hbytes));
-                TB_TRY(tb_reserve(ctx, ctx->k2_wts, (size_t)n_sites * sizeof(u32)));
-                TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_hist.p, 0, hbytes, ctx->stream));
-                i64 want = tb_div_up(n_sites, 256), capg = (i64)ctx->sm_count * 8;
-                TB_LAUNCH(ctx, tb_k2_weights_kernel, (unsigned)(want < capg ? want : capg), 256, 0, R, ctx->k2_slab.as<u32>(),
-                          (const u64 *)ctx->k2_sites.as<u64>(), n_sites, cap, ctx->k2_wts.as<u32>(), d_sc);
-                i64 pairs = tb_div_up(n_sites, 1024), capp = (ctx->sm_count + 1) / 2;          // one block per SM
-                if (pairs > capp) pairs = capp;
-                if (SD.nc == 13 && SD.ch == 2) {
-                    auto k = tb_k2_hist_smem_kernel<13>;
-                    TB_LAUNCH(ctx, k, (unsigned)(2 * pairs), 1024, sh_bytes, g, R, (const u32 *)ctx->k2_wts.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(),
-                              n_sites, k_flank, bg_shift, cap, SD, ctx->k2_hist.as<u32>(), d_sc);
-                } else {
-                    auto k = tb_k2_hist_smem_kernel<0>;
-                    TB_LAUNCH(ctx, k, (unsigned)(2 * pairs), 1024, sh_bytes, g, R, (const u32 *)ctx->k2_wts.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(),
-                              n_sites, k_flank, bg_shift, cap, SD, ctx->k2_hist.as<u32>(), d_sc);
-                }
-                const int V = 1 << (2 * SD.ch);
-                const int slabs = V >= 64 ? V / 64 : 1;
-                TB_LAUNCH(ctx, tb_k2_fold_kernel, dim3((unsigned)slabs, (unsigned)(4 * SD.nt)), 256, 0, SD, (const u32 *)ctx->k2_hist.as<u32>(), d_acc);
-            } else if (n_sites > 0 && use_hist && (double)n_sites * cap < 4.0e9) {
-                // joint-histogram form: one atomic per (k-mer, chunk pair) into L2-resident tables, then the fold
-                const size_t hbytes = ((size_t)4 * HD.nt << (4 * HD.ch)) * sizeof(u32);
-                TB_TRY(tb_reserve(ctx, ctx->k2_hist, hbytes));
-                TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_hist.p, 0, hbytes, ctx->stream));
-                i64 want = tb_div_up(n_sites, 256), capg = (i64)ctx->sm_count * 8;
-                TB_LAUNCH(ctx, tb_k2_hist_kernel, (unsigned)(want < capg ? want : capg), 256, 0, g, R, ctx->k2_slab.as<u32>(),
-                          (const u64 *)ctx->k2_sites.as<u64>(), n_sites, k_flank, bg_shift, cap, HD, ctx->k2_hist.as<u32>(), d_sc);
-                const int V = 1 << (2 * HD.ch);
-                const int slabs = V >= 64 ? V / 64 : 1;              // 64 table rows per block: 8 per warp
-                TB_LAUNCH(ctx, tb_k2_fold_kernel, dim3((unsigned)slabs, (unsigned)(4 * HD.nt)), 256, 0, HD, (const u32 *)ctx->k2_hist.as<u32>(), d_acc);
-            } else if (n_sites > 0) {
-                i64 n_batches = tb_div_up(n_sites, TB_K2_BATCH);
-                unsigned grid = (unsigned)(n_batches < ctx->sm_count ? n_batches : ctx->sm_count);
-                if (is_dwm) {
-                    auto k = tb_k2_accumulate_kernel<1>;
-                    TB_LAUNCH(ctx, k, grid, 1024, smem, g, R, ctx->k2_slab.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(), n_sites, k_flank,
-                              bg_shift, cap, d_acc, d_sc);
-                } else {
-                    auto k = tb_k2_accumulate_kernel<0>;
-                    TB_LAUNCH(ctx, k, grid, 1024, smem, g, R, ctx->k2_slab.as<u32>(), (const u64 *)ctx->k2_sites.as<u64>(), n_sites, k_flank,
-                              bg_shift, cap, d_acc, d_sc);
-                }
-            }
-            break;
-        }
-        TB_TRY(tb_sync(ctx, "tb_bias_counts chunk"));      // region tables are reused by the next chunk
-        j0 = j1;
     }
+    const i64 n_units = (i64)unit_region.size();
+    TB_TRY(tb_h2d(ctx, ctx->reg_a, ls.data(), sizeof(i64) * n_regions));
+    TB_TRY(tb_h2d(ctx, ctx->reg_b, le.data(), sizeof(i64) * n_regions));
+    TB_TRY(tb_h2d(ctx, ctx->reg_c, es.data(), sizeof(i64) * n_regions));
+    TB_TRY(tb_h2d(ctx, ctx->reg_d, ee.data(), sizeof(i64) * n_regions));
+    TB_TRY(tb_h2d(ctx, ctx->scratch2, unit_region.data(), sizeof(int32_t) * n_units));
+    TB_TRY(tb_h2d(ctx, ctx->scratch3, unit_tile.data(), sizeof(int32_t) * n_units));
+    TB_TRY(tb_reserve(ctx, ctx->reg_e, sizeof(i64) * 2 * n_regions));
+    tb_k2_regions R{ctx->reg_a.as<i64>(), ctx->reg_b.as<i64>(), ctx->reg_c.as<i64>(), ctx->reg_d.as<i64>(), n_regions};
+    const size_t sites_smem = (size_t)tile * 2 * sizeof(unsigned short) + (size_t)TB_K2_LIST * sizeof(u32);
+    {
+        auto k = tb_k2_sites_kernel;
+        TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sites_smem));
+    }
+
+    tb_timer_start(ctx);
+    tb_mark(ctx, 0);
+    {
+        i64 want = tb_div_up(n_regions, 256), capg = (i64)ctx->sm_count * 8;
+        TB_LAUNCH(ctx, tb_k2_ranges_kernel, (unsigned)(want < capg ? want : capg), 256, 0, rv.lstart, rv.n, R, ctx->max_read_len,
+                  ctx->reads_sorted ? 1 : 0, ctx->reg_e.as<i64>());
+    }
+    i64 n_sites = 0;
+    for (;;) {
+        TB_TRY(tb_reserve(ctx, ctx->k2_sites, (size_t)site_cap * sizeof(u64)));
+        TB_TRY(tb_reserve(ctx, ctx->k2_wts, (size_t)site_cap * sizeof(u32)));
+        TB_CUDA(ctx, cudaMemsetAsync(d_ctr, 0, 2 * sizeof(u64), ctx->stream));
+        TB_CUDA(ctx, cudaMemsetAsync(d_sc, 0, sizeof(u64), ctx->stream));
+        const unsigned grid = (unsigned)(n_units < ctx->sm_count ? n_units : ctx->sm_count);
+        TB_LAUNCH(ctx, tb_k2_sites_kernel, grid, 1024, sites_smem, rv, R, (const i64 *)ctx->reg_e.as<i64>(),
+                  (const int32_t *)ctx->scratch2.as<int32_t>(), (const int32_t *)ctx->scratch3.as<int32_t>(), n_units, tile, shift_fwd,
+                  shift_rev, cap, ctx->k2_sites.as<u64>(), ctx->k2_wts.as<u32>(), site_cap, d_ctr, d_sc);
+        unsigned long long hc[2];
+        TB_TRY(tb_d2h(ctx, hc, d_ctr, sizeof(hc)));
+        n_sites = (i64)hc[0];
+        if (!hc[1]) break;
+        site_cap = n_sites + n_sites / 8 + 1024;        // site list too small (records spanning many tiny regions): grow, redo
+    }
+    tb_mark(ctx, 1);
+    TB_TRY(tb_genome_fence(ctx, 0, ctx->n_contigs - 1));      // the k-mer kernels read the genome
+    const u32 *d_wts = ctx->k2_wts.as<u32>();
+    const u64 *d_sites = ctx->k2_sites.as<u64>();
+    if (n_sites > 0 && use_smem_hist && (double)n_sites * cap < 4.0e9) {
+        // joint histograms of 2-base chunks in shared memory (even blocks: bias k-mers, odd blocks: background k-mers), then the fold
+        const size_t hbytes = ((size_t)4 * SD.nt << (4 * SD.ch)) * sizeof(u32);
+        TB_TRY(tb_reserve(ctx, ctx->k2_hist, hbytes));
+        TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_hist.p, 0, hbytes, ctx->stream));
+        i64 pairs = tb_div_up(n_sites, 1024), capp = (ctx->sm_count + 1) / 2;          // one block per SM
+        if (pairs > capp) pairs = capp;
+        if (SD.nc == 13 && SD.ch == 2) {
+            auto k = tb_k2_hist_smem_kernel<13>;
+            TB_LAUNCH(ctx, k, (unsigned)(2 * pairs), 1024, sh_bytes, g, R, d_wts, d_sites, n_sites, k_flank, bg_shift, cap, SD,
+                      ctx->k2_hist.as<u32>(), d_sc);
+        } else {
+            auto k = tb_k2_hist_smem_kernel<0>;
+            TB_LAUNCH(ctx, k, (unsigned)(2 * pairs), 1024, sh_bytes, g, R, d_wts, d_sites, n_sites, k_flank, bg_shift, cap, SD,
+                      ctx->k2_hist.as<u32>(), d_sc);
+        }
+        const int V = 1 << (2 * SD.ch);
+        const int slabs = V >= 64 ? V / 64 : 1;
+        TB_LAUNCH(ctx, tb_k2_fold_kernel, dim3((unsigned)slabs, (unsigned)(4 * SD.nt)), 256, 0, SD, (const u32 *)ctx->k2_hist.as<u32>(), d_acc);
+    } else if (n_sites > 0 && use_hist && (double)n_sites * cap < 4.0e9) {
+        // joint-histogram form: one atomic per (k-mer, chunk pair) into L2-resident tables, then the fold
+        const size_t hbytes = ((size_t)4 * HD.nt << (4 * HD.ch)) * sizeof(u32);
+        TB_TRY(tb_reserve(ctx, ctx->k2_hist, hbytes));
+        TB_CUDA(ctx, cudaMemsetAsync(ctx->k2_hist.p, 0, hbytes, ctx->stream));
+        i64 want = tb_div_up(n_sites, 256), capg = (i64)ctx->sm_count * 8;
+        TB_LAUNCH(ctx, tb_k2_hist_kernel, (unsigned)(want < capg ? want : capg), 256, 0, g, R, d_wts, d_sites, n_sites, k_flank, bg_shift, cap,
+                  HD, ctx->k2_hist.as<u32>(), d_sc);
+        const int V = 1 << (2 * HD.ch);
+        const int slabs = V >= 64 ? V / 64 : 1;              // 64 table rows per block: 8 per warp
+        TB_LAUNCH(ctx, tb_k2_fold_kernel, dim3((unsigned)slabs, (unsigned)(4 * HD.nt)), 256, 0, HD, (const u32 *)ctx->k2_hist.as<u32>(), d_acc);
+    } else if (n_sites > 0) {
+        i64 n_batches = tb_div_up(n_sites, TB_K2_BATCH);
+        unsigned grid = (unsigned)(n_batches < ctx->sm_count ? n_batches : ctx->sm_count);
+        if (is_dwm) {
+            auto k = tb_k2_accumulate_kernel<1>;
+            TB_LAUNCH(ctx, k, grid, 1024, smem, g, R, d_wts, d_sites, n_sites, k_flank, bg_shift, cap, d_acc, d_sc);
+        } else {
+            auto k = tb_k2_accumulate_kernel<0>;
+            TB_LAUNCH(ctx, k, grid, 1024, smem, g, R, d_wts, d_sites, n_sites, k_flank, bg_shift, cap, d_acc, d_sc);
+        }
+    }
+    tb_mark(ctx, 2);
     tb_timer_stop(ctx);
+    tb_marks_collect(ctx, 3);      // stage_ms: [0] site list (ranges + sites kernels), [1] counts from the sites
+    TB_TRY(tb_sync(ctx, "tb_bias_counts"));
 
     std::vector<u64> h(n_acc + 8);
     TB_TRY(tb_d2h(ctx, h.data(), d_acc, (n_acc + 8) * sizeof(u64)));
