@@ -44,6 +44,7 @@ struct dim3 {
 };
 struct double2 { double x, y; };
 struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 struct float4 { float x, y, z, w; };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };

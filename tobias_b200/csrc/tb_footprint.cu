@@ -243,6 +243,150 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
     }
 }
 
+// ---- second form of the footprint scan: TWO footprint starts per thread, every flank-width array staged at once ----
+// For a fixed flank width the score table acc(s, e) = max_fw ( L_fw[s] + R_fw[e] ) (e = s + pw: end of the footprint) is a max-plus product of
+// the left-flank column and the right-flank row, so the register tile of a thread is widened like a GEMM micro-tile: starts s0 = 2t and
+// s0 + 1 share their right-flank values (33 values serve 64 accumulators), read as 17 aligned 8-byte shared-memory loads -- half the
+// shared-memory wavefronts and three quarters of the instructions of one start per thread.  All W_fw arrays of the tile are staged
+// before the loop (21 x ~940 floats = 79 KB for the CLI defaults), so the flank-width loop runs without barriers; the spread of every score over
+// its footprint goes through one table G[c][start] of suffix maxima in the same memory (two halves of 16 widths: 4 barriers instead of 31).
+// Used when there are at most 32 footprint widths and the W arrays fit; the kernel above handles every other parameter set.
+#define TB_K4B_MAXT 512          // threads per block (2 starts each)
+template <int OUT_MODE>
+__global__ void __launch_bounds__(TB_K4B_MAXT)
+tb_footprint2_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_, int pmin_, int pmax_, int wstride,
+                     void *__restrict__ out_) {
+    TB_DYN_SMEM(smem);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int S = 2 * nthr;                                     // footprint starts per tile
+    const int T = S - (pmax_ - 1);                              // outputs per tile
+    const int npw = pmax_ - pmin_ + 1, nfw = fmax_ - fmin_ + 1;
+    const i64 j = tb_upper_bound(V.tile_off, V.n_regions + 1, (i64)blockIdx.x) - 1;
+    const i64 tile = (i64)blockIdx.x - V.tile_off[j];
+    const i64 Lr = V.ext_off[j + 1] - V.ext_off[j];
+    const i64 p0 = tile * T;                                    // first output position of the tile (region coordinates)
+    const i64 smin = p0 - (pmax_ - 1);                          // first footprint start of the tile
+    const i64 in0 = smin - fmax_;                               // first loaded position
+    const int n_in = S + 2 * fmax_ + pmax_;
+    const i64 limit = Lr - 2 * (i64)fmax_ - pmax_;              // i = s - fw must be < limit
+    double *P = (double *)smem;                                 // n_in + 1
+    double *N = P + (n_in + 1);                                 // n_in + 1
+    float *W = (float *)(N + (n_in + 1));                       // [nfw][wstride], row r shifted by `shift` floats; later G[16][S]
+    __shared__ double wtot[64];
+    const float *sg = signal + V.ext_off[j];
+    // the right-flank values of a thread start at index 2 * tid + fmax + pmin of a row: rows are shifted by one float when that is odd,
+    // so that every thread's first value sits on an 8-byte boundary
+    const int shift = (fmax_ + pmin_) & 1;
+
+    for (int i = tid; i < n_in; i += nthr) {
+        const i64 q = in0 + i;
+        float v = 0.0f;
+        if (q >= 0 && q < Lr) v = (float)tb_prep_value(sg[q], prep);      // `val = arr[i+j]` is a C float (signals.pyx:191)
+        P[i] = v > 0.0f ? (double)v : 0.0;
+        N[i] = v < 0.0f ? (double)v : 0.0;
+    }
+    __syncthreads();
+    tb_block_scan2w(P, N, n_in, wtot);
+    // W_fw[i] = mean of max(v, 0) over [i, i + fw), halved: (P[i + fw] - P[i]) / (2 fw); padding up to the row end reads as 0
+    for (int r = 0; r < nfw; r++) {
+        const int fw = fmin_ + r;
+        const float inv = 1.0f / (2.0f * (float)fw);
+        float *Wr = W + (size_t)r * wstride + shift;
+        for (int i = tid; i < wstride - shift; i += nthr) Wr[i] = i + fw <= n_in ? (float)(P[i + fw] - P[i]) * inv : 0.0f;
+    }
+    __syncthreads();
+
+    const int si = 2 * tid + fmax_;                             // index of start s0 in the loaded range
+    const i64 s0 = smin + 2 * tid;
+    float acc0[TB_K4_NPW], acc1[TB_K4_NPW];
+#pragma unroll
+    for (int c = 0; c < TB_K4_NPW; c++) acc0[c] = acc1[c] = -INFINITY;
+    for (int r = 0; r < nfw; r++) {
+        const int fw = fmin_ + r;
+        const float *Wr = W + (size_t)r * wstride + shift;
+        const i64 i0 = s0 - fw;
+        // a start whose left flank would begin outside [0, limit) does not exist (signals.pyx:199): -inf + finite stays -inf
+        const float l0 = (i0 >= 0 && i0 < limit) ? Wr[si - fw] : -INFINITY;
+        const float l1 = (i0 + 1 >= 0 && i0 + 1 < limit) ? Wr[si + 1 - fw] : -INFINITY;
+        const float2 *w2 = (const float2 *)(Wr + si + pmin_);   // 8-byte aligned by construction
+        float2 cur = w2[0];
+#pragma unroll
+        for (int h = 0; h < TB_K4_NPW / 2; h++) {
+            const float2 nxt = w2[h + 1];
+            acc0[2 * h] = fmaxf(acc0[2 * h], l0 + cur.x);
+            acc0[2 * h + 1] = fmaxf(acc0[2 * h + 1], l0 + cur.y);
+            acc1[2 * h] = fmaxf(acc1[2 * h], l1 + cur.y);
+            acc1[2 * h + 1] = fmaxf(acc1[2 * h + 1], l1 + nxt.x);
+            cur = nxt;
+        }
+    }
+    // acc[c] -> score of (s, pmin + c); widths beyond pmax are padding
+    {
+        const double n0 = N[si], n1 = N[si + 1];
+#pragma unroll
+        for (int c = 0; c < TB_K4_NPW; c++) {
+            const int pw = pmin_ + c;
+            float a = -INFINITY, b = -INFINITY;
+            if (c < npw) {
+                const float ipw = 1.0f / (float)pw;
+                if (acc0[c] > -INFINITY) a = acc0[c] - (float)(N[si + pw] - n0) * ipw;
+                if (acc1[c] > -INFINITY) b = acc1[c] - (float)(N[si + 1 + pw] - n1) * ipw;
+            }
+            acc0[c] = a;
+            acc1[c] = b;
+        }
+    }
+    // suffix maxima over the widths: g[c] = max_{pw >= pmin + c} score(s, pw)
+#pragma unroll
+    for (int c = TB_K4_NPW - 2; c >= 0; c--) {
+        acc0[c] = fmaxf(acc0[c], acc0[c + 1]);
+        acc1[c] = fmaxf(acc1[c], acc1[c + 1]);
+    }
+    // out[pos] = max( max_{d < pmin} g[0](pos - d),  max_{c >= 1} g[c](pos - (pmin - 1 + c)) ), out initialised 0 (signals.pyx:193)
+    float best0 = 0.0f, best1 = 0.0f;
+    float *G = W;                                               // [16][S]
+    const int k0 = 2 * tid;                                     // index of s0 among the tile's starts
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        __syncthreads();                                        // W (or the previous half of G) no longer read
+#pragma unroll
+        for (int cc = 0; cc < TB_K4_NPW / 2; cc++) {
+            const int c = half * (TB_K4_NPW / 2) + cc;
+            *(float2 *)(G + (size_t)cc * S + k0) = make_float2(acc0[c], acc1[c]);
+        }
+        __syncthreads();
+        if (half == 0)
+            for (int d = 0; d < pmin_; d++) {
+                if (k0 - d >= 0) best0 = fmaxf(best0, G[k0 - d]);
+                if (k0 + 1 - d >= 0) best1 = fmaxf(best1, G[k0 + 1 - d]);
+            }
+#pragma unroll
+        for (int cc = 0; cc < TB_K4_NPW / 2; cc++) {
+            const int c = half * (TB_K4_NPW / 2) + cc;
+            if (c >= 1 && c < npw) {                            // block-uniform
+                const int d = pmin_ - 1 + c;
+                if (k0 - d >= 0) best0 = fmaxf(best0, G[(size_t)cc * S + k0 - d]);
+                if (k0 + 1 - d >= 0) best1 = fmaxf(best1, G[(size_t)cc * S + k0 + 1 - d]);
+            }
+        }
+    }
+    // this thread holds out[pos] for pos = s0 and s0 + 1; valid from the tile's first output position on
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const i64 s = s0 + u;
+        const float best = u ? best1 : best0;
+        if (k0 + u >= pmax_ - 1 && s < Lr) {
+            if (OUT_MODE == 2) {
+                ((double *)out_)[V.ext_off[j] + s] = (double)best;
+            } else if (s >= V.flank && s < Lr - V.flank) {
+                const i64 o = V.out_off[j] + (s - V.flank);
+                if (OUT_MODE == 0) ((float *)out_)[o] = best;
+                else ((double *)out_)[o] = (double)best;
+            }
+        }
+    }
+}
+
 // FOS_score (signals.pyx:237-282): exclusive width ranges, plain sums, running minimum from 10000.  One thread per output
 // position; tile-local fp64 prefix sums.  Not reachable from the reference CLI (parsers.py:84); kept for API parity.
 template <int OUT_MODE>
@@ -467,16 +611,56 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
     tb_timer_start(ctx);
     if (fp_like) {
         const bool fos = p->kind == TB_SCORE_FOS;
-        // footprint scan: block size = tile size, picked to waste the fewest thread slots on these region lengths
+        std::vector<std::pair<i64, i64>> hist;               // (region length, count): most output regions have the same length
+        for (i64 i = 0; i < S.n_regions; i++) {
+            const i64 v = S.ext_off[i + 1] - S.ext_off[i];
+            if (!hist.empty() && hist.back().first == v) hist.back().second++;
+            else hist.push_back({v, 1});
+        }
+        const int npw = p->fp_max - p->fp_min + 1, nfw = p->flank_max - p->flank_min + 1;
+        // second form (two starts per thread, all flank-width arrays staged): at most 32 footprint widths, and the arrays must fit
+        int bs2 = 0;
+        size_t smem2 = 0;
+        int wstride2 = 0;
+        if (!fos && npw <= TB_K4_NPW && tb_opt(ctx, "k4_one_start", 0) == 0) {
+            double best_cost = -1.0;
+            for (int cand = 64; cand <= TB_K4B_MAXT; cand += 32) {
+                const i64 per = 2 * cand - (p->fp_max - 1);
+                if (per < 32) continue;
+                const int n_in = 2 * cand + 2 * p->flank_max + p->fp_max;
+                const int wstride = (n_in + 1 + 34 + 3) & ~3;                                  // + the 34 floats a thread reads past its last start
+                size_t need = (size_t)2 * (n_in + 1) * sizeof(double) + (size_t)nfw * wstride * sizeof(float);
+                const size_t gbytes = (size_t)16 * 2 * cand * sizeof(float);
+                if ((size_t)nfw * wstride * sizeof(float) < gbytes) need = (size_t)2 * (n_in + 1) * sizeof(double) + gbytes;
+                if (need > (size_t)200 * 1024) continue;
+                double cost = 0.0;
+                for (const auto &h : hist) cost += (double)tb_div_up(h.first, per) * (double)h.second;
+                cost *= (double)(2 * cand + 2 * p->flank_max + p->fp_max) + 64.0;             // slots incl. the halo every tile re-scans
+                if (best_cost < 0.0 || cost < best_cost) {
+                    best_cost = cost;
+                    bs2 = cand;
+                    smem2 = need;
+                    wstride2 = wstride;
+                }
+            }
+        }
+        if (bs2 > 0) {
+            const i64 per_tile = 2 * bs2 - (p->fp_max - 1);
+            TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles));
+            tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
+#define TB_FP2_CASE(OM)                                                                                                      \
+    {                                                                                                                       \
+        auto k = tb_footprint2_kernel<OM>;                                                                                  \
+        TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));                     \
+        TB_LAUNCH(ctx, k, (unsigned)n_tiles, bs2, smem2, V, (const float *)S.signal.as<float>(), prep, p->flank_min,        \
+                  p->flank_max, p->fp_min, p->fp_max, wstride2, first_out);                                                 \
+    }
+            if (first_mode == 0) TB_FP2_CASE(0) else if (first_mode == 1) TB_FP2_CASE(1) else TB_FP2_CASE(2)
+#undef TB_FP2_CASE
+        } else {
+        // footprint scan, first form: block size = tile size, picked to waste the fewest thread slots on these region lengths
         int bs = TB_K4_THREADS;
         if (!fos) {
-            // (most output regions have the same length: the search runs over runs of equal lengths)
-            std::vector<std::pair<i64, i64>> hist;           // (length, count)
-            for (i64 i = 0; i < S.n_regions; i++) {
-                const i64 v = S.ext_off[i + 1] - S.ext_off[i];
-                if (!hist.empty() && hist.back().first == v) hist.back().second++;
-                else hist.push_back({v, 1});
-            }
             double best_cost = -1.0;
             for (int cand = 128; cand <= TB_K4_THREADS; cand += 32) {
                 const i64 per = cand - (p->fp_max - 1);
@@ -511,6 +695,7 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
             else TB_FP_CASE(tb_fos_kernel, 2)
         }
 #undef TB_FP_CASE
+        }
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_footprint_kernel"));
     } else {
         TB_TRY(tb_tiles(ctx, S.ext_off, TB_ROLL_TILE, ctx->reg_e, n_tiles));
