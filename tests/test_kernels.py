@@ -302,6 +302,35 @@ def test_bias_correction_other_fit_kernels(loaded_ctx, golden, lm_mode):
                 assert np.array_equal(got[t][si], ref)
 
 
+def test_persistent_fit_kernel_equals_the_round_form(loaded_ctx, golden):
+    """One-pass window fits: the persistent kernel (tile of the window data in shared memory, state in registers, lanes share every
+    pass) runs the same arithmetic in the same order as the round kernels it replaces -- fit records and tracks bit-identical, also
+    when fits are parked after 1 or 3 passes and finished by the round kernels, and with tiles of 64 slots."""
+    g = golden.atac
+    _set_model(loaded_ctx, g, "DWM")
+    c, s, e = _cols(g["outreg"])
+    cf = float(g["correction_factor"])
+    loaded_ctx.set_option("k3b_persistent", 0)
+    loaded_ctx.correct_run(c, s, e, correction_factor=cf, lm_exact_order=0)
+    base_trace = loaded_ctx.correct_fit_trace()
+    base = loaded_ctx.correct_download(split_strands=True, as_f64=True, prepost=False)
+    loaded_ctx.set_option("k3b_persistent", -1)
+    try:
+        for cap, tile in ((-1, -1), (1, -1), (3, 64)):
+            loaded_ctx.set_option("k3b_cap", cap)
+            loaded_ctx.set_option("k3b_tile", tile)
+            loaded_ctx.correct_run(c, s, e, correction_factor=cf, lm_exact_order=0)
+            assert np.array_equal(loaded_ctx.correct_fit_trace(), base_trace), (cap, tile)
+            got = loaded_ctx.correct_download(split_strands=True, as_f64=True, prepost=False)
+            for t in TRACKS:
+                for si in range(2):
+                    assert np.array_equal(got[t][si], base[t][si]), (cap, tile, t, si)
+    finally:
+        loaded_ctx.set_option("k3b_cap", -1)
+        loaded_ctx.set_option("k3b_tile", -1)
+    assert (base_trace[:, :, 0] == 0).sum() > 500 and (base_trace[:, :, 5] > 25).sum() > 0      # fits long enough to be parked exist
+
+
 def test_bias_correction_edge_regions(loaded_ctx, golden):
     """Regions the golden set does not hold, against the oracle region by region (PWM mode: every track bit-identical): a region whose
     extension starts at position 0 of a contig and lies in an N block without reads, one whose extension ends at the contig end, a

@@ -150,7 +150,7 @@ extern "C" int tb_init(int device, tb_ctx **out) {
 extern "C" int tb_set_option(tb_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return TB_ERR_ARG;
     static const char *known[] = {"k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_tile", "k2_site_cap", "k2_chunk",
-                                  "k2_no_hist", "k2_smem_chunk", "k2_no_smem_hist", "k4_one_start", "k3b_persistent", "host_trace", nullptr};
+                                  "k2_no_hist", "k2_smem_chunk", "k2_no_smem_hist", "k4_one_start", "k4_threads", "k3b_persistent", "k3b_tile", "k3b_cap", "k3b_threads", "host_trace", nullptr};
     bool ok = false;
     for (int i = 0; known[i]; i++) ok = ok || strcmp(known[i], key) == 0;
     if (!ok) return tb_fail(ctx, TB_ERR_ARG, "tb_set_option: unknown option '%s'", key);
@@ -175,7 +175,7 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
                        &ctx->model[0].vtable, &ctx->model[1].vtable, &ctx->k2_sites, &ctx->k2_hist, &ctx->k2_wts, &ctx->staging_up,
                        &ctx->cor.d_ext_start, &ctx->cor.d_ext_end, &ctx->cor.d_ext_off, &ctx->cor.d_out_off, &ctx->cor.d_win_off,
                        &ctx->cor.pile, &ctx->cor.biasraw, &ctx->cor.fit, &ctx->cor.fitg_x, &ctx->cor.fitg_y, &ctx->cor.fitg_st,
-                       &ctx->cor.fitg_sti, &ctx->cor.fitg_wq, &ctx->cor.fitg_lists, &ctx->cor.tracks, &ctx->cor.prepost,
+                       &ctx->cor.fitg_sti, &ctx->cor.fitg_wq, &ctx->cor.fitg_lists, &ctx->cor.fitg_sw, &ctx->cor.tracks, &ctx->cor.prepost,
                        &ctx->sc.d_ext_off, &ctx->sc.signal, &ctx->sc.work0, &ctx->sc.work1, &ctx->sc.out};
     for (tb_dbuf *b : bufs) tb_release(*b);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

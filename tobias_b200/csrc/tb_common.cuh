@@ -112,7 +112,7 @@ struct tb_ctx {
         tb_dbuf pile;      // u32 [2][ext_total]
         tb_dbuf biasraw;   // f64 [2][ext_total]
         tb_dbuf fit;       // f64 [2][n_windows][6]
-        tb_dbuf fitg_x, fitg_y, fitg_st, fitg_sti, fitg_wq, fitg_lists;   // K3b round form: transposed window data, fit state, work lists
+        tb_dbuf fitg_x, fitg_y, fitg_st, fitg_sti, fitg_wq, fitg_lists, fitg_sw;   // K3b round form: transposed window data, fit state, work lists
         tb_dbuf tracks;    // f64 [4 tracks][2 strands][out_total]
         tb_dbuf prepost;   // f64 [2][3][5][L]
         tb_dbuf dl[4][2];  // packed tracks on their way to the host

@@ -170,12 +170,15 @@ __device__ __forceinline__ void tb_fitg_append(bool want, u32 slot, u32 *__restr
 
 // transposed copy of (bias, signal) of every window position; one block per (region, strand)
 __global__ void tb_fitg_transpose_kernel(tb_cor_view V, const u32 *__restrict__ pile, const double *__restrict__ biasraw, i64 qs,
-                                         i64 qtot, int qm, double *__restrict__ gx, u32 *__restrict__ gy) {
+                                         i64 qtot, int qm, double *__restrict__ gx, u32 *__restrict__ gy, int32_t *__restrict__ slot_win) {
     const i64 j = blockIdx.x;
     const int strand = blockIdx.y;
     const i64 nw = V.win_off[j + 1] - V.win_off[j];
     if (nw <= 0) return;
     const i64 q0 = (i64)strand * qs + V.win_off[j] + (i64)(qm - 1) * j;
+    if (slot_win)          // window (strand * n_windows + index) of every slot of this region, -1 for the qm - 1 slots that only hold window tails
+        for (int u = threadIdx.x; u < nw + qm - 1; u += blockDim.x)
+            slot_win[q0 + u] = u < nw ? (int32_t)((i64)strand * V.n_windows + V.win_off[j] + u) : -1;
     const i64 pos = (i64)strand * V.ext_total + V.ext_off[j] + V.k_flank;
     const int np = (int)(TB_STEP * (nw - 1)) + V.window;
     for (int lp = threadIdx.x; lp < np; lp += blockDim.x) {
@@ -327,6 +330,104 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
         rec[3] = pmax;
         rec[4] = (double)S.info;
         rec[5] = (double)S.nfev;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3b, persistent form (one-pass fits)
+// The round form above sends the state of every fit (144 B) through HBM once per outer iteration and reads the window data through L1
+// from wherever the compacted lists point (one sector per lane once the lists thin out).  Here a block stages a TILE of consecutive
+// slots of the transposed window data in shared memory (10 planes x (TS + 12) slots x 12 B) and its threads fit the windows of the tile
+// to the end with the state in registers: lane l of every warp takes the slots = l (mod 32) of the tile from a shared counter of that
+// residue class, so at any moment the 32 lanes of a warp read 32 different banks whatever windows they hold (the slots a lane reads
+// stay = l + u mod 32 for every lane at point u of a plane), and the 16 lanes sharing a class balance each other.  One loop, one call
+// site of the step function: lanes at different stages of different fits share every pass.  A fit that needs more than `cap` passes
+// is parked (state to HBM, slot appended to the trial list) and finished by the round kernels, so no tile waits for a long fit.
+struct tb_fitp_tile {
+    int ts, tsp;               // slots per tile, plane stride in shared memory (ts + 12)
+};
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+    tb_fitp_kernel(tb_fitg_view G, const int32_t *__restrict__ slot_win, tb_fitp_tile T, i64 n_tiles, int m, int cap,
+                   double *__restrict__ fit, u32 *__restrict__ listt, unsigned long long *ctr) {
+    TB_DYN_SMEM(smem);
+    double *sx = (double *)smem;                                // [10][tsp]
+    u32 *sy = (u32 *)(sx + (size_t)10 * T.tsp);                 // [10][tsp]
+    __shared__ u32 qctr[32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned FULL = 0xffffffffu;
+    for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const i64 t0 = tile * T.ts;
+        __syncthreads();                                        // every fit of the previous tile has ended
+        {   // stage the tile: 16-byte loads (t0, tsp and the plane stride in HBM are multiples of 4)
+            const int nx = T.tsp / 2, ny = T.tsp / 4;
+            for (int i = tid; i < 10 * nx; i += NT) {
+                const int v = i / nx, u = i - v * nx;
+                ((double2 *)(sx + (size_t)v * T.tsp))[u] = ((const double2 *)(G.gx + (i64)v * G.qtot + t0))[u];
+            }
+            for (int i = tid; i < 10 * ny; i += NT) {
+                const int v = i / ny, u = i - v * ny;
+                ((uint4 *)(sy + (size_t)v * T.tsp))[u] = ((const uint4 *)(G.gy + (i64)v * G.qtot + t0))[u];
+            }
+            if (tid < 32) qctr[tid] = 0u;
+        }
+        __syncthreads();
+        tb_lmt S;
+        tb_win_stats st{0.0, 0.0, 0.0};
+        int sl = 0, passes = 0, win = -1;
+        bool busy = false, first = false, drained = false;
+        for (;;) {
+            if (!busy && !drained) {                            // take the next slot of this lane's residue class
+                for (;;) {
+                    const u32 k = atomicAdd(&qctr[lane], 1u);
+                    sl = lane + 32 * (int)k;
+                    if (sl >= T.ts) {
+                        drained = true;
+                        break;
+                    }
+                    win = slot_win[t0 + sl];
+                    if (win >= 0) {
+                        busy = true;
+                        first = true;
+                        passes = 0;
+                        break;
+                    }
+                }
+            }
+            if (!__any_sync(FULL, busy)) break;
+            bool parked = false;
+            if (busy) {
+                const tb_win_ref W{sx + sl, sy + sl, (i64)T.tsp};
+                const bool have = tb_lmt_step_fast(S, st, W, m, first);
+                first = false;
+                passes++;
+                double *rec = fit + (i64)win * TB_FIT_REC;
+                if (!have) {                                    // np.zeros (:304)
+                    rec[0] = 2.0;
+                    rec[1] = rec[2] = rec[3] = rec[4] = rec[5] = 0.0;
+                    busy = false;
+                } else if (S.info != 0) {
+                    double mode, pa, pb, pmax;
+                    tb_lmt_finish_stats(S, st, mode, pa, pb, pmax);
+                    rec[0] = mode;
+                    rec[1] = pa;
+                    rec[2] = pb;
+                    rec[3] = pmax;
+                    rec[4] = (double)S.info;
+                    rec[5] = (double)S.nfev;
+                    busy = false;
+                } else if (passes >= cap) {                     // park: the round kernels finish it
+                    tb_fitg_store(G, win, S);
+                    G.wq[win] = (u32)(t0 + sl);
+                    rec[1] = st.xmax;
+                    rec[2] = st.xmin;
+                    rec[3] = st.bmin;
+                    parked = true;
+                    busy = false;
+                }
+            }
+            tb_fitg_append(parked, (u32)win, listt, ctr + 1);
+        }
     }
 }
 
@@ -867,10 +968,26 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     if (lm_exact_order < 2) {
         // round form (default): state in HBM, compacted work lists, one host read-back of two counters per round
         const int qm = (window + 9) / 10;
-        const i64 qs = C.n_windows + (i64)(qm - 1) * n_regions, qtot = 2 * qs, n_slots = 2 * C.n_windows;
+        const i64 qs = C.n_windows + (i64)(qm - 1) * n_regions, n_slots = 2 * C.n_windows;
+        // persistent form (one-pass fits, window = 100): tiles of TS slots in shared memory; the planes are padded so that every tile (and the 12
+        // slots behind it) can be read with aligned 16-byte loads
+        int persistent = (lm_exact_order == 0 && qm == 10) ? (int)tb_opt(ctx, "k3b_persistent", 1) : 0;
+        const int fitp_threads = tb_opt(ctx, "k3b_threads", 512) == 256 ? 256 : 512;      // 512: one block per SM; 256: two, half the tile each
+#ifdef TB_EMU
+        const int fitp_ts_default = 256;                          // the test emulator runs small tiles (same code)
+#else
+        const int fitp_ts_default = fitp_threads == 256 ? 800 : 1600;
+#endif
+        const int fitp_ts = tb_opt(ctx, "k3b_tile", 0) >= 64 ? (int)(tb_opt(ctx, "k3b_tile", 0) & ~31LL) : fitp_ts_default;
+        const i64 n_ptiles = tb_div_up(2 * qs, fitp_ts);
+        const i64 qtot = persistent ? n_ptiles * fitp_ts + 16 : 2 * qs;
         if (10 * qtot >= ((i64)1 << 32)) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: too many windows for one launch");
         TB_TRY(tb_reserve(ctx, C.fitg_x, (size_t)10 * qtot * sizeof(double)));
         TB_TRY(tb_reserve(ctx, C.fitg_y, (size_t)10 * qtot * sizeof(u32)));
+        if (persistent) {
+            TB_TRY(tb_reserve(ctx, C.fitg_sw, (size_t)qtot * sizeof(int32_t)));
+            TB_CUDA(ctx, cudaMemsetAsync(C.fitg_sw.p, 0xff, (size_t)qtot * sizeof(int32_t), ctx->stream));      // -1: no window
+        }
         TB_TRY(tb_reserve(ctx, C.fitg_st, (size_t)TB_FITG_NST * n_slots * sizeof(double)));
         TB_TRY(tb_reserve(ctx, C.fitg_sti, (size_t)n_slots * sizeof(int4)));
         TB_TRY(tb_reserve(ctx, C.fitg_wq, (size_t)n_slots * sizeof(u32)));
@@ -881,9 +998,28 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         tb_fitg_view G{C.fitg_st.as<double>(), C.fitg_sti.as<int4>(), C.fitg_wq.as<u32>(), C.fitg_x.as<double>(),
                        C.fitg_y.as<u32>(), qtot, n_slots};
         TB_LAUNCH(ctx, tb_fitg_transpose_kernel, dim3((unsigned)n_regions, 2), 256, 0, V, (const u32 *)C.pile.as<u32>(),
-                  (const double *)C.biasraw.as<double>(), qs, qtot, qm, C.fitg_x.as<double>(), C.fitg_y.as<u32>());
+                  (const double *)C.biasraw.as<double>(), qs, qtot, qm, C.fitg_x.as<double>(), C.fitg_y.as<u32>(),
+                  persistent ? C.fitg_sw.as<int32_t>() : (int32_t *)nullptr);
         TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
-        {
+        if (persistent) {
+            const tb_fitp_tile T{fitp_ts, fitp_ts + 12};
+            const size_t psmem = (size_t)10 * T.tsp * (sizeof(double) + sizeof(u32));
+            const int cap_passes = tb_opt(ctx, "k3b_cap", 0) > 0 ? (int)tb_opt(ctx, "k3b_cap", 0) : 8;
+            if (psmem > (size_t)226 * 1024) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: k3b_tile too large for the shared memory");
+            if (fitp_threads == 256) {
+                auto kp = tb_fitp_kernel<256, 2>;
+                TB_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                const i64 capg = (i64)ctx->sm_count * (psmem > (size_t)112 * 1024 ? 1 : 2);
+                TB_LAUNCH(ctx, kp, (unsigned)(n_ptiles < capg ? n_ptiles : capg), 256, psmem, G, (const int32_t *)C.fitg_sw.as<int32_t>(), T,
+                          n_ptiles, window, cap_passes, C.fit.as<double>(), lt[0], ctr);
+            } else {
+                auto kp = tb_fitp_kernel<512, 1>;
+                TB_CUDA(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                const i64 capg = (i64)ctx->sm_count * (psmem > (size_t)112 * 1024 ? 1 : 2);
+                TB_LAUNCH(ctx, kp, (unsigned)(n_ptiles < capg ? n_ptiles : capg), 512, psmem, G, (const int32_t *)C.fitg_sw.as<int32_t>(), T,
+                          n_ptiles, window, cap_passes, C.fit.as<double>(), lt[0], ctr);
+            }
+        } else {
             i64 want = tb_div_up(n_slots, 128), capg = (i64)ctx->sm_count * 16;
             if (lm_exact_order) {
                 TB_LAUNCH(ctx, tb_fitg_init_kernel<false>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lq[0], ctr);

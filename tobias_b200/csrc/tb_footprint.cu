@@ -624,7 +624,9 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
         int wstride2 = 0;
         if (!fos && npw <= TB_K4_NPW && tb_opt(ctx, "k4_one_start", 0) == 0) {
             double best_cost = -1.0;
+            const int forced = (int)tb_opt(ctx, "k4_threads", 0);                                // comparison runs: threads per block of the second form
             for (int cand = 64; cand <= TB_K4B_MAXT; cand += 32) {
+                if (forced >= 64 && cand != (forced & ~31)) continue;
                 const i64 per = 2 * cand - (p->fp_max - 1);
                 if (per < 32) continue;
                 const int n_in = 2 * cand + 2 * p->flank_max + p->fp_max;

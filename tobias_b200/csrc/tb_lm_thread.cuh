@@ -710,6 +710,128 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
     return accepted;
 }
 
+// ---- one-pass form as ONE step function (persistent kernel, tb_correct.cu) -------------------------------------------------------
+// A step = [where to evaluate] -> ONE pass over the window -> [what the pass means].  first: the start of a fit -- the pass runs at
+// p0 = (1, 1), also takes the window statistics, and is followed by tb_lmt_init + the first outer-iteration head (= tb_lmt_start_fast).
+// Otherwise: lmpar step -> pass at the trial point (residual norm + inner products of the Jacobian there) -> trust-region update, and
+// the head of the next outer iteration when the step was accepted (= tb_lmt_trial<true, true>).  Lanes of a warp that are at different
+// stages of different fits share the pass -- the expensive part -- and diverge only in the scalar algebra around it.
+// Same arithmetic in the same order as the two functions it unites: bit-identical fits.  Returns false for a window without signal.
+__device__ __forceinline__ bool tb_lmt_step_fast(tb_lmt &S, tb_win_stats &st, const tb_win_ref W, int m, bool first) {
+    const double epsmch = 2.220446049250313e-16;
+    const double ftol = 1.49012e-8, xtol = 1.49012e-8;
+    const double p1 = 0.1, p5 = 0.5, p25 = 0.25, p75 = 0.75, p0001 = 1e-4;
+    const int maxfev = 600;
+    double wa1[2] = {0.0, 0.0}, wa2[2] = {1.0, 1.0}, pnorm = 0.0;
+    int ipvt[2] = {0, 1};
+    if (!first) {
+        double r[2][2] = {{S.r00, S.r01}, {0.0, S.r11}};
+        ipvt[0] = S.ipvt0;
+        ipvt[1] = 1 - S.ipvt0;
+        const double diag[2] = {S.diag0, S.diag1};
+        const double qtf[2] = {S.qtf0, S.qtf1};
+        double wa3[2];
+        tb_lmpar2(r, ipvt, diag, qtf, S.delta, S.lmp, wa1, wa2);
+        const double par[2] = {S.par0, S.par1};
+        for (int j = 0; j < 2; j++) {
+            wa1[j] = -wa1[j];
+            wa2[j] = par[j] + wa1[j];
+            wa3[j] = diag[j] * wa1[j];
+        }
+        pnorm = tb_enorm2(wa3[0], wa3[1]);
+        if (S.iter == 1) S.delta = fmin(S.delta, pnorm);
+    }
+    // ---- the pass
+    const tb_jac_fast J = tb_jac_fast_at(wa2[0], wa2[1]);
+    tb_gram Gm;
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
+    u32 ymax = 0;
+    double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
+    double ss = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
+    TB_FOR_POINTS_ANY_ORDER(W, m, {
+        if (first) {
+            ymax = eyi > ymax ? eyi : ymax;
+            xmax = fmax(xmax, ex);
+            xmin = fmin(xmin, ex);
+            if (eyi != 0u) bmin = fmin(bmin, ex);               // ~isclose(signal, 0)
+        }
+        double f, j0, j1;
+        J.eval(ex, ey, f, j0, j1);
+        ss += f * f;
+        g00 += j0 * j0;
+        g01 += j0 * j1;
+        g11 += j1 * j1;
+        gf0 += j0 * f;
+        gf1 += j1 * f;
+    })
+    Gm.g00 = g00; Gm.g01 = g01; Gm.g11 = g11; Gm.gf0 = gf0; Gm.gf1 = gf1;
+    const double fnorm1 = sqrt(ss);
+    if (first) {
+        st.xmax = xmax;
+        st.xmin = xmin;
+        st.bmin = bmin;
+        if (ymax == 0u) return false;
+        tb_lmt_init(S, fnorm1);
+        tb_lmt_qr_from_gram(S, W, m, J, Gm);
+        return true;
+    }
+    // ---- what the trial means (lmdif inner loop)
+    S.nfev++;
+    double actred = -1.0;
+    if (p1 * fnorm1 < S.fnorm) {
+        double t = fnorm1 / S.fnorm;
+        actred = 1.0 - t * t;
+    }
+    double wa3[2];
+    {
+        const double r[2][2] = {{S.r00, S.r01}, {0.0, S.r11}};
+        for (int j = 0; j < 2; j++) {
+            wa3[j] = 0.0;
+            double temp = wa1[ipvt[j]];
+            for (int i = 0; i <= j; i++) wa3[i] += r[i][j] * temp;
+        }
+    }
+    double temp1 = tb_enorm2(wa3[0], wa3[1]) / S.fnorm;
+    double temp2 = sqrt(S.lmp) * pnorm / S.fnorm;
+    double prered = temp1 * temp1 + temp2 * temp2 / p5;
+    double dirder = -(temp1 * temp1 + temp2 * temp2);
+    double ratio = 0.0;
+    if (prered != 0.0) ratio = actred / prered;
+    if (ratio <= p25) {
+        double temp;
+        if (actred >= 0.0) temp = p5;
+        else temp = p5 * dirder / (dirder + p5 * actred);
+        if (p1 * fnorm1 >= S.fnorm || temp < p1) temp = p1;
+        S.delta = temp * fmin(S.delta, pnorm / p1);
+        S.lmp /= temp;
+    } else if (S.lmp == 0.0 || ratio >= p75) {
+        S.delta = pnorm / p5;
+        S.lmp = p5 * S.lmp;
+    }
+    const bool accepted = ratio >= p0001;
+    if (accepted) {
+        S.par0 = wa2[0];
+        S.par1 = wa2[1];
+        S.xnorm = tb_enorm2(S.diag0 * S.par0, S.diag1 * S.par1);
+        S.fnorm = fnorm1;
+        S.iter++;
+    }
+    int info = 0;
+    if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0) info = 1;
+    if (S.delta <= xtol * S.xnorm) info = 2;
+    if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0 && info == 2) info = 3;
+    if (info == 0) {
+        if (S.nfev >= maxfev) info = 5;
+        if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
+        if (S.delta <= epsmch * S.xnorm) info = 7;
+        if (S.gnorm <= epsmch) info = 8;
+    }
+    S.info = info;
+    if (accepted && info == 0) tb_lmt_qr_from_gram(S, W, m, J, Gm);      // head of the next outer iteration (may set S.info)
+    return true;
+}
+
 // scipy's post-conditions (ier in {1,2,3,4}; inv(R) exists and the covariance holds no NaN) and the window record:
 // mode 0: usable fit (a, b), mode 1: the reference's fallback (atacorrect_functions.py:296-299); pmax = max(prediction).
 // The prediction max(0, a*x + b) is monotonic in x (rounding is monotonic), so its maximum sits at max(x) or min(x).
