@@ -82,6 +82,10 @@ int tb_genome_upload(tb_ctx *ctx, int contig, int64_t offset, const uint8_t *asc
  * the device for the contigs it needs, so tb_count_reads / tb_bias_counts on the first contigs overlap with the transfer of the rest */
 int tb_genome_upload_async(tb_ctx *ctx, int contig, int64_t offset, const uint8_t *ascii, int64_t n);
 /* blocks the host until every asynchronous upload has completed */
+/* A contig that is already in the device layout (seq2: (n + 15) / 16 words, base k in bits 2 * (k & 15) of word k >> 4, A0 T1 C2 G3; nmask:
+ * (n + 31) / 32 words, bit (k & 31) of word k >> 5 set for N; bits past the end set).  0.375 bytes per base cross the link instead of 1.
+ * Host packer: tobias_b200/io/hostpack.c (cached next to the FASTA as <fasta>.tb2bit).  async = 1: like tb_genome_upload_async. */
+int tb_genome_upload_packed(tb_ctx *ctx, int contig, const uint32_t *seq2, const uint32_t *nmask, int64_t n_bases, int async);
 int tb_genome_wait(tb_ctx *ctx);
 /* debugging / tests: nucleotide codes (0..4) of contig[start, start+n) */
 int tb_genome_fetch(tb_ctx *ctx, int contig, int64_t start, int64_t n, uint8_t *codes_out);

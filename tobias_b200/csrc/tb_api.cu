@@ -386,6 +386,37 @@ extern "C" int tb_genome_upload_async(tb_ctx *ctx, int contig, int64_t offset, c
 }
 
 // Host-side completion of every asynchronous upload (the host buffers may be reused afterwards).
+// A contig already in the device layout (host packer: tobias_b200/io/hostpack.c): two plain copies straight into place -- contig offsets
+// are multiples of 256 bases, so word boundaries agree.  async != 0: on the copy stream, like tb_genome_upload_async.
+extern "C" int tb_genome_upload_packed(tb_ctx *ctx, int contig, const uint32_t *seq2, const uint32_t *nmask, int64_t n_bases, int async) {
+    if (!ctx || !seq2 || !nmask) return TB_ERR_ARG;
+    if (ctx->n_contigs == 0) return tb_fail(ctx, TB_ERR_STATE, "tb_genome_upload_packed: call tb_genome_create first");
+    if (contig < 0 || contig >= ctx->n_contigs) return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload_packed: contig %d out of range", contig);
+    if (n_bases != ctx->contig_len[contig])
+        return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload_packed: contig %d has %lld bases, got %lld", contig, (i64)ctx->contig_len[contig], (i64)n_bases);
+    const i64 base = ctx->contig_off[contig];
+    u32 *d_seq = ctx->seq2.as<u32>() + (base >> 4), *d_mask = ctx->nmask.as<u32>() + (base >> 5);
+    const size_t b_seq = (size_t)((n_bases + 15) / 16) * sizeof(u32), b_mask = (size_t)((n_bases + 31) / 32) * sizeof(u32);
+    if (!async) {
+        TB_TRY(tb_genome_fence(ctx, contig, contig));
+        TB_CUDA(ctx, cudaMemcpyAsync(d_seq, seq2, b_seq, cudaMemcpyHostToDevice, ctx->stream));
+        TB_CUDA(ctx, cudaMemcpyAsync(d_mask, nmask, b_mask, cudaMemcpyHostToDevice, ctx->stream));
+        return tb_sync(ctx, "tb_genome_upload_packed");
+    }
+    if ((int)ctx->contig_ready.size() < ctx->n_contigs) {
+        size_t have = ctx->contig_ready.size();
+        ctx->contig_ready.resize(ctx->n_contigs, nullptr);
+        for (size_t c = have; c < ctx->contig_ready.size(); c++)
+            TB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->contig_ready[c], cudaEventDisableTiming));
+    }
+    ctx->contig_pending.resize(ctx->n_contigs, 0);
+    TB_CUDA(ctx, cudaMemcpyAsync(d_seq, seq2, b_seq, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(d_mask, nmask, b_mask, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TB_CUDA(ctx, cudaEventRecord(ctx->contig_ready[contig], ctx->copy_stream));
+    ctx->contig_pending[contig] = 1;
+    return tb_check(ctx, cudaGetLastError(), "tb_genome_upload_packed");
+}
+
 extern "C" int tb_genome_wait(tb_ctx *ctx) {
     if (!ctx) return TB_ERR_ARG;
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));

@@ -6,10 +6,116 @@ contig names + lengths (tobias/tools/atacorrect.py:143-146) and `fetch(chrom, st
 (tobias/utils/sequences.pyx:388).  Contigs are returned as uint8 ASCII arrays so that they can be
 handed to the C-ABI (`tb_genome_upload`) without a Python-level per-base loop.
 """
+import ctypes
 import mmap
 import os
+import subprocess
 
 import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PACK = None
+
+
+def _packer():
+    """Native helper (hostpack.c, compiled with gcc on first use): ASCII bases -> 2-bit words + N mask."""
+    global _PACK
+    if _PACK is None:
+        so, src = os.path.join(_HERE, "_hostpack.so"), os.path.join(_HERE, "hostpack.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-o", so, src])
+        _PACK = ctypes.CDLL(so)
+    return _PACK
+
+
+def pack_ascii(ascii_arr, seq2=None, nmask=None):
+    """(seq2 uint32[(n + 15) // 16], nmask uint32[(n + 31) // 32]) of an ASCII base array: the device genome layout
+    (include/tobias_b200.h, tb_genome_upload_packed).  Optional preallocated (e.g. pinned) outputs."""
+    a = np.ascontiguousarray(ascii_arr, dtype=np.uint8)
+    n = int(a.shape[0])
+    seq2 = np.empty((n + 15) // 16, dtype=np.uint32) if seq2 is None else seq2
+    nmask = np.empty((n + 31) // 32, dtype=np.uint32) if nmask is None else nmask
+    assert seq2.dtype == np.uint32 and nmask.dtype == np.uint32 and seq2.size >= (n + 15) // 16 and nmask.size >= (n + 31) // 32
+    vp = ctypes.c_void_p
+    _packer().tb_pack_ascii(a.ctypes.data_as(vp), ctypes.c_int64(n), seq2.ctypes.data_as(vp), nmask.ctypes.data_as(vp))
+    return seq2, nmask
+
+
+def unpack_codes(seq2, nmask, n):
+    out = np.empty(int(n), dtype=np.uint8)
+    vp = ctypes.c_void_p
+    _packer().tb_unpack_codes(np.ascontiguousarray(seq2).ctypes.data_as(vp), np.ascontiguousarray(nmask).ctypes.data_as(vp),
+                              ctypes.c_int64(int(n)), out.ctypes.data_as(vp))
+    return out
+
+
+class PackedGenome:
+    """The contigs of a FASTA file in the device layout, cached next to it as `<fasta>.tb2bit` (like a .fai: built on first use, reused
+    while it is newer than the FASTA).  File: magic, contig count, per contig (name length, name, n_bases), then the word arrays."""
+    MAGIC = b"TB2BIT01"
+
+    def __init__(self, names, lengths, seq2, nmask):
+        self.references, self.lengths, self.seq2, self.nmask = list(names), [int(x) for x in lengths], seq2, nmask
+
+    @staticmethod
+    def from_fasta(fasta, names=None, cache=True):
+        path = fasta.filename + ".tb2bit"
+        if cache and os.path.exists(path) and os.path.getmtime(path) >= os.path.getmtime(fasta.filename):
+            pg = PackedGenome.load(path)
+            if names is None or all(n in pg.references for n in names):
+                return pg if names is None else pg.subset(names)
+        allnames = list(fasta.references)
+        seq2, nmask = [], []
+        for n in allnames:
+            a, b = pack_ascii(fasta.fetch_array(n))
+            seq2.append(a)
+            nmask.append(b)
+        pg = PackedGenome(allnames, [fasta.get_reference_length(n) for n in allnames], seq2, nmask)
+        if cache:
+            try:
+                pg.save(path)
+            except OSError:
+                pass                      # read-only genome directory: pack again next time
+        return pg if names is None else pg.subset(names)
+
+    def subset(self, names):
+        idx = [self.references.index(n) for n in names]
+        return PackedGenome([self.references[i] for i in idx], [self.lengths[i] for i in idx], [self.seq2[i] for i in idx],
+                            [self.nmask[i] for i in idx])
+
+    def save(self, path):
+        tmp = path + ".tmp%d" % os.getpid()
+        with open(tmp, "wb") as fh:
+            fh.write(self.MAGIC + np.int64(len(self.references)).tobytes())
+            for n, ln in zip(self.references, self.lengths):
+                b = n.encode()
+                fh.write(np.int64(len(b)).tobytes() + b + np.int64(ln).tobytes())
+            for a, b in zip(self.seq2, self.nmask):
+                fh.write(a.tobytes())
+                fh.write(b.tobytes())
+        os.replace(tmp, path)
+
+    @staticmethod
+    def load(path):
+        buf = np.memmap(path, dtype=np.uint8, mode="r")
+        if bytes(buf[:8]) != PackedGenome.MAGIC:
+            raise ValueError("%s is not a tobias_b200 packed genome" % path)
+        off = 8
+        n = int(np.frombuffer(buf[off:off + 8], dtype=np.int64)[0])
+        off += 8
+        names, lengths = [], []
+        for _ in range(n):
+            ln = int(np.frombuffer(buf[off:off + 8], dtype=np.int64)[0])
+            names.append(bytes(buf[off + 8:off + 8 + ln]).decode())
+            lengths.append(int(np.frombuffer(buf[off + 8 + ln:off + 16 + ln], dtype=np.int64)[0]))
+            off += 16 + ln
+        seq2, nmask = [], []
+        for ln in lengths:
+            a, b = 4 * ((ln + 15) // 16), 4 * ((ln + 31) // 32)
+            seq2.append(np.frombuffer(buf[off:off + a], dtype=np.uint32))
+            nmask.append(np.frombuffer(buf[off + a:off + a + b], dtype=np.uint32))
+            off += a + b
+        return PackedGenome(names, lengths, seq2, nmask)
 
 
 class FastaFile:

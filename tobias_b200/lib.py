@@ -48,6 +48,7 @@ _PROTOS = {
     "tb_genome_create": (_i, [_vp, _i, _vp]),
     "tb_genome_upload": (_i, [_vp, _i, _i64, _vp, _i64]),
     "tb_genome_upload_async": (_i, [_vp, _i, _i64, _vp, _i64]),
+    "tb_genome_upload_packed": (_i, [_vp, _i, _vp, _vp, _i64, _i]),
     "tb_genome_wait": (_i, [_vp]),
     "tb_genome_fetch": (_i, [_vp, _i, _i64, _i64, _vp]),
     "tb_reads_upload": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -211,6 +212,15 @@ class Context:
         self._pending_uploads = getattr(self, "_pending_uploads", [])
         self._pending_uploads.append(a)
         self._ck(self._lib.tb_genome_upload_async(self._h, int(contig), int(offset), _ptr(a), int(a.shape[0])))
+
+    def genome_upload_packed(self, contig, seq2, nmask, n_bases, wait=True):
+        """A contig in the device layout (tobias_b200.io.fasta.pack_ascii / PackedGenome).  wait=False: enqueued on the copy stream; the
+        arrays (ideally pinned) must stay alive and untouched until genome_wait()."""
+        a, b = _arr(seq2, np.uint32), _arr(nmask, np.uint32)
+        if not wait:
+            self._pending_uploads = getattr(self, "_pending_uploads", [])
+            self._pending_uploads += [a, b]
+        self._ck(self._lib.tb_genome_upload_packed(self._h, int(contig), _ptr(a), _ptr(b), int(n_bases), int(not wait)))
 
     def genome_wait(self):
         self._ck(self._lib.tb_genome_wait(self._h))
