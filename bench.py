@@ -156,8 +156,12 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
         ctx.reads_upload(*host["reads"])
         mark("reads_h2d")
         # the genome streams in on the copy stream while the read counts and the first contigs' training counts run
-        for i, g in enumerate(host["genome"]):
-            ctx.genome_upload_async(i, g)
+        if host["packed"] is not None:
+            for i, (sq, nm) in enumerate(host["packed"]):
+                ctx.genome_upload_packed(i, sq, nm, host["lengths"][i], wait=False)
+        else:
+            for i, g in enumerate(host["genome"]):
+                ctx.genome_upload_async(i, g)
         if trace:
             marks.append(("genome_h2d enqueued (no sync)", time.perf_counter()))
     # --- normalisation counters + bias-training counts, then the one exchange step of the path
@@ -291,11 +295,21 @@ def bench_b200(args):
         p = ctx.pinned_empty(a.shape, a.dtype)
         p[...] = a
         cols.append(p)
-    host = {"lengths": ds.lengths, "genome": ds.genome, "reads": cols}
+    # the genome waits on the host in the device layout (2 bit + N mask, what tobias_b200.io.fasta.PackedGenome caches next to a FASTA):
+    # 0.375 bytes per base cross the link every step instead of 1 (--ascii-genome: the ASCII contigs, packed on the device)
+    packed = None
+    if not args.ascii_genome:
+        from tobias_b200.io.fasta import pack_ascii
+        packed = []
+        for g in ds.genome:
+            n = int(g.shape[0])
+            packed.append(pack_ascii(g, ctx.pinned_empty(((n + 15) // 16,), np.uint32), ctx.pinned_empty(((n + 31) // 32,), np.uint32)))
+    host = {"lengths": ds.lengths, "genome": ds.genome, "reads": cols, "packed": packed}
     c, s, e = arrays["output_regions"]
     out_bp = int((e - s).sum())
     out = {"tracks": {t: ctx.pinned_empty((out_bp,), np.float32) for t in lib.TRACKS}, "footprint": ctx.pinned_empty((out_bp,), np.float32)}
-    h2d = sum(int(g.nbytes) for g in ds.genome) + sum(int(a.nbytes) for a in cols) + sum(int(x.nbytes) for v in arrays.values() for x in v)
+    genome_bytes = sum(int(g.nbytes) for g in ds.genome) if packed is None else sum(int(a.nbytes) + int(b.nbytes) for a, b in packed)
+    h2d = genome_bytes + sum(int(a.nbytes) for a in cols) + sum(int(x.nbytes) for v in arrays.values() for x in v)
     d2h = 5 * out_bp * 4 + 2 * 3 * 5 * 25 * 8
     setup_s = time.time() - t_setup
 
@@ -372,6 +386,7 @@ def bench_b200(args):
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": dict(bench_config(wl, world), out_bp_total=int(total_out_bp), extended_bp_total=int(total_ext_bp), reads_this_rank=int(len(rc)),
+                       genome_host_format="ascii" if args.ascii_genome else "2 bit + N mask (packed once on the host, as the .tb2bit cache of a FASTA)",
                        **({"options": args.opt} if args.opt else {})),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "bp/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -826,6 +841,7 @@ def main():
     ap.add_argument("--lm-exact", action="store_true")
     ap.add_argument("--fit-stats", action="store_true")
     ap.add_argument("--lm-mode", type=int, default=None, help="2 / 3: first-generation warp-per-window fit kernels (comparison runs)")
+    ap.add_argument("--ascii-genome", action="store_true", help="e2e: upload the genome as ASCII (packed on the device) instead of the host-packed 2-bit form")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="tb_set_option switch for comparison runs (recorded in config)")
     args = ap.parse_args()
     global LM_EXACT

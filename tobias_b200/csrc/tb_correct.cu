@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(TB_FIT_WARPS * 32, TB_FIT_MINBLOCKS) tb_fit_ke
 // the 32 lanes of every warp always execute the same phase on live windows; nothing waits for a neighbour's longer
 // fit.  The window data are read through L1 from a transposed copy (plane v = position mod 10, slot q = window index
 // + 9 per preceding region), in which the lanes of a warp (consecutive windows) read consecutive addresses.
-#define TB_FITG_NST 16
+#define TB_FITG_NST 17
 
 struct tb_fitg_view {
     double *st;             // [TB_FITG_NST][n_slots] fit state, structure of arrays
@@ -144,7 +144,7 @@ __device__ __forceinline__ void tb_fitg_load(const tb_fitg_view &G, i64 slot, tb
     const i64 n = G.n_slots;
     S.par0 = p[0 * n]; S.par1 = p[1 * n]; S.fnorm = p[2 * n]; S.diag0 = p[3 * n]; S.diag1 = p[4 * n]; S.delta = p[5 * n];
     S.lmp = p[6 * n]; S.xnorm = p[7 * n]; S.gnorm = p[8 * n]; S.r00 = p[9 * n]; S.r01 = p[10 * n]; S.r11 = p[11 * n];
-    S.qtf0 = p[12 * n]; S.qtf1 = p[13 * n]; S.acn0 = p[14 * n]; S.acn1 = p[15 * n];
+    S.qtf0 = p[12 * n]; S.qtf1 = p[13 * n]; S.acn0 = p[14 * n]; S.acn1 = p[15 * n]; S.tyy = p[16 * n];
     int4 v = G.sti[slot];
     S.ipvt0 = v.x; S.iter = v.y; S.nfev = v.z; S.info = v.w;
 }
@@ -153,7 +153,7 @@ __device__ __forceinline__ void tb_fitg_store(const tb_fitg_view &G, i64 slot, c
     const i64 n = G.n_slots;
     p[0 * n] = S.par0; p[1 * n] = S.par1; p[2 * n] = S.fnorm; p[3 * n] = S.diag0; p[4 * n] = S.diag1; p[5 * n] = S.delta;
     p[6 * n] = S.lmp; p[7 * n] = S.xnorm; p[8 * n] = S.gnorm; p[9 * n] = S.r00; p[10 * n] = S.r01; p[11 * n] = S.r11;
-    p[12 * n] = S.qtf0; p[13 * n] = S.qtf1; p[14 * n] = S.acn0; p[15 * n] = S.acn1;
+    p[12 * n] = S.qtf0; p[13 * n] = S.qtf1; p[14 * n] = S.acn0; p[15 * n] = S.acn1; p[16 * n] = S.tyy;
     G.sti[slot] = int4{S.ipvt0, S.iter, S.nfev, S.info};
 }
 // warp-aggregated append of `slot` to list[ctr] for the lanes with `want`; every lane of the warp must call it
@@ -189,8 +189,9 @@ __global__ void tb_fitg_transpose_kernel(tb_cor_view V, const u32 *__restrict__ 
 }
 
 // per window: tile slot, residual norm at p0, empty-window record, initial state, first Q list
-// FAST_HEAD (one-pass form): the same pass also runs the first outer-iteration head, the window goes to the trial-only list
-template <bool FAST_HEAD>
+// FAST_HEAD (one-pass forms; 1: forward-difference inner products, 2: moments of the active set): the same pass also runs the first
+// outer-iteration head, the window goes to the trial-only list
+template <int FAST_HEAD>
 __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int qm, double *__restrict__ fit, u32 *__restrict__ listq,
                                     unsigned long long *ctr) {
     const i64 n_round = ((G.n_slots + 31) / 32) * 32;
@@ -206,7 +207,8 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
             tb_win_stats st;
             tb_lmt S;
             const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
-            const double f0 = FAST_HEAD ? tb_lmt_start_fast(S, W, V.window, st) : tb_lmt_fnorm0_stats(W, V.window, st);
+            const double f0 = FAST_HEAD == 2 ? tb_lmt_start_moments(S, W, V.window, st)
+                                             : (FAST_HEAD == 1 ? tb_lmt_start_fast(S, W, V.window, st) : tb_lmt_fnorm0_stats(W, V.window, st));
             if (f0 >= 0.0) {                                           // signalmax > 0 (:290)
                 if (!FAST_HEAD) tb_lmt_init(S, f0);
                 tb_fitg_store(G, slot, S);
@@ -236,7 +238,8 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
 #define TB_FITG_FUSE 1      // 0: separate Jacobian and trial passes in the one-pass form (comparison builds)
 #endif
 // One-pass form: five blocks per SM (96 registers) measured 58.2 ms on hg38 against 59.8 with four (128) and 59.5 with six (80).
-template <bool WITH_QR, bool FAST>
+// FAST: 0 MINPACK-exact arithmetic, 1 one-pass form with forward-difference inner products, 2 one-pass form with the moments of the active set
+template <bool WITH_QR, int FAST>
 __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MINBLOCKS)
     tb_fitg_round_kernel(tb_fitg_view G, int m, const u32 *__restrict__ list, i64 n_list, double *__restrict__ fit,
                          u32 *__restrict__ nextq, u32 *__restrict__ nextt, unsigned long long *ctr) {
@@ -269,12 +272,13 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
             }
 #endif
             if (WITH_QR) {
-                if (FAST) tb_lmt_qr_fast(S, W, m);
+                if (FAST == 2) tb_lmt_qr_moments(S, W, m);
+                else if (FAST == 1) tb_lmt_qr_fast(S, W, m);
                 else tb_lmt_qr(S, W, m);
             }
-            // one-pass form: fused trial + next head, so every surviving window continues on the trial-only list
+            // one-pass forms: fused trial + next head, so every surviving window continues on the trial-only list
             bool accepted = false;
-            if (S.info == 0) accepted = tb_lmt_trial<FAST, FAST && TB_FITG_FUSE>(S, W, m);
+            if (S.info == 0) accepted = tb_lmt_trial<FAST != 0, FAST && TB_FITG_FUSE, FAST == 2>(S, W, m);
             if (S.info != 0) {
                 double mode, pa, pb, pmax;
                 double *rec = fit + (i64)slot * TB_FIT_REC;
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
                 rec[5] = (double)S.nfev;
             } else {
                 tb_fitg_store(G, slot, S);
-                to_q = accepted && !(FAST && TB_FITG_FUSE);
+                to_q = accepted && !(FAST == 2 || (FAST && TB_FITG_FUSE));
                 to_t = !to_q;
             }
         }
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
 // Tail of the rounds: once few windows are left a round costs the latency of one thread's iteration plus a launch and a host
 // read-back, whatever the count.  The remaining windows are then finished in ONE launch, every thread iterating its window to the end
 // (lanes diverge, but the GPU is almost idle at that point anyway).
-template <bool FAST>
+template <int FAST>
 __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
     tb_fitg_finish_kernel(tb_fitg_view G, int m, const u32 *__restrict__ listq, i64 nq, const u32 *__restrict__ listt, i64 nt,
                           double *__restrict__ fit) {
@@ -314,10 +318,14 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
         const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
         for (;;) {
             if (need_qr) {
-                if (FAST) tb_lmt_qr_fast(S, W, m);
+                if (FAST == 2) tb_lmt_qr_moments(S, W, m);
+                else if (FAST == 1) tb_lmt_qr_fast(S, W, m);
                 else tb_lmt_qr(S, W, m);
             }
-            if (S.info == 0) need_qr = tb_lmt_trial<FAST>(S, W, m);
+            if (S.info == 0) {
+                const bool accepted = tb_lmt_trial<FAST != 0, false, FAST == 2>(S, W, m);
+                need_qr = accepted && FAST != 2;          // moment form: the next head ran inside the trial
+            }
             if (S.info != 0) break;
         }
         double mode, pa, pb, pmax;
@@ -965,13 +973,17 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     tr("K1 + K3a enqueued");
     tb_cor_view V{C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), C.d_out_off.as<i64>(), C.d_win_off.as<i64>(),
                   n_regions, C.ext_total, C.out_total, C.n_windows, k_flank, window, L, f_extend};
-    if (lm_exact_order < 2) {
+    // window fits: lm_exact_order 0 -> moment form of the one-pass fits (fit_form 2), 4 -> one-pass fits with forward-difference inner
+    // products (fit_form 1: the first one-pass form, comparison runs), 1 -> MINPACK-exact (fit_form 0); 2 / 3: first-generation warp kernels
+    const int fit_form = lm_exact_order == 0 ? 2 : (lm_exact_order == 4 ? 1 : 0);
+    if (lm_exact_order < 2 || lm_exact_order == 4) {
         // round form (default): state in HBM, compacted work lists, one host read-back of two counters per round
         const int qm = (window + 9) / 10;
         const i64 qs = C.n_windows + (i64)(qm - 1) * n_regions, n_slots = 2 * C.n_windows;
         // persistent form (one-pass fits, window = 100): tiles of TS slots in shared memory; the planes are padded so that every tile (and the 12
         // slots behind it) can be read with aligned 16-byte loads
-        int persistent = (lm_exact_order == 0 && qm == 10) ? (int)tb_opt(ctx, "k3b_persistent", 1) : 0;
+        // (persistent form: forward-difference one-pass fits only; measured slower than the rounds on hg38 -- 75.6 vs 53.6 ms -- and off by default)
+        int persistent = (fit_form == 1 && qm == 10) ? (int)tb_opt(ctx, "k3b_persistent", 0) : 0;
         const int fitp_threads = tb_opt(ctx, "k3b_threads", 512) == 256 ? 256 : 512;      // 512: one block per SM; 256: two, half the tile each
 #ifdef TB_EMU
         const int fitp_ts_default = 256;                          // the test emulator runs small tiles (same code)
@@ -1021,10 +1033,12 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
             }
         } else {
             i64 want = tb_div_up(n_slots, 128), capg = (i64)ctx->sm_count * 16;
-            if (lm_exact_order) {
-                TB_LAUNCH(ctx, tb_fitg_init_kernel<false>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lq[0], ctr);
-            } else {      // one-pass form: the first head ran in the init pass, every window starts on the trial-only list
-                TB_LAUNCH(ctx, tb_fitg_init_kernel<true>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lt[0], ctr + 1);
+            if (fit_form == 0) {
+                TB_LAUNCH(ctx, tb_fitg_init_kernel<0>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lq[0], ctr);
+            } else if (fit_form == 1) {      // one-pass forms: the first head ran in the init pass, every window starts on the trial-only list
+                TB_LAUNCH(ctx, tb_fitg_init_kernel<1>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lt[0], ctr + 1);
+            } else {
+                TB_LAUNCH(ctx, tb_fitg_init_kernel<2>, (unsigned)(want < capg ? want : capg), 128, 0, V, G, qs, qm, C.fit.as<double>(), lt[0], ctr + 1);
             }
         }
         unsigned long long hc[2] = {0, 0};
@@ -1034,10 +1048,10 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         const i64 tail_at = (i64)ctx->sm_count * 128;      // one block per SM's worth of windows: finish them in one launch
         for (int round = 0; nq + nt > 0; round++) {
             if (round > 700) return tb_fail(ctx, TB_ERR_STATE, "tb_correct_run: window fits did not terminate");
-            const i64 capg = (i64)ctx->sm_count * (lm_exact_order ? TB_FITG_MINBLOCKS : TB_FITG_MINBLOCKS + 1);      // resident blocks (launch bounds of the round kernels)
+            const i64 capg = (i64)ctx->sm_count * (fit_form == 0 ? TB_FITG_MINBLOCKS : TB_FITG_MINBLOCKS + 1);      // resident blocks (launch bounds of the round kernels)
             if (nq + nt <= tail_at) {
                 i64 want = tb_div_up(nq + nt, 128);
-                auto kf = lm_exact_order ? tb_fitg_finish_kernel<false> : tb_fitg_finish_kernel<true>;
+                auto kf = fit_form == 0 ? tb_fitg_finish_kernel<0> : (fit_form == 1 ? tb_fitg_finish_kernel<1> : tb_fitg_finish_kernel<2>);
                 TB_LAUNCH(ctx, kf, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lq[cur], nq, (const u32 *)lt[cur], nt,
                           C.fit.as<double>());
                 break;
@@ -1045,13 +1059,13 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
             TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
             if (nq > 0) {
                 i64 want = tb_div_up(nq, 128);
-                auto kq = lm_exact_order ? tb_fitg_round_kernel<true, false> : tb_fitg_round_kernel<true, true>;
+                auto kq = fit_form == 0 ? tb_fitg_round_kernel<true, 0> : (fit_form == 1 ? tb_fitg_round_kernel<true, 1> : tb_fitg_round_kernel<true, 2>);
                 TB_LAUNCH(ctx, kq, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lq[cur], nq, C.fit.as<double>(),
                           lq[cur ^ 1], lt[cur ^ 1], ctr);
             }
             if (nt > 0) {
                 i64 want = tb_div_up(nt, 128);
-                auto kt = lm_exact_order ? tb_fitg_round_kernel<false, false> : tb_fitg_round_kernel<false, true>;
+                auto kt = fit_form == 0 ? tb_fitg_round_kernel<false, 0> : (fit_form == 1 ? tb_fitg_round_kernel<false, 1> : tb_fitg_round_kernel<false, 2>);
                 TB_LAUNCH(ctx, kt, (unsigned)(want < capg ? want : capg), 128, 0, G, window, (const u32 *)lt[cur], nt, C.fit.as<double>(),
                           lq[cur ^ 1], lt[cur ^ 1], ctr);
             }
@@ -1086,7 +1100,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_TRY(tb_genome_fence(ctx, 0, ctx->n_contigs - 1));
         tb_genome_view g{ctx->seq2.as<u32>(), ctx->nmask.as<u32>(), ctx->genome_bases};
         // the O(1) rolling sums need every row of the 10-row mean to count everywhere (k_flank >= window / 10: no NaN in the bias prediction)
-        int fast = (lm_exact_order == 0 && k_flank >= window / TB_STEP) ? 2 : 0;
+        int fast = (fit_form != 0 && k_flank >= window / TB_STEP) ? 2 : 0;
         if (fast) fast = (int)tb_opt(ctx, "k3c_fast", fast);      // comparison runs: 0 literal, 1 literal bias-prediction sum only
         const tb_k3c_layout Y = tb_k3c_make_layout(tile_len, window, L, fast != 0);
         const size_t smem = (size_t)Y.total;

@@ -179,6 +179,7 @@ __device__ __forceinline__ void tb_enorm_add(tb_enorm_acc &t, double v, int n) {
 struct tb_lmt {
     double par0, par1, fnorm, diag0, diag1, delta, lmp, xnorm, gnorm;
     double r00, r01, r11, qtf0, qtf1, acn0, acn1;
+    double tyy;                                         // moment form: sum of signal^2 over the window (a constant of the fit)
     int ipvt0, iter, nfev, info;
 };
 
@@ -236,6 +237,7 @@ __device__ __forceinline__ void tb_lmt_init(tb_lmt &S, double fnorm0) {
     S.diag0 = S.diag1 = 0.0;
     S.delta = S.lmp = S.xnorm = S.gnorm = 0.0;
     S.r00 = S.r01 = S.r11 = S.qtf0 = S.qtf1 = S.acn0 = S.acn1 = 0.0;
+    S.tyy = 0.0;
     S.ipvt0 = 0;
     S.iter = 1;
     S.nfev = 1;
@@ -469,7 +471,8 @@ __device__ __forceinline__ tb_jac_fast tb_jac_fast_at(double par0, double par1) 
     J.h1inv = 1.0 / h;
     return J;
 }
-__device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref W, int m, const tb_jac_fast &J, const tb_gram &Gm);
+__device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref W, int m, const tb_jac_fast &J, const tb_gram &Gm,
+                                                    int nrows_known = -1);
 
 __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, int m) {
     const tb_jac_fast J = tb_jac_fast_at(S.par0, S.par1);
@@ -528,7 +531,8 @@ __device__ __forceinline__ double tb_lmt_start_fast(tb_lmt &S, const tb_win_ref 
 
 // R, Q^T fvec, column norms and the outer-iteration bookkeeping from the inner products (no pass over the window unless the columns look
 // dependent); counts the two function evaluations of the forward differences
-__device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref W, int m, const tb_jac_fast &J, const tb_gram &Gm) {
+__device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref W, int m, const tb_jac_fast &J, const tb_gram &Gm,
+                                                    int nrows_known) {
     const double factor = 100.0;
     S.nfev += 2;
     const double g00 = Gm.g00, g01 = Gm.g01, g11 = Gm.g11, gf0 = Gm.gf0, gf1 = Gm.gf1;
@@ -568,12 +572,15 @@ __device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref 
     // structural rank deficiency (fewer than two rows with a non-zero Jacobian row) must give r11 = 0 exactly, as in MINPACK, where
     // the inner products leave rounding noise: count the rows, but only when the columns look (nearly) dependent
     if (rest2 > 0.0 && !(rest2 > 1e-12 * gQQ)) {
-        int nrows = 0;
-        TB_FOR_POINTS_ANY_ORDER(W, m, {
-            double f, j0, j1;
-            J.eval(ex, ey, f, j0, j1);
-            nrows += (j0 != 0.0 || j1 != 0.0) ? 1 : 0;
-        })
+        int nrows = nrows_known;
+        if (nrows < 0) {
+            nrows = 0;
+            TB_FOR_POINTS_ANY_ORDER(W, m, {
+                double f, j0, j1;
+                J.eval(ex, ey, f, j0, j1);
+                nrows += (j0 != 0.0 || j1 != 0.0) ? 1 : 0;
+            })
+        }
         if (nrows < 2) rest2 = 0.0;
     }
     double ajnorm1 = rest2 > 0.0 ? sqrt(rest2) : 0.0;
@@ -594,13 +601,142 @@ __device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref 
     tb_lmt_qr_tail(S, swap);
 }
 
+// ---- moment form of the one-pass fits (lm_exact_order = 0, the DWM default) ------------------------------------------------------------
+// The model max(0, a x + b) is piecewise linear: on the ACTIVE set A(a, b) = { i : a x_i + b > 0 } the residual is a x_i + b - y_i with the
+// Jacobian row (x_i, 1); elsewhere the residual is -y_i and the row is zero.  So everything an LM iteration needs at a parameter point is a
+// function of five moments of the active set,  n = |A|, Sx, Sy, Sxx, Sxy,  and of the window constant Tyy = sum of y^2 over all points:
+//     |f|^2 = Tyy + a^2 Sxx + 2 a b Sx + b^2 n - 2 a Sxy - 2 b Sy         J'J = [[Sxx, Sx], [Sx, n]]         J'f = (a Sxx + b Sx - Sxy, a Sx + b n - Sy)
+// One pass costs a multiply-add for the activity test and five masked accumulations per point (~20 instructions) instead of three model
+// evaluations, two difference quotients and six products (~70).  The Jacobian is the exact derivative where scipy takes forward
+// differences (h ~ 1.5e-8 |p|): the two agree to the rounding of the difference quotient (~1e-8 relative) except for points within h of
+// the kink, and the iteration -- lmpar, trust region, termination tests, the counting of function evaluations (2 per Jacobian, as
+// fdjac2) -- is MINPACK's.  Same fit-vs-fallback decisions; parameters as close to scipy's as the forward-difference one-pass form was
+// (bench.py `parity`: tracks within the stated tolerance on every window the reference itself keeps stable).
+struct tb_moments {
+    double sx, sy, sxx, sxy;
+    int n;
+};
+__device__ __forceinline__ bool tb_active(double a, double b, double x) {
+    return __dadd_rn(__dmul_rn(a, x), b) > 0.0;                  // np.maximum(0.0, a * x + b) is non-zero
+}
+__device__ __forceinline__ tb_moments tb_moments_at(const tb_win_ref W, int m, double a, double b) {
+    double sx = 0.0, sy = 0.0, sxx = 0.0, sxy = 0.0;
+    int n = 0;
+    TB_FOR_POINTS_ANY_ORDER(W, m, {
+        const bool act = tb_active(a, b, ex);
+        const double xm = act ? ex : 0.0;
+        const double ym = act ? ey : 0.0;
+        n += act ? 1 : 0;
+        sx += xm;
+        sy += ym;
+        sxx = fma(xm, ex, sxx);
+        sxy = fma(xm, ey, sxy);
+    })
+    return tb_moments{sx, sy, sxx, sxy, n};
+}
+__device__ __forceinline__ double tb_moments_ss(const tb_moments &M, double tyy, double a, double b) {
+    const double q = fma(a, fma(a, M.sxx, 2.0 * (b * M.sx - M.sxy)), b * fma(b, (double)M.n, -2.0 * M.sy));
+    const double ss = tyy + q;
+    return ss > 0.0 ? ss : 0.0;
+}
+// inner products + rows 0 and 1 at (a, b), in the form tb_lmt_qr_from_gram takes
+__device__ __forceinline__ tb_gram tb_moments_gram(const tb_moments &M, const tb_win_ref W, double a, double b) {
+    tb_gram G;
+    G.g00 = M.sxx;
+    G.g01 = M.sx;
+    G.g11 = (double)M.n;
+    G.gf0 = fma(a, M.sxx, b * M.sx) - M.sxy;
+    G.gf1 = fma(a, M.sx, b * (double)M.n) - M.sy;
+    const double x0 = W.x[0], y0 = tb_u32_to_double(W.y[0]), x1 = W.x[W.stride], y1 = tb_u32_to_double(W.y[W.stride]);
+    const bool a0 = tb_active(a, b, x0), a1 = tb_active(a, b, x1);
+    G.f0 = (a0 ? __dadd_rn(__dmul_rn(a, x0), b) : 0.0) - y0;
+    G.a0 = a0 ? x0 : 0.0;
+    G.b0 = a0 ? 1.0 : 0.0;
+    G.f1 = (a1 ? __dadd_rn(__dmul_rn(a, x1), b) : 0.0) - y1;
+    G.a1 = a1 ? x1 : 0.0;
+    G.b1 = a1 ? 1.0 : 0.0;
+    return G;
+}
+// The exact derivative and scipy's forward differences part ways when the active set is (nearly) degenerate -- fewer than two active points,
+// or all of them at the same bias value: the difference quotient also sees the points that the step h pushes across the kink, which can
+// make scipy's R non-singular (a usable fit) where the exact Jacobian has rank one (the reference's fallback).  Such heads are rare; they
+// are recomputed with the forward-difference inner products, so the fit-vs-fallback decision stays scipy's.
+__device__ __forceinline__ bool tb_moments_degenerate(const tb_gram &G) {
+    return !(G.g00 * G.g11 - G.g01 * G.g01 > 1e-8 * (G.g00 * G.g11));
+}
+__device__ __noinline__ void tb_gram_fd(const tb_win_ref W, int m, double a, double b, tb_gram &Gm) {
+    const tb_jac_fast J = tb_jac_fast_at(a, b);
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
+    double g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
+    TB_FOR_POINTS_ANY_ORDER(W, m, {
+        double f, j0, j1;
+        J.eval(ex, ey, f, j0, j1);
+        g00 += j0 * j0;
+        g01 += j0 * j1;
+        g11 += j1 * j1;
+        gf0 += j0 * f;
+        gf1 += j1 * f;
+    })
+    Gm.g00 = g00; Gm.g01 = g01; Gm.g11 = g11; Gm.gf0 = gf0; Gm.gf1 = gf1;
+}
+// start of a fit: statistics, Tyy and the moments at p0 = (1, 1) in one pass, then the first outer-iteration head.  -1: no signal.
+__device__ __forceinline__ double tb_lmt_start_moments(tb_lmt &S, const tb_win_ref W, int m, tb_win_stats &st) {
+    u32 ymax = 0;
+    double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
+    double sx = 0.0, sy = 0.0, sxx = 0.0, sxy = 0.0, tyy = 0.0;
+    int n = 0;
+    TB_FOR_POINTS_ANY_ORDER(W, m, {
+        ymax = eyi > ymax ? eyi : ymax;
+        xmax = fmax(xmax, ex);
+        xmin = fmin(xmin, ex);
+        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
+        const bool act = tb_active(1.0, 1.0, ex);
+        const double xm = act ? ex : 0.0;
+        const double ym = act ? ey : 0.0;
+        n += act ? 1 : 0;
+        sx += xm;
+        sy += ym;
+        sxx = fma(xm, ex, sxx);
+        sxy = fma(xm, ey, sxy);
+        tyy = fma(ey, ey, tyy);
+    })
+    st.xmax = xmax;
+    st.xmin = xmin;
+    st.bmin = bmin;
+    if (ymax == 0u) return -1.0;
+    const tb_moments M{sx, sy, sxx, sxy, n};
+    const double f0 = sqrt(tb_moments_ss(M, tyy, 1.0, 1.0));
+    tb_lmt_init(S, f0);
+    S.tyy = tyy;
+    tb_gram Gm = tb_moments_gram(M, W, 1.0, 1.0);
+    int nrows = n;
+    if (tb_moments_degenerate(Gm)) {
+        tb_gram_fd(W, m, 1.0, 1.0, Gm);
+        nrows = -1;
+    }
+    tb_lmt_qr_from_gram(S, W, m, tb_jac_fast_at(1.0, 1.0), Gm, nrows);
+    return f0;
+}
+// outer-iteration head at the current parameters (finish kernel: a step was accepted in an earlier launch)
+__device__ __forceinline__ void tb_lmt_qr_moments(tb_lmt &S, const tb_win_ref W, int m) {
+    const tb_moments M = tb_moments_at(W, m, S.par0, S.par1);
+    tb_gram Gm = tb_moments_gram(M, W, S.par0, S.par1);
+    int nrows = M.n;
+    if (tb_moments_degenerate(Gm)) {
+        tb_gram_fd(W, m, S.par0, S.par1, Gm);
+        nrows = -1;
+    }
+    tb_lmt_qr_from_gram(S, W, m, tb_jac_fast_at(S.par0, S.par1), Gm, nrows);
+}
+
 // one inner iteration of lmdif: lmpar step, trial residual, trust-region update, termination tests.
 // returns true when the step was accepted (the next round starts with tb_lmt_qr); S.info != 0 ends the fit.
 // FUSE (one-pass form only): the pass that forms the trial residual norm also forms the inner products of the Jacobian columns AT THE
 // TRIAL POINT, and when the step is accepted the head of the next outer iteration (tb_lmt_qr_from_gram) follows at once -- an accepted
 // step then costs one pass over the window instead of two, and the next round needs no Jacobian pass.  Same arithmetic in the same
 // order as the separate passes: the fits are bit-identical.  A rejected step wastes the two extra model evaluations per point.
-template <bool FAST, bool FUSE = false>
+template <bool FAST, bool FUSE = false, bool MOMENTS = false>
 __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int m) {
     const double epsmch = 2.220446049250313e-16;
     const double ftol = 1.49012e-8, xtol = 1.49012e-8;
@@ -623,9 +759,20 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
     double fnorm1;
     tb_jac_fast J;
     tb_gram Gm;
+    int nrows = -1;
     {
         const double ta = wa2[0], tb_ = wa2[1];
-        if (FAST && FUSE) {
+        if (MOMENTS) {                               // moment form: always fused (the moments give the residual norm AND the next head)
+            const tb_moments M = tb_moments_at(W, m, ta, tb_);
+            fnorm1 = sqrt(tb_moments_ss(M, S.tyy, ta, tb_));
+            Gm = tb_moments_gram(M, W, ta, tb_);
+            J = tb_jac_fast_at(ta, tb_);
+            nrows = M.n;
+            if (tb_moments_degenerate(Gm)) {
+                tb_gram_fd(W, m, ta, tb_, Gm);
+                nrows = -1;
+            }
+        } else if (FAST && FUSE) {
             J = tb_jac_fast_at(ta, tb_);
             J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
             J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
@@ -706,7 +853,7 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
         if (S.gnorm <= epsmch) info = 8;
     }
     S.info = info;
-    if (FAST && FUSE && accepted && info == 0) tb_lmt_qr_from_gram(S, W, m, J, Gm);      // head of the next outer iteration (may set S.info)
+    if ((MOMENTS || (FAST && FUSE)) && accepted && info == 0) tb_lmt_qr_from_gram(S, W, m, J, Gm, nrows);      // head of the next outer iteration (may set S.info)
     return accepted;
 }
 

@@ -175,12 +175,18 @@ class Engine:
         self.lengths = [int(len(c)) for c in contigs]
         self.ctx.genome_load(contigs)
 
-    def load_genome_fasta(self, fasta, names=None):
+    def load_genome_fasta(self, fasta, names=None, packed=True):
         names = list(names) if names is not None else list(fasta.references)
         self.names = names
         self.index = {n: i for i, n in enumerate(names)}
         self.lengths = [fasta.get_reference_length(n) for n in names]
         self.ctx.genome_create(self.lengths)
+        if packed:            # 2 bit + N mask, packed on the host cores once and cached next to the FASTA (<fasta>.tb2bit)
+            from .io.fasta import PackedGenome
+            pg = PackedGenome.from_fasta(fasta, names)
+            for i in range(len(names)):
+                self.ctx.genome_upload_packed(i, pg.seq2[i], pg.nmask[i], self.lengths[i])
+            return
         chunk = 1 << 26
         for i, n in enumerate(names):
             for off in range(0, self.lengths[i], chunk):
