@@ -208,6 +208,12 @@ int tb_score_regions(tb_ctx *ctx, const float *signal, int64_t n_regions, const 
  * float32 as a bigWig would store it, zero outside the output regions) as the signal of the same regions
  * extended by p->flank. */
 int tb_signal_from_corrected(tb_ctx *ctx, int flank);
+/* The same for ANY scoring regions (sorted by contig and start; each extended by `flank` internally, which must stay inside its contig):
+ * every position reads the corrected track where an output region of the last tb_correct_run covers it and 0 elsewhere -- what
+ * `TOBIAS ScoreBigwig --signal <prefix>_corrected.bw --regions ...` sees (score_bigwig.py:136-170 merges the peaks but does not split them at
+ * 50 kb as ATACorrect does, atacorrect.py:233; pass the merged regions to reproduce it across the split pieces). */
+int tb_signal_from_corrected_regions(tb_ctx *ctx, int flank, int64_t n_regions, const int32_t *contig, const int64_t *start,
+                                     const int64_t *end);
 
 /* fast_rolling_math(arr, w, "sum"|"mean") (tobias/utils/signals.pyx:102-177) on one float64 array; NaN flanks. */
 int tb_rolling(tb_ctx *ctx, const double *arr, int64_t n, int w, int is_mean, double *out);

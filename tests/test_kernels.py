@@ -603,3 +603,41 @@ def test_chain_corrected_to_footprints(loaded_ctx, golden):
     loaded_ctx.score_run(loaded_ctx.score_params("footprint", flank=30, as_f64=True))
     loaded_ctx.correct_download_wait()
     assert np.array_equal(later["corrected"], both) and np.array_equal(loaded_ctx.score_download(), got)
+
+
+def test_chain_reads_the_track_like_a_bigwig(loaded_ctx, golden):
+    """tb_signal_from_corrected: the flank of an output region takes the values of an abutting neighbour (50-kb split pieces) and 0
+    where the track holds nothing -- what ScoreBigwig reads from the corrected bigWig; tb_signal_from_corrected_regions scores regions
+    of one's own choice (here: the merged region, as score_bigwig.py:136-170 would build it) over the same track."""
+    g = golden.atac
+    _set_model(loaded_ctx, g, "DWM")
+    regs = np.array([(0, 20000, 20700), (0, 20700, 21300), (0, 21300, 21900), (0, 25000, 25600), (1, 9000, 9800)])
+    c, s, e = _cols(regs)
+    loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=0)
+    both = loaded_ctx.correct_download(split_strands=False, as_f64=False, tracks=("corrected",), prepost=False)["corrected"]
+    off = np.concatenate([[0], np.cumsum(e - s)])
+    track = {}                                                   # (contig, position) -> value: the bigWig
+    for i, (ci, a, b) in enumerate(regs):
+        for k, p in enumerate(range(a, b)):
+            track[(ci, p)] = both[off[i] + k]
+
+    def read(ci, a, b):
+        return np.array([track.get((ci, p), 0.0) for p in range(a, b)], dtype=np.float32)
+    p30 = loaded_ctx.score_params("footprint", flank=30, as_f64=True)
+    loaded_ctx.signal_from_corrected(30, e - s)
+    loaded_ctx.score_run(p30)
+    got = loaded_ctx.score_download()
+    ext = [read(ci, a - 30, b + 30) for (ci, a, b) in regs]
+    ref = loaded_ctx.score_regions(np.concatenate(ext), [x.shape[0] for x in ext], p30)
+    assert np.array_equal(got, ref)
+    assert np.any(ext[0][-30:] != 0) and np.all(ext[3][:30] == 0)          # a neighbour's values / nothing
+    merged = np.array([(0, 20000, 21900), (0, 25000, 25600), (1, 9000, 9800)])
+    mc, ms, me = _cols(merged)
+    loaded_ctx.signal_from_corrected_regions(30, mc, ms, me)
+    loaded_ctx.score_run(p30)
+    got_m = loaded_ctx.score_download()
+    ext_m = [read(ci, a - 30, b + 30) for (ci, a, b) in merged]
+    ref_m = loaded_ctx.score_regions(np.concatenate(ext_m), [x.shape[0] for x in ext_m], p30)
+    assert np.array_equal(got_m, ref_m) and got_m.shape[0] == int((me - ms).sum())
+    with pytest.raises(lib.TobiasB200Error):
+        loaded_ctx.signal_from_corrected_regions(30, [0], [10], [500])             # flank leaves the contig

@@ -486,16 +486,23 @@ __global__ void tb_rolling_kernel(tb_sc_view V, const void *__restrict__ in_, tb
     }
 }
 
-// the corrected track of the last tb_correct_run as the float32 signal of the same regions extended by `flank`
-__global__ void tb_corrected_to_signal_kernel(const double *__restrict__ cf, const double *__restrict__ cr, const i64 *__restrict__ out_off,
-                                              const i64 *__restrict__ sig_off, i64 n_regions, i64 total, int flank, float *__restrict__ sig) {
+// The corrected track of the last tb_correct_run, read the way ScoreBigwig reads the corrected bigWig (score_bigwig.py:52-53): every
+// position of the scoring regions (already extended by `flank`) takes the float32 value of the output region that covers it -- its own
+// or an abutting neighbour (50-kb split pieces) -- and 0 where the track holds nothing (nan_to_num of the bigWig's NaN).
+// sc_lstart: linear start of every extended scoring region; out_lstart: linear start of every output region (ascending).
+__global__ void tb_corrected_to_signal_kernel(const double *__restrict__ cf, const double *__restrict__ cr, const i64 *__restrict__ out_lstart,
+                                              const i64 *__restrict__ out_off, i64 n_out, const i64 *__restrict__ sc_lstart,
+                                              const i64 *__restrict__ sig_off, i64 n_regions, i64 total, float *__restrict__ sig) {
     i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
-        i64 j = tb_upper_bound(sig_off, n_regions + 1, x) - 1;
-        i64 q = x - sig_off[j] - flank;
-        i64 len = out_off[j + 1] - out_off[j];
+        const i64 r = tb_upper_bound(sig_off, n_regions + 1, x) - 1;
+        const i64 lin = sc_lstart[r] + (x - sig_off[r]);
+        const i64 j = tb_upper_bound(out_lstart, n_out, lin) - 1;
         float v = 0.0f;
-        if (q >= 0 && q < len) v = (float)(cf[out_off[j] + q] + cr[out_off[j] + q]);
+        if (j >= 0) {
+            const i64 q = lin - out_lstart[j];
+            if (q < out_off[j + 1] - out_off[j]) v = (float)(cf[out_off[j] + q] + cr[out_off[j] + q]);
+        }
         sig[x] = v;
     }
 }
@@ -525,28 +532,60 @@ extern "C" int tb_signal_upload(tb_ctx *ctx, const float *signal, int64_t n_regi
     return TB_OK;
 }
 
+static int tb_signal_from_corrected_linear(tb_ctx *ctx, int flank, i64 n, const std::vector<i64> &sc_lstart, const std::vector<int64_t> &ext_len) {
+    auto &C = ctx->cor;
+    ctx->sc.have_signal = false;
+    TB_TRY(tb_sc_layout(ctx, n, ext_len.data()));
+    auto &S = ctx->sc;
+    TB_TRY(tb_reserve(ctx, S.signal, (size_t)S.ext_total * sizeof(float)));
+    if (S.ext_total > 0) {
+        std::vector<i64> out_lstart(C.n_regions);
+        for (i64 i = 0; i < C.n_regions; i++) out_lstart[i] = C.ext_start[i] + C.k_flank + C.window / 2;
+        TB_TRY(tb_h2d(ctx, ctx->reg_a, out_lstart.data(), sizeof(i64) * (size_t)C.n_regions));
+        TB_TRY(tb_h2d(ctx, ctx->reg_b, sc_lstart.data(), sizeof(i64) * (size_t)n));
+        i64 want = tb_div_up(S.ext_total, 256), capg = (i64)ctx->sm_count * 16;
+        const double *cf = C.tracks.as<double>() + ((i64)3 * 2 + 0) * C.out_total;
+        const double *cr = C.tracks.as<double>() + ((i64)3 * 2 + 1) * C.out_total;
+        TB_LAUNCH(ctx, tb_corrected_to_signal_kernel, (unsigned)(want < capg ? want : capg), 256, 0, cf, cr, (const i64 *)ctx->reg_a.as<i64>(),
+                  (const i64 *)C.d_out_off.as<i64>(), C.n_regions, (const i64 *)ctx->reg_b.as<i64>(), (const i64 *)S.d_ext_off.as<i64>(), n,
+                  S.ext_total, S.signal.as<float>());
+    }
+    TB_TRY(tb_sync(ctx, "tb_signal_from_corrected"));
+    S.have_signal = true;
+    return TB_OK;
+}
+
 extern "C" int tb_signal_from_corrected(tb_ctx *ctx, int flank) {
     if (!ctx) return TB_ERR_ARG;
     auto &C = ctx->cor;
     if (!C.valid) return tb_fail(ctx, TB_ERR_STATE, "tb_signal_from_corrected: no completed tb_correct_run");
     if (flank < 0) return tb_fail(ctx, TB_ERR_ARG, "tb_signal_from_corrected: negative flank");
     std::vector<int64_t> ext_len(C.n_regions);
-    for (i64 i = 0; i < C.n_regions; i++) ext_len[i] = (C.out_off[i + 1] - C.out_off[i]) + 2 * (i64)flank;
-    ctx->sc.have_signal = false;
-    TB_TRY(tb_sc_layout(ctx, C.n_regions, ext_len.data()));
-    auto &S = ctx->sc;
-    TB_TRY(tb_reserve(ctx, S.signal, (size_t)S.ext_total * sizeof(float)));
-    if (S.ext_total > 0) {
-        i64 want = tb_div_up(S.ext_total, 256), capg = (i64)ctx->sm_count * 16;
-        const double *cf = C.tracks.as<double>() + ((i64)3 * 2 + 0) * C.out_total;
-        const double *cr = C.tracks.as<double>() + ((i64)3 * 2 + 1) * C.out_total;
-        TB_LAUNCH(ctx, tb_corrected_to_signal_kernel, (unsigned)(want < capg ? want : capg), 256, 0, cf, cr,
-                  (const i64 *)C.d_out_off.as<i64>(), (const i64 *)S.d_ext_off.as<i64>(), C.n_regions, S.ext_total, flank,
-                  S.signal.as<float>());
+    std::vector<i64> sc_lstart(C.n_regions);
+    for (i64 i = 0; i < C.n_regions; i++) {
+        ext_len[i] = (C.out_off[i + 1] - C.out_off[i]) + 2 * (i64)flank;
+        sc_lstart[i] = C.ext_start[i] + C.k_flank + C.window / 2 - flank;
     }
-    TB_TRY(tb_sync(ctx, "tb_signal_from_corrected"));
-    S.have_signal = true;
-    return TB_OK;
+    return tb_signal_from_corrected_linear(ctx, flank, C.n_regions, sc_lstart, ext_len);
+}
+
+extern "C" int tb_signal_from_corrected_regions(tb_ctx *ctx, int flank, int64_t n_regions, const int32_t *contig, const int64_t *start,
+                                                const int64_t *end) {
+    if (!ctx || n_regions < 0 || (n_regions > 0 && (!contig || !start || !end))) return TB_ERR_ARG;
+    auto &C = ctx->cor;
+    if (!C.valid) return tb_fail(ctx, TB_ERR_STATE, "tb_signal_from_corrected_regions: no completed tb_correct_run");
+    if (flank < 0) return tb_fail(ctx, TB_ERR_ARG, "tb_signal_from_corrected_regions: negative flank");
+    std::vector<i64> ls, le;
+    TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
+    std::vector<int64_t> ext_len(n_regions);
+    std::vector<i64> sc_lstart(n_regions);
+    for (i64 i = 0; i < n_regions; i++) {
+        if (start[i] - flank < 0 || end[i] + flank > ctx->contig_len[contig[i]])
+            return tb_fail(ctx, TB_ERR_ARG, "tb_signal_from_corrected_regions: region %lld extended by %d leaves contig %d", i, flank, contig[i]);
+        ext_len[i] = (le[i] - ls[i]) + 2 * (i64)flank;
+        sc_lstart[i] = ls[i] - flank;
+    }
+    return tb_signal_from_corrected_linear(ctx, flank, n_regions, sc_lstart, ext_len);
 }
 
 template <int IN_MODE>

@@ -74,6 +74,7 @@ _PROTOS = {
     "tb_score_gather": (_i, [_vp, _i64, _vp, _vp]),
     "tb_score_regions": (_i, [_vp, _vp, _i64, _vp, C.POINTER(ScoreParams), _vp]),
     "tb_signal_from_corrected": (_i, [_vp, _i]),
+    "tb_signal_from_corrected_regions": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "tb_rolling": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
 }
 
@@ -393,6 +394,12 @@ class Context:
     def signal_from_corrected(self, flank, out_len):
         self._ck(self._lib.tb_signal_from_corrected(self._h, int(flank)))
         self._sc_ext = _arr(out_len, np.int64) + 2 * int(flank)
+
+    def signal_from_corrected_regions(self, flank, contig, start, end):
+        """Scoring regions of one's own choice over the corrected track of the last correct_run (0 where the track holds nothing)."""
+        c, s, e = self._regions(contig, start, end)
+        self._ck(self._lib.tb_signal_from_corrected_regions(self._h, int(flank), int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e)))
+        self._sc_ext = (e - s) + 2 * int(flank)
 
     def score_run(self, params):
         self._ck(self._lib.tb_score_run(self._h, C.byref(params)))
