@@ -108,6 +108,10 @@ int tb_count_reads(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const 
  * the concatenated per-region arrays (sum of region lengths), uint32.  Regions sorted by (contig, start). */
 int tb_pileup(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start,
               const int64_t *end, int shift_fwd, int shift_rev, uint32_t *out_fwd, uint32_t *out_rev);
+/* ReadList.signal(region) (tobias/utils/ngs.pyx:186-199) over the resident records: values[cut - start - 1] += 1 for every record with
+ * start < cut <= end -- no overlap test and the upper bound inclusive, unlike the filtered pileup above.  Same output layout. */
+int tb_read_signal(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end,
+                   int shift_fwd, int shift_rev, uint32_t *out_fwd, uint32_t *out_rev);
 
 /* ------------------------------------------------------------------------------------------------ K2
  * bias_estimation (tobias/tools/atacorrect_functions.py:109-181) over all input regions at once, i.e. the
@@ -215,7 +219,16 @@ int tb_signal_from_corrected(tb_ctx *ctx, int flank);
 int tb_signal_from_corrected_regions(tb_ctx *ctx, int flank, int64_t n_regions, const int32_t *contig, const int64_t *start,
                                      const int64_t *end);
 
-/* fast_rolling_math(arr, w, "sum"|"mean") (tobias/utils/signals.pyx:102-177) on one float64 array; NaN flanks. */
+/* Array-level mirror of SequenceMatrix.add_sequence / add_background (tobias/utils/sequences.pyx:63-105 PWM, :178-223 DWM) for a batch of
+ * explicit k-mers: kmers int64 [n][L] codes (A0 T1 C2 G3 N4), amounts double [n].  The increments are ADDED to the caller's arrays: counts
+ * [5][L] (PWM) or [5][5][L][L] (DWM); neg_counts [5][L] receives the non-positive amounts of a PWM add_sequence (may be NULL otherwise);
+ * *total += the amounts that were added (no_bias / no_bg).  A k-mer holding N is skipped, except by the PWM add_background (:100-102). */
+int tb_add_kmers(tb_ctx *ctx, int L, int is_dwm, int is_background, int64_t n, const int64_t *kmers, const double *amounts,
+                 double *counts, double *neg_counts, double *total);
+
+/* fast_rolling_math(arr, w, operation) (tobias/utils/signals.pyx:102-177) on one float64 array.  is_mean: 0 "sum", 1 "mean" (NaN
+ * flanks, C-float accumulator), 2 "max", 3 "min" (C-float extremum, every position defined, index 0 never inspected -- the reference's
+ * `start_i + j > 0`), 4 "prod". */
 int tb_rolling(tb_ctx *ctx, const double *arr, int64_t n, int w, int is_mean, double *out);
 
 #ifdef __cplusplus

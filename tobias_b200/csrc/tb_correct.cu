@@ -15,7 +15,7 @@
 #include "tb_lm_thread.cuh"
 
 int tb_pileup_device(tb_ctx *ctx, i64 n_regions, const i64 *d_lstart, const i64 *d_lend, const i64 *d_off, i64 total,
-                     int shift_fwd, int shift_rev, u32 *d_out);
+                     int shift_fwd, int shift_rev, u32 *d_out, int list_semantics = 0);
 int tb_score_device(tb_ctx *ctx, const i64 *d_ext_start, const i64 *d_ext_off, i64 n_regions, i64 total, int strand_mask,
                     int nan_invalid, double *d_out_fwd, double *d_out_rev);
 

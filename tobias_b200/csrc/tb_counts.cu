@@ -773,3 +773,57 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     }
     return TB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ array-level mirror of the Cython API
+// SequenceMatrix.add_sequence / add_background for a batch of explicit k-mers (sequences.pyx:63-105 PWM, :178-223 DWM) -- the
+// unit-level entry point the reference exposes next to the batched path above (tobias_b200.sequences uses it for its shims).
+__global__ void tb_add_kmers_kernel(int L, int is_dwm, int is_background, i64 n, const i64 *__restrict__ kmers, const double *__restrict__ amounts,
+                                    double *__restrict__ counts, double *__restrict__ neg, double *__restrict__ total) {
+    const i64 per = is_dwm ? (i64)L * L : (i64)L;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < n * per; t += stride) {
+        const i64 i = t / per;
+        const int r = (int)(t - i * per);
+        const i64 *k = kmers + i * L;
+        const double amount = amounts[i];
+        bool has_n = false;
+        for (int m = 0; m < L; m++) has_n = has_n || k[m] >= 4 || k[m] < 0;
+        // add_sequence (both kinds) and the DWM add_background return at the first N; the PWM add_background counts it in row 4 (:100-102)
+        if (has_n && (is_dwm || !is_background)) continue;
+        if (is_dwm) {
+            const int m = r / L, nn = r % L;
+            atomicAdd(&counts[(((size_t)k[m] * 5 + k[nn]) * L + m) * L + nn], amount);
+        } else {
+            const int m = r;
+            const int sm = (int)(k[m] < 0 || k[m] > 4 ? 4 : k[m]);
+            if (is_background || amount > 0) atomicAdd(&counts[(size_t)sm * L + m], amount);
+            else atomicAdd(&neg[(size_t)sm * L + m], amount);
+        }
+        if (r == 0) atomicAdd(total, amount);
+    }
+}
+
+extern "C" int tb_add_kmers(tb_ctx *ctx, int L, int is_dwm, int is_background, int64_t n, const int64_t *kmers, const double *amounts,
+                            double *counts, double *neg_counts, double *total) {
+    if (!ctx || n < 0 || !counts || !total || (n > 0 && (!kmers || !amounts))) return TB_ERR_ARG;
+    if (L < 1 || L > 64) return tb_fail(ctx, TB_ERR_ARG, "tb_add_kmers: L must be in [1, 64]");
+    if (n == 0) return TB_OK;
+    const size_t nc = is_dwm ? (size_t)25 * L * L : (size_t)5 * L;
+    TB_TRY(tb_h2d(ctx, ctx->scratch2, kmers, sizeof(i64) * (size_t)n * L));
+    TB_TRY(tb_h2d(ctx, ctx->scratch3, amounts, sizeof(double) * (size_t)n));
+    TB_TRY(tb_reserve(ctx, ctx->scratch4, sizeof(double) * (nc + (size_t)5 * L + 1)));
+    TB_CUDA(ctx, cudaMemsetAsync(ctx->scratch4.p, 0, sizeof(double) * (nc + (size_t)5 * L + 1), ctx->stream));
+    double *d_counts = ctx->scratch4.as<double>(), *d_neg = d_counts + nc, *d_total = d_neg + 5 * L;
+    const i64 work = (i64)n * (is_dwm ? L * L : L);
+    const i64 want = tb_div_up(work, 256), capg = (i64)ctx->sm_count * 16;
+    TB_LAUNCH(ctx, tb_add_kmers_kernel, (unsigned)(want < capg ? want : capg), 256, 0, L, is_dwm, is_background, (i64)n,
+              (const i64 *)ctx->scratch2.as<i64>(), (const double *)ctx->scratch3.as<double>(), d_counts, d_neg, d_total);
+    TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_add_kmers_kernel"));
+    std::vector<double> h(nc + (size_t)5 * L + 1);
+    TB_TRY(tb_d2h(ctx, h.data(), d_counts, sizeof(double) * h.size()));
+    for (size_t i = 0; i < nc; i++) counts[i] += h[i];
+    if (neg_counts)
+        for (size_t i = 0; i < (size_t)5 * L; i++) neg_counts[i] += h[nc + i];
+    *total += h[nc + (size_t)5 * L];
+    return TB_OK;
+}

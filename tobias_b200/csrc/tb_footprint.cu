@@ -472,6 +472,25 @@ __global__ void tb_rolling_kernel(tb_sc_view V, const void *__restrict__ in_, tb
         if (pos >= Lr) break;
         double r;
         if (w <= 0) r = buf[t];
+        else if (is_mean >= 2) {
+            // "max" / "min" / "prod" (signals.pyx:118-146, 166-175): defined at every position; the window is clipped to 0 < index < L
+            // (index 0 is never looked at, as in the reference); maxval / minval are C floats (:116), prod is a double
+            const double centre = buf[t + lf];
+            float ext = (float)centre;
+            double prod = 1.0;
+            for (int u = 0; u < w; u++) {
+                const i64 idx = pos - lf + u;
+                if (idx > 0 && idx < Lr) {
+                    const double v = buf[t + u];
+                    if (is_mean == 2) {
+                        if (v > (double)ext) ext = (float)v;
+                    } else if (is_mean == 3) {
+                        if (v < (double)ext) ext = (float)v;
+                    } else prod *= v;
+                }
+            }
+            r = is_mean == 4 ? prod : (double)ext;
+        }
         else if (pos >= lf && pos - lf + w <= Lr) {
             float acc = 0.0f;
             for (int u = 0; u < w; u++) acc = (float)((double)acc + buf[t + u]);

@@ -27,7 +27,8 @@ __device__ __forceinline__ i64 tb_cut_pos(const tb_reads_view &r, i64 i, int shi
     return s - r.clip[i] + shift_fwd;                            // (ref_start - clip5 + 1 + shift) - 1
 }
 
-// mode 0: pileup (start < cut < end) into out[strand][off[j] + pos]; mode 1: count (start < cut <= end)
+// mode 0: pileup (start < cut < end) into out[strand][off[j] + pos]; mode 1: count (start < cut <= end);
+// mode 2: ReadList.signal (ngs.pyx:186-199): start < cut <= end for EVERY record of the list, whether or not its alignment overlaps the region
 template <int MODE>
 __global__ void tb_pileup_kernel(tb_reads_view r, int shift_fwd, int shift_rev, i64 n_regions, const i64 *__restrict__ lstart,
                                  const i64 *__restrict__ lend, const i64 *__restrict__ off, u32 *__restrict__ out_fwd,
@@ -44,8 +45,8 @@ __global__ void tb_pileup_kernel(tb_reads_view r, int shift_fwd, int shift_rev, 
         i64 j = tb_upper_bound(lend, n_regions, p + slack - 1);      // first region with lend - slack >= p
         for (; j < n_regions && lstart[j] <= p; j++) {
             if (p > lend[j] - slack) continue;
-            if (!(rs < lend[j] && re > lstart[j])) continue;         // fetch(): alignment must overlap the region
-            if (MODE == 0) {
+            if (MODE != 2 && !(rs < lend[j] && re > lstart[j])) continue;         // fetch(): alignment must overlap the region
+            if (MODE != 1) {
                 u32 *dst = rev ? out_rev : out_fwd;
                 atomicAdd(&dst[off[j] + (p - lstart[j])], 1u);
             } else {
@@ -70,7 +71,7 @@ static int tb_reads_ready(tb_ctx *ctx, tb_reads_view &rv) {
 
 // shared by tb_pileup and tb_correct_run: fills d_out (u32 [2][total]) for regions given in linear coordinates
 int tb_pileup_device(tb_ctx *ctx, i64 n_regions, const i64 *d_lstart, const i64 *d_lend, const i64 *d_off, i64 total,
-                     int shift_fwd, int shift_rev, u32 *d_out) {
+                     int shift_fwd, int shift_rev, u32 *d_out, int list_semantics = 0) {
     tb_reads_view rv;
     tb_reads_ready(ctx, rv);
     TB_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)total * 2 * sizeof(u32), ctx->stream));
@@ -79,14 +80,32 @@ int tb_pileup_device(tb_ctx *ctx, i64 n_regions, const i64 *d_lstart, const i64 
     i64 want = tb_div_up(rv.n, block);
     i64 cap = (i64)ctx->sm_count * 16;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    auto k = tb_pileup_kernel<0>;
-    TB_LAUNCH(ctx, k, grid, block, 0, rv, shift_fwd, shift_rev, n_regions, d_lstart, d_lend, d_off, d_out, d_out + total,
-              (u64 *)nullptr);
+    if (list_semantics) {
+        auto k = tb_pileup_kernel<2>;
+        TB_LAUNCH(ctx, k, grid, block, 0, rv, shift_fwd, shift_rev, n_regions, d_lstart, d_lend, d_off, d_out, d_out + total, (u64 *)nullptr);
+    } else {
+        auto k = tb_pileup_kernel<0>;
+        TB_LAUNCH(ctx, k, grid, block, 0, rv, shift_fwd, shift_rev, n_regions, d_lstart, d_lend, d_off, d_out, d_out + total, (u64 *)nullptr);
+    }
     return tb_check(ctx, cudaGetLastError(), "tb_pileup_kernel");
 }
 
+static int tb_pileup_any(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end, int shift_fwd,
+                         int shift_rev, uint32_t *out_fwd, uint32_t *out_rev, int list_semantics);
+
 extern "C" int tb_pileup(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end,
                          int shift_fwd, int shift_rev, uint32_t *out_fwd, uint32_t *out_rev) {
+    return tb_pileup_any(ctx, n_regions, contig, start, end, shift_fwd, shift_rev, out_fwd, out_rev, 0);
+}
+
+// ReadList.signal(region) of the resident records (tobias/utils/ngs.pyx:186-199): values[cut - start - 1] += 1 for start < cut <= end
+extern "C" int tb_read_signal(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end,
+                              int shift_fwd, int shift_rev, uint32_t *out_fwd, uint32_t *out_rev) {
+    return tb_pileup_any(ctx, n_regions, contig, start, end, shift_fwd, shift_rev, out_fwd, out_rev, 1);
+}
+
+static int tb_pileup_any(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end, int shift_fwd,
+                         int shift_rev, uint32_t *out_fwd, uint32_t *out_rev, int list_semantics) {
     if (!ctx) return TB_ERR_ARG;
     std::vector<i64> ls, le;
     TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
@@ -100,7 +119,7 @@ extern "C" int tb_pileup(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, 
     TB_TRY(tb_reserve(ctx, ctx->scratch0, (size_t)total * 2 * sizeof(u32)));
     tb_timer_start(ctx);
     TB_TRY(tb_pileup_device(ctx, n_regions, ctx->reg_a.as<i64>(), ctx->reg_b.as<i64>(), ctx->reg_c.as<i64>(), total, shift_fwd,
-                            shift_rev, ctx->scratch0.as<u32>()));
+                            shift_rev, ctx->scratch0.as<u32>(), list_semantics));
     tb_timer_stop(ctx);
     if (out_fwd) TB_TRY(tb_d2h(ctx, out_fwd, ctx->scratch0.as<u32>(), (size_t)total * sizeof(u32)));
     if (out_rev) TB_TRY(tb_d2h(ctx, out_rev, ctx->scratch0.as<u32>() + total, (size_t)total * sizeof(u32)));

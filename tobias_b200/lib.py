@@ -54,6 +54,7 @@ _PROTOS = {
     "tb_reads_upload": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tb_count_reads": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, C.POINTER(_i64)]),
     "tb_pileup": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "tb_read_signal": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "tb_bias_counts": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "tb_nccl_unique_id": (_i, [_vp]),
     "tb_nccl_init": (_i, [_vp, _vp, _i, _i]),
@@ -76,6 +77,7 @@ _PROTOS = {
     "tb_signal_from_corrected": (_i, [_vp, _i]),
     "tb_signal_from_corrected_regions": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "tb_rolling": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "tb_add_kmers": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -265,11 +267,13 @@ class Context:
                                           int(read_shift[1]), C.byref(out)))
         return out.value
 
-    def pileup(self, contig, start, end, read_shift=(4, -5)):
+    def pileup(self, contig, start, end, read_shift=(4, -5), list_semantics=False):
+        """list_semantics: ReadList.signal (ngs.pyx:186-199) -- every resident record, start < cut <= end."""
         c, s, e = self._regions(contig, start, end)
         total = int((e - s).sum())
         fwd, rev = np.zeros(total, dtype=np.uint32), np.zeros(total, dtype=np.uint32)
-        self._ck(self._lib.tb_pileup(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), int(read_shift[0]),
+        fn = self._lib.tb_read_signal if list_semantics else self._lib.tb_pileup
+        self._ck(fn(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), int(read_shift[0]),
                                      int(read_shift[1]), _ptr(fwd), _ptr(rev)))
         return fwd, rev
 
@@ -428,8 +432,19 @@ class Context:
         self.score_run(params)
         return self.score_download()
 
+    def add_kmers(self, kmers, amounts, counts, neg_counts=None, is_dwm=True, is_background=False):
+        """Batch form of SequenceMatrix.add_sequence / add_background: adds into `counts` (and `neg_counts`) in place, returns the total added."""
+        k = _arr(kmers, np.int64).reshape(-1, counts.shape[-1])
+        a = _arr(amounts, np.float64).reshape(-1)
+        assert k.shape[0] == a.shape[0] and counts.dtype == np.float64 and counts.flags.c_contiguous
+        total = np.zeros(1, dtype=np.float64)
+        self._ck(self._lib.tb_add_kmers(self._h, int(counts.shape[-1]), int(bool(is_dwm)), int(bool(is_background)), int(k.shape[0]), _ptr(k),
+                                        _ptr(a), _ptr(counts), _ptr(neg_counts), _ptr(total)))
+        return float(total[0])
+
     def rolling(self, arr, w, operation="sum"):
         a = _arr(arr, np.float64)
         out = np.empty_like(a)
-        self._ck(self._lib.tb_rolling(self._h, _ptr(a), int(a.shape[0]), int(w), int(operation == "mean"), _ptr(out)))
+        op = {"sum": 0, "mean": 1, "max": 2, "min": 3, "prod": 4}[operation]
+        self._ck(self._lib.tb_rolling(self._h, _ptr(a), int(a.shape[0]), int(w), op, _ptr(out)))
         return out

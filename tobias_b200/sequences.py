@@ -28,6 +28,32 @@ class SequenceMatrix:
         self.no_bias += obj.no_bias
         self.no_bg += obj.no_bg
 
+    # ---- array-level mirrors of the Cython methods (sequences.pyx:63-105, :178-223), computed through the C-ABI ----------------------
+    def _add(self, sequence, amount, background, ctx):
+        from . import signals
+        ctx = ctx or signals._default_ctx()
+        kmers = np.ascontiguousarray(sequence, dtype=np.int64).reshape(-1, self.length)
+        amounts = np.broadcast_to(np.asarray(amount, dtype=np.float64), (kmers.shape[0],))
+        target = self.bg_counts if background else self.counts
+        target = np.ascontiguousarray(target, dtype=np.float64)
+        neg = None if (background or self.stype == "DWM") else np.ascontiguousarray(self.neg_counts, dtype=np.float64)
+        added = ctx.add_kmers(kmers, amounts, target, neg, is_dwm=self.stype == "DWM", is_background=background)
+        if background:
+            self.bg_counts = target
+            self.no_bg += added
+        else:
+            self.counts = target
+            if neg is not None:
+                self.neg_counts = neg
+            self.no_bias += added
+
+    def add_sequence(self, sequence, amount=1.0, ctx=None):
+        """One k-mer (int64[L] codes A0 T1 C2 G3 N4) `amount` times -- or a batch: [n, L] with `amount` a scalar or [n]."""
+        self._add(sequence, amount, False, ctx)
+
+    def add_background(self, sequence, amount=1.0, ctx=None):
+        self._add(sequence, amount, True, ctx)
+
     # ---- device round trip -------------------------------------------------------------------------
     def upload(self, ctx, strand):
         """Hand the prepared tables of this strand (0 forward, 1 reverse) to the GPU context."""

@@ -18,9 +18,10 @@ def _default_ctx():
 
 
 def fast_rolling_math(arr, w, operation, ctx=None):
-    """signals.pyx:102-177 -- "sum" and "mean" (the operations of the hot path); NaN in the flanks."""
-    if operation not in ("sum", "mean"):
-        raise NotImplementedError("fast_rolling_math on the GPU supports 'sum' and 'mean' (the hot-path operations)")
+    """signals.pyx:102-177 -- "sum" / "mean" (the operations of the hot path; NaN in the flanks, C-float accumulator), "max" / "min" /
+    "prod" with the reference's window clipping.  Any other operation returns the all-NaN array, as the reference does."""
+    if operation not in ("sum", "mean", "max", "min", "prod"):
+        return np.full(np.asarray(arr).shape[0], np.nan)
     return (ctx or _default_ctx()).rolling(np.asarray(arr, dtype=np.float64), int(w), operation)
 
 
