@@ -45,6 +45,9 @@ def workload(name):
     if name == "hg38":
         return dict(lengths=dict(synth.HG38_LENGTHS), n_peaks=150000, n_records=50_000_000,
                     desc="ATACorrect+ScoreBigwig, synthetic hg38-sized genome (3.1 Gb, 150k peaks, 50M reads)")
+    if name == "batch24":                # one sample of the batch: the hg38-sized genome and peaks with 5 M records
+        return dict(lengths=dict(synth.HG38_LENGTHS), n_peaks=150000, n_records=5_000_000,
+                    desc="one sample of the batch: synthetic hg38-sized genome (3.1 Gb, 150k peaks), 5M records")
     if name == "chr50mb":
         return dict(lengths={"chr1": 50_000_000}, n_peaks=20000, n_records=5_000_000,
                     desc="ATACorrect+ScoreBigwig, synthetic 50 Mb chromosome, 20k 500bp peaks, 5M reads")
@@ -139,8 +142,9 @@ def allreduce_np(buf, device):
     return buf
 
 
-def run_step(eng, arrays, device, resident, host=None, out=None):
-    """One pass of the hot path over this rank's shard.  Returns (AtacBias, stage_ms list)."""
+def run_step(eng, arrays, device, resident, host=None, out=None, genome_resident=False, collective=True):
+    """One pass of the hot path over this rank's shard.  Returns (AtacBias, stage_ms list).
+    genome_resident (batch of samples over one genome): only the records of the sample travel in an e2e step."""
     from tobias_b200.pipeline import AtacBias, STRANDS
     ctx = eng.ctx
     trace = os.environ.get("TB_BENCH_TRACE") and (not resident or os.environ.get("TB_BENCH_TRACE") == "2")   # diagnostic: host wall clock per phase (stderr)
@@ -151,7 +155,10 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
             import torch
             torch.cuda.synchronize()
         marks.append((name, time.perf_counter()))
-    if not resident:                      # e2e: inputs come from (pinned) host buffers every step
+    if not resident and genome_resident:
+        ctx.reads_upload(*host["reads"])
+        mark("reads_h2d")
+    elif not resident:                    # e2e: inputs come from (pinned) host buffers every step
         ctx.genome_create(host["lengths"])
         ctx.reads_upload(*host["reads"])
         mark("reads_h2d")
@@ -170,11 +177,12 @@ def run_step(eng, arrays, device, resident, host=None, out=None):
     mark("count_reads")
     counts, scalars = ctx.bias_counts(*arrays["input_regions"], K_FLANK, BG_SHIFT, READ_SHIFT, 10, True)
     k2_ms = ctx.last_kernel_ms()
-    if not resident:
+    if not resident and not genome_resident:
         ctx.genome_wait()
     mark("bias_counts")
     packed = np.concatenate([counts.ravel(), scalars, np.array([reads_peaks, reads_nonpeaks], dtype=np.int64)])
-    allreduce_np(packed, device)
+    if collective:
+        allreduce_np(packed, device)
     counts = packed[:counts.size].reshape(counts.shape)
     scalars = packed[counts.size:counts.size + 5]
     reads_peaks, reads_nonpeaks = int(packed[-2]), int(packed[-1])
@@ -505,7 +513,7 @@ def reference_sample(workload_name, seed=None):
     names = [n for n in wl["lengths"] if n != "chrM"]
     sample_names = sorted(names, key=lambda n: wl["lengths"][n])[:2] if len(names) > 2 else names
     tot = float(sum(wl["lengths"].values()))
-    cap = {"hg38": 24_000_000, "chr50mb": 50_000_000}.get(workload_name, 6_000_000)
+    cap = {"hg38": 24_000_000, "batch24": 24_000_000, "chr50mb": 50_000_000}.get(workload_name, 6_000_000)
     lengths = {n: min(wl["lengths"][n], cap) for n in sample_names}
     frac = sum(lengths.values()) / tot
     ds = synth_torch.TorchDataset((SEED + 999) if seed is None else seed, lengths, max(4, int(wl["n_peaks"] * frac)),
@@ -830,13 +838,366 @@ def bench_config(wl, world):
             "l2": "inputs (2-bit genome + read columns + per-position arrays) far exceed the 126 MB L2; no flush needed"}
 
 
+# ---------------------------------------------------------------------------------------------------- configs[3]: whole-genome footprint scan
+FPG_VARIANTS = {"cli_default_flank10-30_fp20-50_651": dict(flank_min=10, flank_max=30, fp_min=20, fp_max=50),
+                "flank100_fp20-50_31": dict(flank_min=100, flank_max=100, fp_min=20, fp_max=50)}
+FPG_HEADLINE = "cli_default_flank10-30_fp20-50_651"
+
+
+def fp_track(key, length, device):
+    """Synthetic corrected-like track of one contig: N(0, 0.5) rounded to 5 decimals, ~70 % exact zeros, float32."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(np.random.SeedSequence([SEED, 77, key]).generate_state(1)[0]))
+    v = torch.randn(length, generator=g, device=device, dtype=torch.float32) * 0.5
+    v = torch.round(v * 1e5) / 1e5
+    v[torch.rand(length, generator=g, device=device) < 0.7] = 0.0
+    return v
+
+
+def _fp_ref_worker(task):
+    arr, p = task
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    return ref.signals.tobias_footprint_array(arr.astype(np.float64), p["flank_min"], p["flank_max"], p["fp_min"], p["fp_max"]).astype(np.float32)
+
+
+def fp_reference(track, variant, seconds_per_core=10.0):
+    """The reference's tobias_footprint_array (signals.pyx:184-230) over multiprocessing on all host cores, on chunks of the track."""
+    import multiprocessing as mp
+    from oracle import ref_loader
+    ref_loader.load()
+    p = FPG_VARIANTS[variant]
+    cores = os.cpu_count() or 1
+    rate = 7000.0 if p["flank_max"] - p["flank_min"] > 0 else 50000.0            # bp/s/core measured at survey time (BASELINE.md section 2): sizes the sample only
+    chunk = 20000
+    n_chunks = cores * max(1, int(round(rate * seconds_per_core / chunk)))
+    rng = np.random.default_rng(7)
+    starts = np.sort(rng.choice(max(1, (track.shape[0] - chunk) // chunk), size=min(n_chunks, max(1, (track.shape[0] - chunk) // chunk)), replace=False)) * chunk
+    arrs = [np.ascontiguousarray(track[a:a + chunk]) for a in starts]
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        outs = pool.map(_fp_ref_worker, [(a, p) for a in arrs], chunksize=max(1, len(arrs) // (cores * 4)))
+        dt = time.perf_counter() - t0
+    bp = sum(a.shape[0] for a in arrs)
+    return {"value": bp / dt, "seconds": dt, "bp": bp, "cores": cores, "starts": starts, "chunk": chunk, "in": arrs, "out": outs}
+
+
+def bench_fp_genome(args):
+    """BASELINE.json configs[3]: ScoreBigwig --score footprint over a whole-genome corrected track (regions = whole contigs)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from tobias_b200 import lib, synth
+    lengths = {n: ln for n, ln in synth.HG38_LENGTHS.items() if n != "chrM"}
+    if args.fp_scale < 1.0:
+        lengths = {n: max(200000, int(ln * args.fp_scale)) for n, ln in lengths.items()}
+    owner = shard_contigs(lengths, world)
+    names = [n for n in lengths if owner[n] == rank]
+    keys = {n: i for i, n in enumerate(lengths)}
+    ctx = lib.Context(local)
+    for kv in args.opt:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+    lens = np.array([lengths[n] for n in names], dtype=np.int64)
+    host = ctx.pinned_empty((int(lens.sum()),), np.float32)
+    off = 0
+    for n in names:
+        host[off:off + lengths[n]] = fp_track(keys[n], lengths[n], "cuda").cpu().numpy()
+        off += lengths[n]
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    results = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches = 0
+    out_all = ctx.pinned_empty((int(lens.sum()),), np.float32)
+    for name, p in FPG_VARIANTS.items():
+        params = ctx.score_params("footprint", flank=p["flank_max"], **p)
+        out_bp = int((lens - 2 * p["flank_max"]).sum())
+        out = out_all[:out_bp]
+        ctx.signal_upload(host, lens)
+        for _ in range(args.warmup):
+            ctx.score_run(params)
+        barrier()
+        l0 = ctx.launch_count()
+        ctx.timer_begin()
+        k4 = 0.0
+        for _ in range(args.steps):
+            ctx.score_run(params)
+            k4 += ctx.last_kernel_ms()
+        ms = ctx.timer_end()
+        barrier()
+        launches += ctx.launch_count() - l0
+        for _ in range(max(1, min(args.warmup, 2))):
+            ctx.signal_upload(host, lens)
+            ctx.score_run(params)
+            ctx.score_download(out=out)
+        barrier()
+        ctx.timer_begin()
+        for _ in range(args.steps):
+            ctx.signal_upload(host, lens)
+            ctx.score_run(params)
+            ctx.score_download(out=out)
+        ms_e2e = ctx.timer_end()
+        barrier()
+        t = torch.tensor([ms, ms_e2e, k4], dtype=torch.float64, device=device)
+        b = torch.tensor([out_bp], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(b)
+        results[name] = {"value": float(b[0]) * args.steps / (float(t[0]) * 1e-3), "ms_per_step": float(t[0]) / args.steps,
+                         "k4_kernel_ms": float(t[2]) / args.steps, "e2e_value": float(b[0]) * args.steps / (float(t[1]) * 1e-3),
+                         "e2e_ms_per_step": float(t[1]) / args.steps, "scored_bp": int(b[0]), "combinations": (p["flank_max"] - p["flank_min"] + 1) * (p["fp_max"] - p["fp_min"] + 1),
+                         "h2d_bytes_per_step": int(host.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                         "out_first": np.array(out[:int(lens[0]) - 2 * p["flank_max"]]) if (world == 1 and not args.no_cpu_baseline) else None}
+    clocks = sampler.stop()
+    head = results[FPG_HEADLINE]
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    achieved = 8.0 * (head["scored_bp"] / world) / (head["k4_kernel_ms"] * 1e-3) / 1e9
+    result = {"metric": METRIC, "value": head["value"], "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": "ScoreBigwig multi-width footprint scan over a whole-genome corrected track (BASELINE.json configs[3]): %d contigs, %.2f Gb, "
+                                     "regions = whole contigs; headline = CLI defaults (flank 10-30 x fp 20-50: 651 combinations); `variants` also holds "
+                                     "flank 100 x fp 20-50 (31 combinations)" % (len(lengths), sum(lengths.values()) / 1e9),
+                         "footprint": FPG_VARIANTS[FPG_HEADLINE], "sharding": "contigs over %d rank(s), no collective" % world,
+                         "l2": "the track (12 GB) far exceeds the 126 MB L2; no flush needed", **({"options": args.opt} if args.opt else {})},
+              "clocks": clocks, "gpu_launches": int(launches),
+              "e2e": {"value": head["e2e_value"], "unit": "bp/s", "ms_per_step": head["e2e_ms_per_step"], "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+                      "d2h_bytes_per_step": head["d2h_bytes_per_step"]},
+              "roofline": {"bound": "hbm", "kernel": "K4_footprint", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                           "algorithmic_bytes_per_launch": 8.0 * head["scored_bp"] / world,
+                           "note": "K4 is bound by fp32 issue / shared-memory bandwidth (651 add-max pairs per footprint start), not by HBM: 8 B per scored bp"},
+              "variants": {k: {kk: vv for kk, vv in v.items() if not kk.startswith("out")} for k, v in results.items()}}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            # reference on chunks of the first contig; the same chunks through the GPU as regions of their own, and the whole-contig GPU
+            # scan at the chunks' interior positions (tile borders of a 248-Mb region), both against the reference's arrays
+            n0 = int(lens[0])
+            track0 = np.asarray(host[:n0])
+            parity = {"tolerance": "identical zero pattern; |gpu - ref| <= 1e-5 |ref| on every non-zero position (float32 outputs)"}
+            base = {}
+            for name, p in FPG_VARIANTS.items():
+                rf = fp_reference(track0, name, seconds_per_core=8.0 if name == FPG_HEADLINE else 4.0)
+                base[name] = {"value": rf["value"], "unit": "bp/s", "cores": rf["cores"], "kind": "reference",
+                              "sample": "%d chunks of %d bp of %s (%d bp) through tobias_footprint_array on %d cores in %.1f s" % (
+                                  len(rf["in"]), rf["chunk"], names[0], rf["bp"], rf["cores"], rf["seconds"])}
+                params = ctx.score_params("footprint", flank=0, **p)
+                got = ctx.score_regions(np.concatenate(rf["in"]), [a.shape[0] for a in rf["in"]], params)
+                ref = np.concatenate(rf["out"])
+                nz = ref != 0
+                ok_chunks = bool(np.array_equal(got == 0, ref == 0) and np.all(np.abs(got[nz] - ref[nz]) <= 1e-5 * np.abs(ref[nz])))
+                whole = results[name]["out_first"]                      # scores of [flank_max, len - flank_max) of the first contig
+                margin = 2 * (p["flank_max"] + p["fp_max"])
+                ok_whole, n_cmp = True, 0
+                for a, o in zip(rf["starts"], rf["out"]):
+                    lo, hi = int(a) + margin, int(a) + rf["chunk"] - margin
+                    w = whole[lo - p["flank_max"]:hi - p["flank_max"]]
+                    r = o[margin:rf["chunk"] - margin]
+                    nzr = r != 0
+                    ok_whole = ok_whole and bool(np.array_equal(w == 0, r == 0) and np.all(np.abs(w[nzr] - r[nzr]) <= 1e-5 * np.abs(r[nzr])))
+                    n_cmp += r.shape[0]
+                parity[name] = {"chunks_as_regions_ok": ok_chunks, "whole_contig_interior_ok": ok_whole, "bp_compared": int(ref.shape[0]), "interior_bp_compared": n_cmp}
+            parity["green"] = all(v["chunks_as_regions_ok"] and v["whole_contig_interior_ok"] for k, v in parity.items() if isinstance(v, dict))
+            result["cpu_baseline"] = base[FPG_HEADLINE]
+            result["cpu_baseline_variants"] = base
+            result["parity"] = parity
+        except Exception as ex:
+            result["cpu_baseline"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(result))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_fp_genome_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from tobias_b200 import synth
+    n = min(synth.HG38_LENGTHS["chr21"], 8_000_000)
+    track = fp_track(list(synth.HG38_LENGTHS).index("chr21"), n, "cpu").numpy()
+    vals = []
+    for it in range(args.warmup + args.steps):
+        rf = fp_reference(track, FPG_HEADLINE, seconds_per_core=6.0)
+        if it >= args.warmup:
+            vals.append(rf)
+    v = float(np.mean([r["value"] for r in vals]))
+    r = vals[-1]
+    base = {"value": v, "unit": "bp/s", "cores": r["cores"], "kind": "reference",
+            "sample": "%d chunks of %d bp (%d bp) through tobias_footprint_array (651 combinations) on %d cores in %.1f s per step" % (
+                len(r["in"]), r["chunk"], r["bp"], r["cores"], r["seconds"])}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * r["seconds"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "ScoreBigwig multi-width footprint scan (BASELINE.json configs[3]), CLI defaults: 651 combinations",
+                                 "footprint": FPG_VARIANTS[FPG_HEADLINE]},
+                      "cpu_baseline": base, "e2e": {"value": v, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------- configs[4]: batch of samples
+def bench_batch24(args):
+    """BASELINE.json configs[4]: 24 pseudobulk samples (5 M records each) over one genome and one peak set, 3 samples per GPU, each through
+    its own bias training + correction + footprint scoring (the reference runs one ATACorrect per BAM, atacorrect.py:53-487).  Replicas mode:
+    the genome is resident once per GPU, every sample has its own bias model, no collective.  Weak scaling: 3 samples per GPU at every N."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from tobias_b200 import lib, synth_torch
+    from tobias_b200.io.fasta import pack_ascii
+    from tobias_b200.pipeline import Engine, prepare_regions
+    from tobias_b200.regions import OneRegion, RegionList, to_arrays
+    per_gpu, n_rec = 3, 5_000_000
+    wl = workload("hg38")
+    t_setup = time.time()
+    ds = synth_torch.TorchDataset(SEED, wl["lengths"], wl["n_peaks"], n_rec, device="cuda", pin=False, keep_codes=True)
+    sample_ids = [rank * per_gpu + j for j in range(per_gpu)]
+    read_sets = [ds.reads_for(SEED + 1000 + sid, n_rec) for sid in sample_ids]
+    ds._state = None
+    torch.cuda.empty_cache()
+    names = ds.names
+    chrom_info = {n: ln for n, ln in zip(names, ds.lengths) if n != "chrM"}
+    regs = prepare_regions(RegionList([OneRegion(list(p)) for p in ds.peaks]), chrom_info, [n for n in names if n in chrom_info], extend=EXTEND,
+                           k_flank=K_FLANK, window=WINDOW)
+    index = {n: i for i, n in enumerate(names)}
+    arrays = {k: to_arrays(sorted(regs[k], key=lambda r: (index[r.chrom], r.start, r.end)), index)
+              for k in ("peak_regions", "nonpeak_regions", "input_regions", "output_regions")}
+    eng = Engine(local)
+    ctx = eng.ctx
+    for kv in args.opt:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+    eng.names, eng.index, eng.lengths = names, index, ds.lengths
+    ctx.genome_create(ds.lengths)
+    for i, g in enumerate(ds.genome):                        # the genome: once per GPU, untimed (shared by every sample of the batch)
+        sq, nm = pack_ascii(g)
+        ctx.genome_upload_packed(i, sq, nm, int(g.shape[0]))
+    hosts = []
+    for rc in read_sets:
+        flags = (rc.is_reverse.astype(np.uint8) * lib.TB_READ_REVERSE | rc.five_prime_is_match().astype(np.uint8) * lib.TB_READ_5P_MATCH
+                 | (~rc.usable()).astype(np.uint8) * lib.TB_READ_SKIP)
+        cols = []
+        for a in (rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags):
+            p = ctx.pinned_empty(a.shape, a.dtype)
+            p[...] = a
+            cols.append(p)
+        hosts.append({"lengths": ds.lengths, "reads": cols, "packed": None, "genome": None})
+    c, s, e = arrays["output_regions"]
+    out_bp = int((e - s).sum())
+    out = {"tracks": {t: ctx.pinned_empty((out_bp,), np.float32) for t in lib.TRACKS}, "footprint": ctx.pinned_empty((out_bp,), np.float32)}
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_batch(download):
+        acc = {}
+        for h in hosts:                                      # a sample: its records in, its own model, its tracks (and footprints) out
+            if download:
+                _b, st, _p = run_step(eng, arrays, device, False, h, out, genome_resident=True, collective=False)
+            else:
+                ctx.reads_upload(*h["reads"])
+                _b, st, _p = run_step(eng, arrays, device, True, h, out, collective=False)
+            for k, v in st.items():
+                acc[k] = acc.get(k, 0.0) + v
+        return acc
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(args.warmup):
+        one_batch(False)
+    barrier()
+    l0 = ctx.launch_count()
+    ctx.timer_begin()
+    stages = {}
+    for _ in range(args.steps):
+        for k, v in one_batch(False).items():
+            stages[k] = stages.get(k, 0.0) + v / args.steps
+    ms = ctx.timer_end()
+    barrier()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    for _ in range(max(1, min(args.warmup, 2))):
+        one_batch(True)
+    barrier()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        one_batch(True)
+    ms_e2e = ctx.timer_end()
+    barrier()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n_samples = per_gpu * world
+    total_bp = float(out_bp) * n_samples
+    value, e2e_value = total_bp * args.steps / (float(t[0]) * 1e-3), total_bp * args.steps / (float(t[1]) * 1e-3)
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    ext_bp = float((e - s + 124).sum())
+    dom = max(stages, key=lambda k: stages[k])
+    alg = {"K1_pileup": 5.0 * n_rec + 8.0 * ext_bp, "K2_counts": 5.0 * n_rec, "K3a_score": 16.375 * ext_bp, "K3b_fit": 24.0 * ext_bp,
+           "K3c_correct": 25.9 * out_bp, "K4_footprint": 8.0 * out_bp}
+    achieved = per_gpu * alg[dom] / (stages[dom] * 1e-3) / 1e9
+    reads_bytes = sum(int(a.nbytes) for h in hosts for a in h["reads"])
+    result = {"metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": dict(bench_config(wl, world), workload="batch of %d pseudobulk samples (5M records each) over one synthetic hg38-sized genome and 150k peaks, "
+                             "%d samples per GPU, bias training + correction + footprints per sample (BASELINE.json configs[4])" % (n_samples, per_gpu),
+                             sharding="%d samples per GPU on %d GPU(s): replicas, genome resident once per GPU, one bias model per sample, no collective" % (per_gpu, world),
+                             samples=n_samples, out_bp_per_sample=out_bp, **({"options": args.opt} if args.opt else {})),
+              "samples_per_s": n_samples * args.steps / (float(t[0]) * 1e-3), "clocks": clocks, "gpu_launches": int(launches),
+              "e2e": {"value": e2e_value, "unit": "bp/s", "ms_per_step": float(t[1]) / args.steps, "samples_per_s": n_samples * args.steps / (float(t[1]) * 1e-3),
+                      "h2d_bytes_per_step": reads_bytes + per_gpu * sum(int(x.nbytes) for v in arrays.values() for x in v), "d2h_bytes_per_step": per_gpu * (5 * out_bp * 4 + 1500),
+                      "note": "a step = the GPU's %d samples; every sample: its record columns H2D from pinned memory, four float32 tracks + footprints D2H; the genome "
+                              "(shared by the batch) is uploaded once per GPU outside the timed region" % per_gpu},
+              "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                           "algorithmic_bytes_per_launch": alg[dom]},
+              "stages": {k: {"ms_per_batch": round(v, 3)} for k, v in stages.items()}, "setup_s": round(setup_s, 1)}
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        try:
+            a2 = argparse.Namespace(**vars(args))
+            a2.workload = "batch24"
+            result["cpu_baseline"] = cpu_reference(a2, steps=1, warmup=0)["cpu_baseline"]
+        except Exception as ex:
+            result["cpu_baseline"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(result))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="hg38", choices=["hg38", "chr50mb", "small"])
+    ap.add_argument("--workload", default="hg38", choices=["hg38", "chr50mb", "small", "fp_genome", "batch24"])
+    ap.add_argument("--fp-scale", type=float, default=1.0, help="fp_genome: scale every contig length (quick runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lm-exact", action="store_true")
     ap.add_argument("--fit-stats", action="store_true")
@@ -846,7 +1207,11 @@ def main():
     args = ap.parse_args()
     global LM_EXACT
     LM_EXACT = args.lm_mode if args.lm_mode is not None else int(bool(args.lm_exact))
-    if args.impl == "reference":
+    if args.workload == "fp_genome":
+        (bench_fp_genome_reference if args.impl == "reference" else bench_fp_genome)(args)
+    elif args.workload == "batch24":
+        (bench_reference if args.impl == "reference" else bench_batch24)(args)
+    elif args.impl == "reference":
         bench_reference(args)
     else:
         bench_b200(args)

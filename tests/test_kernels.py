@@ -361,17 +361,17 @@ def test_persistent_fit_kernel_equals_the_round_form(loaded_ctx, golden):
 
 
 def test_fit_forms_agree(loaded_ctx, golden):
-    """The three arithmetic forms of the window fits -- MINPACK-exact (1), one pass with forward-difference inner products (4), one pass
-    with the moments of the active set (0, the DWM default) -- take the same fit / fallback / empty decision on every window of the
-    golden data and agree on the normalised prediction parameters to 1e-5."""
+    """The three arithmetic forms of the window fits -- MINPACK-exact (1), one pass with forward-difference inner products (0, the DWM
+    default), one pass with the moments of the active set (5, opt-in) -- take the same fit / fallback / empty decision on every window of
+    the golden data and agree on the fitted parameters to 1e-5."""
     g = golden.atac
     _set_model(loaded_ctx, g, "DWM")
     c, s, e = _cols(g["outreg"])
     tr = {}
-    for lm in (1, 4, 0):
+    for lm in (1, 0, 5):
         loaded_ctx.correct_run(c, s, e, correction_factor=1.0, lm_exact_order=lm)
         tr[lm] = loaded_ctx.correct_fit_trace()
-    for lm in (4, 0):
+    for lm in (0, 5):
         assert np.array_equal(tr[lm][:, :, 0], tr[1][:, :, 0]), lm
         fitted = tr[1][:, :, 0] == 0
         for k in (1, 2, 3):

@@ -57,7 +57,8 @@ def _outside(pos, width, blocks):
 
 def make_reads_contig(seed, k, codes, blocks, pk, n_frag, pwm, device, read_len=50, frip=0.3, dup_frac=0.02, clip_frac=0.01,
                       unmapped_frac=0.01, hot_frac=0.0005):
-    """Columns (torch tensors on `device`) of one contig, sorted by ref_start."""
+    """Columns (torch tensors on `device`) of one contig, sorted by ref_start.  `seed` only seeds the reads (a second sample of the same
+    genome and peaks: another seed)."""
     g = _gen(device, seed, 4, k)
     ln = codes.shape[0]
     pwm_t = torch.tensor(pwm, dtype=torch.float32, device=device)
@@ -156,7 +157,7 @@ def make_reads_contig(seed, k, codes, blocks, pk, n_frag, pwm, device, read_len=
 class TorchDataset:
     """names, genome (list of uint8 ASCII numpy arrays), peaks [(name, s, e)], reads (ReadColumns)."""
 
-    def __init__(self, seed, lengths, n_peaks, n_records, device=None, skip=("chrM",), pin=False, universe=None):
+    def __init__(self, seed, lengths, n_peaks, n_records, device=None, skip=("chrM",), pin=False, universe=None, keep_codes=False):
         """universe: name -> length of the WHOLE workload when `lengths` is one rank's shard of it.  Every contig is then seeded by its
         index in the universe and receives its share of the universe's peaks / records, so a contig holds the same bases, peaks and
         records whichever rank builds it (n_peaks / n_records are the universe's totals in that case)."""
@@ -180,6 +181,17 @@ class TorchDataset:
             self.genome.append(host.numpy())
         self.nblocks = nblocks
         self.peaks = synth.make_peaks(seed, dict(zip(self.names, self.lengths)), nblocks, n_peaks, skip=skip, universe=universe)
+        self._state = (key, tot, codes_dev, pwm, device, skip)
+        self.reads = self.reads_for(seed, n_records, drop_codes=not keep_codes)
+        if not keep_codes:
+            self._state = None
+        if device != "cpu":
+            torch.cuda.empty_cache()
+
+    def reads_for(self, reads_seed, n_records, drop_codes=False):
+        """Another sample of the same genome and peaks: `n_records` alignment records drawn with `reads_seed` (needs keep_codes=True
+        for calls after construction)."""
+        key, tot, codes_dev, pwm, device, skip = self._state
         by_chrom = {}
         for c, s, e in self.peaks:
             by_chrom.setdefault(c, []).append((s, e))
@@ -191,11 +203,10 @@ class TorchDataset:
             n_frag = int(round(n_records * (ln / tot) / 2.0)) if name not in skip else max(50, int(n_records * 1e-4))
             if n_frag <= 0:
                 continue
-            cols = make_reads_contig(seed, k, codes_dev[name], nblocks[name], by_chrom.get(name, []), n_frag, pwm, device)
+            cols = make_reads_contig(reads_seed, k, codes_dev[name], self.nblocks[name], by_chrom.get(name, []), n_frag, pwm, device)
             n = cols["ref_start"].shape[0]
             parts.append(ReadColumns(self.names, self.lengths, chrom_id=np.full(n, ki, dtype=np.int32),
                                      **{f: v.cpu().numpy() for f, v in cols.items()}))
-            del codes_dev[name]
-        self.reads = ReadColumns.concat(parts)
-        if device != "cpu":
-            torch.cuda.empty_cache()
+            if drop_codes:
+                del codes_dev[name]
+        return ReadColumns.concat(parts)
