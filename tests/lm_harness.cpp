@@ -12,15 +12,17 @@ struct fake_ctx { long launches; };
 static double gx[128], gy[128];
 static int gm, g_seq;
 static tb_lm_result gres;
-static double2 gtxy[10 * TB_FIT_Q];
+static double gtx[10 * TB_FIT_Q];
+static unsigned gty[10 * TB_FIT_Q];
 void kern() {
     int lane = threadIdx.x & 31;
     if (g_seq == 2 || g_seq == 4 || g_seq == 5) {                    // thread-per-window form (tb_lm_thread.cuh): lane 0 fits the window alone
         if (lane == 0) {
             for (int i = 0; i < gm; i++) {
-                gtxy[(i % 10) * TB_FIT_Q + i / 10] = double2{gx[i], (double)(unsigned)gy[i]};
+                gtx[(i % 10) * TB_FIT_Q + i / 10] = gx[i];
+                gty[(i % 10) * TB_FIT_Q + i / 10] = (unsigned)gy[i];
             }
-            tb_win_ref W{gtxy, TB_FIT_Q};
+            tb_win_ref W{gtx, gty, TB_FIT_Q};
             if (g_seq == 2) tb_lm_fit_thread<false>(W, gm, gres); else if (g_seq == 4) tb_lm_fit_thread<true>(W, gm, gres); else tb_lm_fit_thread<true, true>(W, gm, gres);
         }
         return;

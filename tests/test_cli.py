@@ -66,6 +66,9 @@ def test_atacorrect_and_scorebigwig_match_reference_cli(ctx, dataset, mode):
                 assert np.all(diff <= 1e-5 * np.abs(a[c]) + 2e-6 * scale), (mode, track, c, diff.max(), scale)
                 assert np.mean(diff <= 1e-5 * np.abs(a[c]) + 1e-7 * scale) >= 0.999, (mode, track, c)
     assert os.path.exists(os.path.join(out_mine, "x_AtacBias.pickle"))
+    pdf = open(os.path.join(out_mine, "x_atacorrect.pdf"), "rb").read()          # the report: 2 bias-motif pages + 2 pre / post pages
+    assert pdf.startswith(b"%PDF-1.4") and pdf.count(b"/Type /Page ") == 4 and pdf.rstrip().endswith(b"%%EOF")
+    assert b"Tn5 insertion bias of reads \\(forward\\)" in pdf and b"Nucleotide frequency" in pdf
     # ScoreBigwig on the reference's corrected track
     sig = os.path.join(out_ref, "x_corrected.bw")
     for extra in ([], ["--score", "sum", "--window", "50", "--absolute"], ["--smooth", "3", "--fp-max", "40"]):

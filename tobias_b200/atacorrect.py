@@ -241,10 +241,9 @@ def run_atacorrect(args):
         post_var = np.mean(np.var(post_bias[strand].bias_pwm, axis=1)[:4])
         logger.stats("BIAS\tpre-bias variance {0}:\t{1:.7f}".format(strand, pre_var))
         logger.stats("BIAS\tpost-bias variance {0}:\t{1:.7f}".format(strand, post_var))
-    try:
-        import matplotlib  # noqa: F401
-    except ImportError:
-        logger.warning("matplotlib is not available: {0} was not written".format(figures_f))
+    if root:
+        from .plotting import write_report
+        write_report(figures_f, bias_obj, pre_bias, post_bias)          # bias motifs + pre / post nucleotide frequencies (atacorrect.py:347-348,476-478)
     if eng:
         eng.close()
     fasta.close()

@@ -134,7 +134,8 @@ struct tb_fitg_view {
     double *st;             // [TB_FITG_NST][n_slots] fit state, structure of arrays
     int4 *sti;              // [n_slots] ipvt0, iter, nfev, info
     u32 *wq;                // [n_slots] tile slot q of each window
-    const double2 *gxy;     // [10][qtot] (bias, signal)
+    const double *gx;       // [10][qtot] bias
+    const u32 *gy;          // [10][qtot] signal
     i64 qtot, n_slots;
 };
 
@@ -169,7 +170,7 @@ __device__ __forceinline__ void tb_fitg_append(bool want, u32 slot, u32 *__restr
 
 // transposed copy of (bias, signal) of every window position; one block per (region, strand)
 __global__ void tb_fitg_transpose_kernel(tb_cor_view V, const u32 *__restrict__ pile, const double *__restrict__ biasraw, i64 qs,
-                                         i64 qtot, int qm, double2 *__restrict__ gxy, int32_t *__restrict__ slot_win) {
+                                         i64 qtot, int qm, double *__restrict__ gx, u32 *__restrict__ gy, int32_t *__restrict__ slot_win) {
     const i64 j = blockIdx.x;
     const int strand = blockIdx.y;
     const i64 nw = V.win_off[j + 1] - V.win_off[j];
@@ -182,7 +183,8 @@ __global__ void tb_fitg_transpose_kernel(tb_cor_view V, const u32 *__restrict__ 
     const int np = (int)(TB_STEP * (nw - 1)) + V.window;
     for (int lp = threadIdx.x; lp < np; lp += blockDim.x) {
         const i64 at = (i64)(lp % 10) * qtot + q0 + lp / 10;
-        gxy[at] = double2{biasraw[pos + lp], (double)pile[pos + lp]};
+        gx[at] = biasraw[pos + lp];
+        gy[at] = pile[pos + lp];
     }
 }
 
@@ -204,7 +206,7 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
             G.wq[slot] = (u32)q;
             tb_win_stats st;
             tb_lmt S;
-            const tb_win_ref W{G.gxy + q, G.qtot};
+            const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
             const double f0 = FAST_HEAD == 2 ? tb_lmt_start_moments(S, W, V.window, st)
                                              : (FAST_HEAD == 1 ? tb_lmt_start_fast(S, W, V.window, st) : tb_lmt_fnorm0_stats(W, V.window, st));
             if (f0 >= 0.0) {                                           // signalmax > 0 (:290)
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
             tb_lmt S;
             tb_fitg_load(G, slot, S);
             const i64 q = G.wq[slot];
-            const tb_win_ref W{G.gxy + q, G.qtot};
+            const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
 #ifndef TB_EMU
             if (!FAST || TB_FITG_PREFETCH_FAST) {   // (measured: -5 % on the exact form)
                 // The lanes of a warp read consecutive slots q .. q + 31 of a plane and move up by one slot every ten points, so the top
@@ -260,9 +262,11 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
                 const int top = (m - 1) / 10;
 #pragma unroll
                 for (int v = 0; v < 10; v++) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(W.xy + (i64)v * W.stride + top));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(W.x + (i64)v * W.stride + top));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(W.y + (i64)v * W.stride + top));
                     if (FAST) {        // plane-major traversal: the first touch of every plane would otherwise be a miss two points ahead of its use
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(W.xy + (i64)v * W.stride));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(W.x + (i64)v * W.stride));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(W.y + (i64)v * W.stride));
                     }
                 }
             }
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
         tb_lmt S;
         tb_fitg_load(G, slot, S);
         const i64 q = G.wq[slot];
-        const tb_win_ref W{G.gxy + q, G.qtot};
+        const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
         for (;;) {
             if (need_qr) {
                 if (FAST == 2) tb_lmt_qr_moments(S, W, m);
@@ -355,17 +359,23 @@ __global__ void __launch_bounds__(NT, MINB)
     tb_fitp_kernel(tb_fitg_view G, const int32_t *__restrict__ slot_win, tb_fitp_tile T, i64 n_tiles, int m, int cap,
                    double *__restrict__ fit, u32 *__restrict__ listt, unsigned long long *ctr) {
     TB_DYN_SMEM(smem);
-    double2 *sxy = (double2 *)smem;                             // [10][tsp] (bias, signal)
+    double *sx = (double *)smem;                                // [10][tsp]
+    u32 *sy = (u32 *)(sx + (size_t)10 * T.tsp);                 // [10][tsp]
     __shared__ u32 qctr[32];
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned FULL = 0xffffffffu;
     for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const i64 t0 = tile * T.ts;
         __syncthreads();                                        // every fit of the previous tile has ended
-        {   // stage the tile: 16-byte loads
-            for (int i = tid; i < 10 * T.tsp; i += NT) {
-                const int v = i / T.tsp, u = i - v * T.tsp;
-                sxy[(size_t)v * T.tsp + u] = G.gxy[(i64)v * G.qtot + t0 + u];
+        {   // stage the tile: 16-byte loads (t0, tsp and the plane stride in HBM are multiples of 4)
+            const int nx = T.tsp / 2, ny = T.tsp / 4;
+            for (int i = tid; i < 10 * nx; i += NT) {
+                const int v = i / nx, u = i - v * nx;
+                ((double2 *)(sx + (size_t)v * T.tsp))[u] = ((const double2 *)(G.gx + (i64)v * G.qtot + t0))[u];
+            }
+            for (int i = tid; i < 10 * ny; i += NT) {
+                const int v = i / ny, u = i - v * ny;
+                ((uint4 *)(sy + (size_t)v * T.tsp))[u] = ((const uint4 *)(G.gy + (i64)v * G.qtot + t0))[u];
             }
             if (tid < 32) qctr[tid] = 0u;
         }
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(NT, MINB)
             if (!__any_sync(FULL, busy)) break;
             bool parked = false;
             if (busy) {
-                const tb_win_ref W{sxy + sl, (i64)T.tsp};
+                const tb_win_ref W{sx + sl, sy + sl, (i64)T.tsp};
                 const bool have = tb_lmt_step_fast(S, st, W, m, first);
                 first = false;
                 passes++;
@@ -965,8 +975,9 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
                   n_regions, C.ext_total, C.out_total, C.n_windows, k_flank, window, L, f_extend};
     // window fits: lm_exact_order 0 -> one-pass fits with forward-difference inner products (fit_form 1: the DWM default), 1 -> MINPACK-exact
     // (fit_form 0), 5 -> moment form of the one-pass fits (fit_form 2: exact derivative instead of difference quotients -- a third of the
-    // arithmetic, but it leaves scipy's path on more of the windows that scipy itself does not fit stably; opt-in); 2 / 3: first-generation
-    // warp kernels (4 is accepted as an alias of 0)
+    // arithmetic, but it leaves scipy's path on more of the windows that scipy itself does not fit stably, and the round kernels are bound
+    // by the L2 traffic of re-reading every window once per pass, not by arithmetic: measured 52.1 vs 53.6 ms; opt-in); 2 / 3:
+    // first-generation warp kernels (4 is accepted as an alias of 0)
     const int fit_form = lm_exact_order == 5 ? 2 : ((lm_exact_order == 0 || lm_exact_order == 4) ? 1 : 0);
     if (lm_exact_order < 2 || lm_exact_order == 4 || lm_exact_order == 5) {
         // round form (default): state in HBM, compacted work lists, one host read-back of two counters per round
@@ -980,13 +991,14 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
 #ifdef TB_EMU
         const int fitp_ts_default = 256;                          // the test emulator runs small tiles (same code)
 #else
-        const int fitp_ts_default = fitp_threads == 256 ? 672 : 1376;
+        const int fitp_ts_default = fitp_threads == 256 ? 800 : 1600;
 #endif
         const int fitp_ts = tb_opt(ctx, "k3b_tile", 0) >= 64 ? (int)(tb_opt(ctx, "k3b_tile", 0) & ~31LL) : fitp_ts_default;
         const i64 n_ptiles = tb_div_up(2 * qs, fitp_ts);
         const i64 qtot = persistent ? n_ptiles * fitp_ts + 16 : 2 * qs;
         if (10 * qtot >= ((i64)1 << 32)) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: too many windows for one launch");
-        TB_TRY(tb_reserve(ctx, C.fitg_x, (size_t)10 * qtot * sizeof(double2)));
+        TB_TRY(tb_reserve(ctx, C.fitg_x, (size_t)10 * qtot * sizeof(double)));
+        TB_TRY(tb_reserve(ctx, C.fitg_y, (size_t)10 * qtot * sizeof(u32)));
         if (persistent) {
             TB_TRY(tb_reserve(ctx, C.fitg_sw, (size_t)qtot * sizeof(int32_t)));
             TB_CUDA(ctx, cudaMemsetAsync(C.fitg_sw.p, 0xff, (size_t)qtot * sizeof(int32_t), ctx->stream));      // -1: no window
@@ -998,14 +1010,15 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         u32 *lists = C.fitg_lists.as<u32>();
         u32 *lq[2] = {lists, lists + n_slots}, *lt[2] = {lists + 2 * n_slots, lists + 3 * n_slots};
         unsigned long long *ctr = (unsigned long long *)(lists + 4 * n_slots);       // [0] Q, [1] T of the list being built
-        tb_fitg_view G{C.fitg_st.as<double>(), C.fitg_sti.as<int4>(), C.fitg_wq.as<u32>(), C.fitg_x.as<double2>(), qtot, n_slots};
+        tb_fitg_view G{C.fitg_st.as<double>(), C.fitg_sti.as<int4>(), C.fitg_wq.as<u32>(), C.fitg_x.as<double>(),
+                       C.fitg_y.as<u32>(), qtot, n_slots};
         TB_LAUNCH(ctx, tb_fitg_transpose_kernel, dim3((unsigned)n_regions, 2), 256, 0, V, (const u32 *)C.pile.as<u32>(),
-                  (const double *)C.biasraw.as<double>(), qs, qtot, qm, C.fitg_x.as<double2>(),
+                  (const double *)C.biasraw.as<double>(), qs, qtot, qm, C.fitg_x.as<double>(), C.fitg_y.as<u32>(),
                   persistent ? C.fitg_sw.as<int32_t>() : (int32_t *)nullptr);
         TB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
         if (persistent) {
             const tb_fitp_tile T{fitp_ts, fitp_ts + 12};
-            const size_t psmem = (size_t)10 * T.tsp * sizeof(double2);
+            const size_t psmem = (size_t)10 * T.tsp * (sizeof(double) + sizeof(u32));
             const int cap_passes = tb_opt(ctx, "k3b_cap", 0) > 0 ? (int)tb_opt(ctx, "k3b_cap", 0) : 8;
             if (psmem > (size_t)226 * 1024) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: k3b_tile too large for the shared memory");
             if (fitp_threads == 256) {

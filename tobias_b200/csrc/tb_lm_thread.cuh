@@ -20,12 +20,11 @@
 #include "tb_common.cuh"
 #include "tb_lm.cuh"
 
-// Window point i = 10 u + v of this thread's window lives at xy[v * stride + u] = (bias, signal as a double): consecutive windows start
-// 10 positions apart, so consecutive windows read consecutive slots.  One 16-byte load per point: the round kernels are bound by the
-// number of L1 requests once the work lists thin out (every lane then reads its own sector), not by arithmetic -- two loads per point
-// (f64 bias + u32 signal, the first layout) cost twice the requests.
+// Window point i = 10 u + v of this thread's window lives at x[v * stride + u] (bias, f64) / y[v * stride + u]
+// (signal, u32 counts): consecutive windows start 10 positions apart, so consecutive windows read consecutive slots.
 struct tb_win_ref {
-    const double2 *xy;
+    const double *x;
+    const u32 *y;
     i64 stride;             // distance between the planes v = 0..9
 };
 // exact u32 -> double without a conversion instruction: (2^52 + k) - 2^52
@@ -33,7 +32,7 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
     return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0;
 }
 
-// for (i = i0; i < m; i++) body(i, ex = bias[i], ey = signal[i] as double), i0 < 10.  Kept compact
+// for (i = i0; i < m; i++) body(i, ex = bias[i], ey = signal[i] as double, eyi = signal[i] as u32), i0 < 10.  Kept compact
 // on purpose (no unrolling): the kernel is a sequence of such passes and must stay resident in the instruction cache.
 // Point i + 1 is loaded while point i is processed (hides the L1 latency); offsets are 32-bit element indices
 // (the host checks 10 * stride < 2^32).
@@ -46,16 +45,21 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
     {                                                                          \
         const u32 _st = (u32)(W).stride, _wrap = 9u * _st - 1u;                \
         u32 _off = (u32)(i0) * _st;                                            \
-        double2 _n = (W).xy[_off];                                             \
+        double _nx = (W).x[_off];                                              \
+        u32 _ny = (W).y[_off];                                                 \
         int _v = (i0);                                                         \
         TB_PRAGMA(unroll TB_FIT_UNROLL)                                        \
         for (int i = (i0); i < (m); i++) {                                     \
-            const double ex = _n.x;                                            \
-            const double ey = _n.y;                                            \
+            const double ex = _nx;                                             \
+            const u32 eyi = _ny;                                               \
             const bool _w10 = ++_v == 10;                                      \
             _off = _w10 ? _off - _wrap : _off + _st;                           \
             _v = _w10 ? 0 : _v;                                                \
-            if (i + 1 < (m)) _n = (W).xy[_off];                                \
+            if (i + 1 < (m)) {                                                 \
+                _nx = (W).x[_off];                                             \
+                _ny = (W).y[_off];                                             \
+            }                                                                  \
+            const double ey = tb_u32_to_double(eyi);                           \
             __VA_ARGS__                                                        \
         }                                                                      \
     }
@@ -70,37 +74,47 @@ __device__ __forceinline__ double tb_u32_to_double(u32 k) {
 #endif
 #define TB_FOR_POINTS_ANY_ORDER(W, m, ...)                                                                  \
     {                                                                                                       \
-        const double2 *_p = (W).xy;                                                                         \
+        const double *_px = (W).x;                                                                          \
+        const u32 *_py = (W).y;                                                                             \
         int _v = 0, _left = ((m) + 9) / 10;            /* points of plane 0 still to load */                \
-        double2 _q[TB_FIT_AHEAD];                                                                           \
+        double _qx[TB_FIT_AHEAD];                                                                           \
+        u32 _qy[TB_FIT_AHEAD];                                                                              \
         _Pragma("unroll") for (int _k = 0; _k < TB_FIT_AHEAD; _k++) {                                       \
-            _q[_k] = double2{0.0, 0.0};                                                                     \
+            _qx[_k] = 0.0;                                                                                  \
+            _qy[_k] = 0u;                                                                                   \
             if (_k < (m)) {                                                                                 \
-                _q[_k] = *_p;                                                                               \
+                _qx[_k] = *_px;                                                                             \
+                _qy[_k] = *_py;                                                                             \
                 if (--_left == 0) {                                                                         \
                     _v++;                                                                                   \
                     _left = ((m) - _v + 9) / 10;                                                            \
-                    _p = (W).xy + (i64)_v * (W).stride;                                                     \
+                    _px = (W).x + (i64)_v * (W).stride;                                                     \
+                    _py = (W).y + (i64)_v * (W).stride;                                                     \
                 } else {                                                                                    \
-                    _p++;                                                                                   \
+                    _px++;                                                                                  \
+                    _py++;                                                                                  \
                 }                                                                                           \
             }                                                                                               \
         }                                                                                                   \
         for (int _i0 = 0; _i0 < (m); _i0 += TB_FIT_AHEAD) {                                                 \
             _Pragma("unroll") for (int _k = 0; _k < TB_FIT_AHEAD; _k++) {                                   \
                 if (_i0 + _k < (m)) {                                                                       \
-                    const double ex = _q[_k].x;                                                             \
-                    const double ey = _q[_k].y;                                                             \
+                    const double ex = _qx[_k];                                                              \
+                    const u32 eyi = _qy[_k];                                                                \
                     if (_i0 + _k + TB_FIT_AHEAD < (m)) {                                                    \
-                        _q[_k] = *_p;                                                                       \
+                        _qx[_k] = *_px;                                                                     \
+                        _qy[_k] = *_py;                                                                     \
                         if (--_left == 0) {                                                                 \
                             _v++;                                                                           \
                             _left = ((m) - _v + 9) / 10;                                                    \
-                            _p = (W).xy + (i64)_v * (W).stride;                                             \
+                            _px = (W).x + (i64)_v * (W).stride;                                             \
+                            _py = (W).y + (i64)_v * (W).stride;                                             \
                         } else {                                                                            \
-                            _p++;                                                                           \
+                            _px++;                                                                          \
+                            _py++;                                                                          \
                         }                                                                                   \
                     }                                                                                       \
+                    const double ey = tb_u32_to_double(eyi);                                                \
                     __VA_ARGS__                                                                             \
                 }                                                                                           \
             }                                                                                               \
@@ -189,13 +203,13 @@ struct tb_win_stats {
 __device__ __forceinline__ double tb_lmt_fnorm0_stats(const tb_win_ref W, int m, tb_win_stats &st) {
     tb_enorm_acc n;
     tb_enorm_init(n);
-    double ymax = 0.0;
+    u32 ymax = 0;
     double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
     TB_FOR_POINTS(W, m, i, {
-        ymax = fmax(ymax, ey);
+        ymax = eyi > ymax ? eyi : ymax;
         xmax = fmax(xmax, ex);
         xmin = fmin(xmin, ex);
-        if (ey != 0.0) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
+        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
         tb_enorm_add(n, tb_relu_res(1.0, 1.0, ex, ey), m);
     })
     st.xmax = xmax;
@@ -208,9 +222,9 @@ __device__ __forceinline__ double tb_lmt_fnorm0_stats(const tb_win_ref W, int m,
 __device__ __forceinline__ double tb_lmt_fnorm0(const tb_win_ref W, int m) {
     tb_enorm_acc n;
     tb_enorm_init(n);
-    double ymax = 0.0;
+    u32 ymax = 0;
     TB_FOR_POINTS(W, m, i, {
-        ymax = fmax(ymax, ey);
+        ymax = eyi > ymax ? eyi : ymax;
         tb_enorm_add(n, tb_relu_res(1.0, 1.0, ex, ey), m);
     })
     return ymax > 0 ? tb_enorm_result(n) : -1.0;
@@ -296,8 +310,8 @@ __device__ __forceinline__ void tb_lmt_qr(tb_lmt &S, const tb_win_ref W, int m) 
     }
     S.nfev += 2;
     // the first two rows take part in the Householder bookkeeping (signs, +1 on the diagonal, R's entries)
-    const double x0 = W.xy[0].x, y0 = W.xy[0].y;
-    const double x1 = W.xy[W.stride].x, y1 = W.xy[W.stride].y;
+    const double x0 = W.x[0], y0 = tb_u32_to_double(W.y[0]);
+    const double x1 = W.x[W.stride], y1 = tb_u32_to_double(W.y[W.stride]);
     double f0, f1, j00, j10;
     J.eval(x0, y0, f0, j00, j10);
     // ---- pass A: column norms (column 0 = d/da as P, column 1 = d/db as Q)
@@ -463,8 +477,8 @@ __device__ __forceinline__ void tb_lmt_qr_from_gram(tb_lmt &S, const tb_win_ref 
 __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, int m) {
     const tb_jac_fast J = tb_jac_fast_at(S.par0, S.par1);
     tb_gram Gm;
-    J.eval(W.xy[0].x, W.xy[0].y, Gm.f0, Gm.a0, Gm.b0);
-    J.eval(W.xy[W.stride].x, W.xy[W.stride].y, Gm.f1, Gm.a1, Gm.b1);
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
     double g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
     TB_FOR_POINTS_ANY_ORDER(W, m, {
         double f, j0, j1;
@@ -485,16 +499,16 @@ __device__ __forceinline__ void tb_lmt_qr_fast(tb_lmt &S, const tb_win_ref W, in
 __device__ __forceinline__ double tb_lmt_start_fast(tb_lmt &S, const tb_win_ref W, int m, tb_win_stats &st) {
     const tb_jac_fast J = tb_jac_fast_at(1.0, 1.0);
     tb_gram Gm;
-    J.eval(W.xy[0].x, W.xy[0].y, Gm.f0, Gm.a0, Gm.b0);
-    J.eval(W.xy[W.stride].x, W.xy[W.stride].y, Gm.f1, Gm.a1, Gm.b1);
-    double ymax = 0.0;
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
+    u32 ymax = 0;
     double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
     double ss = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
     TB_FOR_POINTS_ANY_ORDER(W, m, {
-        ymax = fmax(ymax, ey);
+        ymax = eyi > ymax ? eyi : ymax;
         xmax = fmax(xmax, ex);
         xmin = fmin(xmin, ex);
-        if (ey != 0.0) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
+        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
         double f, j0, j1;
         J.eval(ex, ey, f, j0, j1);
         ss += f * f;
@@ -507,7 +521,7 @@ __device__ __forceinline__ double tb_lmt_start_fast(tb_lmt &S, const tb_win_ref 
     st.xmax = xmax;
     st.xmin = xmin;
     st.bmin = bmin;
-    if (ymax == 0.0) return -1.0;
+    if (ymax == 0u) return -1.0;
     Gm.g00 = g00; Gm.g01 = g01; Gm.g11 = g11; Gm.gf0 = gf0; Gm.gf1 = gf1;
     const double f0 = sqrt(ss);
     tb_lmt_init(S, f0);
@@ -633,7 +647,7 @@ __device__ __forceinline__ tb_gram tb_moments_gram(const tb_moments &M, const tb
     G.g11 = (double)M.n;
     G.gf0 = fma(a, M.sxx, b * M.sx) - M.sxy;
     G.gf1 = fma(a, M.sx, b * (double)M.n) - M.sy;
-    const double x0 = W.xy[0].x, y0 = W.xy[0].y, x1 = W.xy[W.stride].x, y1 = W.xy[W.stride].y;
+    const double x0 = W.x[0], y0 = tb_u32_to_double(W.y[0]), x1 = W.x[W.stride], y1 = tb_u32_to_double(W.y[W.stride]);
     const bool a0 = tb_active(a, b, x0), a1 = tb_active(a, b, x1);
     G.f0 = (a0 ? __dadd_rn(__dmul_rn(a, x0), b) : 0.0) - y0;
     G.a0 = a0 ? x0 : 0.0;
@@ -652,8 +666,8 @@ __device__ __forceinline__ bool tb_moments_degenerate(const tb_gram &G) {
 }
 __device__ __noinline__ void tb_gram_fd(const tb_win_ref W, int m, double a, double b, tb_gram &Gm) {
     const tb_jac_fast J = tb_jac_fast_at(a, b);
-    J.eval(W.xy[0].x, W.xy[0].y, Gm.f0, Gm.a0, Gm.b0);
-    J.eval(W.xy[W.stride].x, W.xy[W.stride].y, Gm.f1, Gm.a1, Gm.b1);
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
     double g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
     TB_FOR_POINTS_ANY_ORDER(W, m, {
         double f, j0, j1;
@@ -668,15 +682,15 @@ __device__ __noinline__ void tb_gram_fd(const tb_win_ref W, int m, double a, dou
 }
 // start of a fit: statistics, Tyy and the moments at p0 = (1, 1) in one pass, then the first outer-iteration head.  -1: no signal.
 __device__ __forceinline__ double tb_lmt_start_moments(tb_lmt &S, const tb_win_ref W, int m, tb_win_stats &st) {
-    double ymax = 0.0;
+    u32 ymax = 0;
     double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
     double sx = 0.0, sy = 0.0, sxx = 0.0, sxy = 0.0, tyy = 0.0;
     int n = 0;
     TB_FOR_POINTS_ANY_ORDER(W, m, {
-        ymax = fmax(ymax, ey);
+        ymax = eyi > ymax ? eyi : ymax;
         xmax = fmax(xmax, ex);
         xmin = fmin(xmin, ex);
-        if (ey != 0.0) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
+        if (eyi != 0u) bmin = fmin(bmin, ex);                   // ~isclose(signal, 0)
         const bool act = tb_active(1.0, 1.0, ex);
         const double xm = act ? ex : 0.0;
         const double ym = act ? ey : 0.0;
@@ -690,7 +704,7 @@ __device__ __forceinline__ double tb_lmt_start_moments(tb_lmt &S, const tb_win_r
     st.xmax = xmax;
     st.xmin = xmin;
     st.bmin = bmin;
-    if (ymax == 0.0) return -1.0;
+    if (ymax == 0u) return -1.0;
     const tb_moments M{sx, sy, sxx, sxy, n};
     const double f0 = sqrt(tb_moments_ss(M, tyy, 1.0, 1.0));
     tb_lmt_init(S, f0);
@@ -760,8 +774,8 @@ __device__ __forceinline__ bool tb_lmt_trial(tb_lmt &S, const tb_win_ref W, int 
             }
         } else if (FAST && FUSE) {
             J = tb_jac_fast_at(ta, tb_);
-            J.eval(W.xy[0].x, W.xy[0].y, Gm.f0, Gm.a0, Gm.b0);
-            J.eval(W.xy[W.stride].x, W.xy[W.stride].y, Gm.f1, Gm.a1, Gm.b1);
+            J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+            J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
             double ss = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
             TB_FOR_POINTS_ANY_ORDER(W, m, {
                 double f, j0, j1;
@@ -877,17 +891,17 @@ __device__ __forceinline__ bool tb_lmt_step_fast(tb_lmt &S, tb_win_stats &st, co
     // ---- the pass
     const tb_jac_fast J = tb_jac_fast_at(wa2[0], wa2[1]);
     tb_gram Gm;
-    J.eval(W.xy[0].x, W.xy[0].y, Gm.f0, Gm.a0, Gm.b0);
-    J.eval(W.xy[W.stride].x, W.xy[W.stride].y, Gm.f1, Gm.a1, Gm.b1);
-    double ymax = 0.0;
+    J.eval(W.x[0], tb_u32_to_double(W.y[0]), Gm.f0, Gm.a0, Gm.b0);
+    J.eval(W.x[W.stride], tb_u32_to_double(W.y[W.stride]), Gm.f1, Gm.a1, Gm.b1);
+    u32 ymax = 0;
     double xmax = -INFINITY, xmin = INFINITY, bmin = INFINITY;
     double ss = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0, gf0 = 0.0, gf1 = 0.0;
     TB_FOR_POINTS_ANY_ORDER(W, m, {
         if (first) {
-            ymax = fmax(ymax, ey);
+            ymax = eyi > ymax ? eyi : ymax;
             xmax = fmax(xmax, ex);
             xmin = fmin(xmin, ex);
-            if (ey != 0.0) bmin = fmin(bmin, ex);               // ~isclose(signal, 0)
+            if (eyi != 0u) bmin = fmin(bmin, ex);               // ~isclose(signal, 0)
         }
         double f, j0, j1;
         J.eval(ex, ey, f, j0, j1);
@@ -904,7 +918,7 @@ __device__ __forceinline__ bool tb_lmt_step_fast(tb_lmt &S, tb_win_stats &st, co
         st.xmax = xmax;
         st.xmin = xmin;
         st.bmin = bmin;
-        if (ymax == 0.0) return false;
+        if (ymax == 0u) return false;
         tb_lmt_init(S, fnorm1);
         tb_lmt_qr_from_gram(S, W, m, J, Gm);
         return true;
@@ -1001,7 +1015,7 @@ __device__ __forceinline__ void tb_lmt_finish(const tb_lmt &S, const tb_win_ref 
     TB_FOR_POINTS(W, m, i, {
         st.xmax = fmax(st.xmax, ex);
         st.xmin = fmin(st.xmin, ex);
-        if (ey != 0.0) st.bmin = fmin(st.bmin, ex);             // ~isclose(signal, 0)
+        if (eyi != 0u) st.bmin = fmin(st.bmin, ex);             // ~isclose(signal, 0)
         (void)ey;
     })
     tb_lmt_finish_stats(S, st, mode, pa, pb, pmax);
