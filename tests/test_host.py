@@ -99,6 +99,42 @@ def test_bam_roundtrip_and_fetch_semantics(tmp_path):
     assert np.array_equal(idx, brute)
 
 
+def test_bam_reader_by_contig_indexes_and_corruption(tmp_path):
+    """Bounded batches (a partial record is carried into the next batch), records of unwanted contigs skipped during the walk, and --
+    with a .bai or the .tbidx sidecar -- only the blocks of the wanted contigs inflated; a corrupt length field is an error."""
+    ds = synth.SynthDataset(31, {"chr1": 50000, "chr2": 42000, "chr3": 36000, "chrM": 5000}, n_peaks=12, n_records=36000)
+    path = str(tmp_path / "x.bam")
+    bam.write_bam(path, ds.reads, bai=True)
+    full = ds.reads
+    r = bam.BamReader(path)
+    from_bai = r._index()
+    assert from_bai is not None and from_bai[0] == r.header_end and np.all(np.diff(from_bai) > 0)
+    for contigs, batch in ((["chr3"], 256 << 20), (["chr2", "chrM"], 70000), (["chr1"], 50000)):
+        ids = [full.references.index(c) for c in contigs]
+        m = np.isin(full.chrom_id, ids)
+        got = r.read(contigs=contigs, batch_bytes=batch)
+        for f in ("chrom_id", "ref_start", "ref_end", "left_soft", "right_soft", "flag", "first_op", "last_op", "tlen"):
+            assert np.array_equal(getattr(got, f), getattr(full, f)[m]), (contigs, f)
+    assert len(r.read(contigs=["nope"])) == 0
+    r.close()
+    os.remove(path + ".bai")
+    r = bam.BamReader(path)
+    assert not r.has_index()
+    assert np.array_equal(r.read(contigs=["chr2"], batch_bytes=60000).ref_start, full.ref_start[full.chrom_id == 1])      # no index: walks from the start
+    assert np.array_equal(r.build_index(batch_bytes=80000), from_bai) and os.path.exists(path + ".tbidx") and r.has_index()
+    assert np.array_equal(r.read(contigs=["chr3"]).ref_end, full.ref_end[full.chrom_id == 2])
+    raw = bytearray(bam.bgzf_decompress(open(path, "rb").read()))
+    raw[r.header_end + 12] = raw[r.header_end + 13] = 0xFF                      # n_cigar_op of the first record: 65535 operations
+    r.close()
+    bad = str(tmp_path / "bad.bam")
+    open(bad, "wb").write(bam.bgzf_compress(bytes(raw)))
+    with pytest.raises(ValueError, match="malformed alignment record"):
+        bam.read_bam(bad)
+    open(bad, "wb").write(open(path, "rb").read()[:-5000])                      # truncated file
+    with pytest.raises(ValueError):
+        bam.read_bam(bad)
+
+
 def test_bigwig_roundtrip_many_sections(tmp_path):
     rng = np.random.default_rng(1)
     path = str(tmp_path / "t.bw")
@@ -122,6 +158,16 @@ def test_bigwig_roundtrip_many_sections(tmp_path):
     assert r.header()["nBasesCovered"] == pos.size + 10
     with pytest.raises(RuntimeError):
         r.values("chrA", 0, 6000)
+    # zoom levels (genome browsers ask for them): every level summarises every data point once; a record agrees with the data under it
+    assert r.zoom_levels >= 3 and [z[0] for z in r.zoom_headers()][:3] == [64, 256, 1024]
+    for lv in range(r.zoom_levels):
+        red, rec = r.zoom_records(lv)
+        assert rec["valid"].sum() == pos.size + 10 and np.all(rec["end"] > rec["start"]) and np.all(rec["end"] - rec["start"] <= red)
+        b = rec[rec["chrom"] == 0]
+        k = len(b) // 2
+        seg = full[int(b["start"][k]):int(b["end"][k])]
+        seg = seg[~np.isnan(seg)]
+        assert b["valid"][k] == seg.size and b["min"][k] == seg.min() and b["max"][k] == seg.max() and abs(b["sum"][k] - seg.sum()) < 1e-3
     r.close()
 
 

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import lib
 from .dist import Comm, shard_contigs
-from .io.bam import read_bam
+from .io.bam import BamReader
 from .io.bigwig import BigWigWriter
 from .io.fasta import FastaFile
 from .logger import TobiasLogger
@@ -40,17 +40,27 @@ def check_files(paths, action="r"):
 
 def write_track(path, header, regions, values, region_offsets):
     """bigwig_writer semantics (tobias/utils/utilities.py:129-232): regions in header order, non-zero positions only,
-    float32 values, span 1.  `values` is the concatenated track, region i at region_offsets[i]."""
+    float32 values, span 1.  `values` is the concatenated track, region i at region_offsets[i].  One add_entries call per contig: the
+    non-zero positions of all its regions at once (sections are compressed in parallel, zoom levels follow)."""
     order = {c: i for i, (c, _) in enumerate(header)}
     idx = sorted(range(len(regions)), key=lambda i: (order[regions[i].chrom], regions[i].start))
     w = BigWigWriter(path)
     w.add_header(header)
-    for i in idx:
-        r = regions[i]
-        sig = values[region_offsets[i]:region_offsets[i] + (r.end - r.start)]
-        nz = np.flatnonzero(sig)
-        if nz.size:
-            w.add_entries(r.chrom, nz.astype(np.int64) + r.start, sig[nz])
+    values = np.asarray(values)
+    k = 0
+    while k < len(idx):
+        chrom = regions[idx[k]].chrom
+        pos_parts, val_parts = [], []
+        while k < len(idx) and regions[idx[k]].chrom == chrom:
+            r = regions[idx[k]]
+            sig = values[region_offsets[idx[k]]:region_offsets[idx[k]] + (r.end - r.start)]
+            nz = np.flatnonzero(sig)
+            if nz.size:
+                pos_parts.append(nz.astype(np.int64) + r.start)
+                val_parts.append(sig[nz])
+            k += 1
+        if pos_parts:
+            w.add_entries(chrom, np.concatenate(pos_parts), np.concatenate(val_parts))
     w.close()
 
 
@@ -61,6 +71,13 @@ def run_atacorrect(args):
         sys.exit("Error: No .fasta-file given")
     if args.peaks is None:
         sys.exit("Error: No .peaks-file given")
+    import time
+    phases, t_last = OrderedDict(), [time.perf_counter()]
+
+    def phase(name):                    # wall clock per phase of the run (bench.py --cli reports it)
+        now = time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + (now - t_last[0])
+        t_last[0] = now
     comm = Comm.init_from_env()
     root = comm.rank == 0
     args.prefix = os.path.splitext(os.path.basename(args.bam))[0] if args.prefix is None else args.prefix
@@ -91,9 +108,9 @@ def run_atacorrect(args):
     check_files(bigwigs, "w")
 
     logger.info("Reading info from .bam file")
-    reads = read_bam(args.bam)
-    bam_references = list(reads.references)
-    bam_chrom_info = dict(zip(reads.references, reads.lengths))
+    bam = BamReader(args.bam)                   # header + BGZF block table only; the records follow once this rank knows its contigs
+    bam_references = list(bam.references)
+    bam_chrom_info = dict(zip(bam.references, bam.lengths))
     logger.info("Reading info from .fasta file")
     fasta = FastaFile(args.genome)
     fasta_chrom_info = dict(zip(fasta.references, fasta.lengths))
@@ -134,19 +151,32 @@ def run_atacorrect(args):
         logger.error("No regions found - exiting!")
         sys.exit()
 
+    phase("headers_and_regions")
     # ---- shard by contig, make this rank's data resident on its GPU
     owner = shard_contigs(chrom_info, comm.world)
     mine = [c for c in bam_references if owner[c] == comm.rank]
     local = {k: RegionList([r for r in rd[k] if owner[r.chrom] == comm.rank]) for k in
              ("input_regions", "output_regions", "peak_regions", "nonpeak_regions")}
     device = int(os.environ.get("LOCAL_RANK", args.device))
+    # every rank inflates and decodes the BGZF blocks of its own contigs only; without a .bai / .tbidx rank 0 first walks the file once
+    # (no records kept) and leaves the contig offsets next to the BAM
+    if comm.world > 1:
+        if root and not bam.has_index():
+            logger.info("Indexing {0} (one pass, contig offsets only)".format(args.bam))
+            bam.build_index()
+        comm.barrier()
     eng = None
     if mine:              # a rank without contigs (more ranks than kept contigs) holds no data: it adds zeros to the all-reduces, nothing to the gathers
         eng = Engine(device)
+        phase("gpu_context")
         eng.load_genome_fasta(fasta, mine)
-        name_to_old = {n: i for i, n in enumerate(reads.references)}
-        sel = np.isin(reads.chrom_id, [name_to_old[c] for c in mine])
-        eng.load_reads(reads.select(sel))
+        phase("genome_pack_and_upload")
+        rc_mine = bam.read(contigs=mine)
+        phase("bam_decode")
+        eng.load_reads(rc_mine)
+        del rc_mine
+        phase("reads_upload")
+    bam.close()
     read_shift = tuple(args.read_shift)
 
     logger.comment("")
@@ -171,6 +201,7 @@ def run_atacorrect(args):
         logger.info("Normalization was switched off")
         correct_factor = 1.0
     logger.stats("CORRECTION_FACTOR:\t{0:.5f}".format(correct_factor))
+    phase("count_reads")
 
     logger.comment("")
     if args.bias_pkl is None:
@@ -190,6 +221,7 @@ def run_atacorrect(args):
         bias_obj.bias[strand].prepare_mat()
     if root:
         bias_obj.to_pickle(os.path.join(args.outdir, args.prefix + "_AtacBias.pickle"))
+    phase("bias_estimation")
 
     logger.comment("")
     logger.info("----- Correcting reads from .bam within output regions -----")
@@ -206,6 +238,7 @@ def run_atacorrect(args):
     else:
         got, prepost = {}, np.zeros((2, 3, 5, 2 * args.k_flank + 1))
     comm.allreduce_sum(prepost)
+    phase("bias_correction")
 
     # ---- rank 0 gathers and writes the bigWigs (header = contigs in BAM order, like the reference)
     header = [(c, bam_chrom_info[c]) for c in bam_references]
@@ -228,6 +261,7 @@ def run_atacorrect(args):
                 logger.info("Closing {0} (this might take some time)".format(output_bws[track][strand]))
                 write_track(output_bws[track][strand], header, regs, np.concatenate(parts) if parts else np.zeros(0, np.float32), offs)
 
+    phase("write_bigwigs")
     logger.comment("")
     logger.info("Verifying bias correction")
     pre_bias, post_bias = prepost_to_matrices(prepost, 2 * args.k_flank + 1)
@@ -247,8 +281,10 @@ def run_atacorrect(args):
     if eng:
         eng.close()
     fasta.close()
+    phase("verification_and_report")
     logger.end()
-    return {"correction_factor": correct_factor, "bias": bias_obj, "pre_bias": pre_bias, "post_bias": post_bias}
+    return {"correction_factor": correct_factor, "bias": bias_obj, "pre_bias": pre_bias, "post_bias": post_bias,
+            "phases_s": {k: round(v, 3) for k, v in phases.items()}}
 
 
 def main(argv=None):

@@ -4,14 +4,20 @@ Minimal bigWig codec (pyBigWig / libBigWig are absent from the image).
 Writer: what `bigwig_writer` needs (tobias/utils/utilities.py:129-232): a header of (chrom, length) pairs in file order
 and `addEntries(chrom, positions, values=..., span=1)` calls in sorted order; values are stored as float32, only the
 positions handed in are written (the reference passes the non-zero positions, :193-200).  Entries become
-variableStep sections (type 2, span 1) of <= 1024 items, zlib-compressed, followed by the chromosome B+ tree and a
-packed R-tree over the sections -- the layout any bigWig reader (UCSC tools, pyBigWig, IGV) understands.  No zoom levels.
+variableStep sections (type 2, span 1) of <= 1024 items, zlib-compressed in parallel on the host cores by a native helper
+(bwcodec.c), followed by the chromosome B+ tree, a packed R-tree over the sections and ZOOM LEVELS (summary records of
+64, 256, 1024, ... bases with their own R-trees, as pyBigWig / bedGraphToBigWig write them) -- the layout any bigWig reader
+(UCSC tools, pyBigWig, IGV) understands, including the genome browsers that refuse files without zoom levels.
 
 Reader: what `OneRegion.get_signal` / `calculate_scores` need (tobias/utils/regions.py:163-188,
 tobias/tools/score_bigwig.py:37-39): `chroms()` and `values(chrom, start, end)` -> float32 array with NaN where the
-file holds no data.  Decodes bedGraph (1), variableStep (2) and fixedStep (3) sections, compressed or not.
+file holds no data.  Decodes bedGraph (1), variableStep (2) and fixedStep (3) sections, compressed or not; `zoom_records(level)`
+returns the summaries of a zoom level.
 """
+import ctypes
+import os
 import struct
+import subprocess
 import zlib
 
 import numpy as np
@@ -20,17 +26,48 @@ BIGWIG_MAGIC = 0x888FFC26
 CHROM_TREE_MAGIC = 0x78CA8C91
 RTREE_MAGIC = 0x2468ACE0
 ITEMS_PER_SECTION = 1024
+ZOOM_ITEMS_PER_BLOCK = 512
 RTREE_BLOCK = 256
+MAX_ZOOM = 8
+FIRST_REDUCTION = 64
 _VAR_ITEM = np.dtype([("start", "<u4"), ("value", "<f4")])
 _BED_ITEM = np.dtype([("start", "<u4"), ("end", "<u4"), ("value", "<f4")])
+_ZOOM_REC = np.dtype([("chrom", "<u4"), ("start", "<u4"), ("end", "<u4"), ("valid", "<u4"), ("min", "<f4"), ("max", "<f4"),
+                      ("sum", "<f4"), ("sumsq", "<f4")])
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _codec():
+    global _LIB
+    if _LIB is None:
+        so, src = os.path.join(_HERE, "_bwcodec.so"), os.path.join(_HERE, "bwcodec.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", so, src, "-lz"])
+        _LIB = ctypes.CDLL(so)
+        for f in ("tb_bw_bound", "tb_bw_sections", "tb_bw_zoom", "tb_bw_pack"):
+            getattr(_LIB, f).restype = ctypes.c_int64
+    return _LIB
+
+
+def _vp(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _reduce_sorted(keys, valid, mn, mx, sm, sq):
+    """Summaries of runs of equal keys (keys ascending): first index of every run and the reduced columns."""
+    first = np.flatnonzero(np.concatenate([[True], keys[1:] != keys[:-1]]))
+    return (first, np.add.reduceat(valid, first), np.minimum.reduceat(mn, first), np.maximum.reduceat(mx, first),
+            np.add.reduceat(sm, first), np.add.reduceat(sq, first))
 
 
 class BigWigWriter:
-    def __init__(self, path):
+    def __init__(self, path, zoom=True, level=6):
         self.path = path
         self._fh = open(path, "wb")
         self._chroms = None
-        self._sections = []          # (chrom_id, start, end, file_offset, size)
+        self._sec = []               # per add_entries call: (chrom id, starts, ends, file offsets, sizes) of its sections
+        self._zoom0 = []             # level-0 summary columns per call: (chrom id array, bin, valid, min, max, sum, sumsq)
         self._last = (-1, -1)
         self._n_valid = 0
         self._min = np.inf
@@ -39,15 +76,17 @@ class BigWigWriter:
         self._sumsq = 0.0
         self._max_uncompressed = 0
         self._closed = False
+        self._zoom = bool(zoom)
+        self._level = int(level)
 
     def add_header(self, header):
         self._chroms = [(str(c), int(n)) for c, n in header]
         self._id = {c: i for i, (c, _) in enumerate(self._chroms)}
         key = max(len(c.encode()) for c, _ in self._chroms)
         self._key_size = key
-        # fixed-size prologue: header (64) + total summary (40) + chromosome tree (32 + 4 + n * (key + 8)) + section count (8)
-        self._summary_offset = 64
-        self._chrom_tree_offset = 64 + 40
+        # fixed-size prologue: header (64) + zoom headers (24 x MAX_ZOOM) + total summary (40) + chromosome tree (32 + 4 + n * (key + 8)) + section count (8)
+        self._summary_offset = 64 + 24 * MAX_ZOOM
+        self._chrom_tree_offset = self._summary_offset + 40
         tree_size = 32 + 4 + len(self._chroms) * (key + 8)
         self._data_offset = self._chrom_tree_offset + tree_size
         self._fh.write(b"\0" * (self._data_offset + 8))
@@ -70,72 +109,134 @@ class BigWigWriter:
             raise RuntimeError("entries must be added in sorted order (chromosome order of the header, ascending positions)")
         self._last = (cid, int(pos[-1]))
         v64 = val.astype(np.float64)
+        sq64 = v64 * v64
         self._n_valid += pos.size
         self._min = min(self._min, float(v64.min()))
         self._max = max(self._max, float(v64.max()))
         self._sum += float(v64.sum())
-        self._sumsq += float((v64 * v64).sum())
-        items = np.empty(pos.size, dtype=_VAR_ITEM)
-        items["start"] = pos
-        items["value"] = val
-        fh = self._fh
-        for a in range(0, pos.size, ITEMS_PER_SECTION):
-            b = min(a + ITEMS_PER_SECTION, pos.size)
-            start, end = int(pos[a]), int(pos[b - 1]) + 1
-            raw = struct.pack("<IIIIIBBH", cid, start, end, 0, 1, 2, 0, b - a) + items[a:b].tobytes()
-            self._max_uncompressed = max(self._max_uncompressed, len(raw))
-            comp = zlib.compress(raw, 6)
-            off = fh.tell()
-            fh.write(comp)
-            self._sections.append((cid, start, end, off, len(comp)))
+        self._sumsq += float(sq64.sum())
+        # ---- data sections: built and compressed in parallel by the native helper
+        from .bam import parallel_ranges
+        lib = _codec()
+        n_sec = (pos.size + ITEMS_PER_SECTION - 1) // ITEMS_PER_SECTION
+        slot = int(lib.tb_bw_bound(ctypes.c_int64(24 + 8 * ITEMS_PER_SECTION)))
+        out = np.empty(n_sec * slot, dtype=np.uint8)
+        off, ln = np.empty(n_sec, np.int64), np.empty(n_sec, np.int64)
+        st, en = np.empty(n_sec, np.int32), np.empty(n_sec, np.int32)
+        parallel_ranges(lambda a, b: lib.tb_bw_sections(ctypes.c_int32(cid), _vp(pos), _vp(val), ctypes.c_int64(pos.size),
+                                                        ctypes.c_int32(ITEMS_PER_SECTION), ctypes.c_int32(self._level), ctypes.c_int64(a),
+                                                        ctypes.c_int64(b), _vp(out), ctypes.c_int64(slot), _vp(ln), _vp(st), _vp(en)), 0, n_sec, 64)
+        total = lib.tb_bw_pack(_vp(out), ctypes.c_int64(n_sec), ctypes.c_int64(slot), _vp(ln), _vp(off))
+        if total < 0:
+            raise RuntimeError("bigWig section compression failed (%d)" % total)
+        self._max_uncompressed = max(self._max_uncompressed, 24 + 8 * min(pos.size, ITEMS_PER_SECTION))
+        base = self._fh.tell()
+        self._fh.write(out[:total].tobytes())
+        self._sec.append((cid, st.astype(np.int64), en.astype(np.int64), off + base, ln))
+        # ---- first zoom level: one summary per FIRST_REDUCTION bases that hold data
+        if self._zoom:
+            bins = pos // FIRST_REDUCTION
+            first, valid, mn, mx, sm, sq = _reduce_sorted(bins, np.ones(pos.size, np.int64), v64, v64, v64, sq64)
+            self._zoom0.append((cid, bins[first], valid, mn, mx, sm, sq))
 
     # ------------------------------------------------------------------ index
-    def _write_rtree(self):
+    def _write_rtree(self, sc, sb, ec, eb, off, size):
+        """Packed R-tree (cirTree) over blocks given as columns: start chrom / base, end chrom / base, file offset, size."""
         fh = self._fh
         index_offset = fh.tell()
-        secs = self._sections
-        n = len(secs)
+        n = int(sc.shape[0])
         if n == 0:
             fh.write(struct.pack("<IIQIIIIQII", RTREE_MAGIC, RTREE_BLOCK, 0, 0, 0, 0, 0, index_offset, 1, 0))
             fh.write(struct.pack("<BBH", 1, 0, 0))
             return index_offset
-        # levels[0] = leaves' items; each upper level summarises RTREE_BLOCK children
-        level_items = [[(s[0], s[1], s[0], s[2], s[3], s[4]) for s in secs]]
-        while len(level_items[-1]) > RTREE_BLOCK:
-            prev = level_items[-1]
-            cur = []
-            for a in range(0, len(prev), RTREE_BLOCK):
-                grp = prev[a:a + RTREE_BLOCK]
-                end_c, end_b = max((g[2], g[3]) for g in grp)
-                cur.append((grp[0][0], grp[0][1], end_c, end_b, None, None))
-            level_items.append(cur)
-        level_items.reverse()                      # root level first; last = section items
-        header_size = 48
-        # node sizes per level: node = 4 bytes + count * item_size (24 non-leaf, 32 leaf)
-        offsets = []                               # offsets[level][node] file offset
-        pos = index_offset + header_size
-        n_levels = len(level_items)
-        for li, items in enumerate(level_items):
-            item_size = 32 if li == n_levels - 1 else 24
-            offs = []
-            for a in range(0, len(items), RTREE_BLOCK):
-                offs.append(pos)
-                pos += 4 + min(RTREE_BLOCK, len(items) - a) * item_size
-            offsets.append(offs)
-        first, last = secs[0], max(secs, key=lambda s: (s[0], s[2]))
-        fh.write(struct.pack("<IIQIIIIQII", RTREE_MAGIC, RTREE_BLOCK, n, first[0], first[1], last[0], last[2], index_offset, 1, 0))
-        for li, items in enumerate(level_items):
+        # levels[-1] = the blocks themselves; each upper level summarises RTREE_BLOCK children
+        levels = [(sc, sb, ec, eb)]
+        while levels[-1][0].shape[0] > RTREE_BLOCK:
+            psc, psb, pec, peb = levels[-1]
+            first = np.arange(0, psc.shape[0], RTREE_BLOCK)
+            key = pec.astype(np.int64) << 32 | peb.astype(np.int64)
+            kmax = np.maximum.reduceat(key, first)
+            levels.append((psc[first], psb[first], (kmax >> 32).astype(np.int64), (kmax & 0xFFFFFFFF).astype(np.int64)))
+        levels.reverse()                           # root level first
+        n_levels = len(levels)
+        pos = index_offset + 48
+        node_off = []                              # per level: file offset of every node
+        for li, lv in enumerate(levels):
+            item = 32 if li == n_levels - 1 else 24
+            cnt = lv[0].shape[0]
+            per_node = np.minimum(RTREE_BLOCK, cnt - np.arange(0, cnt, RTREE_BLOCK))
+            sizes = 4 + per_node * item
+            offs = pos + np.concatenate([[0], np.cumsum(sizes)[:-1]])
+            node_off.append(offs)
+            pos += int(sizes.sum())
+        kall = ec.astype(np.int64) << 32 | eb.astype(np.int64)
+        kl = int(kall.max())
+        fh.write(struct.pack("<IIQIIIIQII", RTREE_MAGIC, RTREE_BLOCK, n, int(sc[0]), int(sb[0]), kl >> 32, kl & 0xFFFFFFFF, index_offset, 1, 0))
+        leaf_dt = np.dtype([("sc", "<u4"), ("sb", "<u4"), ("ec", "<u4"), ("eb", "<u4"), ("off", "<u8"), ("size", "<u8")])
+        node_dt = np.dtype([("sc", "<u4"), ("sb", "<u4"), ("ec", "<u4"), ("eb", "<u4"), ("off", "<u8")])
+        for li, (lsc, lsb, lec, leb) in enumerate(levels):
             leaf = li == n_levels - 1
-            for node, a in enumerate(range(0, len(items), RTREE_BLOCK)):
-                grp = items[a:a + RTREE_BLOCK]
-                assert fh.tell() == offsets[li][node]
-                fh.write(struct.pack("<BBH", 1 if leaf else 0, 0, len(grp)))
-                for k, it in enumerate(grp):
-                    if leaf:
-                        fh.write(struct.pack("<IIIIQQ", it[0], it[1], it[2], it[3], it[4], it[5]))
-                    else:
-                        fh.write(struct.pack("<IIIIQ", it[0], it[1], it[2], it[3], offsets[li + 1][a + k]))
+            cnt = lsc.shape[0]
+            items = np.empty(cnt, dtype=leaf_dt if leaf else node_dt)
+            items["sc"], items["sb"], items["ec"], items["eb"] = lsc, lsb, lec, leb
+            if leaf:
+                items["off"], items["size"] = off, size
+            else:
+                items["off"] = node_off[li + 1]
+            raw = items.tobytes()
+            isz = items.dtype.itemsize
+            for node, a in enumerate(range(0, cnt, RTREE_BLOCK)):
+                k = min(RTREE_BLOCK, cnt - a)
+                assert fh.tell() == node_off[li][node]
+                fh.write(struct.pack("<BBH", 1 if leaf else 0, 0, k) + raw[a * isz:(a + k) * isz])
         return index_offset
+
+    def _write_zoom_levels(self):
+        """(reduction, data offset, index offset) of every zoom level written."""
+        if not self._zoom or not self._zoom0:
+            return []
+        lib = _codec()
+        fh = self._fh
+        cid = np.concatenate([np.full(z[1].shape[0], z[0], dtype=np.int64) for z in self._zoom0])
+        bins, valid, mn, mx, sm, sq = (np.concatenate([z[k] for z in self._zoom0]) for k in range(1, 7))
+        lens = np.array([n for _, n in self._chroms], dtype=np.int64)
+        out_levels = []
+        red = FIRST_REDUCTION
+        while len(out_levels) < MAX_ZOOM:
+            n = cid.shape[0]
+            rec = np.empty(n, dtype=_ZOOM_REC)
+            rec["chrom"], rec["start"] = cid, bins * red
+            rec["end"] = np.minimum((bins + 1) * red, lens[cid])
+            rec["valid"], rec["min"], rec["max"], rec["sum"], rec["sumsq"] = valid, mn, mx, sm, sq
+            from .bam import parallel_ranges
+            n_blk = (n + ZOOM_ITEMS_PER_BLOCK - 1) // ZOOM_ITEMS_PER_BLOCK
+            slot = int(lib.tb_bw_bound(ctypes.c_int64(32 * ZOOM_ITEMS_PER_BLOCK)))
+            buf = np.empty(n_blk * slot, dtype=np.uint8)
+            boff, blen = np.empty(n_blk, np.int64), np.empty(n_blk, np.int64)
+            raw = np.frombuffer(rec.tobytes(), dtype=np.uint8)
+            parallel_ranges(lambda a, b: lib.tb_bw_zoom(_vp(raw), ctypes.c_int64(n), ctypes.c_int32(ZOOM_ITEMS_PER_BLOCK), ctypes.c_int32(self._level),
+                                                        ctypes.c_int64(a), ctypes.c_int64(b), _vp(buf), ctypes.c_int64(slot), _vp(blen)), 0, n_blk, 64)
+            total = lib.tb_bw_pack(_vp(buf), ctypes.c_int64(n_blk), ctypes.c_int64(slot), _vp(blen), _vp(boff))
+            if total < 0:
+                raise RuntimeError("bigWig zoom compression failed (%d)" % total)
+            self._max_uncompressed = max(self._max_uncompressed, 32 * min(n, ZOOM_ITEMS_PER_BLOCK))
+            data_offset = fh.tell()
+            fh.write(struct.pack("<I", n))
+            base = fh.tell()
+            fh.write(buf[:total].tobytes())
+            first = np.arange(0, n, ZOOM_ITEMS_PER_BLOCK)
+            last = np.minimum(first + ZOOM_ITEMS_PER_BLOCK, n) - 1
+            index_offset = self._write_rtree(cid[first], rec["start"][first].astype(np.int64), cid[last], rec["end"][last].astype(np.int64),
+                                             boff + base, blen)
+            out_levels.append((red, data_offset, index_offset))
+            if n <= ZOOM_ITEMS_PER_BLOCK:
+                break
+            # next level: four times coarser, reduced from this one
+            key = cid << 40 | (bins // 4)
+            f2, valid, mn, mx, sm, sq = _reduce_sorted(key, valid, mn, mx, sm, sq)
+            cid, bins = cid[f2], (bins // 4)[f2]
+            red *= 4
+        return out_levels
 
     def close(self):
         if self._closed:
@@ -145,10 +246,20 @@ class BigWigWriter:
         if self._chroms is None:
             fh.close()
             return
-        index_offset = self._write_rtree()
+        if self._sec:
+            sc = np.concatenate([np.full(s[1].shape[0], s[0], dtype=np.int64) for s in self._sec])
+            sb, eb, off, size = (np.concatenate([s[k] for s in self._sec]) for k in range(1, 5))
+        else:
+            sc = sb = eb = off = size = np.zeros(0, dtype=np.int64)
+        n_sections = int(sc.shape[0])
+        index_offset = self._write_rtree(sc, sb, sc, eb, off, size)
+        zooms = self._write_zoom_levels()
         fh.seek(0)
-        fh.write(struct.pack("<IHHQQQHHQQIQ", BIGWIG_MAGIC, 4, 0, self._chrom_tree_offset, self._data_offset, index_offset,
+        fh.write(struct.pack("<IHHQQQHHQQIQ", BIGWIG_MAGIC, 4, len(zooms), self._chrom_tree_offset, self._data_offset, index_offset,
                              0, 0, 0, self._summary_offset, self._max_uncompressed, 0))
+        for red, doff, ioff in zooms:
+            fh.write(struct.pack("<IIQQ", red, 0, doff, ioff))
+        fh.seek(self._summary_offset)
         n = self._n_valid
         fh.write(struct.pack("<Qdddd", n, self._min if n else 0.0, self._max if n else 0.0, self._sum, self._sumsq))
         nchrom = len(self._chroms)
@@ -157,7 +268,7 @@ class BigWigWriter:
         for name, _ in sorted(self._chroms):       # B+ tree keys are sorted
             cid = self._id[name]
             fh.write(name.encode().ljust(self._key_size, b"\0") + struct.pack("<II", cid, self._chroms[cid][1]))
-        fh.write(struct.pack("<Q", len(self._sections)))
+        fh.write(struct.pack("<Q", n_sections))
         fh.close()
 
 
@@ -283,6 +394,32 @@ class BigWigReader:
                     if a < b:
                         out[a - start:b - start] = v
         return out
+
+    def zoom_headers(self):
+        """[(reduction level, data offset, index offset)] of the zoom levels."""
+        self._fh.seek(64)
+        raw = self._fh.read(24 * self.zoom_levels)
+        return [struct.unpack_from("<IIQQ", raw, 24 * i)[::1] for i in range(self.zoom_levels)]
+
+    def zoom_records(self, level):
+        """All summary records of one zoom level (numpy structured array: chrom, start, end, valid, min, max, sum, sumsq), via its R-tree."""
+        red, _res, _doff, ioff = self.zoom_headers()[level]
+        save = self.index_offset
+        self.index_offset = ioff
+        try:
+            blocks = []
+            for cid in sorted(self._ids.values()):
+                blocks += self._blocks(cid, 0, 0xFFFFFFFF)
+        finally:
+            self.index_offset = save
+        out = []
+        for off, size in sorted(set(blocks)):
+            self._fh.seek(off)
+            raw = self._fh.read(size)
+            if self.uncompress_buf:
+                raw = zlib.decompress(raw)
+            out.append(np.frombuffer(raw, dtype=_ZOOM_REC))
+        return red, (np.concatenate(out) if out else np.zeros(0, dtype=_ZOOM_REC))
 
     def close(self):
         self._fh.close()

@@ -23,7 +23,7 @@ def _packer():
     if _PACK is None:
         so, src = os.path.join(_HERE, "_hostpack.so"), os.path.join(_HERE, "hostpack.c")
         if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-            subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-o", so, src])
+            subprocess.check_call(["gcc", "-O3", "-fPIC", "-shared", "-o", so, src])
         _PACK = ctypes.CDLL(so)
     return _PACK
 
@@ -37,7 +37,10 @@ def pack_ascii(ascii_arr, seq2=None, nmask=None):
     nmask = np.empty((n + 31) // 32, dtype=np.uint32) if nmask is None else nmask
     assert seq2.dtype == np.uint32 and nmask.dtype == np.uint32 and seq2.size >= (n + 15) // 16 and nmask.size >= (n + 31) // 32
     vp = ctypes.c_void_p
-    _packer().tb_pack_ascii(a.ctypes.data_as(vp), ctypes.c_int64(n), seq2.ctypes.data_as(vp), nmask.ctypes.data_as(vp))
+    from .bam import parallel_ranges
+    lib = _packer()
+    parallel_ranges(lambda g0, g1: lib.tb_pack_ascii(a.ctypes.data_as(vp), ctypes.c_int64(n), seq2.ctypes.data_as(vp), nmask.ctypes.data_as(vp),
+                                                     ctypes.c_int64(g0), ctypes.c_int64(g1)), 0, (n + 31) // 32, 1 << 15)
     return seq2, nmask
 
 

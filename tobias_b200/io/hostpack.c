@@ -5,7 +5,9 @@
  * A genome packed once (tobias_b200.io.fasta.PackedGenome, cached next to the FASTA like a .fai) travels to the GPU as
  * 0.375 bytes per base instead of 1.
  *
- * Build: gcc -O3 -fopenmp -fPIC -shared -o _hostpack.so hostpack.c
+ * No OpenMP (the helpers also run in forked worker processes, where libgomp hangs): the Python side splits a contig over threads.
+ *
+ * Build: gcc -O3 -fPIC -shared -o _hostpack.so hostpack.c
  */
 #include <stdint.h>
 
@@ -21,11 +23,9 @@ static inline uint32_t code_of(uint8_t c, uint32_t *is_n) {
     }
 }
 
-/* seq2: (n + 15) / 16 words, nmask: (n + 31) / 32 words; positions past n read as N. */
-void tb_pack_ascii(const uint8_t *ascii, int64_t n, uint32_t *seq2, uint32_t *nmask) {
-    const int64_t groups = (n + 31) / 32;
-#pragma omp parallel for schedule(static)
-    for (int64_t g = 0; g < groups; g++) {
+/* seq2: (n + 15) / 16 words, nmask: (n + 31) / 32 words; positions past n read as N.  Packs the groups of 32 bases [g0, g1). */
+void tb_pack_ascii(const uint8_t *ascii, int64_t n, uint32_t *seq2, uint32_t *nmask, int64_t g0, int64_t g1) {
+    for (int64_t g = g0; g < g1; g++) {
         uint32_t w0 = 0, w1 = 0, m = 0;
         const int64_t first = g * 32;
         for (int i = 0; i < 32; i++) {
@@ -42,7 +42,6 @@ void tb_pack_ascii(const uint8_t *ascii, int64_t n, uint32_t *seq2, uint32_t *nm
 
 /* the inverse, for tests and for callers that want bases back: codes 0..3, 4 = N */
 void tb_unpack_codes(const uint32_t *seq2, const uint32_t *nmask, int64_t n, uint8_t *codes) {
-#pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < n; k++) {
         const uint32_t isn = (nmask[k >> 5] >> (k & 31)) & 1u;
         codes[k] = isn ? 4 : (uint8_t)((seq2[k >> 4] >> (2 * (k & 15))) & 3u);
