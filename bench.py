@@ -37,7 +37,7 @@ METRIC = "corrected+footprint-scored bp/s"
 SEED = 20261019
 K_FLANK, WINDOW, BG_SHIFT, EXTEND, READ_SHIFT = 12, 100, 100, 100, (4, -5)
 FP = dict(flank_min=10, flank_max=30, fp_min=20, fp_max=50)
-LM_EXACT = 0          # fit kernel: 0 = one-pass outer iterations (DWM default), 1 = MINPACK-exact arithmetic (--lm-exact); --lm-mode 2 / 3 = first-generation warp kernels
+LM_EXACT = 0          # fit kernel: 0 = one-pass outer iterations (DWM default), 1 = MINPACK-exact arithmetic (--lm-exact); --lm-mode 5 = moment form (opt-in)
 
 
 def workload(name):
@@ -1244,7 +1244,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lm-exact", action="store_true")
     ap.add_argument("--fit-stats", action="store_true")
-    ap.add_argument("--lm-mode", type=int, default=None, help="2 / 3: first-generation warp-per-window fit kernels (comparison runs)")
+    ap.add_argument("--lm-mode", type=int, default=None, help="5: moment form of the one-pass fits (comparison runs); 2 / 3 need a -DTB_FIRST_GEN_FITS build")
     ap.add_argument("--cli", action="store_true", help="time `TOBIAS ATACorrect` + `TOBIAS ScoreBigwig` from files (host I/O included); prints its own JSON line")
     ap.add_argument("--ascii-genome", action="store_true", help="e2e: upload the genome as ASCII (packed on the device) instead of the host-packed 2-bit form")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="tb_set_option switch for comparison runs (recorded in config)")

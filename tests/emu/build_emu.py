@@ -33,7 +33,7 @@ def build(force=False):
     procs, objs = [], []
     for src in SOURCES:
         obj = os.path.join(OUT, src.replace(".cu", ".o"))
-        cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-DTB_EMU", "-mfma", "-ffp-contract=off", "-I", HERE, "-x", "c++",
+        cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-DTB_EMU", "-DTB_FIRST_GEN_FITS", "-mfma", "-ffp-contract=off", "-I", HERE, "-x", "c++",
                "-Wno-unused-value", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

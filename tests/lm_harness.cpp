@@ -3,6 +3,7 @@
 // usage: lm_harness <file> <seq 0|1|2>   (0 warp-tree sums, 1 warp with MINPACK-order sums, 2 thread-per-window exact, 4 thread-per-window one-pass form, 5 the same with the fused trial + next head)     file: repeated blocks, a line "W <m>" followed by m lines "<x> <y>"
 // prints one line per window: a b info nfev usable   (%.17g)
 #define TB_EMU 1
+#define TB_FIRST_GEN_FITS 1
 #include "tb_common.cuh"
 #include "tb_lm.cuh"
 #include "tb_lm_thread.cuh"

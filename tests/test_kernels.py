@@ -312,12 +312,17 @@ def test_bias_correction_tracks(loaded_ctx, golden, mode, lm):
             assert np.all(np.abs(both[t].astype(np.float64) - ref32) <= 1e-5 * np.abs(ref32) + 2e-5)
 
 
-@pytest.mark.parametrize("lm_mode", [0, 2, 3])
+@pytest.mark.parametrize("lm_mode", [0, 5, 2, 3])
 def test_bias_correction_other_fit_kernels(loaded_ctx, golden, lm_mode):
-    """lm_exact_order = 0: one-pass (inner product) outer iterations, the DWM default; 2 / 3: first-generation warp-per-window
-    kernels (warp-tree sums / MINPACK-order sums), kept for comparison runs: same tracks within the DWM-mode tolerance even on
-    the bit-exact PWM bias input (bit-identical for mode 3)."""
+    """lm_exact_order = 0: one-pass (inner product) outer iterations, the DWM default; 5: the moment form (opt-in); 2 / 3:
+    first-generation warp-per-window kernels (warp-tree sums / MINPACK-order sums), compiled into test / comparison builds only
+    (-DTB_FIRST_GEN_FITS; the product library refuses them): same tracks within the DWM-mode tolerance even on the bit-exact PWM bias
+    input (bit-identical for mode 3)."""
     g = golden.atac
+    if lm_mode in (2, 3) and not loaded_ctx.device_info()["is_emulator"]:
+        with pytest.raises(lib.TobiasB200Error, match="not part of this build"):
+            loaded_ctx.correct_run(*_cols(g["outreg"]), correction_factor=1.0, lm_exact_order=lm_mode)
+        return
     _set_model(loaded_ctx, g, "PWM")
     c, s, e = _cols(g["outreg"])
     loaded_ctx.correct_run(c, s, e, correction_factor=float(g["correction_factor"]), lm_exact_order=lm_mode)

@@ -36,6 +36,7 @@ __device__ __forceinline__ int tb_n_windows(i64 reg_len, int k_flank, int window
     return span > 0 ? (int)((span + TB_STEP - 1) / TB_STEP) : 0;
 }
 
+#ifdef TB_FIRST_GEN_FITS      // first-generation warp-per-window fit kernel (lm_exact_order 2 / 3): test / comparison builds only
 // ------------------------------------------------------------------------------------------------ K3b
 #define TB_FIT_WARPS 8      // warps per block of the fit kernel
 #ifndef TB_FIT_MINBLOCKS
@@ -120,6 +121,8 @@ __global__ void __launch_bounds__(TB_FIT_WARPS * 32, TB_FIT_MINBLOCKS) tb_fit_ke
         }
     }
 }
+
+#endif  // TB_FIRST_GEN_FITS
 
 // ------------------------------------------------------------------------------------------------ K3b, round form
 // One THREAD per window (tb_lm_thread.cuh); the fits advance in ROUNDS over the whole launch: the state of a
@@ -1079,6 +1082,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         }
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_fitg_round_kernel"));
     } else {
+#ifdef TB_FIRST_GEN_FITS
         const int seq_sums = lm_exact_order != 2;       // warp-per-window kernels: 2 = tree sums, 3 = MINPACK-order sums
         int block = TB_FIT_WARPS * 32;
         i64 want = tb_div_up(2 * C.n_windows, block / 32), capg = (i64)ctx->sm_count * 8;
@@ -1096,6 +1100,10 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         }
 #undef TB_FIT_CASE
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_fit_kernel"));
+#else
+        return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: lm_exact_order %d (first-generation warp-per-window fits) is not part of this build "
+                       "(compile with -DTB_FIRST_GEN_FITS); use 0, 1 or 5", lm_exact_order);
+#endif
     }
     tb_mark(ctx, 3);
     tr("K3b rounds done (host)");

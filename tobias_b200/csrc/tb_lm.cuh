@@ -39,6 +39,7 @@ __device__ __forceinline__ double tb_warp_min(double v) {
     return v;
 }
 
+#ifdef TB_FIRST_GEN_FITS      // warp-per-window kernels of the first generation: test / comparison builds only (tests/emu, variants/)
 // MINPACK enorm (three accumulators: large / intermediate / small components), sequential over v[first..m).
 __device__ __forceinline__ double tb_enorm_seq(const double *v, int first, int m) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
@@ -142,6 +143,8 @@ __device__ __forceinline__ double tb_dot_warp(const double (&a)[PPL], const doub
     }
     return tb_warp_sum(s);
 }
+
+#endif  // TB_FIRST_GEN_FITS
 
 // MINPACK enorm for the 2-vectors of the trust-region algebra (three-accumulator form).
 __device__ __noinline__ double tb_enorm2(double x0, double x1) {
@@ -323,6 +326,7 @@ struct tb_lm_result {
     int usable;      // 1: curve_fit would return popt; 0: it raises (RuntimeError / OptimizeWarning) -> fallback
 };
 
+#ifdef TB_FIRST_GEN_FITS
 template <int PPL>
 __device__ __forceinline__ void tb_relu_residuals(const double (&x)[PPL], const double (&y)[PPL], double a, double b,
                                                   double (&f)[PPL]) {
@@ -556,3 +560,4 @@ __device__ void tb_lm_fit_warp(const double (&x)[PPL], const double (&y)[PPL], i
     }
     res.usable = usable;
 }
+#endif  // TB_FIRST_GEN_FITS
