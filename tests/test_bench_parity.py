@@ -23,7 +23,8 @@ def _tiny(name):
 def _check(par, need_green):
     assert par["read_counts_exact"] and par["count_tensors_exact"] and par["log_tables_exact"], par
     fit = par["lm_windows"]
-    assert fit["regions_with_call_count_mismatch"] == 0 and fit["stable_mismatches"] == 0, fit
+    assert fit["regions_with_call_count_mismatch"] == 0 and fit["stable_decision_flips"] == 0, fit
+    assert fit["stable_mismatches"] <= fit["stable_mismatch_budget"], fit
     assert fit["fitted_ref"] + fit["fallback_ref"] + fit["empty"] == fit["windows"]
     assert par["tracks"]["uncorrected"]["max_abs"] == 0.0
     assert par["tracks"]["bias"]["ok"], par["tracks"]["bias"]

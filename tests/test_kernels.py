@@ -492,6 +492,28 @@ def test_footprint_many_regions_and_tiles(ctx):
     assert off == got.shape[0]
 
 
+def test_footprint_two_starts_form(ctx, golden):
+    """Option k4_two_starts: the register-tiled form of the footprint scan (two starts per thread, all flank-width arrays staged at once)
+    against the golden data and the first form -- same zero pattern, scores within rtol 1e-5 (both round fp64 prefix differences to float)."""
+    s = golden.signals
+    a = s["fp_in"].astype(np.float32)
+    rng = np.random.default_rng(8)
+    lens = [760] * 4 + [61, 140, 2100]
+    sig = [np.where(rng.random(n) < 0.5, 0, rng.standard_t(3, size=n)).astype(np.float32) for n in lens]
+    try:
+        ctx.set_option("k4_two_starts", 1)
+        for tag in ("default", "flank100", "narrow"):
+            fmin, fmax, pmin, pmax = [int(x) for x in s["fp_%s_args" % tag]]
+            p = ctx.score_params("footprint", flank=0, flank_min=fmin, flank_max=fmax, fp_min=pmin, fp_max=pmax, as_f64=True)
+            _fp_close(ctx.score_regions(a, [a.shape[0]], p), s["fp_" + tag])
+        p = ctx.score_params("footprint", flank=30, as_f64=True)
+        two = ctx.score_regions(np.concatenate(sig), lens, p)
+    finally:
+        ctx.set_option("k4_two_starts", -1)
+    one = ctx.score_regions(np.concatenate(sig), lens, p)
+    assert np.array_equal(two == 0, one == 0) and np.all(np.abs(two - one) <= 1e-5 * np.abs(one))
+
+
 def test_footprint_width_ranges_and_tile_sizes(ctx):
     """more than 32 footprint widths (second batch: per-width sliding maximum), a single width, regions of very different
     lengths (the host picks the block size from them) -- against the oracle's restatement of tobias_footprint_array."""

@@ -142,21 +142,26 @@ struct tb_fitg_view {
     i64 qtot, n_slots;
 };
 
+// TYY: the moment form carries one more constant of the fit (17th plane); the other forms neither load nor store it
+template <bool TYY = false>
 __device__ __forceinline__ void tb_fitg_load(const tb_fitg_view &G, i64 slot, tb_lmt &S) {
     const double *p = G.st + slot;
     const i64 n = G.n_slots;
     S.par0 = p[0 * n]; S.par1 = p[1 * n]; S.fnorm = p[2 * n]; S.diag0 = p[3 * n]; S.diag1 = p[4 * n]; S.delta = p[5 * n];
     S.lmp = p[6 * n]; S.xnorm = p[7 * n]; S.gnorm = p[8 * n]; S.r00 = p[9 * n]; S.r01 = p[10 * n]; S.r11 = p[11 * n];
-    S.qtf0 = p[12 * n]; S.qtf1 = p[13 * n]; S.acn0 = p[14 * n]; S.acn1 = p[15 * n]; S.tyy = p[16 * n];
+    S.qtf0 = p[12 * n]; S.qtf1 = p[13 * n]; S.acn0 = p[14 * n]; S.acn1 = p[15 * n];
+    S.tyy = TYY ? p[16 * n] : 0.0;
     int4 v = G.sti[slot];
     S.ipvt0 = v.x; S.iter = v.y; S.nfev = v.z; S.info = v.w;
 }
+template <bool TYY = false>
 __device__ __forceinline__ void tb_fitg_store(const tb_fitg_view &G, i64 slot, const tb_lmt &S) {
     double *p = G.st + slot;
     const i64 n = G.n_slots;
     p[0 * n] = S.par0; p[1 * n] = S.par1; p[2 * n] = S.fnorm; p[3 * n] = S.diag0; p[4 * n] = S.diag1; p[5 * n] = S.delta;
     p[6 * n] = S.lmp; p[7 * n] = S.xnorm; p[8 * n] = S.gnorm; p[9 * n] = S.r00; p[10 * n] = S.r01; p[11 * n] = S.r11;
-    p[12 * n] = S.qtf0; p[13 * n] = S.qtf1; p[14 * n] = S.acn0; p[15 * n] = S.acn1; p[16 * n] = S.tyy;
+    p[12 * n] = S.qtf0; p[13 * n] = S.qtf1; p[14 * n] = S.acn0; p[15 * n] = S.acn1;
+    if (TYY) p[16 * n] = S.tyy;
     G.sti[slot] = int4{S.ipvt0, S.iter, S.nfev, S.info};
 }
 // warp-aggregated append of `slot` to list[ctr] for the lanes with `want`; every lane of the warp must call it
@@ -214,7 +219,7 @@ __global__ void tb_fitg_init_kernel(tb_cor_view V, tb_fitg_view G, i64 qs, int q
                                              : (FAST_HEAD == 1 ? tb_lmt_start_fast(S, W, V.window, st) : tb_lmt_fnorm0_stats(W, V.window, st));
             if (f0 >= 0.0) {                                           // signalmax > 0 (:290)
                 if (!FAST_HEAD) tb_lmt_init(S, f0);
-                tb_fitg_store(G, slot, S);
+                tb_fitg_store<FAST_HEAD == 2>(G, slot, S);
                 double *rec = fit + slot * TB_FIT_REC;                 // parked in the window's record until its fit ends
                 rec[1] = st.xmax;
                 rec[2] = st.xmin;
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
         if (k < n_list) {
             slot = list[k];
             tb_lmt S;
-            tb_fitg_load(G, slot, S);
+            tb_fitg_load<FAST == 2>(G, slot, S);
             const i64 q = G.wq[slot];
             const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
 #ifndef TB_EMU
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(128, FAST ? TB_FITG_MINBLOCKS + 1 : TB_FITG_MI
                 rec[4] = (double)S.info;
                 rec[5] = (double)S.nfev;
             } else {
-                tb_fitg_store(G, slot, S);
+                tb_fitg_store<FAST == 2>(G, slot, S);
                 to_q = accepted && !(FAST == 2 || (FAST && TB_FITG_FUSE));
                 to_t = !to_q;
             }
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(128, TB_FITG_MINBLOCKS)
         const u32 slot = k < nq ? listq[k] : listt[k - nq];
         bool need_qr = k < nq;
         tb_lmt S;
-        tb_fitg_load(G, slot, S);
+        tb_fitg_load<FAST == 2>(G, slot, S);
         const i64 q = G.wq[slot];
         const tb_win_ref W{G.gx + q, G.gy + q, G.qtot};
         for (;;) {

@@ -680,7 +680,9 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
         int bs2 = 0;
         size_t smem2 = 0;
         int wstride2 = 0;
-        if (!fos && npw <= TB_K4_NPW && tb_opt(ctx, "k4_one_start", 0) == 0) {
+        // (measured on the hg38 workload: 28.0 ms against 26.0 ms of the first form -- 107 registers leave one 416-thread block per SM, so the
+        // load / scan / staging / spread phases of a tile no longer overlap with another tile's width loop; opt-in until that is solved)
+        if (!fos && npw <= TB_K4_NPW && tb_opt(ctx, "k4_two_starts", 0) != 0) {
             double best_cost = -1.0;
             const int forced = (int)tb_opt(ctx, "k4_threads", 0);                                // comparison runs: threads per block of the second form
             for (int cand = 64; cand <= TB_K4B_MAXT; cand += 32) {
