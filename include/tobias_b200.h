@@ -219,6 +219,16 @@ int tb_signal_from_corrected(tb_ctx *ctx, int flank);
 int tb_signal_from_corrected_regions(tb_ctx *ctx, int flank, int64_t n_regions, const int32_t *contig, const int64_t *start,
                                      const int64_t *end);
 
+/* Gathers of the two downstream tools that read the tracks this path writes, over the signal of the last tb_signal_upload
+ * (one uploaded region = one BED region / one site window; NaN reads as 0 like OneRegion.get_signal, tobias/utils/regions.py:172):
+ * tb_signal_summary: ScoreBed's score functions (tobias/tools/score_bed.py:30-54) per region -- op 0 start, 1 mid (index int(len / 2)),
+ *   2 end, 3 min, 4 max, 5 mean, 6 sum; out: double [n_regions].
+ * tb_signal_aggregate: PlotAggregate's column means over the rows of a signal matrix (tobias/tools/plot_aggregate.py:236-257): all regions
+ *   of one width; reverse[r] != 0 reads row r back to front (minus-strand sites), keep[r] == 0 leaves it out (outlier removal), both may be
+ *   NULL; log_transform: sign(v) log2(|v| + 1); out: double [width]. */
+int tb_signal_summary(tb_ctx *ctx, int op, double *out);
+int tb_signal_aggregate(tb_ctx *ctx, const uint8_t *reverse, const uint8_t *keep, int log_transform, double *out);
+
 /* Array-level mirror of SequenceMatrix.add_sequence / add_background (tobias/utils/sequences.pyx:63-105 PWM, :178-223 DWM) for a batch of
  * explicit k-mers: kmers int64 [n][L] codes (A0 T1 C2 G3 N4), amounts double [n].  The increments are ADDED to the caller's arrays: counts
  * [5][L] (PWM) or [5][5][L][L] (DWM); neg_counts [5][L] receives the non-positive amounts of a PWM add_sequence (may be NULL otherwise);

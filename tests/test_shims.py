@@ -80,3 +80,54 @@ def test_readlist_signal(ctx, ref, golden, tmp_path):
                 got = m.signal(reg, ctx=ctx)
                 assert np.array_equal(got, want), (chrom, a, b, reg.start)
     assert rl.signal(OneRegion([golden.names[0], 50, 50]), ctx=ctx).shape == (0,)
+
+
+def test_scorebed_and_plotaggregate_gathers(ctx, tmp_path):
+    """the per-base steps of ScoreBed (tobias/tools/score_bed.py:30-54,118-131) and PlotAggregate (plot_aggregate.py:236-268)
+    against their numpy statements in the reference, on a bigWig written by this package."""
+    from tobias_b200 import gathers
+    from tobias_b200.io import bigwig
+    rng = np.random.default_rng(2)
+    path = str(tmp_path / "t.bw")
+    w = bigwig.BigWigWriter(path)
+    w.add_header([("c1", 60000), ("c2", 5000)])
+    pos = np.sort(rng.choice(60000, 30000, replace=False))
+    val = rng.normal(0, 2, size=pos.size).astype(np.float32)
+    w.add_entries("c1", pos, val)
+    w.close()
+    bw = bigwig.BigWigReader(path)
+    full = np.zeros(60000, np.float32)
+    full[pos] = val
+    regions = [("c1", int(a), int(a) + int(n)) for a, n in zip(rng.integers(0, 59000, 40), rng.integers(1, 900, 40))] + [("c3", 5, 50), ("c2", 10, 60)]
+    for position, math in (("start", None), ("mid", None), ("end", None), ("full", "min"), ("full", "max"), ("full", "mean"), ("full", "sum")):
+        got = gathers.score_bed_regions(bw, regions, position, math or "mean", null="NA", ctx=ctx)
+        for (c, s, e), g in zip(regions, got):
+            if c == "c3":
+                assert g == "NA"
+                continue
+            signal = np.nan_to_num(full[s:e] if c == "c1" else np.zeros(e - s, np.float32))
+            want = {"start": lambda x: x[0], "mid": lambda x: x[int(len(x) / 2.0)], "end": lambda x: x[-1]}.get(position) or \
+                {"min": np.min, "max": np.max, "mean": np.mean, "sum": np.sum}[math]
+            assert abs(g - round(float(want(signal)), 5)) <= 2e-5 * max(1.0, abs(float(want(signal)))), (position, math, c, s, e)
+    width = 120
+    sites = [("c1", int(a), int(a) + width, "-" if k % 3 == 0 else "+") for k, a in enumerate(rng.integers(200, 59000, 300))]
+    mat = np.array([np.nan_to_num(full[s:e])[::-1] if st == "-" else np.nan_to_num(full[s:e]) for (_c, s, e, st) in sites])
+    for frac, logt, norm, smooth in ((1.0, False, False, 1), (0.9, True, False, 1), (1.0, False, True, 5)):
+        got = gathers.aggregate_signal(bw, sites, width, frac, logt, norm, smooth, ctx=ctx)
+        m = mat[np.max(mat, axis=1) <= np.percentile(np.max(mat, axis=1), [100 * frac])[0]]
+        if logt:
+            lg = np.log2(np.abs(m) + 1)
+            lg[m < 0] *= -1
+            m = lg
+        want = np.nanmean(m.astype(np.float64), axis=0)
+        if norm:
+            want = (want - want.min()) / (want.max() - want.min())
+        if smooth > 1:
+            want = restate_roll(np.pad(want, smooth, "edge"), smooth)[smooth:-smooth]
+        assert np.allclose(got, want, rtol=1e-6, atol=1e-7), (frac, logt, norm, smooth)
+    bw.close()
+
+
+def restate_roll(a, w):
+    from oracle import restate
+    return restate.fast_rolling_math(a.astype(np.float64), w, "mean")

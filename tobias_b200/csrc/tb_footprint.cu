@@ -852,3 +852,90 @@ extern "C" int tb_rolling(tb_ctx *ctx, const double *arr, int64_t n, int w, int 
     tb_timer_stop(ctx);
     return tb_d2h(ctx, out, ctx->scratch1.p, (size_t)n * sizeof(double));
 }
+
+// ------------------------------------------------------------------------------------------------ gathers of ScoreBed / PlotAggregate
+// Per-region summaries of the uploaded signal (tb_signal_upload: one extended region = one BED region; NaN -> 0 as
+// OneRegion.get_signal does, tobias/utils/regions.py:172): what ScoreBed's score functions compute (tobias/tools/score_bed.py:30-54).
+// op 0 start, 1 mid (index int(len / 2)), 2 end, 3 min, 4 max, 5 mean, 6 sum.  One warp per region, fp64 accumulation.
+__global__ void tb_signal_summary_kernel(const float *__restrict__ sig, const i64 *__restrict__ off, i64 n_regions, int op, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 r = warp; r < n_regions; r += n_warps) {
+        const i64 a = off[r], b = off[r + 1], len = b - a;
+        auto val = [&](i64 i) { float v = sig[a + i]; return (v != v) ? 0.0 : (double)(v > FLT_MAX ? FLT_MAX : (v < -FLT_MAX ? -FLT_MAX : v)); };
+        double res = 0.0;
+        if (op <= 2) {
+            res = val(op == 0 ? 0 : (op == 1 ? (i64)((double)len / 2.0) : len - 1));
+        } else {
+            double acc = op == 3 ? INFINITY : (op == 4 ? -INFINITY : 0.0);
+            for (i64 i = lane; i < len; i += 32) {
+                const double v = val(i);
+                acc = op == 3 ? fmin(acc, v) : (op == 4 ? fmax(acc, v) : acc + v);
+            }
+            for (int d = 16; d > 0; d >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, acc, d);
+                acc = op == 3 ? fmin(acc, o) : (op == 4 ? fmax(acc, o) : acc + o);
+            }
+            res = op == 5 ? acc / (double)len : acc;
+        }
+        if (lane == 0) out[r] = res;
+    }
+}
+
+extern "C" int tb_signal_summary(tb_ctx *ctx, int op, double *out) {
+    if (!ctx || !out) return TB_ERR_ARG;
+    auto &S = ctx->sc;
+    if (!S.have_signal) return tb_fail(ctx, TB_ERR_STATE, "tb_signal_summary: no signal (tb_signal_upload)");
+    if (op < 0 || op > 6) return tb_fail(ctx, TB_ERR_ARG, "tb_signal_summary: op must be in [0, 6]");
+    if (S.n_regions == 0) return TB_OK;
+    TB_TRY(tb_reserve(ctx, ctx->scratch0, sizeof(double) * (size_t)S.n_regions));
+    const i64 want = tb_div_up(S.n_regions * 32, 256), capg = (i64)ctx->sm_count * 16;
+    TB_LAUNCH(ctx, tb_signal_summary_kernel, (unsigned)(want < capg ? want : capg), 256, 0, (const float *)S.signal.as<float>(),
+              (const i64 *)S.d_ext_off.as<i64>(), S.n_regions, op, ctx->scratch0.as<double>());
+    TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_signal_summary_kernel"));
+    return tb_d2h(ctx, out, ctx->scratch0.p, sizeof(double) * (size_t)S.n_regions);
+}
+
+// Column means over the rows of a signal matrix = the uploaded regions, all of one width (PlotAggregate, tobias/tools/plot_aggregate.py:
+// 236-257): rows with keep[r] == 0 are left out (outlier removal), rows with reverse[r] != 0 are read back to front (OneRegion.get_signal on
+// the minus strand, regions.py:174-175), log_transform: sign(v) * log2(|v| + 1).  One thread per column, fp64 sums.
+__global__ void tb_signal_aggregate_kernel(const float *__restrict__ sig, i64 n_rows, int width, const uint8_t *__restrict__ reverse,
+                                           const uint8_t *__restrict__ keep, int log_transform, double *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= width) return;
+    double acc = 0.0;
+    i64 n = 0;
+    for (i64 r = 0; r < n_rows; r++) {
+        if (keep && !keep[r]) continue;
+        float v = sig[r * width + ((reverse && reverse[r]) ? width - 1 - c : c)];
+        double d = (v != v) ? 0.0 : (double)v;
+        if (log_transform) d = d < 0.0 ? -log2(-d + 1.0) : log2(d + 1.0);
+        acc += d;
+        n++;
+    }
+    out[c] = n > 0 ? acc / (double)n : (double)NAN;
+}
+
+extern "C" int tb_signal_aggregate(tb_ctx *ctx, const uint8_t *reverse, const uint8_t *keep, int log_transform, double *out) {
+    if (!ctx || !out) return TB_ERR_ARG;
+    auto &S = ctx->sc;
+    if (!S.have_signal || S.n_regions == 0) return tb_fail(ctx, TB_ERR_STATE, "tb_signal_aggregate: no signal (tb_signal_upload)");
+    const i64 width = S.ext_off[1] - S.ext_off[0];
+    for (i64 r = 0; r < S.n_regions; r++)
+        if (S.ext_off[r + 1] - S.ext_off[r] != width) return tb_fail(ctx, TB_ERR_ARG, "tb_signal_aggregate: regions differ in width (%lld)", (long long)r);
+    if (width > (1 << 24)) return tb_fail(ctx, TB_ERR_ARG, "tb_signal_aggregate: width too large");
+    const uint8_t *d_rev = nullptr, *d_keep = nullptr;
+    if (reverse) {
+        TB_TRY(tb_h2d(ctx, ctx->reg_a, reverse, (size_t)S.n_regions));
+        d_rev = ctx->reg_a.as<uint8_t>();
+    }
+    if (keep) {
+        TB_TRY(tb_h2d(ctx, ctx->reg_b, keep, (size_t)S.n_regions));
+        d_keep = ctx->reg_b.as<uint8_t>();
+    }
+    TB_TRY(tb_reserve(ctx, ctx->scratch0, sizeof(double) * (size_t)width));
+    TB_LAUNCH(ctx, tb_signal_aggregate_kernel, (unsigned)tb_div_up(width, 128), 128, 0, (const float *)S.signal.as<float>(), S.n_regions, (int)width,
+              d_rev, d_keep, log_transform, ctx->scratch0.as<double>());
+    TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_signal_aggregate_kernel"));
+    return tb_d2h(ctx, out, ctx->scratch0.p, sizeof(double) * (size_t)width);
+}

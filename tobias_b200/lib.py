@@ -77,6 +77,8 @@ _PROTOS = {
     "tb_signal_from_corrected": (_i, [_vp, _i]),
     "tb_signal_from_corrected_regions": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "tb_rolling": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "tb_signal_summary": (_i, [_vp, _i, _vp]),
+    "tb_signal_aggregate": (_i, [_vp, _vp, _vp, _i, _vp]),
     "tb_add_kmers": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
 }
 
@@ -425,6 +427,22 @@ class Context:
         idx = _arr(index, np.int64)
         out = np.empty(idx.shape[0], dtype=np.float64)
         self._ck(self._lib.tb_score_gather(self._h, int(idx.shape[0]), _ptr(idx), _ptr(out)))
+        return out
+
+    SUMMARY_OPS = {"start": 0, "mid": 1, "end": 2, "min": 3, "max": 4, "mean": 5, "sum": 6}
+
+    def signal_summary(self, op):
+        """Per-region summary of the uploaded signal (ScoreBed's score functions): float64 [n_regions]."""
+        out = np.empty(self._sc_ext.shape[0], dtype=np.float64)
+        self._ck(self._lib.tb_signal_summary(self._h, self.SUMMARY_OPS[op], _ptr(out)))
+        return out
+
+    def signal_aggregate(self, reverse=None, keep=None, log_transform=False):
+        """Column means over the uploaded equal-width regions (PlotAggregate): float64 [width]."""
+        out = np.empty(int(self._sc_ext[0]), dtype=np.float64)
+        rv = None if reverse is None else _arr(reverse, np.uint8)
+        kp = None if keep is None else _arr(keep, np.uint8)
+        self._ck(self._lib.tb_signal_aggregate(self._h, _ptr(rv), _ptr(kp), int(bool(log_transform)), _ptr(out)))
         return out
 
     def score_regions(self, signal, ext_len, params):
