@@ -380,7 +380,7 @@ def bench_b200(args):
     achieved = alg[dom] / (stages[dom] * 1e-3) / 1e9
     per_stage = {k: {"ms": round(v, 4), "alg_GBps": round(alg[k] / (v * 1e-3) / 1e9, 2) if v > 0 else None} for k, v in stages.items()}
     try:                                   # binding unit of every kernel, from the committed ncu summary of this round (not a live measurement)
-        roofs = json.load(open(os.path.join(ROOT, "profiles", "r01_roofs.json")))
+        roofs = json.load(open(os.path.join(ROOT, "profiles", "r02_roofs.json")))
         for k in per_stage:
             if k in roofs:
                 per_stage[k]["bound"] = roofs[k]["bound"]
@@ -404,7 +404,7 @@ def bench_b200(args):
                      "algorithmic_bytes_per_launch": alg[dom], "peak_source": peak_src,
                      "binding_unit": roofs.get(dom, {}).get("bound"), "binding_unit_util_pct_ncu": roofs.get(dom, {}).get("bound_util_pct"),
                      "note": "achieved = algorithmic bytes of the stage (SURVEY 8d) / its CUDA-event time (all launches of the stage); none of K2-K4 is "
-                             "HBM bound -- the unit that binds each kernel and its ncu utilisation are in `stages` (profiles/r01_summary.md); "
+                             "HBM bound -- the unit that binds each kernel and its ncu utilisation are in `stages` (profiles/r02_summary.md); "
                              "traffic: the ncu --set full capture of this kernel in this workload committed under profiles/ (null for other workloads / ranks)"},
         "stages": per_stage, "wall_ms_per_step": wall_res / args.steps, "setup_s": round(setup_s, 1),
         # host clock around every library call of the timed steps (one entry per step; resident: each call returns synchronised, so these
