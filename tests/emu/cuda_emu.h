@@ -46,6 +46,7 @@ struct double2 { double x, y; };
 struct float2 { float x, y; };
 inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct uint2 { unsigned x, y; };

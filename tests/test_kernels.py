@@ -492,26 +492,36 @@ def test_footprint_many_regions_and_tiles(ctx):
     assert off == got.shape[0]
 
 
-def test_footprint_two_starts_form(ctx, golden):
-    """Option k4_two_starts: the register-tiled form of the footprint scan (two starts per thread, all flank-width arrays staged at once)
-    against the golden data and the first form -- same zero pattern, scores within rtol 1e-5 (both round fp64 prefix differences to float)."""
+@pytest.mark.parametrize("form", [0, 32])
+def test_footprint_forms_agree(ctx, golden, form):
+    """Option k4_form: the first form of the footprint scan (one start per thread, 0) and the single-pass variant of the register-tiled
+    form (32) against the golden data and the default (register tile of 4 starts x 16 widths, two passes) -- same zero pattern, scores
+    within rtol 1e-5 (all round fp64 prefix differences to float, in different places).  Forced block sizes move the tile borders."""
     s = golden.signals
     a = s["fp_in"].astype(np.float32)
     rng = np.random.default_rng(8)
-    lens = [760] * 4 + [61, 140, 2100]
+    lens = [760] * 4 + [61, 140, 2100, 91, 92, 5000]
     sig = [np.where(rng.random(n) < 0.5, 0, rng.standard_t(3, size=n)).astype(np.float32) for n in lens]
     try:
-        ctx.set_option("k4_two_starts", 1)
+        ctx.set_option("k4_form", form)
         for tag in ("default", "flank100", "narrow"):
             fmin, fmax, pmin, pmax = [int(x) for x in s["fp_%s_args" % tag]]
             p = ctx.score_params("footprint", flank=0, flank_min=fmin, flank_max=fmax, fp_min=pmin, fp_max=pmax, as_f64=True)
             _fp_close(ctx.score_regions(a, [a.shape[0]], p), s["fp_" + tag])
         p = ctx.score_params("footprint", flank=30, as_f64=True)
-        two = ctx.score_regions(np.concatenate(sig), lens, p)
+        other = ctx.score_regions(np.concatenate(sig), lens, p)
     finally:
-        ctx.set_option("k4_two_starts", -1)
-    one = ctx.score_regions(np.concatenate(sig), lens, p)
-    assert np.array_equal(two == 0, one == 0) and np.all(np.abs(two - one) <= 1e-5 * np.abs(one))
+        ctx.set_option("k4_form", -1)
+    outs = [ctx.score_regions(np.concatenate(sig), lens, p)]
+    try:
+        for nthr in (64, 160):
+            ctx.set_option("k4_threads", nthr)
+            outs.append(ctx.score_regions(np.concatenate(sig), lens, p))
+    finally:
+        ctx.set_option("k4_threads", -1)
+    for o in outs[1:]:                                     # other tile borders: other reference points of the fp32 window sums
+        assert np.array_equal(o == 0, outs[0] == 0) and np.all(np.abs(o - outs[0]) <= 2e-6 * np.abs(outs[0]))
+    assert np.array_equal(other == 0, outs[0] == 0) and np.all(np.abs(other - outs[0]) <= 1e-5 * np.abs(outs[0]))
 
 
 def test_footprint_width_ranges_and_tile_sizes(ctx):

@@ -150,7 +150,7 @@ extern "C" int tb_init(int device, tb_ctx **out) {
 extern "C" int tb_set_option(tb_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return TB_ERR_ARG;
     static const char *known[] = {"k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_tile", "k2_site_cap", "k2_chunk",
-                                  "k2_no_hist", "k2_smem_chunk", "k2_no_smem_hist", "k4_two_starts", "k4_threads", "k3b_persistent", "k3b_tile", "k3b_cap", "k3b_threads", "host_trace", nullptr};
+                                  "k2_no_hist", "k2_smem_chunk", "k2_no_smem_hist", "k4_form", "k4_threads", "k3b_persistent", "k3b_tile", "k3b_cap", "k3b_threads", "host_trace", nullptr};
     bool ok = false;
     for (int i = 0; known[i]; i++) ok = ok || strcmp(known[i], key) == 0;
     if (!ok) return tb_fail(ctx, TB_ERR_ARG, "tb_set_option: unknown option '%s'", key);

@@ -243,145 +243,307 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
     }
 }
 
-// ---- second form of the footprint scan: TWO footprint starts per thread, every flank-width array staged at once ----
+// ---- register-tiled form of the footprint scan: 4 footprint starts x NW footprint widths per thread ----
 // For a fixed flank width the score table acc(s, e) = max_fw ( L_fw[s] + R_fw[e] ) (e = s + pw: end of the footprint) is a max-plus product of
-// the left-flank column and the right-flank row, so the register tile of a thread is widened like a GEMM micro-tile: starts s0 = 2t and
-// s0 + 1 share their right-flank values (33 values serve 64 accumulators), read as 17 aligned 8-byte shared-memory loads -- half the
-// shared-memory wavefronts and three quarters of the instructions of one start per thread.  All W_fw arrays of the tile are staged
-// before the loop (21 x ~940 floats = 79 KB for the CLI defaults), so the flank-width loop runs without barriers; the spread of every score over
-// its footprint goes through one table G[c][start] of suffix maxima in the same memory (two halves of 16 widths: 4 barriers instead of 31).
-// Used when there are at most 32 footprint widths and the W arrays fit; the kernel above handles every other parameter set.
-#define TB_K4B_MAXT 512          // threads per block (2 starts each)
-template <int OUT_MODE>
-__global__ void __launch_bounds__(TB_K4B_MAXT)
-tb_footprint2_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_, int pmin_, int pmax_, int wstride,
-                     void *__restrict__ out_) {
+// the left-flank column and the right-flank row, so a thread keeps a register tile of accumulators like a GEMM micro-kernel: starts
+// 4t .. 4t + 3 against NW consecutive widths need 4 left values and NW + 3 right values of a flank-width row -- 7 16-byte shared-memory loads
+// serve 64 (add, max) pairs where the first form issues one 4-byte load per pair (it is bound by the shared-memory pipe).  Two rows are folded per
+// step, acc = max(acc, l0 + r0, l1 + r1): the three-input maximum (FMNMX3) costs what the two-input one does, so the ALU pipe, which binds
+// the arithmetic (measured: FMNMX and FMNMX3 2 cycles per warp, FADD 1), does half the work.  All flank-width rows of a tile are staged once
+// (row r + 1 from row r by one fp32 add per element: W_{fw+1}[i] = W_fw[i] + max(v[i + fw], 0), sums of non-negative terms, no cancellation),
+// so the row loop runs without barriers; NW = 16 runs two passes over the widths (64 accumulators, two blocks per SM).
+// Left values sit at 4t + (fmax - fw): their misalignment against 16 bytes is the same for every thread and known per row, so the row step is
+// instantiated for the four cases and picks its registers statically.  A start whose left flank would begin before the region exists in no
+// row (signals.pyx:199): those row entries are staged as -inf (they are never read as right values by a valid start); starts beyond the last
+// valid one are masked per row in the few threads that have any.
+// Centre term: mid(u, c) = (N[s_u + pw] - N[s_3]) + (N[s_3] - N[s_u]), two same-signed fp32 numbers (sums of non-positive values), so rounding
+// the fp64 prefix differences once per window position instead of once per (start, width) loses nothing.
+// Spreading a score over its footprint: as in the first form, through a table G[c][start] of suffix maxima over the widths, GW widths at a time.
+#define TB_K4T_MAXT 256
+#define TB_K4T_GW 4              // widths per exchange through shared memory
+#define TB_K4T_EPT 8             // row elements a thread stages at most
+
+// 16-byte shared-memory load that the compiler may neither split nor narrow to the components in use (a thread's stride is 16 bytes: whole
+// vectors are conflict free, scalar loads of single components are 4-way conflicts)
+__device__ __forceinline__ float4 tb_lds128(const float *p) {
+#ifdef TB_EMU
+    return *(const float4 *)p;
+#else
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return r;
+#endif
+}
+
+template <int NW, int RHO, bool TWO>
+__device__ __forceinline__ void tb_k4t_step(const float *__restrict__ Wr, int wstride, int lb, int rb, bool edge, int e0, int r,
+                                            float (&acc)[4][NW]) {
+    // left values of row r: 4 floats starting RHO floats behind the aligned index lb; of row r + 1: one float earlier
+    float l0[4], l1[4];
+    {
+        const float4 a = tb_lds128(Wr + lb);
+        float t[8] = {a.x, a.y, a.z, a.w, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (RHO != 0) {
+            const float4 b = tb_lds128(Wr + lb + 4);
+            t[4] = b.x, t[5] = b.y, t[6] = b.z, t[7] = b.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) l0[u] = t[RHO + u];
+    }
+    if (TWO) {
+        constexpr int R1 = (RHO + 3) & 3;
+        const float *W1 = Wr + wstride;
+        const int lb1 = RHO == 0 ? lb - 4 : lb;
+        const float4 a = tb_lds128(W1 + lb1);
+        float t[8] = {a.x, a.y, a.z, a.w, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (R1 != 0) {
+            const float4 b = tb_lds128(W1 + lb1 + 4);
+            t[4] = b.x, t[5] = b.y, t[6] = b.z, t[7] = b.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) l1[u] = t[R1 + u];
+    }
+    if (edge) {                                                 // starts at or beyond `limit` for this flank width do not exist
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (r <= e0 + u) l0[u] = -INFINITY;
+            if (TWO && r + 1 <= e0 + u) l1[u] = -INFINITY;
+        }
+    }
+    float v0[NW + 4], v1[NW + 4];
+#pragma unroll
+    for (int m = 0; m < NW / 4 + 1; m++) {
+        const float4 q = tb_lds128(Wr + rb + 4 * m);
+        v0[4 * m] = q.x, v0[4 * m + 1] = q.y, v0[4 * m + 2] = q.z, v0[4 * m + 3] = q.w;
+        if (TWO) {
+            const float4 p = tb_lds128(Wr + wstride + rb + 4 * m);
+            v1[4 * m] = p.x, v1[4 * m + 1] = p.y, v1[4 * m + 2] = p.z, v1[4 * m + 3] = p.w;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int c = 0; c < NW; c++) {
+            if (TWO) acc[u][c] = fmaxf(fmaxf(acc[u][c], l0[u] + v0[u + c]), l1[u] + v1[u + c]);
+            else acc[u][c] = fmaxf(acc[u][c], l0[u] + v0[u + c]);
+        }
+}
+
+// Stages the rows: W_r[i] = mean of max(v, 0) over [i, i + fw), halved: sum / (2 fw); row r + 1 from row r by one add per element.  Thread t owns
+// the elements t, t + nthr, ... (EPT of them; beyond the row's end they go to one scratch float behind it); entries whose window starts before
+// the region are -inf from the start and stay so.
+template <int EPT>
+__device__ __forceinline__ void tb_k4t_stage(const double *__restrict__ P, const float *__restrict__ vpos, float *__restrict__ W, int wstride,
+                                             int shift, int n_in, i64 in0, int fmin_, int nfw) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lim = wstride - shift;
+    float U[EPT];
+    int so[EPT], lo[EPT];
+#pragma unroll
+    for (int m = 0; m < EPT; m++) {
+        const int i = tid + m * nthr;
+        const bool on = i < lim;
+        U[m] = in0 + i < 0 ? -INFINITY : (on && i + fmin_ <= n_in ? (float)(P[i + fmin_] - P[i]) : 0.0f);
+        so[m] = on ? shift + i : wstride * nfw;                 // off: the scratch float behind the last row (row offsets are added below)
+        lo[m] = on ? i + fmin_ : 0;
+    }
+    for (int r = 0; r < nfw; r++) {
+        const float inv = 1.0f / (2.0f * (float)(fmin_ + r));
+        float *Wr = W + (size_t)r * wstride;
+        const float *vr = vpos + r;
+#pragma unroll
+        for (int m = 0; m < EPT; m++) {
+            const bool on = so[m] < wstride;                    // (constant over the rows)
+            (on ? Wr : W)[so[m]] = U[m] * inv;
+            U[m] += vr[lo[m]];
+        }
+    }
+}
+
+struct tb_k4t_tile {
+    int region, tile;
+};
+
+// OUT_MODE as above.  Shared memory: N[n_in + 2] doubles | P[n_in + 2] doubles | vpos[wstride + fmax + 8] floats (the three: later G[GW][S]) |
+// vneg[wstride] floats (shifted like the rows) | W[nfw][wstride] + 4 floats
+template <int OUT_MODE, int NW>
+__global__ void __launch_bounds__(TB_K4T_MAXT, NW == 16 ? 2 : 1)
+tb_footprint_tile_kernel(tb_sc_view V, const tb_k4t_tile *__restrict__ tiles, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_,
+                         int pmin_, int pmax_, int wstride, int pg_bytes, void *__restrict__ out_) {
     TB_DYN_SMEM(smem);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int S = 2 * nthr;                                     // footprint starts per tile
+    const int S = 4 * nthr;                                     // footprint starts per tile
     const int T = S - (pmax_ - 1);                              // outputs per tile
     const int npw = pmax_ - pmin_ + 1, nfw = fmax_ - fmin_ + 1;
-    const i64 j = tb_upper_bound(V.tile_off, V.n_regions + 1, (i64)blockIdx.x) - 1;
-    const i64 tile = (i64)blockIdx.x - V.tile_off[j];
+    const i64 j = tiles[blockIdx.x].region;
+    const i64 tile = tiles[blockIdx.x].tile;
     const i64 Lr = V.ext_off[j + 1] - V.ext_off[j];
     const i64 p0 = tile * T;                                    // first output position of the tile (region coordinates)
     const i64 smin = p0 - (pmax_ - 1);                          // first footprint start of the tile
     const i64 in0 = smin - fmax_;                               // first loaded position
     const int n_in = S + 2 * fmax_ + pmax_;
-    const i64 limit = Lr - 2 * (i64)fmax_ - pmax_;              // i = s - fw must be < limit
-    double *P = (double *)smem;                                 // n_in + 1
-    double *N = P + (n_in + 1);                                 // n_in + 1
-    float *W = (float *)(N + (n_in + 1));                       // [nfw][wstride], row r shifted by `shift` floats; later G[16][S]
+    const i64 limit = Lr - 2 * (i64)fmax_ - pmax_;              // a start s exists for flank width fw iff 0 <= s - fw < limit
+    double *N = (double *)smem;                                 // n_in + 2
+    double *P = N + (n_in + 2);                                 // n_in + 2
+    float *vpos = (float *)(P + (n_in + 2));                    // max(v, 0) as float, zero padded up to wstride + fmax + 8
+    float *G = (float *)smem;                                   // [GW][S] once the rows are staged and the prefix sums read
+    float *vneg = (float *)(smem + pg_bytes);                   // min(v, 0) as float, shifted like the rows, zero padded up to wstride
+    float *W = vneg + wstride;                                  // [nfw][wstride]
     __shared__ double wtot[64];
+    __shared__ float ipw[32];
     const float *sg = signal + V.ext_off[j];
-    // the right-flank values of a thread start at index 2 * tid + fmax + pmin of a row: rows are shifted by one float when that is odd,
-    // so that every thread's first value sits on an 8-byte boundary
-    const int shift = (fmax_ + pmin_) & 1;
+    const int shift = (4 - ((fmax_ + pmin_) & 3)) & 3;          // rows are shifted so that every thread's first right value is 16-byte aligned
 
-    for (int i = tid; i < n_in; i += nthr) {
+    if (tid < 32) ipw[tid] = 1.0f / (float)(pmin_ + tid);
+    for (int i = tid; i < wstride + fmax_ + 8; i += nthr) {
         const i64 q = in0 + i;
         float v = 0.0f;
-        if (q >= 0 && q < Lr) v = (float)tb_prep_value(sg[q], prep);      // `val = arr[i+j]` is a C float (signals.pyx:191)
-        P[i] = v > 0.0f ? (double)v : 0.0;
-        N[i] = v < 0.0f ? (double)v : 0.0;
+        if (i < n_in && q >= 0 && q < Lr) v = (float)tb_prep_value(sg[q], prep);      // `val = arr[i+j]` is a C float (signals.pyx:191)
+        if (i < n_in) {
+            P[i] = v > 0.0f ? (double)v : 0.0;
+            N[i] = v < 0.0f ? (double)v : 0.0;
+        }
+        vpos[i] = v > 0.0f ? v : 0.0f;
+        if (i < wstride - shift) vneg[shift + i] = v < 0.0f ? v : 0.0f;
     }
+    if (tid < shift) vneg[tid] = 0.0f;
     __syncthreads();
     tb_block_scan2w(P, N, n_in, wtot);
-    // W_fw[i] = mean of max(v, 0) over [i, i + fw), halved: (P[i + fw] - P[i]) / (2 fw); padding up to the row end reads as 0
-    for (int r = 0; r < nfw; r++) {
-        const int fw = fmin_ + r;
-        const float inv = 1.0f / (2.0f * (float)fw);
-        float *Wr = W + (size_t)r * wstride + shift;
-        for (int i = tid; i < wstride - shift; i += nthr) Wr[i] = i + fw <= n_in ? (float)(P[i + fw] - P[i]) * inv : 0.0f;
+
+    switch ((wstride - shift + nthr - 1) / nthr) {
+    case 1: case 2: case 3: case 4: case 5: tb_k4t_stage<5>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
+    case 6: tb_k4t_stage<6>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
+    case 7: tb_k4t_stage<7>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
+    default: tb_k4t_stage<TB_K4T_EPT>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
     }
+    for (int r = 0; r < nfw; r++)
+        if (tid < shift) W[(size_t)r * wstride + tid] = 0.0f;
+
+    const int si = 4 * tid + fmax_;                             // index of start s_0 in the loaded range
+    const i64 s0 = smin + 4 * tid;
+    // right edge: start s_u exists in row r iff s_u - fmin - r < limit  <=>  r > e0 + u
+    const i64 ed = s0 - fmin_ - limit;
+    const int e0 = (int)(ed < -8 ? -8 : (ed > 100000 ? 100000 : ed));
+    const bool edge = e0 + 3 >= 0;
+    const int X = fmax_ + shift - fmin_;                        // left values of row r start at float 4 * tid + X - r of the row
+    const int k0 = 4 * tid;                                     // index of s_0 among the tile's starts
+    // centre term: N[s_u + pw] - N[s_u] = (N[s_u + pw] - N[s_3]) + (N[s_3] - N[s_u]); the first bracket starts from one fp64 difference per
+    // pass and grows by fp32 adds of min(v, 0) (same-signed terms)
+    float lf[4], mf0[32 / NW];
+    {
+        const double n3 = N[si + 3];
+#pragma unroll
+        for (int u = 0; u < 4; u++) lf[u] = (float)(N[si + u] - n3);       // negated: subtracted below
+#pragma unroll
+        for (int ps = 0; ps < 32 / NW; ps++) mf0[ps] = (float)(N[min(si + pmin_ + ps * NW, n_in)] - n3);
+    }
+    float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};                   // out[pos] for pos = smin + tid + m * nthr (footprint_scores starts at 0, signals.pyx:193)
+    float carry[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     __syncthreads();
 
-    const int si = 2 * tid + fmax_;                             // index of start s0 in the loaded range
-    const i64 s0 = smin + 2 * tid;
-    float acc0[TB_K4_NPW], acc1[TB_K4_NPW];
 #pragma unroll
-    for (int c = 0; c < TB_K4_NPW; c++) acc0[c] = acc1[c] = -INFINITY;
-    for (int r = 0; r < nfw; r++) {
-        const int fw = fmin_ + r;
-        const float *Wr = W + (size_t)r * wstride + shift;
-        const i64 i0 = s0 - fw;
-        // a start whose left flank would begin outside [0, limit) does not exist (signals.pyx:199): -inf + finite stays -inf
-        const float l0 = (i0 >= 0 && i0 < limit) ? Wr[si - fw] : -INFINITY;
-        const float l1 = (i0 + 1 >= 0 && i0 + 1 < limit) ? Wr[si + 1 - fw] : -INFINITY;
-        const float2 *w2 = (const float2 *)(Wr + si + pmin_);   // 8-byte aligned by construction
-        float2 cur = w2[0];
+    for (int pass = 32 / NW - 1; pass >= 0; pass--) {
+        const int c0 = pass * NW;                               // first width index of the pass
+        if (c0 >= npw) continue;                                // block-uniform
+        float acc[4][NW];
 #pragma unroll
-        for (int h = 0; h < TB_K4_NPW / 2; h++) {
-            const float2 nxt = w2[h + 1];
-            acc0[2 * h] = fmaxf(acc0[2 * h], l0 + cur.x);
-            acc0[2 * h + 1] = fmaxf(acc0[2 * h + 1], l0 + cur.y);
-            acc1[2 * h] = fmaxf(acc1[2 * h], l1 + cur.y);
-            acc1[2 * h + 1] = fmaxf(acc1[2 * h + 1], l1 + nxt.x);
-            cur = nxt;
-        }
-    }
-    // acc[c] -> score of (s, pmin + c); widths beyond pmax are padding
-    {
-        const double n0 = N[si], n1 = N[si + 1];
+        for (int u = 0; u < 4; u++)
 #pragma unroll
-        for (int c = 0; c < TB_K4_NPW; c++) {
-            const int pw = pmin_ + c;
-            float a = -INFINITY, b = -INFINITY;
-            if (c < npw) {
-                const float ipw = 1.0f / (float)pw;
-                if (acc0[c] > -INFINITY) a = acc0[c] - (float)(N[si + pw] - n0) * ipw;
-                if (acc1[c] > -INFINITY) b = acc1[c] - (float)(N[si + 1 + pw] - n1) * ipw;
-            }
-            acc0[c] = a;
-            acc1[c] = b;
-        }
-    }
-    // suffix maxima over the widths: g[c] = max_{pw >= pmin + c} score(s, pw)
-#pragma unroll
-    for (int c = TB_K4_NPW - 2; c >= 0; c--) {
-        acc0[c] = fmaxf(acc0[c], acc0[c + 1]);
-        acc1[c] = fmaxf(acc1[c], acc1[c + 1]);
-    }
-    // out[pos] = max( max_{d < pmin} g[0](pos - d),  max_{c >= 1} g[c](pos - (pmin - 1 + c)) ), out initialised 0 (signals.pyx:193)
-    float best0 = 0.0f, best1 = 0.0f;
-    float *G = W;                                               // [16][S]
-    const int k0 = 2 * tid;                                     // index of s0 among the tile's starts
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        __syncthreads();                                        // W (or the previous half of G) no longer read
-#pragma unroll
-        for (int cc = 0; cc < TB_K4_NPW / 2; cc++) {
-            const int c = half * (TB_K4_NPW / 2) + cc;
-            *(float2 *)(G + (size_t)cc * S + k0) = make_float2(acc0[c], acc1[c]);
-        }
-        __syncthreads();
-        if (half == 0)
-            for (int d = 0; d < pmin_; d++) {
-                if (k0 - d >= 0) best0 = fmaxf(best0, G[k0 - d]);
-                if (k0 + 1 - d >= 0) best1 = fmaxf(best1, G[k0 + 1 - d]);
-            }
-#pragma unroll
-        for (int cc = 0; cc < TB_K4_NPW / 2; cc++) {
-            const int c = half * (TB_K4_NPW / 2) + cc;
-            if (c >= 1 && c < npw) {                            // block-uniform
-                const int d = pmin_ - 1 + c;
-                if (k0 - d >= 0) best0 = fmaxf(best0, G[(size_t)cc * S + k0 - d]);
-                if (k0 + 1 - d >= 0) best1 = fmaxf(best1, G[(size_t)cc * S + k0 + 1 - d]);
+            for (int c = 0; c < NW; c++) acc[u][c] = -INFINITY;
+        const int rb = 4 * tid + fmax_ + pmin_ + shift + c0;
+        int r = 0;
+        for (; r + 1 < nfw; r += 2) {
+            const float *Wr = W + (size_t)r * wstride;
+            const int lb = 4 * tid + ((X - r) & ~3);
+            switch ((X - r) & 3) {
+            case 0: tb_k4t_step<NW, 0, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+            case 1: tb_k4t_step<NW, 1, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+            case 2: tb_k4t_step<NW, 2, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+            default: tb_k4t_step<NW, 3, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
             }
         }
-    }
-    // this thread holds out[pos] for pos = s0 and s0 + 1; valid from the tile's first output position on
+        if (r < nfw) {
+            const float *Wr = W + (size_t)r * wstride;
+            const int lb = 4 * tid + ((X - r) & ~3);
+            switch ((X - r) & 3) {
+            case 0: tb_k4t_step<NW, 0, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+            case 1: tb_k4t_step<NW, 1, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+            case 2: tb_k4t_step<NW, 2, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+            default: tb_k4t_step<NW, 3, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+            }
+        }
+        // centre term and suffix maxima over the widths: g[u][c] = max_{pw >= pmin + c0 + c} score(s_u, pw)
+        {
+            float mf[NW + 4];
+            mf[0] = mf0[pass];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-        const i64 s = s0 + u;
-        const float best = u ? best1 : best0;
-        if (k0 + u >= pmax_ - 1 && s < Lr) {
+            for (int m = 0; m < NW / 4 + 1; m++) {
+                const float4 q = tb_lds128(vneg + rb + 4 * m);
+                if (4 * m + 1 < NW + 4) mf[4 * m + 1] = mf[4 * m] + q.x;
+                if (4 * m + 2 < NW + 4) mf[4 * m + 2] = mf[4 * m + 1] + q.y;
+                if (4 * m + 3 < NW + 4) mf[4 * m + 3] = mf[4 * m + 2] + q.z;
+                if (4 * m + 4 < NW + 4) mf[4 * m + 4] = mf[4 * m + 3] + q.w;
+            }
+#pragma unroll
+            for (int c = NW - 1; c >= 0; c--) {
+                if (c0 + c < npw) {                             // block-uniform
+                    const float ip = ipw[(c0 + c) & 31];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        carry[u] = fmaxf(carry[u], fmaf(lf[u] - mf[u + c], ip, acc[u][c]));
+                        acc[u][c] = carry[u];
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u][c] = -INFINITY;
+                }
+            }
+        }
+        // out[pos] = max( max_{d < pmin} g[0](pos - d),  max_{c >= 1} g[c](pos - (pmin - 1 + c)) ); written by the starts' owners, read by
+        // position: thread t takes the positions t, t + nthr, ... of the tile (consecutive threads, consecutive floats)
+#pragma unroll
+        for (int g0 = 0; g0 < NW; g0 += TB_K4T_GW) {
+            if (c0 + g0 < npw) {                                // block-uniform
+                __syncthreads();                                // the prefix sums / the previous group of G no longer read
+#pragma unroll
+                for (int cc = 0; cc < TB_K4T_GW; cc++)
+                    *(float4 *)(G + (size_t)cc * S + k0) = make_float4(acc[0][g0 + cc], acc[1][g0 + cc], acc[2][g0 + cc], acc[3][g0 + cc]);
+                __syncthreads();
+#pragma unroll
+                for (int cc = 0; cc < TB_K4T_GW; cc++) {
+                    const int c = c0 + g0 + cc;
+                    if (c >= 1 && c < npw) {
+                        const int b = tid - (pmin_ - 1 + c);
+                        const float *g = G + (size_t)cc * S + b;
+#pragma unroll
+                        for (int m = 0; m < 4; m++)
+                            if (b + m * nthr >= 0) best[m] = fmaxf(best[m], g[m * nthr]);
+                    }
+                }
+                if (c0 + g0 == 0) {
+                    for (int d = 0; d < pmin_; d++) {
+#pragma unroll
+                        for (int m = 0; m < 4; m++)
+                            if (tid + m * nthr - d >= 0) best[m] = fmaxf(best[m], G[tid + m * nthr - d]);
+                    }
+                }
+            }
+        }
+    }
+    // this thread holds out[pos] for the tile's positions smin + tid + m * nthr; valid from the tile's first output position on
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int k = tid + m * nthr;
+        const i64 s = smin + k;
+        if (k >= pmax_ - 1 && s < Lr) {
             if (OUT_MODE == 2) {
-                ((double *)out_)[V.ext_off[j] + s] = (double)best;
+                ((double *)out_)[V.ext_off[j] + s] = (double)best[m];
             } else if (s >= V.flank && s < Lr - V.flank) {
                 const i64 o = V.out_off[j] + (s - V.flank);
-                if (OUT_MODE == 0) ((float *)out_)[o] = best;
-                else ((double *)out_)[o] = (double)best;
+                if (OUT_MODE == 0) ((float *)out_)[o] = best[m];
+                else ((double *)out_)[o] = (double)best[m];
             }
         }
     }
@@ -676,48 +838,65 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
             else hist.push_back({v, 1});
         }
         const int npw = p->fp_max - p->fp_min + 1, nfw = p->flank_max - p->flank_min + 1;
-        // second form (two starts per thread, all flank-width arrays staged): at most 32 footprint widths, and the arrays must fit
-        int bs2 = 0;
+        // register-tiled form (4 starts x 16 or 32 widths per thread, all flank-width rows staged): at most 32 footprint widths, and the rows
+        // must fit; option k4_form: 0 = first form, 16 / 32 = widths per pass of the tiled form (default 16: two blocks per SM)
+        int bs2 = 0, wstride2 = 0, pg2 = 0, nw2 = 0;
         size_t smem2 = 0;
-        int wstride2 = 0;
-        // (measured on the hg38 workload: 28.0 ms against 26.0 ms of the first form -- 107 registers leave one 416-thread block per SM, so the
-        // load / scan / staging / spread phases of a tile no longer overlap with another tile's width loop; opt-in until that is solved)
-        if (!fos && npw <= TB_K4_NPW && tb_opt(ctx, "k4_two_starts", 0) != 0) {
+        const int form = (int)tb_opt(ctx, "k4_form", 16);
+        if (!fos && npw <= 32 && (form == 16 || form == 32)) {
             double best_cost = -1.0;
-            const int forced = (int)tb_opt(ctx, "k4_threads", 0);                                // comparison runs: threads per block of the second form
-            for (int cand = 64; cand <= TB_K4B_MAXT; cand += 32) {
+            const int forced = (int)tb_opt(ctx, "k4_threads", 0);                                // comparison runs: threads per block
+            for (int cand = 64; cand <= TB_K4T_MAXT; cand += 32) {
                 if (forced >= 64 && cand != (forced & ~31)) continue;
-                const i64 per = 2 * cand - (p->fp_max - 1);
+                const int Sx = 4 * cand;
+                const i64 per = Sx - (p->fp_max - 1);
                 if (per < 32) continue;
-                const int n_in = 2 * cand + 2 * p->flank_max + p->fp_max;
-                const int wstride = (n_in + 1 + 34 + 3) & ~3;                                  // + the 34 floats a thread reads past its last start
-                size_t need = (size_t)2 * (n_in + 1) * sizeof(double) + (size_t)nfw * wstride * sizeof(float);
-                const size_t gbytes = (size_t)16 * 2 * cand * sizeof(float);
-                if ((size_t)nfw * wstride * sizeof(float) < gbytes) need = (size_t)2 * (n_in + 1) * sizeof(double) + gbytes;
-                if (need > (size_t)200 * 1024) continue;
+                const int n_in = Sx + 2 * p->flank_max + p->fp_max;
+                const int wstride = (std::max(n_in + 4, Sx + p->flank_max + p->fp_min + 40) + 3) & ~3;
+                if (wstride > TB_K4T_EPT * cand) continue;
+                const size_t pg = (std::max((size_t)16 * (n_in + 2) + (size_t)4 * (wstride + p->flank_max + 8), (size_t)TB_K4T_GW * Sx * 4) + 15) & ~(size_t)15;
+                const size_t need = pg + (size_t)4 * wstride + (size_t)nfw * wstride * 4 + 16;
+                if (need > (size_t)220 * 1024) continue;
+                const int by_smem = (int)(((size_t)227 * 1024) / (need + 1024 + 400));
+                const int by_regs = form == 16 ? 65536 / (128 * cand) : 65536 / (255 * cand);
+                const int bps = std::max(1, std::min(std::min(by_smem, by_regs), 2048 / cand));
                 double cost = 0.0;
                 for (const auto &h : hist) cost += (double)tb_div_up(h.first, per) * (double)h.second;
-                cost *= (double)(2 * cand + 2 * p->flank_max + p->fp_max) + 64.0;             // slots incl. the halo every tile re-scans
+                // work of a tile ~ its slots incl. the halo; few warps per SM hide the staging / exchange phases badly
+                cost *= ((double)n_in + 64.0) * (bps * cand >= 384 ? 1.0 : 1.3);
                 if (best_cost < 0.0 || cost < best_cost) {
                     best_cost = cost;
                     bs2 = cand;
                     smem2 = need;
                     wstride2 = wstride;
+                    pg2 = (int)pg;
+                    nw2 = form;
                 }
             }
         }
         if (bs2 > 0) {
-            const i64 per_tile = 2 * bs2 - (p->fp_max - 1);
-            TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles));
-            tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
-#define TB_FP2_CASE(OM)                                                                                                      \
+            const i64 per_tile = 4 * bs2 - (p->fp_max - 1);
+            std::vector<tb_k4t_tile> tl;
+            for (i64 i = 0; i < S.n_regions; i++) {
+                const i64 nt = tb_div_up(S.ext_off[i + 1] - S.ext_off[i], per_tile);
+                for (i64 t = 0; t < nt; t++) tl.push_back({(int)i, (int)t});
+            }
+            n_tiles = (i64)tl.size();
+            if (n_tiles > 0x7fffffffLL || S.n_regions > 0x7fffffffLL) return tb_fail(ctx, TB_ERR_ARG, "too many tiles (%lld)", n_tiles);
+            TB_TRY(tb_h2d(ctx, ctx->reg_e, tl.data(), sizeof(tb_k4t_tile) * tl.size()));
+            tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), nullptr, S.n_regions, p->flank};
+#define TB_FP2_CASE(OM, NWX)                                                                                                 \
     {                                                                                                                       \
-        auto k = tb_footprint2_kernel<OM>;                                                                                  \
+        auto k = tb_footprint_tile_kernel<OM, NWX>;                                                                         \
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));                     \
-        TB_LAUNCH(ctx, k, (unsigned)n_tiles, bs2, smem2, V, (const float *)S.signal.as<float>(), prep, p->flank_min,        \
-                  p->flank_max, p->fp_min, p->fp_max, wstride2, first_out);                                                 \
+        TB_LAUNCH(ctx, k, (unsigned)n_tiles, bs2, smem2, V, (const tb_k4t_tile *)ctx->reg_e.p, (const float *)S.signal.as<float>(), prep,   \
+                  p->flank_min, p->flank_max, p->fp_min, p->fp_max, wstride2, pg2, first_out);                              \
     }
-            if (first_mode == 0) TB_FP2_CASE(0) else if (first_mode == 1) TB_FP2_CASE(1) else TB_FP2_CASE(2)
+            if (nw2 == 16) {
+                if (first_mode == 0) TB_FP2_CASE(0, 16) else if (first_mode == 1) TB_FP2_CASE(1, 16) else TB_FP2_CASE(2, 16)
+            } else {
+                if (first_mode == 0) TB_FP2_CASE(0, 32) else if (first_mode == 1) TB_FP2_CASE(1, 32) else TB_FP2_CASE(2, 32)
+            }
 #undef TB_FP2_CASE
         } else {
         // footprint scan, first form: block size = tile size, picked to waste the fewest thread slots on these region lengths
