@@ -331,56 +331,101 @@ __device__ __forceinline__ void tb_k4t_step(const float *__restrict__ Wr, int ws
         }
 }
 
+// All rows of one pass.  X0 = X & 3 is the misalignment of row 0's left values; it drops by one per row, so over four rows the steps repeat.
+template <int NW, int X0>
+__device__ __forceinline__ void tb_k4t_rows(const float *__restrict__ W, int wstride, int t4, int X, int rb, bool edge, int e0, int nfw,
+                                            float (&acc)[4][NW]) {
+    int r = 0;
+    const float *Wr = W;
+    int lb = t4 + (X & ~3);                                     // aligned index at or below the left values of row r
+    for (; r + 3 < nfw; r += 4) {
+        tb_k4t_step<NW, X0, true>(Wr, wstride, lb, rb, edge, e0, r, acc);
+        // rows r + 2, r + 3: misalignment X0 - 2; the aligned index steps down when that wraps
+        tb_k4t_step<NW, (X0 + 2) & 3, true>(Wr + 2 * wstride, wstride, X0 < 2 ? lb - 4 : lb, rb, edge, e0, r + 2, acc);
+        Wr += 4 * wstride;
+        lb -= 4;
+    }
+    if (r + 1 < nfw) {
+        tb_k4t_step<NW, X0, true>(Wr, wstride, lb, rb, edge, e0, r, acc);
+        r += 2;
+        if (r < nfw) tb_k4t_step<NW, (X0 + 2) & 3, false>(Wr + 2 * wstride, wstride, X0 < 2 ? lb - 4 : lb, rb, edge, e0, r, acc);
+    } else if (r < nfw) {
+        tb_k4t_step<NW, X0, false>(Wr, wstride, lb, rb, edge, e0, r, acc);
+    }
+}
+
 // Stages the rows: W_r[i] = mean of max(v, 0) over [i, i + fw), halved: sum / (2 fw); row r + 1 from row r by one add per element.  Thread t owns
-// the elements t, t + nthr, ... (EPT of them; beyond the row's end they go to one scratch float behind it); entries whose window starts before
-// the region are -inf from the start and stay so.
+// the elements t, t + nthr, ... (EPT of them, the last one only where it is inside the row); entries whose window starts before the region are
+// -inf from the start and stay so.
 template <int EPT>
 __device__ __forceinline__ void tb_k4t_stage(const double *__restrict__ P, const float *__restrict__ vpos, float *__restrict__ W, int wstride,
-                                             int shift, int n_in, i64 in0, int fmin_, int nfw) {
+                                             int shift, int n_in, i64 in0, int fmin_, int nfw, const float *__restrict__ invf) {
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lim = wstride - shift;
+    const bool last_on = tid + (EPT - 1) * nthr < wstride - shift;
     float U[EPT];
-    int so[EPT], lo[EPT];
 #pragma unroll
     for (int m = 0; m < EPT; m++) {
         const int i = tid + m * nthr;
-        const bool on = i < lim;
-        U[m] = in0 + i < 0 ? -INFINITY : (on && i + fmin_ <= n_in ? (float)(P[i + fmin_] - P[i]) : 0.0f);
-        so[m] = on ? shift + i : wstride * nfw;                 // off: the scratch float behind the last row (row offsets are added below)
-        lo[m] = on ? i + fmin_ : 0;
+        U[m] = in0 + i < 0 ? -INFINITY : (i + fmin_ <= n_in ? (float)(P[i + fmin_] - P[i]) : 0.0f);
     }
+    float *wp = W + shift + tid;
+    const float *vp = vpos + fmin_ + tid;
+#pragma unroll 3
     for (int r = 0; r < nfw; r++) {
-        const float inv = 1.0f / (2.0f * (float)(fmin_ + r));
-        float *Wr = W + (size_t)r * wstride;
-        const float *vr = vpos + r;
+        const float inv = r < 64 ? invf[r] : 1.0f / (2.0f * (float)(fmin_ + r));
 #pragma unroll
-        for (int m = 0; m < EPT; m++) {
-            const bool on = so[m] < wstride;                    // (constant over the rows)
-            (on ? Wr : W)[so[m]] = U[m] * inv;
-            U[m] += vr[lo[m]];
+        for (int m = 0; m < EPT - 1; m++) {
+            wp[m * nthr] = U[m] * inv;
+            U[m] += vp[m * nthr];
         }
+        if (last_on) {
+            wp[(EPT - 1) * nthr] = U[EPT - 1] * inv;
+            U[EPT - 1] += vp[(EPT - 1) * nthr];
+        }
+        wp += wstride;
+        vp += 1;
     }
 }
 
 struct tb_k4t_tile {
-    int region, tile;
+    i64 ext0, out0;              // offsets of the region in the concatenated signal / trimmed output
+    i64 len;                     // length of the (flank-extended) region
+    i64 tile;                    // tile index within the region
 };
 
-// OUT_MODE as above.  Shared memory: N[n_in + 2] doubles | P[n_in + 2] doubles | vpos[wstride + fmax + 8] floats (the three: later G[GW][S]) |
-// vneg[wstride] floats (shifted like the rows) | W[nfw][wstride] + 4 floats
+// tile table from the per-region prefix of tile counts (built on the device: a whole-genome scan has millions of tiles)
+__global__ void tb_k4t_tiles_kernel(const i64 *__restrict__ ext_off, const i64 *__restrict__ out_off, const i64 *__restrict__ tile_off,
+                                    i64 n_regions, i64 n_tiles, tb_k4t_tile *__restrict__ tiles) {
+    const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_tiles) return;
+    const i64 j = tb_upper_bound(tile_off, n_regions + 1, b) - 1;
+    tb_k4t_tile t;
+    t.ext0 = ext_off[j];
+    t.out0 = out_off[j];
+    t.len = ext_off[j + 1] - ext_off[j];
+    t.tile = b - tile_off[j];
+    tiles[b] = t;
+}
+
+#define TB_K4T_LD 8              // input elements a thread loads at most
+// padding (floats of -inf) in front of the exchange rows: the furthest thread / start a position reads from
+__host__ __device__ __forceinline__ int tb_k4t_epad(int pmax) { return (pmax / 4 + 16) & ~3; }
+__host__ __device__ __forceinline__ int tb_k4t_gpad(int pmax) { return (pmax + 8) & ~3; }
+
+// OUT_MODE as above.  Shared memory: N[n_in + 2] doubles | P[n_in + 2] doubles | vpos[wstride + fmax + 8] floats -- the three later hold the
+// exchange rows E[NW + 3][nthr + epad] and G0[gpad + S] -- | vneg[wstride] floats (shifted like the rows) | W[nfw][wstride]
 template <int OUT_MODE, int NW>
 __global__ void __launch_bounds__(TB_K4T_MAXT, NW == 16 ? 2 : 1)
-tb_footprint_tile_kernel(tb_sc_view V, const tb_k4t_tile *__restrict__ tiles, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_,
+tb_footprint_tile_kernel(const tb_k4t_tile *__restrict__ tiles, int flank, const float *__restrict__ signal, tb_prep prep, int fmin_, int fmax_,
                          int pmin_, int pmax_, int wstride, int pg_bytes, void *__restrict__ out_) {
     TB_DYN_SMEM(smem);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int S = 4 * nthr;                                     // footprint starts per tile
     const int T = S - (pmax_ - 1);                              // outputs per tile
     const int npw = pmax_ - pmin_ + 1, nfw = fmax_ - fmin_ + 1;
-    const i64 j = tiles[blockIdx.x].region;
-    const i64 tile = tiles[blockIdx.x].tile;
-    const i64 Lr = V.ext_off[j + 1] - V.ext_off[j];
-    const i64 p0 = tile * T;                                    // first output position of the tile (region coordinates)
+    const tb_k4t_tile td = tiles[blockIdx.x];
+    const i64 Lr = td.len;
+    const i64 p0 = td.tile * T;                                 // first output position of the tile (region coordinates)
     const i64 smin = p0 - (pmax_ - 1);                          // first footprint start of the tile
     const i64 in0 = smin - fmax_;                               // first loaded position
     const int n_in = S + 2 * fmax_ + pmax_;
@@ -388,35 +433,51 @@ tb_footprint_tile_kernel(tb_sc_view V, const tb_k4t_tile *__restrict__ tiles, co
     double *N = (double *)smem;                                 // n_in + 2
     double *P = N + (n_in + 2);                                 // n_in + 2
     float *vpos = (float *)(P + (n_in + 2));                    // max(v, 0) as float, zero padded up to wstride + fmax + 8
-    float *G = (float *)smem;                                   // [GW][S] once the rows are staged and the prefix sums read
+    const int epad = tb_k4t_epad(pmax_), gpad = tb_k4t_gpad(pmax_), estride = nthr + epad;
+    float *E = (float *)smem;                                   // [NW + 3][estride] once the rows are staged and the prefix sums read
+    float *G0 = E + (size_t)(NW + 3) * estride;                 // [gpad + S]
     float *vneg = (float *)(smem + pg_bytes);                   // min(v, 0) as float, shifted like the rows, zero padded up to wstride
     float *W = vneg + wstride;                                  // [nfw][wstride]
     __shared__ double wtot[64];
-    __shared__ float ipw[32];
-    const float *sg = signal + V.ext_off[j];
+    __shared__ float ipw[32], invf[64];                         // 1 / pw, 1 / (2 fw)
+    const float *sg = signal + td.ext0;
     const int shift = (4 - ((fmax_ + pmin_) & 3)) & 3;          // rows are shifted so that every thread's first right value is 16-byte aligned
 
     if (tid < 32) ipw[tid] = 1.0f / (float)(pmin_ + tid);
-    for (int i = tid; i < wstride + fmax_ + 8; i += nthr) {
-        const i64 q = in0 + i;
-        float v = 0.0f;
-        if (i < n_in && q >= 0 && q < Lr) v = (float)tb_prep_value(sg[q], prep);      // `val = arr[i+j]` is a C float (signals.pyx:191)
-        if (i < n_in) {
-            P[i] = v > 0.0f ? (double)v : 0.0;
-            N[i] = v < 0.0f ? (double)v : 0.0;
+    if (tid < 64) invf[tid] = 1.0f / (2.0f * (float)(fmin_ + tid));
+    {
+        // all loads of the thread first (independent), then the conversions
+        const int n_ld = wstride + fmax_ + 8;
+        float v[TB_K4T_LD];
+#pragma unroll
+        for (int m = 0; m < TB_K4T_LD; m++) {
+            const int i = tid + m * nthr;
+            const i64 q = in0 + i;
+            v[m] = (i < n_in && q >= 0 && q < Lr) ? sg[q] : 0.0f;
         }
-        vpos[i] = v > 0.0f ? v : 0.0f;
-        if (i < wstride - shift) vneg[shift + i] = v < 0.0f ? v : 0.0f;
+#pragma unroll
+        for (int m = 0; m < TB_K4T_LD; m++) {
+            const int i = tid + m * nthr;
+            if (i < n_ld) {
+                const float x = (float)tb_prep_value(v[m], prep);                     // `val = arr[i+j]` is a C float (signals.pyx:191)
+                if (i < n_in) {
+                    P[i] = x > 0.0f ? (double)x : 0.0;
+                    N[i] = x < 0.0f ? (double)x : 0.0;
+                }
+                vpos[i] = x > 0.0f ? x : 0.0f;
+                if (i < wstride - shift) vneg[shift + i] = x < 0.0f ? x : 0.0f;
+            }
+        }
     }
     if (tid < shift) vneg[tid] = 0.0f;
     __syncthreads();
     tb_block_scan2w(P, N, n_in, wtot);
 
     switch ((wstride - shift + nthr - 1) / nthr) {
-    case 1: case 2: case 3: case 4: case 5: tb_k4t_stage<5>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
-    case 6: tb_k4t_stage<6>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
-    case 7: tb_k4t_stage<7>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
-    default: tb_k4t_stage<TB_K4T_EPT>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw); break;
+    case 1: case 2: case 3: case 4: case 5: tb_k4t_stage<5>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw, invf); break;
+    case 6: tb_k4t_stage<6>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw, invf); break;
+    case 7: tb_k4t_stage<7>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw, invf); break;
+    default: tb_k4t_stage<TB_K4T_EPT>(P, vpos, W, wstride, shift, n_in, in0, fmin_, nfw, invf); break;
     }
     for (int r = 0; r < nfw; r++)
         if (tid < shift) W[(size_t)r * wstride + tid] = 0.0f;
@@ -439,111 +500,115 @@ tb_footprint_tile_kernel(tb_sc_view V, const tb_k4t_tile *__restrict__ tiles, co
 #pragma unroll
         for (int ps = 0; ps < 32 / NW; ps++) mf0[ps] = (float)(N[min(si + pmin_ + ps * NW, n_in)] - n3);
     }
-    float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};                   // out[pos] for pos = smin + tid + m * nthr (footprint_scores starts at 0, signals.pyx:193)
+    float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};                   // out[pos] for pos = s_u (footprint_scores starts at 0, signals.pyx:193)
     float carry[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     __syncthreads();
 
+    bool first_exchange = true;
 #pragma unroll
     for (int pass = 32 / NW - 1; pass >= 0; pass--) {
         const int c0 = pass * NW;                               // first width index of the pass
-        if (c0 >= npw) continue;                                // block-uniform
+        if (c0 < npw) {                                         // block-uniform
         float acc[4][NW];
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
             for (int c = 0; c < NW; c++) acc[u][c] = -INFINITY;
         const int rb = 4 * tid + fmax_ + pmin_ + shift + c0;
-        int r = 0;
-        for (; r + 1 < nfw; r += 2) {
-            const float *Wr = W + (size_t)r * wstride;
-            const int lb = 4 * tid + ((X - r) & ~3);
-            switch ((X - r) & 3) {
-            case 0: tb_k4t_step<NW, 0, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
-            case 1: tb_k4t_step<NW, 1, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
-            case 2: tb_k4t_step<NW, 2, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
-            default: tb_k4t_step<NW, 3, true>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
+        switch (X & 3) {
+        case 0: tb_k4t_rows<NW, 0>(W, wstride, 4 * tid, X, rb, edge, e0, nfw, acc); break;
+        case 1: tb_k4t_rows<NW, 1>(W, wstride, 4 * tid, X, rb, edge, e0, nfw, acc); break;
+        case 2: tb_k4t_rows<NW, 2>(W, wstride, 4 * tid, X, rb, edge, e0, nfw, acc); break;
+        default: tb_k4t_rows<NW, 3>(W, wstride, 4 * tid, X, rb, edge, e0, nfw, acc); break;
+        }
+        // centre term: mf[k] = N[s_0 + pmin + c0 + k] - N[s_3]
+        float mf[NW + 4];
+        mf[0] = pass == 0 ? mf0[0] : mf0[32 / NW - 1];
+#pragma unroll
+        for (int m = 0; m < NW / 4 + 1; m++) {
+            const float4 q = tb_lds128(vneg + rb + 4 * m);
+            if (4 * m + 1 < NW + 4) mf[4 * m + 1] = mf[4 * m] + q.x;
+            if (4 * m + 2 < NW + 4) mf[4 * m + 2] = mf[4 * m + 1] + q.y;
+            if (4 * m + 3 < NW + 4) mf[4 * m + 3] = mf[4 * m + 2] + q.z;
+            if (4 * m + 4 < NW + 4) mf[4 * m + 4] = mf[4 * m + 3] + q.w;
+        }
+        // Scores, from the widest width down; g[u][c] = max_{pw >= pmin + c} score(s_u, pw) is carried across the widths and passes.  Spreading
+        // a score over its footprint:
+        //     out[pos] = max( max_{d < pmin} g[0](pos - d),  max_{c >= 1} g[c](pos - (pmin - 1 + c)) ).
+        // The second term is a maximum along anti-diagonals of the (start, width) table; the part of every anti-diagonal inside a thread's
+        // four starts is folded in registers first, e[t] = max_{u + c = t} g[c](s_u), which belongs to the position s_0 + pmin - 1 + t:
+        // NW + 3 values per thread and pass go through shared memory instead of 4 NW, in one exchange (two barriers) per pass.
+        float e[NW + 3];
+#pragma unroll
+        for (int t = 0; t < NW + 3; t++) e[t] = -INFINITY;
+#pragma unroll
+        for (int cc = NW - 1; cc >= 0; cc--) {
+            if (c0 + cc < npw) {                                // block-uniform
+                const float ip = ipw[(c0 + cc) & 31];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float sc = fmaf(lf[u] - mf[u + cc], ip, acc[u][cc]);
+                    if (c0 + cc >= 1) e[u + cc] = fmaxf(fmaxf(e[u + cc], carry[u]), sc);
+                    carry[u] = fmaxf(carry[u], sc);
+                }
             }
         }
-        if (r < nfw) {
-            const float *Wr = W + (size_t)r * wstride;
-            const int lb = 4 * tid + ((X - r) & ~3);
-            switch ((X - r) & 3) {
-            case 0: tb_k4t_step<NW, 0, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
-            case 1: tb_k4t_step<NW, 1, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
-            case 2: tb_k4t_step<NW, 2, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
-            default: tb_k4t_step<NW, 3, false>(Wr, wstride, lb, rb, edge, e0, r, acc); break;
-            }
+        __syncthreads();                                        // the prefix sums / the previous pass's rows no longer read
+        if (first_exchange) {
+            for (int i = tid; i < (NW + 3) * epad; i += nthr) E[(size_t)(i / epad) * estride + i % epad] = -INFINITY;
+            for (int i = tid; i < gpad; i += nthr) G0[i] = -INFINITY;
+            first_exchange = false;
         }
-        // centre term and suffix maxima over the widths: g[u][c] = max_{pw >= pmin + c0 + c} score(s_u, pw)
+#pragma unroll
+        for (int t = 0; t < NW + 3; t++) E[(size_t)t * estride + epad + tid] = e[t];
+        if (pass == 0) *(float4 *)(G0 + gpad + k0) = make_float4(carry[0], carry[1], carry[2], carry[3]);
+        __syncthreads();
         {
-            float mf[NW + 4];
-            mf[0] = mf0[pass];
+            // position s_0 + u takes e[t] of the thread q before this one for t = 4 q + u - (pmin - 1)
+            const int base = pmin_ - 1 + c0;                    // t = c0 + t', t' the row of E
+            const int qlo = max(0, (base - 3) >> 2), qhi = (base + NW + 2) >> 2;
+            for (int q = qlo; q <= qhi; q++) {
+                const float *er = E + epad + tid - q;
 #pragma unroll
-            for (int m = 0; m < NW / 4 + 1; m++) {
-                const float4 q = tb_lds128(vneg + rb + 4 * m);
-                if (4 * m + 1 < NW + 4) mf[4 * m + 1] = mf[4 * m] + q.x;
-                if (4 * m + 2 < NW + 4) mf[4 * m + 2] = mf[4 * m + 1] + q.y;
-                if (4 * m + 3 < NW + 4) mf[4 * m + 3] = mf[4 * m + 2] + q.z;
-                if (4 * m + 4 < NW + 4) mf[4 * m + 4] = mf[4 * m + 3] + q.w;
+                for (int u = 0; u < 4; u++) {
+                    const int tp = 4 * q + u - base;
+                    if (tp >= 0 && tp < NW + 3) best[u] = fmaxf(best[u], er[(size_t)tp * estride]);
+                }
             }
+        }
+        if (pass == 0) {
+            // width index 0: window maximum over the pmin starts pos - (pmin - 1) .. pos
+            for (int jq = 0; 4 * jq - 3 < pmin_; jq++) {
+                const float4 g = *(const float4 *)(G0 + gpad + k0 - 4 * jq);     // starts k0 - 4 jq + (0 .. 3)
+                const float ge[4] = {g.x, g.y, g.z, g.w};
+                if (jq >= 1 && 4 * jq + 3 < pmin_) {
+                    const float m4 = fmaxf(fmaxf(g.x, g.y), fmaxf(g.z, g.w));
 #pragma unroll
-            for (int c = NW - 1; c >= 0; c--) {
-                if (c0 + c < npw) {                             // block-uniform
-                    const float ip = ipw[(c0 + c) & 31];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        carry[u] = fmaxf(carry[u], fmaf(lf[u] - mf[u + c], ip, acc[u][c]));
-                        acc[u][c] = carry[u];
-                    }
+                    for (int u = 0; u < 4; u++) best[u] = fmaxf(best[u], m4);
                 } else {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) acc[u][c] = -INFINITY;
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                            const int dist = u + 4 * jq - x;
+                            if (dist >= 0 && dist < pmin_) best[u] = fmaxf(best[u], ge[x]);
+                        }
                 }
             }
         }
-        // out[pos] = max( max_{d < pmin} g[0](pos - d),  max_{c >= 1} g[c](pos - (pmin - 1 + c)) ); written by the starts' owners, read by
-        // position: thread t takes the positions t, t + nthr, ... of the tile (consecutive threads, consecutive floats)
-#pragma unroll
-        for (int g0 = 0; g0 < NW; g0 += TB_K4T_GW) {
-            if (c0 + g0 < npw) {                                // block-uniform
-                __syncthreads();                                // the prefix sums / the previous group of G no longer read
-#pragma unroll
-                for (int cc = 0; cc < TB_K4T_GW; cc++)
-                    *(float4 *)(G + (size_t)cc * S + k0) = make_float4(acc[0][g0 + cc], acc[1][g0 + cc], acc[2][g0 + cc], acc[3][g0 + cc]);
-                __syncthreads();
-#pragma unroll
-                for (int cc = 0; cc < TB_K4T_GW; cc++) {
-                    const int c = c0 + g0 + cc;
-                    if (c >= 1 && c < npw) {
-                        const int b = tid - (pmin_ - 1 + c);
-                        const float *g = G + (size_t)cc * S + b;
-#pragma unroll
-                        for (int m = 0; m < 4; m++)
-                            if (b + m * nthr >= 0) best[m] = fmaxf(best[m], g[m * nthr]);
-                    }
-                }
-                if (c0 + g0 == 0) {
-                    for (int d = 0; d < pmin_; d++) {
-#pragma unroll
-                        for (int m = 0; m < 4; m++)
-                            if (tid + m * nthr - d >= 0) best[m] = fmaxf(best[m], G[tid + m * nthr - d]);
-                    }
-                }
-            }
         }
     }
-    // this thread holds out[pos] for the tile's positions smin + tid + m * nthr; valid from the tile's first output position on
+    // this thread holds out[pos] for pos = s_0 .. s_0 + 3; valid from the tile's first output position on
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
-        const int k = tid + m * nthr;
-        const i64 s = smin + k;
-        if (k >= pmax_ - 1 && s < Lr) {
+    for (int u = 0; u < 4; u++) {
+        const i64 s = s0 + u;
+        if (k0 + u >= pmax_ - 1 && s < Lr) {
             if (OUT_MODE == 2) {
-                ((double *)out_)[V.ext_off[j] + s] = (double)best[m];
-            } else if (s >= V.flank && s < Lr - V.flank) {
-                const i64 o = V.out_off[j] + (s - V.flank);
-                if (OUT_MODE == 0) ((float *)out_)[o] = best[m];
-                else ((double *)out_)[o] = (double)best[m];
+                ((double *)out_)[td.ext0 + s] = (double)best[u];
+            } else if (s >= flank && s < Lr - flank) {
+                const i64 o = td.out0 + (s - flank);
+                if (OUT_MODE == 0) ((float *)out_)[o] = best[u];
+                else ((double *)out_)[o] = (double)best[u];
             }
         }
     }
@@ -671,20 +736,44 @@ __global__ void tb_rolling_kernel(tb_sc_view V, const void *__restrict__ in_, tb
 // position of the scoring regions (already extended by `flank`) takes the float32 value of the output region that covers it -- its own
 // or an abutting neighbour (50-kb split pieces) -- and 0 where the track holds nothing (nan_to_num of the bigWig's NaN).
 // sc_lstart: linear start of every extended scoring region; out_lstart: linear start of every output region (ascending).
+// A warp takes runs of 1024 consecutive positions: two lanes find the scoring regions and the output regions the run can touch (binary
+// searches over the whole tables, once per run); every position then searches those few entries only.
+#define TB_C2S_RUN 1024
 __global__ void tb_corrected_to_signal_kernel(const double *__restrict__ cf, const double *__restrict__ cr, const i64 *__restrict__ out_lstart,
                                               const i64 *__restrict__ out_off, i64 n_out, const i64 *__restrict__ sc_lstart,
                                               const i64 *__restrict__ sig_off, i64 n_regions, i64 total, float *__restrict__ sig) {
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
-        const i64 r = tb_upper_bound(sig_off, n_regions + 1, x) - 1;
-        const i64 lin = sc_lstart[r] + (x - sig_off[r]);
-        const i64 j = tb_upper_bound(out_lstart, n_out, lin) - 1;
-        float v = 0.0f;
-        if (j >= 0) {
-            const i64 q = lin - out_lstart[j];
-            if (q < out_off[j + 1] - out_off[j]) v = (float)(cf[out_off[j] + q] + cr[out_off[j] + q]);
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 x0 = warp * TB_C2S_RUN; x0 < total; x0 += nwarps * TB_C2S_RUN) {
+        const i64 x1 = (x0 + TB_C2S_RUN < total ? x0 + TB_C2S_RUN : total) - 1;
+        i64 rr = 0;
+        if (lane < 2) rr = tb_upper_bound(sig_off, n_regions + 1, lane == 0 ? x0 : x1) - 1;
+        const i64 r0 = __shfl_sync(0xffffffffu, rr, 0), r1 = __shfl_sync(0xffffffffu, rr, 1);
+        // output regions between the one covering the first scoring region's start and the one covering the run's last position
+        i64 jj = 0;
+        if (lane == 0) jj = tb_upper_bound(out_lstart, n_out, sc_lstart[r0]) - 1;
+        if (lane == 1) jj = tb_upper_bound(out_lstart, n_out, sc_lstart[r1] + (x1 - sig_off[r1])) - 1;
+        i64 j0 = __shfl_sync(0xffffffffu, jj, 0);
+        const i64 j1 = __shfl_sync(0xffffffffu, jj, 1);
+        if (j0 < 0) j0 = 0;
+        for (i64 x = x0 + lane; x <= x1; x += 32) {
+            const i64 r = r0 + tb_upper_bound(sig_off + r0 + 1, r1 - r0, x);
+            const i64 lin = sc_lstart[r] + (x - sig_off[r]);
+            i64 j = -1;
+            if (j1 >= j0) {
+                j = j0 + tb_upper_bound(out_lstart + j0, j1 - j0 + 1, lin) - 1;
+                // scoring regions out of order: the bracket does not hold, search everything
+                if ((j < j0 && j0 > 0) || (j == j1 && j1 + 1 < n_out && out_lstart[j1 + 1] <= lin)) j = tb_upper_bound(out_lstart, n_out, lin) - 1;
+            } else if (n_out > 0 && out_lstart[0] <= lin) {
+                j = tb_upper_bound(out_lstart, n_out, lin) - 1;
+            }
+            float v = 0.0f;
+            if (j >= 0) {
+                const i64 q = lin - out_lstart[j];
+                if (q < out_off[j + 1] - out_off[j]) v = (float)(cf[out_off[j] + q] + cr[out_off[j] + q]);
+            }
+            sig[x] = v;
         }
-        sig[x] = v;
     }
 }
 
@@ -724,7 +813,7 @@ static int tb_signal_from_corrected_linear(tb_ctx *ctx, int flank, i64 n, const 
         for (i64 i = 0; i < C.n_regions; i++) out_lstart[i] = C.ext_start[i] + C.k_flank + C.window / 2;
         TB_TRY(tb_h2d(ctx, ctx->reg_a, out_lstart.data(), sizeof(i64) * (size_t)C.n_regions));
         TB_TRY(tb_h2d(ctx, ctx->reg_b, sc_lstart.data(), sizeof(i64) * (size_t)n));
-        i64 want = tb_div_up(S.ext_total, 256), capg = (i64)ctx->sm_count * 16;
+        i64 want = tb_div_up(S.ext_total, (i64)TB_C2S_RUN * 8), capg = (i64)ctx->sm_count * 16;
         const double *cf = C.tracks.as<double>() + ((i64)3 * 2 + 0) * C.out_total;
         const double *cr = C.tracks.as<double>() + ((i64)3 * 2 + 1) * C.out_total;
         TB_LAUNCH(ctx, tb_corrected_to_signal_kernel, (unsigned)(want < capg ? want : capg), 256, 0, cf, cr, (const i64 *)ctx->reg_a.as<i64>(),
@@ -852,9 +941,10 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
                 const i64 per = Sx - (p->fp_max - 1);
                 if (per < 32) continue;
                 const int n_in = Sx + 2 * p->flank_max + p->fp_max;
-                const int wstride = (std::max(n_in + 4, Sx + p->flank_max + p->fp_min + 40) + 3) & ~3;
-                if (wstride > TB_K4T_EPT * cand) continue;
-                const size_t pg = (std::max((size_t)16 * (n_in + 2) + (size_t)4 * (wstride + p->flank_max + 8), (size_t)TB_K4T_GW * Sx * 4) + 15) & ~(size_t)15;
+                const int wstride = (Sx + p->flank_max + p->fp_min + 40 + 3) & ~3;         // the last index a thread reads, incl. widths beyond pmax
+                if (wstride > TB_K4T_EPT * cand || wstride + p->flank_max + 8 > TB_K4T_LD * cand) continue;
+                const size_t xch = (size_t)4 * ((size_t)(form + 3) * (cand + tb_k4t_epad(p->fp_max)) + tb_k4t_gpad(p->fp_max) + Sx);
+                const size_t pg = (std::max((size_t)16 * (n_in + 2) + (size_t)4 * (wstride + p->flank_max + 8), xch) + 15) & ~(size_t)15;
                 const size_t need = pg + (size_t)4 * wstride + (size_t)nfw * wstride * 4 + 16;
                 if (need > (size_t)220 * 1024) continue;
                 const int by_smem = (int)(((size_t)227 * 1024) / (need + 1024 + 400));
@@ -876,20 +966,15 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
         }
         if (bs2 > 0) {
             const i64 per_tile = 4 * bs2 - (p->fp_max - 1);
-            std::vector<tb_k4t_tile> tl;
-            for (i64 i = 0; i < S.n_regions; i++) {
-                const i64 nt = tb_div_up(S.ext_off[i + 1] - S.ext_off[i], per_tile);
-                for (i64 t = 0; t < nt; t++) tl.push_back({(int)i, (int)t});
-            }
-            n_tiles = (i64)tl.size();
-            if (n_tiles > 0x7fffffffLL || S.n_regions > 0x7fffffffLL) return tb_fail(ctx, TB_ERR_ARG, "too many tiles (%lld)", n_tiles);
-            TB_TRY(tb_h2d(ctx, ctx->reg_e, tl.data(), sizeof(tb_k4t_tile) * tl.size()));
-            tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), nullptr, S.n_regions, p->flank};
+            TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles));
+            TB_TRY(tb_reserve(ctx, ctx->scratch4, sizeof(tb_k4t_tile) * (size_t)std::max<i64>(n_tiles, 1)));
+            TB_LAUNCH(ctx, tb_k4t_tiles_kernel, (unsigned)tb_div_up(std::max<i64>(n_tiles, 1), 256), 256, 0, S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(),
+                      ctx->reg_e.as<i64>(), S.n_regions, n_tiles, (tb_k4t_tile *)ctx->scratch4.p);
 #define TB_FP2_CASE(OM, NWX)                                                                                                 \
     {                                                                                                                       \
         auto k = tb_footprint_tile_kernel<OM, NWX>;                                                                         \
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));                     \
-        TB_LAUNCH(ctx, k, (unsigned)n_tiles, bs2, smem2, V, (const tb_k4t_tile *)ctx->reg_e.p, (const float *)S.signal.as<float>(), prep,   \
+        TB_LAUNCH(ctx, k, (unsigned)n_tiles, bs2, smem2, (const tb_k4t_tile *)ctx->scratch4.p, p->flank, (const float *)S.signal.as<float>(), prep,   \
                   p->flank_min, p->flank_max, p->fp_min, p->fp_max, wstride2, pg2, first_out);                              \
     }
             if (nw2 == 16) {
