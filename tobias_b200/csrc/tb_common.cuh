@@ -25,6 +25,7 @@
 #define TB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -152,6 +153,19 @@ int tb_genome_fence(tb_ctx *ctx, int c_lo, int c_hi);      // `stream` waits for
 void tb_release(tb_dbuf &b);
 int tb_pinned(tb_ctx *ctx, size_t bytes);
 int tb_check(tb_ctx *ctx, cudaError_t e, const char *what);
+// host clock at the phase borders of an entry point, to stderr (option "host_trace"; comparison runs)
+struct tb_tracer {
+    const char *name;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    tb_tracer(const tb_ctx *ctx, const char *name_) : name(name_), on(tb_opt(ctx, "host_trace", 0) != 0), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) const {
+        if (on) fprintf(stderr, "[%s] %-28s %9.3f ms\n", name, what,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+    ~tb_tracer() { mark("return"); }
+};
+
 int tb_h2d(tb_ctx *ctx, tb_dbuf &dst, const void *src, size_t bytes);          // reserve + async copy on ctx->stream
 int tb_d2h(tb_ctx *ctx, void *dst, const void *src, size_t bytes);            // sync copy
 int tb_sync(tb_ctx *ctx, const char *what);

@@ -571,6 +571,7 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     memset(counts_out, 0, n_out * sizeof(int64_t));
     memset(scalars_out, 0, 5 * sizeof(int64_t));
     std::vector<i64> ls, le;
+    const tb_tracer tr(ctx, "tb_bias_counts");
     TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
     if (n_regions == 0 || ctx->n_reads == 0) return TB_OK;
 
@@ -671,6 +672,7 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sites_smem));
     }
 
+    tr.mark("tables uploaded");
     tb_timer_start(ctx);
     tb_mark(ctx, 0);
     {
@@ -695,6 +697,7 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         site_cap = n_sites + n_sites / 8 + 1024;        // site list too small (records spanning many tiny regions): grow, redo
     }
     tb_mark(ctx, 1);
+    tr.mark("sites listed (host read-back)");
     TB_TRY(tb_genome_fence(ctx, 0, ctx->n_contigs - 1));      // the k-mer kernels read the genome
     const u32 *d_wts = ctx->k2_wts.as<u32>();
     const u64 *d_sites = ctx->k2_sites.as<u64>();

@@ -805,6 +805,7 @@ extern "C" int tb_signal_upload(tb_ctx *ctx, const float *signal, int64_t n_regi
 static int tb_signal_from_corrected_linear(tb_ctx *ctx, int flank, i64 n, const std::vector<i64> &sc_lstart, const std::vector<int64_t> &ext_len) {
     auto &C = ctx->cor;
     ctx->sc.have_signal = false;
+    const tb_tracer tr(ctx, "tb_signal_from_corrected");
     TB_TRY(tb_sc_layout(ctx, n, ext_len.data()));
     auto &S = ctx->sc;
     TB_TRY(tb_reserve(ctx, S.signal, (size_t)S.ext_total * sizeof(float)));
@@ -813,6 +814,7 @@ static int tb_signal_from_corrected_linear(tb_ctx *ctx, int flank, i64 n, const 
         for (i64 i = 0; i < C.n_regions; i++) out_lstart[i] = C.ext_start[i] + C.k_flank + C.window / 2;
         TB_TRY(tb_h2d(ctx, ctx->reg_a, out_lstart.data(), sizeof(i64) * (size_t)C.n_regions));
         TB_TRY(tb_h2d(ctx, ctx->reg_b, sc_lstart.data(), sizeof(i64) * (size_t)n));
+        tr.mark("tables uploaded");
         i64 want = tb_div_up(S.ext_total, (i64)TB_C2S_RUN * 8), capg = (i64)ctx->sm_count * 16;
         const double *cf = C.tracks.as<double>() + ((i64)3 * 2 + 0) * C.out_total;
         const double *cr = C.tracks.as<double>() + ((i64)3 * 2 + 1) * C.out_total;
@@ -887,6 +889,7 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
     if (!ctx || !p) return TB_ERR_ARG;
     auto &S = ctx->sc;
     if (!S.have_signal) return tb_fail(ctx, TB_ERR_STATE, "tb_score_run: no signal (tb_signal_upload / tb_signal_from_corrected)");
+    const tb_tracer tr(ctx, "tb_score_run");
     S.have_out = false;
     if (p->flank < 0) return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: negative flank");
     const bool fp_like = p->kind == TB_SCORE_FOOTPRINT || p->kind == TB_SCORE_FOS;
@@ -917,6 +920,7 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
     void *first_out = smooth ? S.work0.p : S.out.p;
     i64 n_tiles = 0;
 
+    tr.mark("tables, buffers");
     tb_timer_start(ctx);
     if (fp_like) {
         const bool fos = p->kind == TB_SCORE_FOS;
@@ -1034,6 +1038,7 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
         tb_sc_view V{S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(), ctx->reg_e.as<i64>(), S.n_regions, p->flank};
         TB_TRY(tb_launch_rolling<1>(ctx, V, n_tiles, S.work0.p, prep, p->smooth, 1, p->as_f64 ? 1 : 0, S.out.p));
     }
+    tr.mark("kernels enqueued");
     tb_timer_stop(ctx);
     TB_TRY(tb_sync(ctx, "tb_score_run"));
     S.have_out = true;

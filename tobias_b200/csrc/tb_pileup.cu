@@ -130,6 +130,7 @@ extern "C" int tb_count_reads(tb_ctx *ctx, int64_t n_regions, const int32_t *con
                               int shift_fwd, int shift_rev, int64_t *count_out) {
     if (!ctx || !count_out) return TB_ERR_ARG;
     std::vector<i64> ls, le;
+    const tb_tracer tr(ctx, "tb_count_reads");
     TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
     *count_out = 0;
     tb_reads_view rv;
@@ -139,6 +140,7 @@ extern "C" int tb_count_reads(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     TB_TRY(tb_h2d(ctx, ctx->reg_b, le.data(), sizeof(i64) * n_regions));
     TB_TRY(tb_reserve(ctx, ctx->reg_d, 64));
     TB_CUDA(ctx, cudaMemsetAsync(ctx->reg_d.p, 0, 64, ctx->stream));
+    tr.mark("tables uploaded");
     int block = 256;
     i64 want = tb_div_up(rv.n, block);
     i64 cap = (i64)ctx->sm_count * 16;
