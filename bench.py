@@ -200,22 +200,22 @@ def run_step(eng, arrays, device, resident, host=None, out=None, genome_resident
     mark("counts+model")
     # --- correction + footprints of this rank's output regions
     c, s, e = arrays["output_regions"]
+    if not resident:                      # the four tracks travel to the host chunk by chunk while the correction's last stage and the footprint kernels run
+        n_out = int((e - s).sum())
+        ctx.correct_set_sink(out["tracks"], n_out, K_FLANK, as_f64=False, prepost=True)
     ctx.correct_run(c, s, e, K_FLANK, WINDOW, bias.correction_factor, READ_SHIFT, LM_EXACT)
     stage = ctx.stage_ms(4)
     mark("correct_run")
-    if not resident:                      # the four tracks travel to the host while the footprint kernels run
-        ctx.correct_download(split_strands=False, as_f64=False, prepost=True, out=out["tracks"], wait=False)
-        if trace:
-            marks.append(("download_begin(no sync)", time.perf_counter()))
     ctx.signal_from_corrected(FP["flank_max"], e - s)
+    if not resident:
+        ctx.score_set_sink(out["footprint"])
     ctx.score_run(ctx.score_params("footprint", flank=FP["flank_max"], **FP))
     k4_ms = ctx.last_kernel_ms()
     mark("footprints")
     if not resident:
-        ctx.correct_download_wait()
+        ctx.correct_download_wait()       # waits for the copy stream: tracks and footprint scores
+        ctx.score_sink_wait()
         mark("tracks_d2h_wait")
-        ctx.score_download(out=out["footprint"])
-        mark("footprint_d2h")
     if trace:
         sys.stderr.write(("e2e" if not resident else "resident") + " trace (ms): " + ", ".join("%s %.1f" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])) + "\n")
     phases = {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}

@@ -175,6 +175,12 @@ int tb_correct_download(tb_ctx *ctx, int split_strands, int as_f64, void *tracks
  * The host buffers (pinned for real overlap) are complete when _wait returns.  tb_correct_download = _begin + _wait. */
 int tb_correct_download_begin(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out);
 int tb_correct_download_wait(tb_ctx *ctx);
+/* Streaming form: names the destination of the NEXT tb_correct_run's tracks (same arguments as tb_correct_download; tracks = NULL
+ * withdraws it).  That run then computes its last stage in chunks of output regions and packs / copies every finished chunk to the
+ * host on the second stream while the next one computes -- what the reference's writer processes do with the queues the workers fill
+ * (atacorrect.py:379-424).  The run returns as before (compute stream drained); the host buffers are complete after
+ * tb_correct_download_wait.  A sink serves one run. */
+int tb_correct_set_sink(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out);
 /* per-window fit diagnostics of the last tb_correct_run (tests): double [2 strands][n_windows_total][6] =
  * { mode (0 fit, 1 fallback, 2 empty window), a, b (bias_min for mode 1), max(prediction), MINPACK info, nfev };
  * n may be queried with out=NULL. */
@@ -201,6 +207,11 @@ typedef struct tb_score_params {
 int tb_signal_upload(tb_ctx *ctx, const float *signal, int64_t n_regions, const int64_t *ext_len);
 int tb_score_run(tb_ctx *ctx, const tb_score_params *p);
 int tb_score_download(tb_ctx *ctx, void *out);
+/* Streaming form: destination of the NEXT tb_score_run's output (element type as in its tb_score_params; NULL withdraws it).  The footprint
+ * scan then runs in chunks of regions whose scores are copied out on the second stream while the next chunk computes; complete after
+ * tb_score_sink_wait (or tb_correct_download_wait: both wait for the second stream). */
+int tb_score_set_sink(tb_ctx *ctx, void *out);
+int tb_score_sink_wait(tb_ctx *ctx);
 /* Scores of the last tb_score_run at `n` positions of its concatenated output space (region offsets = prefix sums of the
  * trimmed region lengths), as doubles, without downloading the track: the reads BINDetect's scan_and_score makes from the
  * footprint bigWig -- the middle of every TFBS and the random background positions of every region

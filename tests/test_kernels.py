@@ -642,6 +642,57 @@ def test_chain_corrected_to_footprints(loaded_ctx, golden):
     assert np.array_equal(later["corrected"], both) and np.array_equal(loaded_ctx.score_download(), got)
 
 
+def test_streaming_sinks(loaded_ctx, golden):
+    """tb_correct_set_sink / tb_score_set_sink: the run hands its tracks (chunks of output regions, last stage launched per chunk) and the
+    footprint scan its scores to the host while the next chunk computes -- the same arrays as the downloads after the run, for every
+    chunk count, and a sink serves one run only."""
+    g = golden.atac
+    _set_model(loaded_ctx, g, "DWM")
+    c, s, e = _cols(g["outreg"])
+    n_out = int((e - s).sum())
+    cf = float(g["correction_factor"])
+    p30 = loaded_ctx.score_params("footprint", flank=30)
+    loaded_ctx.correct_run(c, s, e, correction_factor=cf, lm_exact_order=0)
+    base = loaded_ctx.correct_download(split_strands=False, as_f64=False, prepost=True)
+    loaded_ctx.signal_from_corrected(30, e - s)
+    loaded_ctx.score_run(p30)
+    fp = loaded_ctx.score_download()
+    try:
+        for chunks in (1, 2, 6):
+            loaded_ctx.set_option("k3c_chunks", chunks)
+            loaded_ctx.set_option("k4_chunks", chunks)
+            bufs = {t: loaded_ctx.pinned_empty((n_out + 5,), np.float32) for t in ("uncorrected", "bias", "expected", "corrected")}
+            for b in bufs.values():
+                b[:] = -7.0
+            views = loaded_ctx.correct_set_sink(bufs, n_out, as_f64=False, prepost=True)
+            loaded_ctx.correct_run(c, s, e, correction_factor=cf, lm_exact_order=0)
+            loaded_ctx.signal_from_corrected(30, e - s)
+            out = loaded_ctx.pinned_empty((fp.shape[0] + 3,), np.float32)
+            out[:] = -7.0
+            loaded_ctx.score_set_sink(out)
+            loaded_ctx.score_run(p30)
+            loaded_ctx.correct_download_wait()
+            loaded_ctx.score_sink_wait()
+            for t in bufs:
+                assert np.array_equal(views[t], base[t], equal_nan=True), (chunks, t)
+                assert np.all(bufs[t][n_out:] == -7.0)
+            assert np.allclose(views["prepost"], base["prepost"], rtol=1e-12, atol=1e-9)      # fp64 atomics: the order of the tiles differs
+            assert np.array_equal(out[:fp.shape[0]], fp) and np.all(out[fp.shape[0]:] == -7.0)
+    finally:
+        loaded_ctx.set_option("k3c_chunks", -1)
+        loaded_ctx.set_option("k4_chunks", -1)
+    # the sinks are spent: the next runs leave the buffers alone
+    for b in bufs.values():
+        b[:] = -7.0
+    out[:] = -7.0
+    loaded_ctx.correct_run(c, s, e, correction_factor=cf, lm_exact_order=0)
+    loaded_ctx.signal_from_corrected(30, e - s)
+    loaded_ctx.score_run(p30)
+    loaded_ctx.correct_download_wait()
+    assert all(np.all(b == -7.0) for b in bufs.values()) and np.all(out == -7.0)
+    assert np.array_equal(loaded_ctx.score_download(), fp)
+
+
 def test_chain_reads_the_track_like_a_bigwig(loaded_ctx, golden):
     """tb_signal_from_corrected: the flank of an output region takes the values of an abutting neighbour (50-kb split pieces) and 0
     where the track holds nothing -- what ScoreBigwig reads from the corrected bigWig; tb_signal_from_corrected_regions scores regions

@@ -138,6 +138,7 @@ extern "C" int tb_init(int device, tb_ctx **out) {
     }
     bool marks_ok = true;
     for (int i = 0; i < 8; i++) marks_ok = marks_ok && cudaEventCreate(&ctx->marks[i]) == cudaSuccess;
+    for (int i = 0; i < 8; i++) marks_ok = marks_ok && cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
     if (!marks_ok) {
         delete ctx;
         return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
@@ -149,7 +150,7 @@ extern "C" int tb_init(int device, tb_ctx **out) {
 // Switches between kernel variants / chunk sizes that produce the same results (comparison runs and tests; never needed in production).
 extern "C" int tb_set_option(tb_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return TB_ERR_ARG;
-    static const char *known[] = {"k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_tile", "k2_site_cap", "k2_chunk",
+    static const char *known[] = {"k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k3c_chunks", "k4_chunks", "k2_tile", "k2_site_cap", "k2_chunk",
                                   "k2_no_hist", "k2_smem_chunk", "k2_no_smem_hist", "k4_form", "k4_threads", "k3b_persistent", "k3b_tile", "k3b_cap", "k3b_threads", "host_trace", nullptr};
     bool ok = false;
     for (int i = 0; known[i]; i++) ok = ok || strcmp(known[i], key) == 0;
@@ -185,6 +186,8 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_copy);
+    for (auto &e : ctx->ev_chunk)
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->contig_ready)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->copy_stream);

@@ -65,6 +65,7 @@ struct tb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // device-to-host copies that overlap with later kernels (tb_correct_download_begin)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // chunks of a run handed to the copy stream
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float last_ms = 0.f;
@@ -119,6 +120,11 @@ struct tb_ctx {
         tb_dbuf dl[4][2];  // packed tracks on their way to the host
         double *pp_pinned = nullptr, *pp_dst = nullptr;   // pinned staging of prepost, caller's destination (set by _begin)
         bool valid = false;
+        // destination of the next run's tracks (tb_correct_set_sink): the run hands them out in chunks while it computes
+        bool sink_on = false;
+        int sink_split = 0, sink_f64 = 0;
+        void *sink_ptr[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+        double *sink_pp = nullptr;
     } cor;
 
     // state of K4
@@ -132,6 +138,7 @@ struct tb_ctx {
         int out_f64 = 0;
         int flank = -1;
         bool have_signal = false, have_out = false;
+        void *sink = nullptr;   // destination of the next tb_score_run's output (tb_score_set_sink)
     } sc;
 
     int k3a_tmem_groups = 0;    // K3a: pair groups kept in tensor memory (0 = default 5; option "k3a_tmem_groups" = 1..5, comparison runs)

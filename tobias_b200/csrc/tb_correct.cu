@@ -527,12 +527,18 @@ static inline tb_k3c_layout tb_k3c_make_layout(int tile_len, int w, int L, bool 
 
 // FAST = 2: all sums O(1); FAST = 1: the rolling sum of the bias prediction keeps the literal float accumulator (it is the denominator of
 // `expected`, whose ~3e-7 scatter the subtraction uncorrected - expected can amplify), the rescaling sums are O(1); FAST = 0: all literal.
+// float32 strand sums of the four tracks, written next to the fp64 per-strand tracks when a sink asks for them (NULL: track not wanted):
+// the reverse-strand pass of a tile adds the forward value the same thread stored before -- what tb_pack_track_kernel would compute later
+struct tb_k3c_pk {
+    float *p[4];
+};
+
 template <int FAST>
 __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
     tb_correct_kernel(tb_genome_view g, tb_cor_view V, const int32_t *__restrict__ tile_region,
                       const int32_t *__restrict__ tile_start, i64 n_tiles, int tile_len, const u32 *__restrict__ pile,
                       const double *__restrict__ biasraw, const double *__restrict__ fit, double cf, tb_k3c_layout Y,
-                      double *__restrict__ tracks, double *__restrict__ prepost) {
+                      double *__restrict__ tracks, double *__restrict__ prepost, tb_k3c_pk PK) {
     TB_DYN_SMEM(smem);
     const int w = V.window, k = V.k_flank, L = V.L;
     const int lf = w / 2;
@@ -772,6 +778,12 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                     tracks[((i64)1 * 2 + strand) * V.out_total + o] = br[q];
                     tracks[((i64)2 * 2 + strand) * V.out_total + o] = e;
                     tracks[((i64)3 * 2 + strand) * V.out_total + o] = c;
+                    if (strand == 1) {
+                        if (PK.p[0]) PK.p[0][o] = (float)(tracks[((i64)0 * 2) * V.out_total + o] + u);
+                        if (PK.p[1]) PK.p[1][o] = (float)(tracks[((i64)1 * 2) * V.out_total + o] + br[q]);
+                        if (PK.p[2]) PK.p[2][o] = (float)(tracks[((i64)2 * 2) * V.out_total + o] + e);
+                        if (PK.p[3]) PK.p[3][o] = (float)(tracks[((i64)3 * 2) * V.out_total + o] + c);
+                    }
                 }
                 bool valid = q > k && q < Lr - k - 1 && (u != 0.0 || c != 0.0);
                 if (valid) valid = tb_nflags(g, gstart + q - k, L) == 0;
@@ -870,6 +882,65 @@ __global__ void tb_pack_track_kernel(const double *__restrict__ a, const double 
 }
 
 // ---------------------------------------------------------------------------------------------- host side
+// Packs the output range [o0, o1) of the tracks the sink asks for and copies it to the host, on the copy stream, ordered after the work the
+// compute stream holds so far.  The last chunk is followed by the verification counts.
+static int tb_sink_chunk(tb_ctx *ctx, int chunk, i64 o0, i64 o1, bool last, bool packed) {
+    auto &C = ctx->cor;
+    const size_t esz = C.sink_f64 ? 8 : 4;
+    const i64 n = C.out_total, len = o1 - o0;
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[chunk & 7], ctx->stream));
+    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[chunk & 7], 0));
+    if (len > 0) {
+        for (int t = 0; t < 4 && !packed; t++)
+            for (int s = 0; s < 2; s++) {
+                if (!C.sink_ptr[t][s]) continue;
+                const double *a = C.tracks.as<double>() + ((i64)t * 2 + (C.sink_split ? s : 0)) * n + o0;
+                const double *b = C.sink_split ? nullptr : C.tracks.as<double>() + ((i64)t * 2 + 1) * n + o0;
+                i64 want = tb_div_up(len, 256), capg = (i64)ctx->sm_count * 4;
+                unsigned grid = (unsigned)(want < capg ? want : capg);
+                if (C.sink_f64) {
+                    auto kp = tb_pack_track_kernel<double>;
+                    TB_LAUNCH_ON(ctx, ctx->copy_stream, kp, grid, 256, 0, a, b, len, C.dl[t][s].as<double>() + o0);
+                } else {
+                    auto kp = tb_pack_track_kernel<float>;
+                    TB_LAUNCH_ON(ctx, ctx->copy_stream, kp, grid, 256, 0, a, b, len, C.dl[t][s].as<float>() + o0);
+                }
+            }
+        for (int t = 0; t < 4; t++)
+            for (int s = 0; s < 2; s++)
+                if (C.sink_ptr[t][s])
+                    TB_CUDA(ctx, cudaMemcpyAsync((char *)C.sink_ptr[t][s] + (size_t)o0 * esz, (const char *)C.dl[t][s].p + (size_t)o0 * esz,
+                                                 (size_t)len * esz, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    if (last) {
+        C.pp_dst = C.sink_pp;
+        if (C.sink_pp) {
+            if (!C.pp_pinned) TB_CUDA(ctx, cudaMallocHost((void **)&C.pp_pinned, (size_t)2 * 3 * 5 * 32 * sizeof(double)));
+            TB_CUDA(ctx, cudaMemcpyAsync(C.pp_pinned, C.prepost.p, (size_t)2 * 3 * 5 * C.L * sizeof(double), cudaMemcpyDeviceToHost,
+                                         ctx->copy_stream));
+        }
+    }
+    return TB_OK;
+}
+
+extern "C" int tb_correct_set_sink(tb_ctx *ctx, int split_strands, int as_f64, void *tracks[4][2], double *prepost_out) {
+    if (!ctx) return TB_ERR_ARG;
+    auto &C = ctx->cor;
+    C.sink_on = false;
+    if (!tracks) return TB_OK;
+    for (int t = 0; t < 4; t++)
+        for (int s = 0; s < 2; s++) {
+            if (tracks[t][s] && !split_strands && s == 1)
+                return tb_fail(ctx, TB_ERR_ARG, "tb_correct_set_sink: tracks[t][1] must be NULL unless split_strands");
+            C.sink_ptr[t][s] = tracks[t][s];
+        }
+    C.sink_split = split_strands ? 1 : 0;
+    C.sink_f64 = as_f64 ? 1 : 0;
+    C.sink_pp = prepost_out;
+    C.sink_on = true;
+    return TB_OK;
+}
+
 extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end,
                               int k_flank, int window, double correction_factor, int shift_fwd, int shift_rev,
                               int lm_exact_order) {
@@ -881,6 +952,9 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
     };
     ctx->cor.valid = false;
+    const bool sink_now = ctx->cor.sink_on;                      // a sink serves this run only, whatever its outcome
+    ctx->cor.sink_on = false;
+    ctx->cor.pp_dst = nullptr;
     if (window < TB_STEP || window > 512) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: window must be in [10, 512]");
     if (ctx->model[0].is_dwm < 0 || ctx->model[1].is_dwm < 0)
         return tb_fail(ctx, TB_ERR_STATE, "tb_correct_run: call tb_set_bias_model for both strands first");
@@ -968,6 +1042,10 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     TB_TRY(tb_reserve(ctx, C.tracks, (size_t)C.out_total * 8 * sizeof(double)));
     TB_TRY(tb_reserve(ctx, C.prepost, (size_t)2 * 3 * 5 * L * sizeof(double)));
     TB_CUDA(ctx, cudaMemsetAsync(C.prepost.p, 0, (size_t)2 * 3 * 5 * L * sizeof(double), ctx->stream));
+    if (sink_now)
+        for (int t = 0; t < 4; t++)
+            for (int s = 0; s < 2; s++)
+                if (C.sink_ptr[t][s]) TB_TRY(tb_reserve(ctx, C.dl[t][s], (size_t)C.out_total * (C.sink_f64 ? 8 : 4)));
 
     tr("tables uploaded, buffers");
     tb_timer_start(ctx);
@@ -1127,9 +1205,30 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 8) per_sm = 8;
         const i64 capg = (i64)ctx->sm_count * per_sm;
-        TB_LAUNCH(ctx, kc, (unsigned)(n_tiles < capg ? n_tiles : capg), TB_K3C_THREADS, smem, g, V, (const int32_t *)ctx->reg_a.as<int32_t>(),
-                  (const int32_t *)ctx->reg_b.as<int32_t>(), n_tiles, tile_len, (const u32 *)C.pile.as<u32>(), (const double *)C.biasraw.as<double>(),
-                  (const double *)C.fit.as<double>(), correction_factor, Y, C.tracks.as<double>(), C.prepost.as<double>());
+        // With a sink (tb_correct_set_sink) the tiles go in chunks that end on region borders; every chunk's tracks are packed and copied to
+        // the host on the copy stream while the next chunk computes.
+        const int n_chunks = sink_now ? (int)std::max<i64>(1, std::min<i64>(tb_opt(ctx, "k3c_chunks", 6), std::min<i64>(8, n_regions))) : 1;
+        // strands combined as float32: the kernel writes the packed values itself, the chunk only has to be copied
+        const bool fused_pack = sink_now && !C.sink_split && !C.sink_f64;
+        tb_k3c_pk PK{{nullptr, nullptr, nullptr, nullptr}};
+        if (fused_pack)
+            for (int t = 0; t < 4; t++) PK.p[t] = C.sink_ptr[t][0] ? C.dl[t][0].as<float>() : nullptr;
+        i64 t_done = 0, r_done = 0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            i64 r_end = ch + 1 == n_chunks ? n_regions : (n_regions * (ch + 1)) / n_chunks;
+            if (r_end <= r_done) continue;
+            i64 t_end = t_done;
+            while (t_end < n_tiles && tile_region[t_end] < r_end) t_end++;
+            const i64 cnt = t_end - t_done;
+            if (cnt > 0)
+                TB_LAUNCH(ctx, kc, (unsigned)(cnt < capg ? cnt : capg), TB_K3C_THREADS, smem, g, V, (const int32_t *)ctx->reg_a.as<int32_t>() + t_done,
+                          (const int32_t *)ctx->reg_b.as<int32_t>() + t_done, cnt, tile_len, (const u32 *)C.pile.as<u32>(),
+                          (const double *)C.biasraw.as<double>(), (const double *)C.fit.as<double>(), correction_factor, Y, C.tracks.as<double>(),
+                          C.prepost.as<double>(), PK);
+            if (sink_now) TB_TRY(tb_sink_chunk(ctx, ch, C.out_off[r_done], C.out_off[r_end], ch + 1 == n_chunks, fused_pack));
+            t_done = t_end;
+            r_done = r_end;
+        }
         TB_TRY(tb_check(ctx, cudaGetLastError(), "tb_correct_kernel"));
     }
     tb_mark(ctx, 4);

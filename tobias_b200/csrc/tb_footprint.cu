@@ -876,13 +876,16 @@ static int tb_launch_rolling(tb_ctx *ctx, const tb_sc_view &V, i64 n_tiles, cons
     return tb_check(ctx, cudaGetLastError(), "tb_rolling_kernel");
 }
 
-static int tb_tiles(tb_ctx *ctx, const std::vector<i64> &ext_off, i64 per_tile, tb_dbuf &d_tile_off, i64 &n_tiles) {
+static int tb_tiles(tb_ctx *ctx, const std::vector<i64> &ext_off, i64 per_tile, tb_dbuf &d_tile_off, i64 &n_tiles,
+                    std::vector<i64> *host_tile_off = nullptr) {
     i64 n = (i64)ext_off.size() - 1;
     std::vector<i64> tile_off(n + 1, 0);
     for (i64 i = 0; i < n; i++) tile_off[i + 1] = tile_off[i] + tb_div_up(ext_off[i + 1] - ext_off[i], per_tile);
     n_tiles = tile_off[n];
     if (n_tiles > 0x7fffffffLL) return tb_fail(ctx, TB_ERR_ARG, "too many tiles (%lld)", n_tiles);
-    return tb_h2d(ctx, d_tile_off, tile_off.data(), sizeof(i64) * (n + 1));
+    TB_TRY(tb_h2d(ctx, d_tile_off, tile_off.data(), sizeof(i64) * (n + 1)));
+    if (host_tile_off) host_tile_off->swap(tile_off);
+    return TB_OK;
 }
 
 extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
@@ -890,6 +893,9 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
     auto &S = ctx->sc;
     if (!S.have_signal) return tb_fail(ctx, TB_ERR_STATE, "tb_score_run: no signal (tb_signal_upload / tb_signal_from_corrected)");
     const tb_tracer tr(ctx, "tb_score_run");
+    void *const sink = S.sink;                                   // serves this run only, whatever its outcome
+    S.sink = nullptr;
+    bool sink_served = false;
     S.have_out = false;
     if (p->flank < 0) return tb_fail(ctx, TB_ERR_ARG, "tb_score_run: negative flank");
     const bool fp_like = p->kind == TB_SCORE_FOOTPRINT || p->kind == TB_SCORE_FOS;
@@ -970,21 +976,45 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
         }
         if (bs2 > 0) {
             const i64 per_tile = 4 * bs2 - (p->fp_max - 1);
-            TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles));
+            std::vector<i64> tile_off;
+            TB_TRY(tb_tiles(ctx, S.ext_off, per_tile, ctx->reg_e, n_tiles, &tile_off));
             TB_TRY(tb_reserve(ctx, ctx->scratch4, sizeof(tb_k4t_tile) * (size_t)std::max<i64>(n_tiles, 1)));
             TB_LAUNCH(ctx, tb_k4t_tiles_kernel, (unsigned)tb_div_up(std::max<i64>(n_tiles, 1), 256), 256, 0, S.d_ext_off.as<i64>(), ctx->reg_d.as<i64>(),
                       ctx->reg_e.as<i64>(), S.n_regions, n_tiles, (tb_k4t_tile *)ctx->scratch4.p);
+            // With a sink (tb_score_set_sink; no smoothing pass) the tiles go in chunks that end on region borders, and every chunk's scores
+            // travel to the host on the copy stream while the next chunk computes.
+            const bool stream_out = sink && !smooth;
+            const int n_chunks = stream_out ? (int)std::max<i64>(1, std::min<i64>(tb_opt(ctx, "k4_chunks", 3), std::min<i64>(8, S.n_regions))) : 1;
+            const size_t esz = p->as_f64 ? 8 : 4;
 #define TB_FP2_CASE(OM, NWX)                                                                                                 \
     {                                                                                                                       \
         auto k = tb_footprint_tile_kernel<OM, NWX>;                                                                         \
         TB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));                     \
-        TB_LAUNCH(ctx, k, (unsigned)n_tiles, bs2, smem2, (const tb_k4t_tile *)ctx->scratch4.p, p->flank, (const float *)S.signal.as<float>(), prep,   \
-                  p->flank_min, p->flank_max, p->fp_min, p->fp_max, wstride2, pg2, first_out);                              \
+        TB_LAUNCH(ctx, k, (unsigned)cnt, bs2, smem2, (const tb_k4t_tile *)ctx->scratch4.p + t_done, p->flank,              \
+                  (const float *)S.signal.as<float>(), prep, p->flank_min, p->flank_max, p->fp_min, p->fp_max, wstride2, pg2, first_out); \
     }
-            if (nw2 == 16) {
-                if (first_mode == 0) TB_FP2_CASE(0, 16) else if (first_mode == 1) TB_FP2_CASE(1, 16) else TB_FP2_CASE(2, 16)
-            } else {
-                if (first_mode == 0) TB_FP2_CASE(0, 32) else if (first_mode == 1) TB_FP2_CASE(1, 32) else TB_FP2_CASE(2, 32)
+            i64 r_done = 0;
+            for (int ch = 0; ch < n_chunks; ch++) {
+                const i64 r_end = ch + 1 == n_chunks ? S.n_regions : (S.n_regions * (ch + 1)) / n_chunks;
+                if (r_end <= r_done) continue;
+                const i64 t_done = tile_off[r_done], cnt = tile_off[r_end] - t_done;
+                if (cnt > 0) {
+                    if (nw2 == 16) {
+                        if (first_mode == 0) TB_FP2_CASE(0, 16) else if (first_mode == 1) TB_FP2_CASE(1, 16) else TB_FP2_CASE(2, 16)
+                    } else {
+                        if (first_mode == 0) TB_FP2_CASE(0, 32) else if (first_mode == 1) TB_FP2_CASE(1, 32) else TB_FP2_CASE(2, 32)
+                    }
+                }
+                if (stream_out) {
+                    const i64 o0 = S.out_off[r_done], o1 = S.out_off[r_end];
+                    TB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[ch & 7], ctx->stream));
+                    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[ch & 7], 0));
+                    if (o1 > o0)
+                        TB_CUDA(ctx, cudaMemcpyAsync((char *)sink + (size_t)o0 * esz, (const char *)S.out.p + (size_t)o0 * esz, (size_t)(o1 - o0) * esz,
+                                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    sink_served = true;
+                }
+                r_done = r_end;
             }
 #undef TB_FP2_CASE
         } else {
@@ -1040,9 +1070,26 @@ extern "C" int tb_score_run(tb_ctx *ctx, const tb_score_params *p) {
     }
     tr.mark("kernels enqueued");
     tb_timer_stop(ctx);
+    if (sink && !sink_served) {                                  // one copy behind the whole run
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0));
+        TB_CUDA(ctx, cudaMemcpyAsync(sink, S.out.p, (size_t)S.out_total * (p->as_f64 ? 8 : 4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
     TB_TRY(tb_sync(ctx, "tb_score_run"));
     S.have_out = true;
     return TB_OK;
+}
+
+extern "C" int tb_score_set_sink(tb_ctx *ctx, void *out) {
+    if (!ctx) return TB_ERR_ARG;
+    ctx->sc.sink = out;
+    return TB_OK;
+}
+
+extern "C" int tb_score_sink_wait(tb_ctx *ctx) {
+    if (!ctx) return TB_ERR_ARG;
+    TB_TRY(tb_check(ctx, cudaStreamSynchronize(ctx->copy_stream), "tb_score_sink_wait"));
+    return tb_check(ctx, cudaGetLastError(), "tb_score_sink_wait");
 }
 
 extern "C" int tb_score_download(tb_ctx *ctx, void *out) {

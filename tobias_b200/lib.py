@@ -68,6 +68,9 @@ _PROTOS = {
     "tb_correct_download": (_i, [_vp, _i, _i, _vp, _vp]),
     "tb_correct_download_begin": (_i, [_vp, _i, _i, _vp, _vp]),
     "tb_correct_download_wait": (_i, [_vp]),
+    "tb_correct_set_sink": (_i, [_vp, _i, _i, _vp, _vp]),
+    "tb_score_set_sink": (_i, [_vp, _vp]),
+    "tb_score_sink_wait": (_i, [_vp]),
     "tb_correct_fit_trace": (_i, [_vp, C.POINTER(_i64), _vp]),
     "tb_signal_upload": (_i, [_vp, _vp, _i64, _vp]),
     "tb_score_run": (_i, [_vp, C.POINTER(ScoreParams)]),
@@ -373,6 +376,36 @@ class Context:
     def correct_download_wait(self):
         self._ck(self._lib.tb_correct_download_wait(self._h))
         self._pending_download = None
+
+    def correct_set_sink(self, out, n_out, k_flank=12, as_f64=False, prepost=True):
+        """Streaming download (strands combined): `out` maps track names to preallocated (pinned) arrays of at least n_out elements; the
+        NEXT correct_run copies its tracks there chunk by chunk while it computes.  Returns the dict of views (+ 'prepost'), complete
+        after correct_download_wait()."""
+        dt = np.float64 if as_f64 else np.float32
+        ptrs = ((_vp * 2) * 4)()
+        views = {}
+        for t, name in enumerate(TRACKS):
+            if name in out:
+                a = out[name]
+                assert a.dtype == dt and a.size >= n_out and a.flags.c_contiguous
+                ptrs[t][0] = a.ctypes.data
+                views[name] = a[:n_out]
+        pp = np.zeros((2, 3, 5, 2 * k_flank + 1), dtype=np.float64) if prepost else None
+        self._ck(self._lib.tb_correct_set_sink(self._h, 0, int(bool(as_f64)), ptrs, _ptr(pp)))
+        if prepost:
+            views["prepost"] = pp
+        self._pending_download = (ptrs, views, out)                    # keeps the destination arrays alive
+        return views
+
+    def score_set_sink(self, out):
+        """Streaming download of the NEXT score_run's output into `out` (preallocated, pinned for overlap); complete after score_sink_wait()."""
+        assert out.flags.c_contiguous
+        self._ck(self._lib.tb_score_set_sink(self._h, _ptr(out)))
+        self._pending_score_sink = out
+
+    def score_sink_wait(self):
+        self._ck(self._lib.tb_score_sink_wait(self._h))
+        self._pending_score_sink = None
 
     def correct_fit_trace(self):
         n = _i64()
