@@ -155,15 +155,19 @@ def run_step(eng, arrays, device, resident, host=None, out=None, genome_resident
             import torch
             torch.cuda.synchronize()
         marks.append((name, time.perf_counter()))
+    upload_reads = ctx.reads_upload_compact if host is not None and host.get("reads_compact") else ctx.reads_upload
     if not resident and genome_resident:
-        ctx.reads_upload(*host["reads"])
+        upload_reads(*host["reads"])
         mark("reads_h2d")
     elif not resident:                    # e2e: inputs come from (pinned) host buffers every step
         ctx.genome_create(host["lengths"])
-        ctx.reads_upload(*host["reads"])
+        upload_reads(*host["reads"])
         mark("reads_h2d")
         # the genome streams in on the copy stream while the read counts and the first contigs' training counts run
-        if host["packed"] is not None:
+        if host["packed"] is not None and host.get("nruns") is not None:
+            for i, ((sq, nm), (rs, re_)) in enumerate(zip(host["packed"], host["nruns"])):
+                ctx.genome_upload_packed_runs(i, sq, rs, re_, host["lengths"][i], wait=False)
+        elif host["packed"] is not None:
             for i, (sq, nm) in enumerate(host["packed"]):
                 ctx.genome_upload_packed(i, sq, nm, host["lengths"][i], wait=False)
         else:
@@ -282,6 +286,9 @@ def bench_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    if world > 1 and not os.environ.get("TB_NO_NUMA_BIND"):      # before any pinned buffer exists (first touch decides the node)
+        from tobias_b200.dist import bind_to_device_numa
+        _NUMA["cpus"] = len(bind_to_device_numa(local) or ())
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
@@ -298,25 +305,36 @@ def bench_b200(args):
     from tobias_b200 import lib
     flags = (rc.is_reverse.astype(np.uint8) * lib.TB_READ_REVERSE | rc.five_prime_is_match().astype(np.uint8) * lib.TB_READ_5P_MATCH
              | (~rc.usable()).astype(np.uint8) * lib.TB_READ_SKIP)
+    # the record columns wait on the host in the compact form a sorted BAM decodes to (9 bytes per record: per-contig offsets, start int32,
+    # reference length and 5' clip uint16, flags; --wide-inputs: the five 4 / 1-byte columns of the first interface)
+    comp = None if args.wide_inputs else lib.compact_read_columns(rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags, len(ds.lengths))
     cols = []
-    for a in (rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags):          # pinned copies of the read columns
+    for a in (comp if comp is not None else (rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags)):          # pinned copies
         p = ctx.pinned_empty(a.shape, a.dtype)
         p[...] = a
         cols.append(p)
-    # the genome waits on the host in the device layout (2 bit + N mask, what tobias_b200.io.fasta.PackedGenome caches next to a FASTA):
-    # 0.375 bytes per base cross the link every step instead of 1 (--ascii-genome: the ASCII contigs, packed on the device)
-    packed = None
+    # the genome waits on the host in the device layout (2 bit per base; the N mask as the runs of N it consists of -- what
+    # tobias_b200.io.fasta.PackedGenome caches next to a FASTA): 0.25 bytes per base cross the link every step instead of 1
+    # (--wide-inputs: 2 bit + mask words, 0.375; --ascii-genome: the ASCII contigs, packed on the device)
+    packed, nruns = None, None
     if not args.ascii_genome:
         from tobias_b200.io.fasta import pack_ascii
         packed = []
         for g in ds.genome:
             n = int(g.shape[0])
             packed.append(pack_ascii(g, ctx.pinned_empty(((n + 15) // 16,), np.uint32), ctx.pinned_empty(((n + 31) // 32,), np.uint32)))
-    host = {"lengths": ds.lengths, "genome": ds.genome, "reads": cols, "packed": packed}
+        if not args.wide_inputs:
+            nruns = [lib.mask_runs(nm, int(g.shape[0])) for (sq, nm), g in zip(packed, ds.genome)]
+    host = {"lengths": ds.lengths, "genome": ds.genome, "reads": cols, "reads_compact": comp is not None, "packed": packed, "nruns": nruns}
     c, s, e = arrays["output_regions"]
     out_bp = int((e - s).sum())
     out = {"tracks": {t: ctx.pinned_empty((out_bp,), np.float32) for t in lib.TRACKS}, "footprint": ctx.pinned_empty((out_bp,), np.float32)}
-    genome_bytes = sum(int(g.nbytes) for g in ds.genome) if packed is None else sum(int(a.nbytes) + int(b.nbytes) for a, b in packed)
+    if packed is None:
+        genome_bytes = sum(int(g.nbytes) for g in ds.genome)
+    elif nruns is not None:
+        genome_bytes = sum(int(a.nbytes) for a, _ in packed) + sum(int(rs.nbytes) + int(re_.nbytes) for rs, re_ in nruns)
+    else:
+        genome_bytes = sum(int(a.nbytes) + int(b.nbytes) for a, b in packed)
     h2d = genome_bytes + sum(int(a.nbytes) for a in cols) + sum(int(x.nbytes) for v in arrays.values() for x in v)
     d2h = 5 * out_bp * 4 + 2 * 3 * 5 * 25 * 8
     setup_s = time.time() - t_setup
@@ -836,9 +854,13 @@ def bench_reference(args):
     print(json.dumps(out))
 
 
+_NUMA = {"cpus": 0}
+
+
 def bench_config(wl, world):
     """`config` of the bench line: the same keys on both arms."""
-    return {"workload": wl["desc"], "score_mat": "DWM", "k_flank": K_FLANK, "window": WINDOW, "footprint": FP, "lm_exact_order": LM_EXACT,
+    return {"host_affinity": ("rank 0 bound to the %d CPUs next to its GPU (NVML)" % _NUMA["cpus"]) if _NUMA["cpus"] else "unbound",
+            "workload": wl["desc"], "score_mat": "DWM", "k_flank": K_FLANK, "window": WINDOW, "footprint": FP, "lm_exact_order": LM_EXACT,
             "sharding": "contigs over %d rank(s), count all-reduce only" % world,
             "l2": "inputs (2-bit genome + read columns + per-position arrays) far exceed the 126 MB L2; no flush needed"}
 
@@ -1099,12 +1121,13 @@ def bench_batch24(args):
     for rc in read_sets:
         flags = (rc.is_reverse.astype(np.uint8) * lib.TB_READ_REVERSE | rc.five_prime_is_match().astype(np.uint8) * lib.TB_READ_5P_MATCH
                  | (~rc.usable()).astype(np.uint8) * lib.TB_READ_SKIP)
+        comp = None if args.wide_inputs else lib.compact_read_columns(rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags, len(ds.lengths))
         cols = []
-        for a in (rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags):
+        for a in (comp if comp is not None else (rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags)):
             p = ctx.pinned_empty(a.shape, a.dtype)
             p[...] = a
             cols.append(p)
-        hosts.append({"lengths": ds.lengths, "reads": cols, "packed": None, "genome": None})
+        hosts.append({"lengths": ds.lengths, "reads": cols, "reads_compact": comp is not None, "packed": None, "genome": None})
     c, s, e = arrays["output_regions"]
     out_bp = int((e - s).sum())
     out = {"tracks": {t: ctx.pinned_empty((out_bp,), np.float32) for t in lib.TRACKS}, "footprint": ctx.pinned_empty((out_bp,), np.float32)}
@@ -1246,6 +1269,7 @@ def main():
     ap.add_argument("--workload", default="hg38", choices=["hg38", "chr50mb", "small", "fp_genome", "batch24"])
     ap.add_argument("--fp-scale", type=float, default=1.0, help="fp_genome: scale every contig length (quick runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wide-inputs", action="store_true", help="e2e: five-column records and N-mask words instead of the compact host forms (comparison runs)")
     ap.add_argument("--lm-exact", action="store_true")
     ap.add_argument("--fit-stats", action="store_true")
     ap.add_argument("--lm-mode", type=int, default=None, help="5: moment form of the one-pass fits (comparison runs); 2 / 3 need a -DTB_FIRST_GEN_FITS build")

@@ -86,6 +86,10 @@ int tb_genome_upload_async(tb_ctx *ctx, int contig, int64_t offset, const uint8_
  * (n + 31) / 32 words, bit (k & 31) of word k >> 5 set for N; bits past the end set).  0.375 bytes per base cross the link instead of 1.
  * Host packer: tobias_b200/io/hostpack.c (cached next to the FASTA as <fasta>.tb2bit).  async = 1: like tb_genome_upload_async. */
 int tb_genome_upload_packed(tb_ctx *ctx, int contig, const uint32_t *seq2, const uint32_t *nmask, int64_t n_bases, int async);
+/* The same with the N mask given as runs [run_start[r], run_end[r]) of contig positions (assembly gaps are few and long: a human
+ * genome then crosses the bus as 0.25 bytes per base); the device builds the mask words. */
+int tb_genome_upload_packed_runs(tb_ctx *ctx, int contig, const uint32_t *seq2, int64_t n_runs, const int64_t *run_start,
+                                 const int64_t *run_end, int64_t n_bases, int async);
 int tb_genome_wait(tb_ctx *ctx);
 /* debugging / tests: nucleotide codes (0..4) of contig[start, start+n) */
 int tb_genome_fetch(tb_ctx *ctx, int contig, int64_t start, int64_t n, uint8_t *codes_out);
@@ -96,6 +100,11 @@ int tb_genome_fetch(tb_ctx *ctx, int contig, int64_t start, int64_t n, uint8_t *
  * for forward reads, query_length - query_alignment_end for reverse reads.  Replaces any earlier read set. */
 int tb_reads_upload(tb_ctx *ctx, int64_t n, const int32_t *contig, const int32_t *ref_start,
                     const int32_t *ref_end, const int32_t *clip5, const uint8_t *flags);
+/* Compact columns of records grouped by contig in the genome's contig order (what a coordinate-sorted BAM gives): the records of
+ * contig c are [rec_off[c], rec_off[c + 1]) (n_contigs + 1 offsets, rec_off[0] = 0, rec_off[n_contigs] = n); reference start int32,
+ * reference length (ref_end - ref_start) and 5' clip as uint16 -- 9 bytes per record instead of 17.  Same flag bits. */
+int tb_reads_upload_compact(tb_ctx *ctx, int64_t n, const int64_t *rec_off, const int32_t *ref_start, const uint16_t *ref_len,
+                            const uint16_t *clip5, const uint8_t *flags);
 
 /* ------------------------------------------------------------------------------------------------ K1
  * count_reads (tobias/tools/atacorrect_functions.py:80-105): number of (read, region) pairs with the read

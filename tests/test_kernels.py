@@ -182,6 +182,44 @@ def test_packed_genome_upload(loaded_ctx, golden, tmp_path):
         loaded_ctx.genome_load(golden.genome)
 
 
+def test_compact_inputs(loaded_ctx, golden):
+    """tb_genome_upload_packed_runs (N mask as runs) and tb_reads_upload_compact (9-byte records) leave the device in the state of the
+    plain uploads: same base codes, same pileup and read counts.  The fixture's genome and reads are restored."""
+    from tobias_b200.io.fasta import pack_ascii
+    rc = golden.reads
+    codes = [loaded_ctx.genome_fetch(i, 0, n) for i, n in enumerate(golden.lengths)]
+    regs = golden.atac["outreg"]
+    c, s, e = _cols(regs)
+    base_pile = loaded_ctx.pileup(c, s, e)
+    base_count = loaded_ctx.count_reads(c, s, e)
+    flags = (rc.is_reverse.astype(np.uint8) * lib.TB_READ_REVERSE | rc.five_prime_is_match().astype(np.uint8) * lib.TB_READ_5P_MATCH
+             | (~rc.usable()).astype(np.uint8) * lib.TB_READ_SKIP)
+    try:
+        for wait in (True, False):
+            loaded_ctx.genome_create(golden.lengths)
+            for i, n in enumerate(golden.lengths):
+                sq, nm = pack_ascii(golden.genome[i])
+                rs, re_ = lib.mask_runs(nm, n)
+                assert np.array_equal(np.flatnonzero(codes[i] == 4), np.concatenate([np.arange(a, b) for a, b in zip(rs, re_)] + [np.zeros(0, np.int64)]))
+                loaded_ctx.genome_upload_packed_runs(i, sq, rs, re_, n, wait=wait)
+            if not wait:
+                loaded_ctx.genome_wait()
+            for i, n in enumerate(golden.lengths):
+                assert np.array_equal(loaded_ctx.genome_fetch(i, 0, n), codes[i]), (wait, i)
+        comp = lib.compact_read_columns(rc.chrom_id, rc.ref_start, rc.ref_end, rc.clip5(), flags, len(golden.lengths))
+        assert comp is not None and comp[0][-1] == rc.chrom_id.shape[0]
+        loaded_ctx.reads_upload_compact(*comp)
+        got = loaded_ctx.pileup(c, s, e)
+        assert np.array_equal(got[0], base_pile[0]) and np.array_equal(got[1], base_pile[1])
+        assert loaded_ctx.count_reads(c, s, e) == base_count
+        assert lib.compact_read_columns(rc.chrom_id[::-1], rc.ref_start, rc.ref_end, rc.clip5(), flags, len(golden.lengths)) is None
+        with pytest.raises(lib.TobiasB200Error):
+            loaded_ctx.genome_upload_packed_runs(0, pack_ascii(golden.genome[0])[0], [5], [golden.lengths[0] + 1], golden.lengths[0])
+    finally:
+        loaded_ctx.genome_load(golden.genome)
+        loaded_ctx.reads_upload_columns(rc)
+
+
 def _set_model(ctx, g, mode):
     for si, st in enumerate(("forward", "reverse")):
         if mode == "DWM":

@@ -179,6 +179,7 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
                        &ctx->cor.fitg_sti, &ctx->cor.fitg_wq, &ctx->cor.fitg_lists, &ctx->cor.fitg_sw, &ctx->cor.tracks, &ctx->cor.prepost,
                        &ctx->sc.d_ext_off, &ctx->sc.signal, &ctx->sc.work0, &ctx->sc.work1, &ctx->sc.out};
     for (tb_dbuf *b : bufs) tb_release(*b);
+    for (tb_dbuf &b : ctx->nrun_buf) tb_release(b);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->cor.pp_pinned) cudaFreeHost(ctx->cor.pp_pinned);
     tb_nccl_teardown(ctx);
@@ -420,6 +421,65 @@ extern "C" int tb_genome_upload_packed(tb_ctx *ctx, int contig, const uint32_t *
     return tb_check(ctx, cudaGetLastError(), "tb_genome_upload_packed");
 }
 
+// bits [s, e) of a bit mask (32 positions per word) set by one warp per run; runs may share a word
+__global__ void tb_mask_runs_kernel(u32 *__restrict__ mask, const i64 *__restrict__ run_start, const i64 *__restrict__ run_end, i64 n_runs) {
+    const i64 r = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_runs) return;
+    const i64 s = run_start[r], e = run_end[r];
+    for (i64 w = (s >> 5) + lane; w <= ((e - 1) >> 5); w += 32) {
+        const i64 lo = w << 5;
+        const int b0 = s > lo ? (int)(s - lo) : 0, b1 = e < lo + 32 ? (int)(e - lo) : 32;
+        const u32 bits = (b1 - b0 == 32) ? 0xffffffffu : (((1u << (b1 - b0)) - 1u) << b0);
+        atomicOr(&mask[w], bits);
+    }
+}
+
+extern "C" int tb_genome_upload_packed_runs(tb_ctx *ctx, int contig, const uint32_t *seq2, int64_t n_runs, const int64_t *run_start,
+                                            const int64_t *run_end, int64_t n_bases, int async) {
+    if (!ctx || !seq2 || n_runs < 0 || (n_runs > 0 && (!run_start || !run_end))) return TB_ERR_ARG;
+    if (ctx->n_contigs == 0) return tb_fail(ctx, TB_ERR_STATE, "tb_genome_upload_packed_runs: call tb_genome_create first");
+    if (contig < 0 || contig >= ctx->n_contigs) return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload_packed_runs: contig %d out of range", contig);
+    if (n_bases != ctx->contig_len[contig])
+        return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload_packed_runs: contig %d has %lld bases, got %lld", contig, (i64)ctx->contig_len[contig], (i64)n_bases);
+    for (i64 r = 0; r < n_runs; r++)
+        if (run_start[r] < 0 || run_end[r] <= run_start[r] || run_end[r] > n_bases)
+            return tb_fail(ctx, TB_ERR_ARG, "tb_genome_upload_packed_runs: run %lld [%lld, %lld) is empty or outside the contig", r, (i64)run_start[r], (i64)run_end[r]);
+    const i64 base = ctx->contig_off[contig];
+    u32 *d_seq = ctx->seq2.as<u32>() + (base >> 4), *d_mask = ctx->nmask.as<u32>() + (base >> 5);
+    const size_t b_seq = (size_t)((n_bases + 15) / 16) * sizeof(u32), b_mask = (size_t)((n_bases + 31) / 32) * sizeof(u32);
+    cudaStream_t st = async ? ctx->copy_stream : ctx->stream;
+    if (async) {
+        if ((int)ctx->contig_ready.size() < ctx->n_contigs) {
+            size_t have = ctx->contig_ready.size();
+            ctx->contig_ready.resize(ctx->n_contigs, nullptr);
+            for (size_t c = have; c < ctx->contig_ready.size(); c++)
+                TB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->contig_ready[c], cudaEventDisableTiming));
+        }
+        ctx->contig_pending.resize(ctx->n_contigs, 0);
+    } else {
+        TB_TRY(tb_genome_fence(ctx, contig, contig));
+    }
+    TB_CUDA(ctx, cudaMemcpyAsync(d_seq, seq2, b_seq, cudaMemcpyHostToDevice, st));
+    TB_CUDA(ctx, cudaMemsetAsync(d_mask, 0, b_mask, st));
+    if (n_runs > 0) {
+        // the run table travels through a buffer of its own per contig (the copies of several contigs are in flight at once)
+        if ((int)ctx->nrun_buf.size() < ctx->n_contigs) ctx->nrun_buf.resize(ctx->n_contigs);
+        tb_dbuf &rb = ctx->nrun_buf[contig];
+        TB_TRY(tb_reserve(ctx, rb, (size_t)2 * n_runs * sizeof(i64)));
+        TB_CUDA(ctx, cudaMemcpyAsync(rb.p, run_start, (size_t)n_runs * sizeof(i64), cudaMemcpyHostToDevice, st));
+        TB_CUDA(ctx, cudaMemcpyAsync(rb.as<i64>() + n_runs, run_end, (size_t)n_runs * sizeof(i64), cudaMemcpyHostToDevice, st));
+        TB_LAUNCH_ON(ctx, st, tb_mask_runs_kernel, (unsigned)tb_div_up(n_runs * 32, 256), 256, 0, d_mask, (const i64 *)rb.as<i64>(),
+                     (const i64 *)(rb.as<i64>() + n_runs), (i64)n_runs);
+    }
+    if (async) {
+        TB_CUDA(ctx, cudaEventRecord(ctx->contig_ready[contig], ctx->copy_stream));
+        ctx->contig_pending[contig] = 1;
+        return tb_check(ctx, cudaGetLastError(), "tb_genome_upload_packed_runs");
+    }
+    return tb_sync(ctx, "tb_genome_upload_packed_runs");
+}
+
 extern "C" int tb_genome_wait(tb_ctx *ctx) {
     if (!ctx) return TB_ERR_ARG;
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
@@ -468,6 +528,55 @@ __global__ void tb_reads_linearise_kernel(i64 n, const int32_t *__restrict__ con
     lstart[i] = contig_off[c] + (i64)ref_start[i];
     rlen[i] = ref_end[i] - ref_start[i];
     if (rlen[i] > stats[0]) atomicMax(&stats[0], rlen[i]);
+}
+
+// Compact columns: the records of contig c are [rec_off[c], rec_off[c + 1]); start int32, reference length and 5' clip uint16.
+__global__ void tb_reads_expand_kernel(i64 n, const i64 *__restrict__ rec_off, int n_contigs, const int32_t *__restrict__ ref_start,
+                                       const unsigned short *__restrict__ len16, const unsigned short *__restrict__ clip16,
+                                       const i64 *__restrict__ contig_off, i64 *__restrict__ lstart, int32_t *__restrict__ rlen,
+                                       int32_t *__restrict__ rclip, int *__restrict__ stats) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(tb_upper_bound(rec_off, (i64)n_contigs + 1, i) - 1);
+    if (i > rec_off[c] && ref_start[i - 1] > ref_start[i]) stats[1] = 1;
+    lstart[i] = contig_off[c] + (i64)ref_start[i];
+    const int l = (int)len16[i];
+    rlen[i] = l;
+    rclip[i] = (int)clip16[i];
+    if (l > stats[0]) atomicMax(&stats[0], l);
+}
+
+extern "C" int tb_reads_upload_compact(tb_ctx *ctx, int64_t n, const int64_t *rec_off, const int32_t *ref_start, const uint16_t *ref_len,
+                                       const uint16_t *clip5, const uint8_t *flags) {
+    if (!ctx) return TB_ERR_ARG;
+    if (ctx->n_contigs == 0) return tb_fail(ctx, TB_ERR_STATE, "tb_reads_upload_compact: call tb_genome_create first");
+    if (n < 0 || !rec_off || (n > 0 && (!ref_start || !ref_len || !clip5 || !flags)))
+        return tb_fail(ctx, TB_ERR_ARG, "tb_reads_upload_compact: NULL column");
+    if (rec_off[0] != 0 || rec_off[ctx->n_contigs] != n) return tb_fail(ctx, TB_ERR_ARG, "tb_reads_upload_compact: rec_off must run from 0 to n");
+    for (int c = 0; c < ctx->n_contigs; c++)
+        if (rec_off[c + 1] < rec_off[c]) return tb_fail(ctx, TB_ERR_ARG, "tb_reads_upload_compact: rec_off must not decrease (contig %d)", c);
+    ctx->n_reads = n;
+    ctx->cor.valid = false;
+    if (n == 0) return TB_OK;
+    TB_TRY(tb_h2d(ctx, ctx->scratch0, rec_off, sizeof(i64) * ((size_t)ctx->n_contigs + 1)));
+    TB_TRY(tb_h2d(ctx, ctx->scratch1, ref_start, (size_t)n * 4));
+    TB_TRY(tb_h2d(ctx, ctx->scratch2, ref_len, (size_t)n * 2));
+    TB_TRY(tb_h2d(ctx, ctx->scratch3, clip5, (size_t)n * 2));
+    TB_TRY(tb_h2d(ctx, ctx->r_flags, flags, (size_t)n));
+    TB_TRY(tb_reserve(ctx, ctx->r_start, (size_t)n * 8));
+    TB_TRY(tb_reserve(ctx, ctx->r_len, (size_t)n * 4));
+    TB_TRY(tb_reserve(ctx, ctx->r_clip, (size_t)n * 4));
+    TB_TRY(tb_reserve(ctx, ctx->reg_e, 2 * sizeof(int)));
+    TB_CUDA(ctx, cudaMemsetAsync(ctx->reg_e.p, 0, 2 * sizeof(int), ctx->stream));
+    TB_LAUNCH(ctx, tb_reads_expand_kernel, (unsigned)tb_div_up(n, 256), 256, 0, (i64)n, (const i64 *)ctx->scratch0.as<i64>(), ctx->n_contigs,
+              (const int32_t *)ctx->scratch1.as<int32_t>(), (const unsigned short *)ctx->scratch2.as<unsigned short>(),
+              (const unsigned short *)ctx->scratch3.as<unsigned short>(), (const i64 *)ctx->d_contig_off.as<i64>(), ctx->r_start.as<i64>(),
+              ctx->r_len.as<int32_t>(), ctx->r_clip.as<int32_t>(), ctx->reg_e.as<int>());
+    int stats[2] = {0, 0};
+    TB_TRY(tb_d2h(ctx, stats, ctx->reg_e.p, sizeof(stats)));
+    ctx->max_read_len = stats[0];
+    ctx->reads_sorted = stats[1] == 0;
+    return tb_sync(ctx, "tb_reads_upload_compact");
 }
 
 extern "C" int tb_reads_upload(tb_ctx *ctx, int64_t n, const int32_t *contig, const int32_t *ref_start,

@@ -92,6 +92,7 @@ struct tb_ctx {
     // asynchronous genome uploads (tb_genome_upload_async): copies + packing run on copy_stream; consumers on `stream` wait for the
     // events of the contigs they read (tb_genome_fence), so work on the first contigs overlaps with the transfer of the later ones
     tb_dbuf staging_up;
+    std::vector<tb_dbuf> nrun_buf;     // N-run tables of tb_genome_upload_packed_runs, one per contig
     std::vector<cudaEvent_t> contig_ready;
     std::vector<char> contig_pending;
 

@@ -87,6 +87,30 @@ class Comm:
         return None
 
 
+def bind_to_device_numa(device_index):
+    """Restricts this process to the CPUs next to its GPU (NVML's CPU affinity of the device), so that the pinned buffers it allocates
+    afterwards and the threads that fill them sit on the GPU's NUMA node: with one process per GPU the host-side copies of the eight
+    ranks then do not cross the socket interconnect.  Returns the CPU set, or None when NVML / the topology gives nothing to do."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = near & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_contigs(lengths, world, weights=None):
     """Greedy longest-first bin packing of contigs onto ranks: dict name -> rank.  `weights` (name -> work estimate,
     e.g. reads + alpha * bp) default to the contig lengths."""

@@ -52,6 +52,8 @@ _PROTOS = {
     "tb_genome_wait": (_i, [_vp]),
     "tb_genome_fetch": (_i, [_vp, _i, _i64, _i64, _vp]),
     "tb_reads_upload": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "tb_reads_upload_compact": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "tb_genome_upload_packed_runs": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _i64, _i]),
     "tb_count_reads": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, C.POINTER(_i64)]),
     "tb_pileup": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "tb_read_signal": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp]),
@@ -230,6 +232,15 @@ class Context:
             self._pending_uploads += [a, b]
         self._ck(self._lib.tb_genome_upload_packed(self._h, int(contig), _ptr(a), _ptr(b), int(n_bases), int(not wait)))
 
+    def genome_upload_packed_runs(self, contig, seq2, run_start, run_end, n_bases, wait=True):
+        """A contig as 2-bit words plus the runs of N positions [run_start, run_end) (mask_runs): the device builds the mask."""
+        a, rs, re_ = _arr(seq2, np.uint32), _arr(run_start, np.int64), _arr(run_end, np.int64)
+        if not wait:
+            self._pending_uploads = getattr(self, "_pending_uploads", [])
+            self._pending_uploads += [a, rs, re_]
+        self._ck(self._lib.tb_genome_upload_packed_runs(self._h, int(contig), _ptr(a), int(rs.shape[0]), _ptr(rs), _ptr(re_), int(n_bases),
+                                                        int(not wait)))
+
     def genome_wait(self):
         self._ck(self._lib.tb_genome_wait(self._h))
         self._pending_uploads = []
@@ -249,6 +260,12 @@ class Context:
         c, s, e = _arr(contig, np.int32), _arr(ref_start, np.int32), _arr(ref_end, np.int32)
         k, f = _arr(clip5, np.int32), _arr(flags, np.uint8)
         self._ck(self._lib.tb_reads_upload(self._h, int(c.shape[0]), _ptr(c), _ptr(s), _ptr(e), _ptr(k), _ptr(f)))
+
+    def reads_upload_compact(self, rec_off, ref_start, ref_len, clip5, flags):
+        """Compact record columns (compact_read_columns): 9 bytes per record over the bus instead of 17."""
+        o, s, ln = _arr(rec_off, np.int64), _arr(ref_start, np.int32), _arr(ref_len, np.uint16)
+        k, f = _arr(clip5, np.uint16), _arr(flags, np.uint8)
+        self._ck(self._lib.tb_reads_upload_compact(self._h, int(s.shape[0]), _ptr(o), _ptr(s), _ptr(ln), _ptr(k), _ptr(f)))
 
     def reads_upload_columns(self, rc):
         """Upload a tobias_b200.reads.ReadColumns."""
@@ -499,3 +516,36 @@ class Context:
         op = {"sum": 0, "mean": 1, "max": 2, "min": 3, "prod": 4}[operation]
         self._ck(self._lib.tb_rolling(self._h, _ptr(a), int(a.shape[0]), int(w), op, _ptr(out)))
         return out
+
+
+
+def compact_read_columns(contig, ref_start, ref_end, clip5, flags, n_contigs):
+    """(rec_off, ref_start, ref_len u16, clip5 u16, flags) for Context.reads_upload_compact, or None when the records do not fit the
+    compact form (not grouped by ascending contig, a contig outside the genome, a reference span or clip of 65536 or more)."""
+    c = np.asarray(contig)
+    if c.size and (c.min() < 0 or c.max() >= n_contigs or np.any(np.diff(c) < 0)):
+        return None
+    ln = np.asarray(ref_end, dtype=np.int64) - np.asarray(ref_start, dtype=np.int64)
+    k = np.asarray(clip5)
+    if c.size and (ln.min() < 0 or ln.max() > 65535 or k.min() < 0 or k.max() > 65535):
+        return None
+    rec_off = np.zeros(n_contigs + 1, dtype=np.int64)
+    rec_off[1:] = np.cumsum(np.bincount(c, minlength=n_contigs))
+    return rec_off, np.ascontiguousarray(ref_start, dtype=np.int32), ln.astype(np.uint16), k.astype(np.uint16), np.ascontiguousarray(flags, dtype=np.uint8)
+
+
+def mask_runs(nmask, n_bases):
+    """Runs [start, end) of set bits in a bit mask of n_bases positions (uint32 words, 32 positions per word, bit 0 first)."""
+    w = np.ascontiguousarray(nmask, dtype=np.uint32)
+    nz = np.flatnonzero(w)
+    if nz.size == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    bits = np.unpackbits(w[nz].view(np.uint8).reshape(-1, 4), axis=1, bitorder="little")      # the non-zero words only
+    pos = (nz[:, None].astype(np.int64) * 32 + np.arange(32, dtype=np.int64)[None, :])[bits.astype(bool)]
+    pos = pos[pos < n_bases]
+    if pos.size == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    brk = np.flatnonzero(np.diff(pos) != 1)
+    starts = np.concatenate([pos[:1], pos[brk + 1]])
+    ends = np.concatenate([pos[brk], pos[-1:]]) + 1
+    return starts.astype(np.int64), ends.astype(np.int64)
