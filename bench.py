@@ -1144,7 +1144,7 @@ def bench_batch24(args):
             if download:
                 _b, st, _p = run_step(eng, arrays, device, False, h, out, genome_resident=True, collective=False)
             else:
-                ctx.reads_upload(*h["reads"])
+                (ctx.reads_upload_compact if h.get("reads_compact") else ctx.reads_upload)(*h["reads"])
                 _b, st, _p = run_step(eng, arrays, device, True, h, out, collective=False)
             for k, v in st.items():
                 acc[k] = acc.get(k, 0.0) + v
