@@ -1,0 +1,111 @@
+"""Writes profiles/r02_summary.md from the tracked artefacts make_summary_r02.py left in this directory (bench lines, launch shares,
+ncu counters, roofs).  usage: python profiles/make_report_r02.py"""
+import json
+import os
+
+P = os.path.dirname(os.path.abspath(__file__)) + "/"
+
+
+def load(name):
+    return json.load(open(P + name))
+
+
+def main():
+    b1, b2, b8 = load("r02_bench_hg38_n1.json"), load("r02_bench_hg38_n2.json"), load("r02_bench_hg38_n8.json")
+    ref = load("r02_bench_hg38_reference_arm.json")
+    fg, t8, cli = load("r02_bench_fp_genome.json"), load("r02_bench_batch24_n8.json"), load("r02_cli_chr50mb.json")
+    t1 = load("r02_bench_batch24_n1.json") if os.path.exists(P + "r02_bench_batch24_n1.json") else None
+    cnt, roofs = load("r02_ncu_chr50mb.json"), load("r02_roofs.json")
+    par = b1["parity"]
+    fit = par["lm_windows"]
+    r1 = {"K1_pileup": 1.15, "K3a_score": 90.76, "K3b_fit": 54.04, "K3c_correct": 43.30, "K2_counts": 16.80, "K4_footprint": 26.05}
+    L = []
+    L.append("# Round 2 profile summary (B200, sm_100a)\n")
+    L.append("All numbers were measured on the GPU box through `gpurun`; none was taken under a profiler unless it says ncu. Raw artefacts in this "
+             "directory: `r02_bench_*.json` (the bench lines as printed), `r02_launches_hg38.csv` + `r02_launch_shares.md` (ncu launch list of the bench "
+             "command), `r02_ncu_chr50mb.json` (counters of one `ncu --set full` launch per kernel, chr50mb workload), `r02_roofs.json` (binding unit per "
+             "stage, read by `bench.py`), `r02_sass_grep.txt` (tcgen05 / TMA / spill mnemonics per kernel of the shipped library), `r02_ncu_fitp.txt` "
+             "(the persistent K3b experiment), `r02_k4_pipe_rates.{cu,txt}` (FADD / FMNMX / FMNMX3 / FADD2 issue rates measured for K4); "
+             "`make_summary_r02.py` builds them from `gpurun_out/`, `make_report_r02.py` writes this file.\n")
+    L.append("## 1. Headline bench line (`python bench.py`, hg38 workload, 1 GPU, %d timed steps after %d warm-up steps)\n" % (b1["steps"], b1["warmup"]))
+    L.append("| quantity | round 1 | round 2 |\n|---|---|---|")
+    L.append("| `value` (inputs resident) | 4.31e8 bp/s, 243.8 ms | **%.3g bp/s, %.1f ms** |" % (b1["value"], b1["ms_per_step"]))
+    L.append("| `e2e` (host buffers; H2D %.2f GB + D2H %.2f GB per step inside the timed region) | 3.40e8 bp/s, 309.1 ms (3.94 GB H2D: ASCII genome, "
+             "17-byte records; tracks copied after the run) | **%.3g bp/s, %.1f ms** (genome as 2 bit + N runs, 9-byte records; tracks and scores "
+             "streamed out while the run computes) |" % (b1["e2e"]["h2d_bytes_per_step"] / 1e9, b1["e2e"]["d2h_bytes_per_step"] / 1e9, b1["e2e"]["value"],
+                                                     b1["e2e"]["ms_per_step"]))
+    L.append("| reference on the box's %d host cores (`cpu_baseline`; `--impl reference`: %.3g bp/s) | 1.1e5 bp/s | %.3g bp/s |"
+             % (b1["cpu_baseline"]["cores"], ref["value"], b1["cpu_baseline"]["value"]))
+    L.append("| clocks during the timed region | 1965 / 1965 MHz | %s / %s MHz, reasons %s |" % (b1["clocks"]["sm_mhz"], b1["clocks"]["sm_max_mhz"], b1["clocks"]["reasons"]))
+    L.append("| `parity.green` (GPU path vs the unmodified reference on the reference arm's sample) | -- | **%s** |\n" % par["green"])
+    L.append("Stage times (CUDA events on the library stream, mean over the timed steps):\n")
+    L.append("| stage | round 1 ms | round 2 ms | algorithmic GB/s | binding unit (ncu, chr50mb) |\n|---|---|---|---|---|")
+    for k, v in b1["stages"].items():
+        L.append("| %s | %.2f | **%.2f** | %s | %s |" % (k, r1[k], v["ms"], v["alg_GBps"], roofs[k]["bound"]))
+    L.append("\nWhat changed: K2 -- the multiplicity slab of a region lives in shared memory (no 24 GB HBM slab); K3c -- O(1) rolling sums from block-wide "
+             "fp64 prefix sums on the DWM path; K4 -- the footprint scan as a register-tiled max-plus product (4 starts x 16 widths per thread, two rows per "
+             "step folded with the three-input maximum; DESIGN.md section 3); e2e -- compact host forms of the inputs and streaming sinks for the outputs. "
+             "K3a / K3b unchanged in time; the experiments on K3b (persistent form, moment form, 16-byte records) are in DESIGN.md section 3 with their numbers.\n")
+    L.append("## 2. Parity block of that line\n")
+    L.append("Sample: %d output regions, %d bp, %d windows. Read counts / count tensors / log tables bit-exact: %s / %s / %s.\n"
+             % (par["regions_compared"], par["bp_compared"], fit["windows"], par["read_counts_exact"], par["count_tensors_exact"], par["log_tables_exact"]))
+    L.append("| track | positions | outside lim | outside, not within reach of an unstable window | > 10 lim (unexplained) | > 100 lim (unexplained) | max abs |\n|---|---|---|---|---|---|---|")
+    for t, a in par["tracks"].items():
+        L.append("| %s | %d | %d (%.3f %%) | %d | %d | %d | %.3g |" % (t, a["n"], a["outside"], a["pct_outside"], a["outside_unexplained"],
+                                                                     a["outside_x10_unexplained"], a["far_outside_unexplained"], a["max_abs"]))
+    L.append("\nWindow fits against the reference's `curve_fit` calls: %d fitted + %d fallback + %d empty; fit-vs-fallback decisions that differ: **%d**; "
+             "windows whose normalised prediction differs by more than 1e-4: **%d** (%d of them unstable in the reference itself under a 1e-13 .. 1e-12 "
+             "change of its input, %d stable; budget %d); `ier` differs on %d, `nfev` on %d windows (rounding-level chaos of which termination test fires first).\n"
+             % (fit["fitted_ref"], fit["fallback_ref"], fit["empty"], fit["decision_flips"], fit["mismatching_windows"], fit["unstable_flips"],
+                fit["stable_mismatches"], fit["stable_mismatch_budget"], fit["ier_differs"], fit["nfev_differs"]))
+    L.append("`tests/test_bench_parity.py` (`-m gpu`) runs the same comparison on BASELINE configs[0] (50 Mb contig, 2048 output regions, 300 k windows) "
+             "in both fit modes: green.\n")
+    L.append("## 3. Scaling (strong, same workload, contigs over ranks, NCCL all-reduce of the counts only)\n")
+    L.append("| GPUs | ms per pass (resident) | bp/s | x one GPU | e2e ms | e2e bp/s | checksums equal to N = 1 |\n|---|---|---|---|---|---|---|")
+    for b in (b1, b2, b8):
+        L.append("| %d | %.1f | %.3g | %.2f | %.1f | %.3g | %s |" % (b["n_gpus"], b["ms_per_step"], b["value"], b["value"] / b1["value"], b["e2e"]["ms_per_step"],
+                                                                   b["e2e"]["value"], b["checksum"]["tracks"] == b1["checksum"]["tracks"]
+                                                                   and b["checksum"]["count_tensors"] == b1["checksum"]["count_tensors"]))
+    s8 = sum(v["ms"] for v in b8["stages"].values())
+    L.append("\nAt N = 8 the six stages take %.1f ms of the %.1f: the rest is host work that does not shrink with N (numpy `prepare_mat` 1.0 ms, the "
+             "ratio-table build 0.9 ms, region tables, the fit rounds' host synchronisation). e2e at N = 8 is bound by the host side of the box: the eight "
+             "ranks together move about 100 GB/s device-to-host against 55 GB/s for one rank alone (`tracks_d2h_wait` in `host_phases_ms`); the box is one "
+             "NUMA node (`nvidia-smi topo -m`: every GPU next to CPUs 0-31), so there is nothing to bind.\n" % (s8, b8["ms_per_step"]))
+    L.append("## 4. Other configurations\n")
+    v = fg["variants"]
+    k651, k31 = "cli_default_flank10-30_fp20-50_651", "flank100_fp20-50_31"
+    L.append("* **configs[3]** `--workload fp_genome` (3.09 Gb scored, regions = whole contigs, 1 GPU): CLI defaults (651 combinations) **%.3g bp/s** resident "
+             "(%.0f ms; round start: 712 ms), %.3g bp/s e2e (12.4 GB up + 12.4 GB down); flank 100 x fp 20-50 (31 combinations) %.3g bp/s (%.0f ms). "
+             "Reference on 16 cores: %.3g / %.3g bp/s. Parity (chunks as regions and whole-contig interior vs `tobias_footprint_array`): %s."
+             % (v[k651]["value"], v[k651]["ms_per_step"], v[k651]["e2e_value"], v[k31]["value"], v[k31]["ms_per_step"],
+                fg["cpu_baseline_variants"][k651]["value"], fg["cpu_baseline_variants"][k31]["value"], fg["parity"]["green"]))
+    if t1:
+        L.append("* **configs[4]** `--workload batch24` (3 samples of 5 M records per GPU, genome resident once per GPU, replicas): 1 GPU %.2f samples/s "
+                 "(%.3g bp/s), e2e %.2f samples/s; 8 GPUs **%.1f samples/s** (%.3g bp/s), e2e %.1f samples/s."
+                 % (t1["samples_per_s"], t1["value"], t1["e2e"]["samples_per_s"], t8["samples_per_s"], t8["value"], t8["e2e"]["samples_per_s"]))
+    else:
+        L.append("* **configs[4]** `--workload batch24` (3 samples of 5 M records per GPU, genome resident once per GPU, replicas): 8 GPUs **%.1f samples/s** "
+                 "(%.3g bp/s), e2e %.1f samples/s." % (t8["samples_per_s"], t8["value"], t8["e2e"]["samples_per_s"]))
+    r = cli["runs"][-1]
+    L.append("* **configs[0] from files** `--workload chr50mb --cli` (16 host cores): ATACorrect %.2f s + ScoreBigwig %.2f s = **%.2f s**; phases of "
+             "ATACorrect: %s." % (r["atacorrect_s"], r["scorebigwig_s"], cli["cli_wall_s"], ", ".join("%s %.2f" % kv for kv in r["atacorrect_phases_s"].items())))
+    L.append("\n## 5. ncu launch list of the bench command (shares; durations are cold-cache and serialised)\n")
+    L.append("`python bench.py --steps 1 --warmup 1 --no-cpu-baseline` under `ncu --metrics gpu__time_duration.sum`: a resident and a streaming (e2e) pass per "
+             "step, which is why the last stage of the correction shows 4 launches per streaming pass x 6 chunks and the footprint scan 3.\n")
+    L.append(open(P + "r02_launch_shares.md").read())
+    L.append("\n## 6. Counters per kernel (`ncu --set full`, chr50mb workload, one launch each)\n")
+    L.append("| kernel | ms | issue % | warps active % | regs | fp64 pipe % | ALU pipe % | L1 / smem % | L2 % | DRAM % | DRAM MB (r + w) | lanes / inst | top stalls |\n"
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    for k, c in cnt.items():
+        L.append("| %s | %.3f | %.1f | %.1f | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.0f + %.0f | %.1f | %s |"
+                 % (k, c["time_ms"], c["issue_active_pct"], c["warps_active_pct"], c["registers"], c.get("fp64_pipe_pct", 0), c.get("alu_pipe_pct", 0),
+                    c.get("l1_smem_throughput_pct", 0), c.get("l2_throughput_pct", 0), c.get("dram_throughput_pct", 0), c.get("dram_read_MB", 0),
+                    c.get("dram_write_MB", 0), c.get("lanes_per_inst", 0), ", ".join("%s %s" % kv for kv in list(c["top_stalls_pct"].items())[:3])))
+    L.append("\nThe K3a capture at hg38 size for `roofline.traffic` (4.06 GB per launch against 2.02 GB algorithmic) is round 1's (`r01_summary.md`): "
+             "the kernel did not change.\n")
+    open(P + "r02_summary.md", "w").write("\n".join(L) + "\n")
+    print("wrote r02_summary.md (%d lines)" % len(L))
+
+
+if __name__ == "__main__":
+    main()
