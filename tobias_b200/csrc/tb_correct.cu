@@ -661,9 +661,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                     double val = 0.0;
                     bool have = false;
                     if (jmax >= r) {
-                        int back = r0 - r;                              // (jmax - r) mod overlaps
-                        if (back < 0) back += overlaps;
-                        const int jw = jmax - back;                     // last window of row r starting at or before q
+                        const int jw = jmax - r0 + r - (r > r0 ? overlaps : 0);         // last window of row r starting at or before q
                         if (k + TB_STEP * jw + w > q) {
                             have = true;
                             const double *f = frec + (jw - jw_lo) * TB_K3C_FREC;
@@ -827,22 +825,28 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                 for (int a = 0; a < 3; a++)
 #pragma unroll
                     for (int s = 0; s < 4; s++) acc[a][s] = 0.0;
-                if (lane < L) {
-                    for (int q = qa; q < qb; q++) {
-                        const double v0 = wpre[q], v1 = expd[q];
-                        if (v0 == 0.0 && v1 == 0.0) continue;                         // every branch here is warp-uniform
-                        const int s = bases[q + lane];
-                        if (v0 != 0.0) {
+                // the sparse weights: 32 positions of the strip are tested per step, the warp visits the ones that carry a weight (in order)
+                for (int q0 = qa; q0 < qb; q0 += 32) {
+                    const int qq = q0 + lane;
+                    const bool nz = qq < qb && (wpre[qq] != 0.0 || expd[qq] != 0.0);
+                    unsigned hit = __ballot_sync(0xffffffffu, nz);
+                    while (hit) {
+                        const int q = q0 + __ffs(hit) - 1;
+                        hit &= hit - 1;
+                        if (lane < L) {
+                            const double v0 = wpre[q], v1 = expd[q];
+                            const int s = bases[q + lane];
 #pragma unroll
-                            for (int b = 0; b < 4; b++)
-                                if (s == b) acc[0][b] += v0;
-                        }
-                        if (v1 != 0.0) {
-#pragma unroll
-                            for (int b = 0; b < 4; b++)
-                                if (s == b) acc[1][b] += v1;
+                            for (int b = 0; b < 4; b++) {
+                                if (s == b) {
+                                    acc[0][b] += v0;                                  // adding 0.0 changes nothing
+                                    acc[1][b] += v1;
+                                }
+                            }
                         }
                     }
+                }
+                if (lane < L) {
                     const double *negw = bp + L - lane;                               // negw[p] = weight of centre p - lane (0 outside the tile)
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
@@ -851,6 +855,7 @@ __global__ void __launch_bounds__(TB_K3C_THREADS, 3)
                         const int ia = warp * per, ib = min(nb, ia + per);
                         const unsigned short *lst = blist + b * bl_cap;
                         double a2 = 0.0;
+#pragma unroll 4
                         for (int i = ia; i < ib; i++) a2 += negw[lst[i]];
                         acc[2][b] = a2;
                     }
