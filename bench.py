@@ -1250,9 +1250,10 @@ def bench_cli(args):
         b = parsers.add_scorebigwig_arguments(argparse.ArgumentParser()).parse_args(
             ["--signal", os.path.join(out, "x_corrected.bw"), "--regions", bed, "--output", os.path.join(out, "x_footprints.bw"), "--verbosity", "0"])
         t0 = time.perf_counter()
-        score_bigwig.run_scorebigwig(b)
+        res_sb = score_bigwig.run_scorebigwig(b)
         t_sb = time.perf_counter() - t0
         runs.append({"atacorrect_s": round(t_ata, 2), "scorebigwig_s": round(t_sb, 2), "atacorrect_phases_s": res["phases_s"],
+                     "scorebigwig_phases_s": res_sb["phases_s"],
                      "output_bytes": {f: os.path.getsize(os.path.join(out, f)) for f in sorted(os.listdir(out))}})
     shutil.rmtree(d, ignore_errors=True)
     print(json.dumps({"metric": "cli_wall_s", "workload": wl["desc"], "cli_wall_s": runs[-1]["atacorrect_s"] + runs[-1]["scorebigwig_s"],

@@ -171,6 +171,48 @@ def test_bigwig_roundtrip_many_sections(tmp_path):
     r.close()
 
 
+def test_bigwig_fixedstep_sections_and_batched_reads(tmp_path):
+    """Runs of consecutive positions are written as fixedStep sections (4 bytes per item), scattered ones as variableStep; both decode to
+    the same values, the zoom levels do not depend on the section type, and values_many reads many intervals (abutting, overlapping,
+    in gaps) exactly as values reads them one by one."""
+    rng = np.random.default_rng(3)
+    starts = np.sort(rng.choice(400, 120, replace=False)) * 1000
+    pos = np.concatenate([np.arange(s, s + rng.integers(300, 900)) for s in starts])
+    val = np.where(rng.random(pos.size) < 0.3, 0, rng.normal(size=pos.size)).astype(np.float32)
+    sparse = np.sort(rng.choice(np.arange(450000, 500000), 3000, replace=False))
+    sval = rng.normal(size=sparse.size).astype(np.float32)
+    sizes, zooms = {}, {}
+    for flag in (True, False):
+        bigwig.FIXED_STEP = flag
+        try:
+            path = str(tmp_path / ("f%d.bw" % flag))
+            w = bigwig.BigWigWriter(path)
+            w.add_header([("chr1", 500000)])
+            w.add_entries("chr1", pos, val)
+            w.add_entries("chr1", sparse, sval)
+            w.close()
+        finally:
+            bigwig.FIXED_STEP = True
+        sizes[flag] = os.path.getsize(path)
+        r = bigwig.BigWigReader(path)
+        full = np.full(500000, np.nan, np.float32)
+        full[pos], full[sparse] = val, sval
+        assert np.array_equal(r.values("chr1", 0, 500000), full, equal_nan=True)
+        zooms[flag] = r.zoom_records(0)[1]
+        a = np.sort(rng.choice(499000, 300, replace=False))
+        b = a + rng.integers(1, 900, size=a.size)                    # overlapping and abutting intervals among them
+        flat, off = r.values_many("chr1", a, b)
+        for i in range(a.size):
+            assert np.array_equal(flat[off[i]:off[i + 1]], full[a[i]:b[i]], equal_nan=True), i
+        flat, off = r.values_many("chr1", a[::-1], b[::-1])          # unsorted: the one-by-one path
+        assert np.array_equal(flat[off[0]:off[1]], full[a[-1]:b[-1]], equal_nan=True)
+        with pytest.raises(RuntimeError):
+            r.values_many("chr1", [10], [600000])
+        r.close()
+    assert sizes[True] < 0.8 * sizes[False]
+    assert np.array_equal(zooms[True], zooms[False])
+
+
 def test_synthetic_data_properties():
     ds = synth.small_config()
     rc = ds.reads

@@ -38,6 +38,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+FIXED_STEP = True          # False: variableStep sections only (comparison runs, tests)
+
+
 def _codec():
     global _LIB
     if _LIB is None:
@@ -45,7 +48,7 @@ def _codec():
         if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
             subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", so, src, "-lz"])
         _LIB = ctypes.CDLL(so)
-        for f in ("tb_bw_bound", "tb_bw_sections", "tb_bw_zoom", "tb_bw_pack"):
+        for f in ("tb_bw_bound", "tb_bw_sections", "tb_bw_sections_fixed", "tb_bw_zoom", "tb_bw_zoom0", "tb_bw_pack"):
             getattr(_LIB, f).restype = ctypes.c_int64
     return _LIB
 
@@ -108,36 +111,59 @@ class BigWigWriter:
         if (cid, int(pos[0])) <= self._last or (pos.size > 1 and np.any(pos[1:] <= pos[:-1])):
             raise RuntimeError("entries must be added in sorted order (chromosome order of the header, ascending positions)")
         self._last = (cid, int(pos[-1]))
-        v64 = val.astype(np.float64)
-        sq64 = v64 * v64
+        # ---- totals and the first zoom level (one summary per FIRST_REDUCTION bases that hold data): one native pass over the items
+        lib = _codec()
+        n_max = int(min(pos.size, (int(pos[-1]) - int(pos[0])) // FIRST_REDUCTION + 2))
+        zb, zn = np.empty(n_max, np.int64), np.empty(n_max, np.int64)
+        zmn, zmx, zsm, zsq = (np.empty(n_max, np.float64) for _ in range(4))
+        tot = np.zeros(4, np.float64)
+        nz = int(lib.tb_bw_zoom0(_vp(pos), _vp(val), ctypes.c_int64(pos.size), ctypes.c_int32(FIRST_REDUCTION), _vp(zb), _vp(zn), _vp(zmn), _vp(zmx),
+                                 _vp(zsm), _vp(zsq), _vp(tot)))
         self._n_valid += pos.size
-        self._min = min(self._min, float(v64.min()))
-        self._max = max(self._max, float(v64.max()))
-        self._sum += float(v64.sum())
-        self._sumsq += float(sq64.sum())
+        self._min = min(self._min, float(tot[0]))
+        self._max = max(self._max, float(tot[1]))
+        self._sum += float(tot[2])
+        self._sumsq += float(tot[3])
+        if self._zoom:
+            self._zoom0.append((cid, zb[:nz].copy(), zn[:nz].copy(), zmn[:nz].copy(), zmx[:nz].copy(), zsm[:nz].copy(), zsq[:nz].copy()))
         # ---- data sections: built and compressed in parallel by the native helper
         from .bam import parallel_ranges
-        lib = _codec()
-        n_sec = (pos.size + ITEMS_PER_SECTION - 1) // ITEMS_PER_SECTION
-        slot = int(lib.tb_bw_bound(ctypes.c_int64(24 + 8 * ITEMS_PER_SECTION)))
+        # runs of consecutive positions (what ATACorrect / ScoreBigwig write: every base of a region) go into fixedStep sections -- 4 bytes per
+        # item instead of the 8 of variableStep, half the bytes through zlib; scattered positions keep variableStep sections of a fixed count
+        brk = np.flatnonzero(np.diff(pos) != 1) + 1
+        if FIXED_STEP and (brk.size + 1) * 16 <= pos.size:
+            run_a = np.concatenate([[0], brk])
+            run_b = np.concatenate([brk, [pos.size]])
+            n_chunks = (run_b - run_a + ITEMS_PER_SECTION - 1) // ITEMS_PER_SECTION
+            first = np.repeat(run_a, n_chunks)
+            within = np.arange(int(n_chunks.sum()), dtype=np.int64) - np.repeat(np.cumsum(n_chunks) - n_chunks, n_chunks)
+            sec_a = np.ascontiguousarray(first + within * ITEMS_PER_SECTION, dtype=np.int64)
+            sec_b = np.ascontiguousarray(np.minimum(sec_a + ITEMS_PER_SECTION, np.repeat(run_b, n_chunks)), dtype=np.int64)
+            n_sec = int(sec_a.shape[0])
+            item_bytes = 4
+        else:
+            sec_a = sec_b = None
+            n_sec = (pos.size + ITEMS_PER_SECTION - 1) // ITEMS_PER_SECTION
+            item_bytes = 8
+        slot = int(lib.tb_bw_bound(ctypes.c_int64(24 + item_bytes * ITEMS_PER_SECTION)))
         out = np.empty(n_sec * slot, dtype=np.uint8)
         off, ln = np.empty(n_sec, np.int64), np.empty(n_sec, np.int64)
         st, en = np.empty(n_sec, np.int32), np.empty(n_sec, np.int32)
-        parallel_ranges(lambda a, b: lib.tb_bw_sections(ctypes.c_int32(cid), _vp(pos), _vp(val), ctypes.c_int64(pos.size),
-                                                        ctypes.c_int32(ITEMS_PER_SECTION), ctypes.c_int32(self._level), ctypes.c_int64(a),
-                                                        ctypes.c_int64(b), _vp(out), ctypes.c_int64(slot), _vp(ln), _vp(st), _vp(en)), 0, n_sec, 64)
+        if sec_a is not None:
+            parallel_ranges(lambda a, b: lib.tb_bw_sections_fixed(ctypes.c_int32(cid), _vp(pos), _vp(val), _vp(sec_a), _vp(sec_b),
+                                                                  ctypes.c_int32(ITEMS_PER_SECTION), ctypes.c_int32(self._level), ctypes.c_int64(a),
+                                                                  ctypes.c_int64(b), _vp(out), ctypes.c_int64(slot), _vp(ln), _vp(st), _vp(en)), 0, n_sec, 64)
+        else:
+            parallel_ranges(lambda a, b: lib.tb_bw_sections(ctypes.c_int32(cid), _vp(pos), _vp(val), ctypes.c_int64(pos.size),
+                                                            ctypes.c_int32(ITEMS_PER_SECTION), ctypes.c_int32(self._level), ctypes.c_int64(a),
+                                                            ctypes.c_int64(b), _vp(out), ctypes.c_int64(slot), _vp(ln), _vp(st), _vp(en)), 0, n_sec, 64)
         total = lib.tb_bw_pack(_vp(out), ctypes.c_int64(n_sec), ctypes.c_int64(slot), _vp(ln), _vp(off))
         if total < 0:
             raise RuntimeError("bigWig section compression failed (%d)" % total)
-        self._max_uncompressed = max(self._max_uncompressed, 24 + 8 * min(pos.size, ITEMS_PER_SECTION))
+        self._max_uncompressed = max(self._max_uncompressed, 24 + item_bytes * min(pos.size, ITEMS_PER_SECTION))
         base = self._fh.tell()
         self._fh.write(out[:total].tobytes())
         self._sec.append((cid, st.astype(np.int64), en.astype(np.int64), off + base, ln))
-        # ---- first zoom level: one summary per FIRST_REDUCTION bases that hold data
-        if self._zoom:
-            bins = pos // FIRST_REDUCTION
-            first, valid, mn, mx, sm, sq = _reduce_sorted(bins, np.ones(pos.size, np.int64), v64, v64, v64, sq64)
-            self._zoom0.append((cid, bins[first], valid, mn, mx, sm, sq))
 
     # ------------------------------------------------------------------ index
     def _write_rtree(self, sc, sb, ec, eb, off, size):
@@ -394,6 +420,71 @@ class BigWigReader:
                     if a < b:
                         out[a - start:b - start] = v
         return out
+
+    def values_many(self, chrom, starts, ends):
+        """values() of many intervals of one chromosome at once (starts ascending): the sections the intervals touch are read in one
+        sweep, inflated on the thread pool and scattered into the concatenated output with array operations.  Returns (flat float32
+        array, offsets: interval i occupies flat[off[i]:off[i + 1]])."""
+        starts, ends = np.asarray(starts, dtype=np.int64), np.asarray(ends, dtype=np.int64)
+        if chrom not in self.chroms or starts.size == 0:
+            raise RuntimeError("Invalid interval bounds!")
+        if starts.min() < 0 or ends.max() > self.chroms[chrom] or np.any(starts >= ends):
+            raise RuntimeError("Invalid interval bounds!")
+        off = np.concatenate([[0], np.cumsum(ends - starts)])
+        out = np.full(int(off[-1]), np.nan, dtype=np.float32)
+        cid = self._ids[chrom]
+        blocks = sorted(set(self._blocks(cid, int(starts.min()), int(ends.max()))))
+        if not blocks or np.any(starts[1:] < starts[:-1]):
+            for i, (a, b) in enumerate(zip(starts.tolist(), ends.tolist())):           # unsorted intervals: one by one
+                out[off[i]:off[i + 1]] = self.values(chrom, a, b)
+            return out, off
+        # the intervals usually cover a small part of the span: keep the sections that overlap one (section spans come with the R-tree leaves
+        # only after inflation, so the test happens on the decoded header)
+        from .bam import parallel_ranges
+        fh = self._fh
+        raws = []
+        for o, size in blocks:
+            fh.seek(o)
+            raws.append(fh.read(size))
+        if self.uncompress_buf:
+            dec = [None] * len(raws)
+
+            def inflate(a, b):
+                for k in range(a, b):
+                    dec[k] = zlib.decompress(raws[k])
+            parallel_ranges(inflate, 0, len(raws), 64)
+        else:
+            dec = raws
+        pos_l, val_l = [], []
+        for raw in dec:
+            c, s0, e0, step, span, typ, _, n = struct.unpack_from("<IIIIIBBH", raw, 0)
+            if c != cid:
+                continue
+            if typ == 3 and span == 1 and step == 1:
+                pos_l.append(np.arange(s0, s0 + n, dtype=np.int64))
+                val_l.append(np.frombuffer(raw, dtype="<f4", count=n, offset=24))
+            elif typ == 2 and span == 1:
+                it = np.frombuffer(raw, dtype=_VAR_ITEM, count=n, offset=24)
+                pos_l.append(it["start"].astype(np.int64))
+                val_l.append(it["value"])
+            else:                                                                      # bedGraph items / wider spans: the general reader
+                for i, (a, b) in enumerate(zip(starts.tolist(), ends.tolist())):
+                    out[off[i]:off[i + 1]] = self.values(chrom, a, b)
+                return out, off
+        if pos_l:
+            pos, val = np.concatenate(pos_l), np.concatenate(val_l)                  # ascending: the sections of a chromosome are in file order
+            if np.any(starts[1:] < ends[:-1]):
+                # overlapping intervals: a position can belong to several of them -- one slice of the data per interval
+                lo, hi = np.searchsorted(pos, starts), np.searchsorted(pos, ends)
+                for i in range(starts.size):
+                    out[off[i] + (pos[lo[i]:hi[i]] - starts[i])] = val[lo[i]:hi[i]]
+            else:
+                r = np.searchsorted(starts, pos, side="right") - 1                    # the interval starting at or before the position
+                ok = r >= 0
+                ok[ok] = pos[ok] < ends[r[ok]]
+                r, pos, val = r[ok], pos[ok], val[ok]
+                out[off[r] + (pos - starts[r])] = val
+        return out, off
 
     def zoom_headers(self):
         """[(reduction level, data offset, index offset)] of the zoom levels."""

@@ -33,12 +33,21 @@ def calculate_scores(regions, args, ctx=None):
     try:
         flank = args.region_flank
         bw = BigWigReader(args.signal)
-        ext, lens, keys = [], [], []
+        ext, lens, keys, spans = [], [], [], []
         for region in regions:
             region.extend_reg(flank)
             keys.append((region.chrom, region.start + flank, region.end - flank))
-            ext.append(bw.values(region.chrom, region.start, region.end))           # float32, NaN where empty
-            lens.append(ext[-1].shape[0])
+            spans.append((region.chrom, region.start, region.end))
+            lens.append(region.end - region.start)
+        # runs of regions on one chromosome with ascending starts are read in one sweep over the bigWig (values_many); float32, NaN where empty
+        i = 0
+        while i < len(spans):
+            j = i + 1
+            while j < len(spans) and spans[j][0] == spans[i][0] and spans[j][1] >= spans[j - 1][1]:
+                j += 1
+            flat, _off = bw.values_many(spans[i][0], [s[1] for s in spans[i:j]], [s[2] for s in spans[i:j]])
+            ext.append(flat)
+            i = j
         bw.close()
         if not ext:
             return 1
@@ -77,6 +86,14 @@ def run_scorebigwig(args):
     logger.arguments_overview(parser, args)
     logger.output_files([args.output])
 
+    import time
+    t_mark = [time.perf_counter()]
+    phases = {}
+
+    def phase(name):
+        now = time.perf_counter()
+        phases[name] = round(now - t_mark[0], 3)
+        t_mark[0] = now
     logger.info("Processing input files")
     logger.info("- Opening input cutsite bigwig")
     bw = BigWigReader(args.signal)
@@ -106,6 +123,7 @@ def run_scorebigwig(args):
     header = [(c, chrom_info[c]) for c in reference_chroms]
     regions.loc_sort(reference_chroms)
 
+    phase("headers_and_regions")
     logger.info("Calculating footprints in regions...")
     q = _ListQueue()
     args.writer_qs = {"scores": q}
@@ -113,9 +131,12 @@ def run_scorebigwig(args):
     calculate_scores(deepcopy(regions), args)
     vals = np.concatenate([x[2] for x in q.items]).astype(np.float32) if q.items else np.zeros(0, np.float32)
     offs = np.concatenate([[0], np.cumsum([x[2].shape[0] for x in q.items])])[:-1].tolist() if q.items else []
+    phase("read_signal_and_score")
     logger.info("Closing {0} (this might take some time)".format(args.output))
     write_track(args.output, header, list(regions), vals, offs)
+    phase("write_bigwig")
     logger.end()
+    return {"phases_s": phases}
 
 
 def main(argv=None):
