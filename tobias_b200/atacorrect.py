@@ -38,30 +38,38 @@ def check_files(paths, action="r"):
                 sys.exit("ERROR: directory {0} does not exist".format(d))
 
 
-def write_track(path, header, regions, values, region_offsets):
-    """bigwig_writer semantics (tobias/utils/utilities.py:129-232): regions in header order, non-zero positions only,
-    float32 values, span 1.  `values` is the concatenated track, region i at region_offsets[i].  One add_entries call per contig: the
-    non-zero positions of all its regions at once (sections are compressed in parallel, zoom levels follow)."""
-    order = {c: i for i, (c, _) in enumerate(header)}
-    idx = sorted(range(len(regions)), key=lambda i: (order[regions[i].chrom], regions[i].start))
+def write_track_arrays(path, header, cid, start, end, values, offsets):
+    """bigwig_writer semantics (tobias/utils/utilities.py:129-232): regions in header order, non-zero positions only, float32 values,
+    span 1.  Region i = (header contig cid[i], start[i], end[i]) holds values[offsets[i] : offsets[i] + end[i] - start[i]].  Array
+    operations throughout: the non-zero positions of the whole track are found at once and handed to the writer contig by contig
+    (sections are compressed in parallel, zoom levels follow)."""
+    cid, start, end, offsets = (np.asarray(a, dtype=np.int64) for a in (cid, start, end, offsets))
+    values = np.asarray(values)
     w = BigWigWriter(path)
     w.add_header(header)
-    values = np.asarray(values)
-    k = 0
-    while k < len(idx):
-        chrom = regions[idx[k]].chrom
-        pos_parts, val_parts = [], []
-        while k < len(idx) and regions[idx[k]].chrom == chrom:
-            r = regions[idx[k]]
-            sig = values[region_offsets[idx[k]]:region_offsets[idx[k]] + (r.end - r.start)]
-            nz = np.flatnonzero(sig)
-            if nz.size:
-                pos_parts.append(nz.astype(np.int64) + r.start)
-                val_parts.append(sig[nz])
-            k += 1
-        if pos_parts:
-            w.add_entries(chrom, np.concatenate(pos_parts), np.concatenate(val_parts))
+    if cid.size:
+        order = np.lexsort((start, cid))
+        cid, start, end, offsets = cid[order], start[order], end[order], offsets[order]
+        lens = end - start
+        # concatenated in header order: out position of every value, then the non-zero ones
+        src = np.repeat(offsets - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(int(lens.sum()), dtype=np.int64)
+        vals = values[src]
+        pos = np.repeat(start - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(int(lens.sum()), dtype=np.int64)
+        reg_cid = np.repeat(cid, lens)
+        nz = np.flatnonzero(vals)
+        pos, vals, reg_cid = pos[nz], vals[nz], reg_cid[nz]
+        cuts = np.flatnonzero(np.diff(reg_cid)) + 1
+        for a, b in zip(np.concatenate([[0], cuts]).tolist(), np.concatenate([cuts, [reg_cid.size]]).tolist()):
+            if b > a:
+                w.add_entries(header[int(reg_cid[a])][0], pos[a:b], vals[a:b])
     w.close()
+
+
+def write_track(path, header, regions, values, region_offsets):
+    """write_track_arrays for a list of regions (objects with chrom / start / end)."""
+    order = {c: i for i, (c, _) in enumerate(header)}
+    write_track_arrays(path, header, [order[r.chrom] for r in regions], [r.start for r in regions], [r.end for r in regions], values,
+                       region_offsets)
 
 
 def run_atacorrect(args):
@@ -244,22 +252,23 @@ def run_atacorrect(args):
     header = [(c, bam_chrom_info[c]) for c in bam_references]
     reg_tbl = np.array([(bam_references.index(r.chrom), r.start, r.end) for r in out_regions], dtype=np.int64).reshape(-1, 3)
     all_tbl = comm.gather_arrays(reg_tbl.ravel())
+    jobs = []
+    if root:
+        tbl = np.concatenate([t.reshape(-1, 3) for t in all_tbl]) if all_tbl else np.zeros((0, 3), np.int64)
+        offs = np.concatenate([[0], np.cumsum(tbl[:, 2] - tbl[:, 1])])[:-1]
     for track in tracks:
         for si, strand in enumerate(strands_out):
             vals = got[track][si] if (args.split_strands and n_out) else (got[track] if n_out else np.zeros(0, np.float32))
             parts = comm.gather_arrays(np.ascontiguousarray(vals))
             if root:
-                from .regions import OneRegion
-                regs, offs, off = [], [], 0
-                for tbl in all_tbl:
-                    for cid, s, e in tbl.reshape(-1, 3):
-                        regs.append(OneRegion([bam_references[int(cid)], int(s), int(e)]))
-                for tbl in all_tbl:
-                    for cid, s, e in tbl.reshape(-1, 3):
-                        offs.append(off)
-                        off += int(e - s)
-                logger.info("Closing {0} (this might take some time)".format(output_bws[track][strand]))
-                write_track(output_bws[track][strand], header, regs, np.concatenate(parts) if parts else np.zeros(0, np.float32), offs)
+                jobs.append((output_bws[track][strand], np.concatenate(parts) if parts else np.zeros(0, np.float32)))
+    if root:
+        # the files are independent: written side by side (numpy and the native helpers release the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        for path, _v in jobs:
+            logger.info("Closing {0} (this might take some time)".format(path))
+        with ThreadPoolExecutor(max(1, min(4, len(jobs)))) as ex:
+            list(ex.map(lambda job: write_track_arrays(job[0], header, tbl[:, 0], tbl[:, 1], tbl[:, 2], job[1], offs), jobs))
 
     phase("write_bigwigs")
     logger.comment("")
