@@ -67,7 +67,7 @@ int tb_host_free(tb_ctx *ctx, void *p);
 int tb_launch_count(tb_ctx *ctx, int64_t *n);
 /* Kernel-variant / chunk-size switches for comparison runs and tests (every setting yields the same results; production code never
  * calls this): "k3a_sum_form", "k3a_no_tmem", "k3a_tmem_groups", "k3c_fast", "k2_tile", "k2_site_cap", "k2_chunk", "k2_no_hist",
- * "k2_smem_chunk", "k2_no_smem_hist", "k4_two_starts", "k4_threads", "k3b_persistent", "k3b_tile", "k3b_cap", "k3b_threads", "host_trace".  value < 0 restores the default.  (These
+ * "k2_smem_chunk", "k2_no_smem_hist", "k3c_chunks", "k4_chunks", "k4_form", "k4_threads", "k3b_persistent", "k3b_tile", "k3b_cap", "k3b_threads", "host_trace".  value < 0 restores the default.  (These
  * replace the environment variables the library read in its first version.) */
 int tb_set_option(tb_ctx *ctx, const char *key, int64_t value);
 
