@@ -90,8 +90,9 @@ def main():
     L.append("* **configs[0] from files** `--workload chr50mb --cli` (16 host cores): ATACorrect %.2f s + ScoreBigwig %.2f s = **%.2f s**; phases of "
              "ATACorrect: %s." % (r["atacorrect_s"], r["scorebigwig_s"], cli["cli_wall_s"], ", ".join("%s %.2f" % kv for kv in r["atacorrect_phases_s"].items())))
     L.append("\n## 5. ncu launch list of the bench command (shares; durations are cold-cache and serialised)\n")
-    L.append("`python bench.py --steps 1 --warmup 1 --no-cpu-baseline` under `ncu --metrics gpu__time_duration.sum`: a resident and a streaming (e2e) pass per "
-             "step, which is why the last stage of the correction shows 4 launches per streaming pass x 6 chunks and the footprint scan 3.\n")
+    L.append("`python bench.py --steps 1 --warmup 1 --no-cpu-baseline` under `ncu --metrics gpu__time_duration.sum`: resident and streaming (e2e) "
+             "passes; a streaming pass launches the last stage of the correction once per chunk of output regions (six) and the footprint scan three "
+             "times, a resident pass once each.\n")
     L.append(open(P + "r02_launch_shares.md").read())
     L.append("\n## 6. Counters per kernel (`ncu --set full`, chr50mb workload, one launch each)\n")
     L.append("| kernel | ms | issue % | warps active % | regs | fp64 pipe % | ALU pipe % | L1 / smem % | L2 % | DRAM % | DRAM MB (r + w) | lanes / inst | top stalls |\n"
