@@ -258,9 +258,9 @@ tb_footprint_kernel(tb_sc_view V, const float *__restrict__ signal, tb_prep prep
 // valid one are masked per row in the few threads that have any.
 // Centre term: mid(u, c) = (N[s_u + pw] - N[s_3]) + (N[s_3] - N[s_u]), two same-signed fp32 numbers (sums of non-positive values), so rounding
 // the fp64 prefix differences once per window position instead of once per (start, width) loses nothing.
-// Spreading a score over its footprint: as in the first form, through a table G[c][start] of suffix maxima over the widths, GW widths at a time.
+// Spreading a score over its footprint: suffix maxima over the widths as in the first form, but the anti-diagonals of the (start, width) table are
+// folded inside the thread first, so one exchange through shared memory per pass is enough (see the kernel).
 #define TB_K4T_MAXT 256
-#define TB_K4T_GW 4              // widths per exchange through shared memory
 #define TB_K4T_EPT 8             // row elements a thread stages at most
 
 // 16-byte shared-memory load that the compiler may neither split nor narrow to the components in use (a thread's stride is 16 bytes: whole
