@@ -97,6 +97,8 @@ struct tb_ctx {
     std::vector<char> contig_pending;
 
     // scratch / per-call device tables
+    std::vector<i64> h64[4];              // host scratch of the entry points (kept: a repeated call touches warm pages)
+    std::vector<int32_t> h32[2];
     tb_dbuf reg_a, reg_b, reg_c, reg_d, reg_e;
     tb_dbuf scratch0, scratch1, scratch2, scratch3, scratch4;
     tb_dbuf staging;   // device staging for uploads
@@ -111,6 +113,8 @@ struct tb_ctx {
         i64 n_regions = 0, ext_total = 0, out_total = 0, n_windows = 0;
         int k_flank = 0, window = 0, L = 0;
         std::vector<i64> ext_start, ext_off, out_off, win_off;   // linear ext start, offsets
+        std::vector<i64> h_ls, h_le, h_ext_end;                  // host scratch of a run, kept so that a second run touches warm pages
+        std::vector<int32_t> h_tile_region, h_tile_start;
         tb_dbuf d_ext_start, d_ext_end, d_ext_off, d_out_off, d_win_off;
         tb_dbuf pile;      // u32 [2][ext_total]
         tb_dbuf biasraw;   // f64 [2][ext_total]

@@ -965,8 +965,9 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         return tb_fail(ctx, TB_ERR_STATE, "tb_correct_run: call tb_set_bias_model for both strands first");
     const int L = ctx->model[0].L;
     if (L != 2 * k_flank + 1) return tb_fail(ctx, TB_ERR_ARG, "tb_correct_run: k_flank %d does not match the model length %d", k_flank, L);
-    std::vector<i64> ls, le;
+    std::vector<i64> &ls = ctx->cor.h_ls, &le = ctx->cor.h_le;
     TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
+    tr("linear regions");
     const int f_extend = k_flank + window / 2;
     auto &C = ctx->cor;
     C.n_regions = n_regions;
@@ -977,8 +978,11 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     C.ext_off.assign(n_regions + 1, 0);
     C.out_off.assign(n_regions + 1, 0);
     C.win_off.assign(n_regions + 1, 0);
-    std::vector<i64> ext_end(n_regions);
-    std::vector<int32_t> tile_region, tile_start;
+    std::vector<i64> &ext_end = C.h_ext_end;
+    std::vector<int32_t> &tile_region = C.h_tile_region, &tile_start = C.h_tile_start;
+    ext_end.resize(n_regions);
+    tile_region.clear();
+    tile_start.clear();
     for (i64 i = 0; i < n_regions; i++) {
         int c = contig[i];
         if (start[i] - f_extend < 0 || end[i] + f_extend > ctx->contig_len[c])
@@ -994,6 +998,42 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         C.out_off[i + 1] = C.out_off[i] + (le[i] - ls[i]);
         C.win_off[i + 1] = C.win_off[i] + nw;
     }
+    tr("offsets");
+    C.ext_total = C.ext_off[n_regions];
+    C.out_total = C.out_off[n_regions];
+    C.n_windows = C.win_off[n_regions];
+    if (n_regions == 0) {
+        C.valid = true;
+        return TB_OK;
+    }
+    // the tables the first two kernels read go up now; the rest (output / window offsets, tiles of the last stage) is prepared on the host
+    // while those kernels run and travels on the copy stream
+    TB_TRY(tb_h2d(ctx, C.d_ext_start, C.ext_start.data(), sizeof(i64) * n_regions));
+    TB_TRY(tb_h2d(ctx, C.d_ext_end, ext_end.data(), sizeof(i64) * n_regions));
+    TB_TRY(tb_h2d(ctx, C.d_ext_off, C.ext_off.data(), sizeof(i64) * (n_regions + 1)));
+    TB_TRY(tb_reserve(ctx, C.pile, (size_t)C.ext_total * 2 * sizeof(u32)));
+    TB_TRY(tb_reserve(ctx, C.biasraw, (size_t)C.ext_total * 2 * sizeof(double)));
+    TB_TRY(tb_reserve(ctx, C.fit, (size_t)C.n_windows * 2 * TB_FIT_REC * sizeof(double)));
+    TB_TRY(tb_reserve(ctx, C.tracks, (size_t)C.out_total * 8 * sizeof(double)));
+    TB_TRY(tb_reserve(ctx, C.prepost, (size_t)2 * 3 * 5 * L * sizeof(double)));
+    TB_TRY(tb_reserve(ctx, C.d_out_off, sizeof(i64) * (n_regions + 1)));
+    TB_TRY(tb_reserve(ctx, C.d_win_off, sizeof(i64) * (n_regions + 1)));
+    TB_CUDA(ctx, cudaMemsetAsync(C.prepost.p, 0, (size_t)2 * 3 * 5 * L * sizeof(double), ctx->stream));
+    if (sink_now)
+        for (int t = 0; t < 4; t++)
+            for (int s = 0; s < 2; s++)
+                if (C.sink_ptr[t][s]) TB_TRY(tb_reserve(ctx, C.dl[t][s], (size_t)C.out_total * (C.sink_f64 ? 8 : 4)));
+
+    tr("tables uploaded, buffers");
+    tb_timer_start(ctx);
+    tb_mark(ctx, 0);
+    TB_TRY(tb_pileup_device(ctx, n_regions, C.d_ext_start.as<i64>(), C.d_ext_end.as<i64>(), C.d_ext_off.as<i64>(), C.ext_total,
+                            shift_fwd, shift_rev, C.pile.as<u32>()));
+    tb_mark(ctx, 1);
+    TB_TRY(tb_score_device(ctx, C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), n_regions, C.ext_total, 3, 0,
+                           C.biasraw.as<double>(), C.biasraw.as<double>() + C.ext_total));
+    tb_mark(ctx, 2);
+    tr("K1 + K3a enqueued");
     // K3c tile length: every tile recomputes a halo of 2 * window positions on each side, so the tile that covers most regions in
     // one piece wins (hg38 peaks: 824-bp regions -> one 832-position tile each instead of two 512-position tiles with halos)
     int tile_len = 512;
@@ -1019,6 +1059,13 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
             }
         }
     }
+    tr("tile length chosen");
+    {
+        i64 est = 0;
+        for (i64 i = 0; i < n_regions; i++) est += tb_div_up(C.ext_off[i + 1] - C.ext_off[i], tile_len);
+        tile_region.reserve((size_t)est);
+        tile_start.reserve((size_t)est);
+    }
     for (i64 i = 0; i < n_regions; i++) {
         const i64 reg_len = C.ext_off[i + 1] - C.ext_off[i];
         for (i64 t = 0; t < reg_len; t += tile_len) {
@@ -1026,42 +1073,16 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
             tile_start.push_back((int32_t)t);
         }
     }
-    C.ext_total = C.ext_off[n_regions];
-    C.out_total = C.out_off[n_regions];
-    C.n_windows = C.win_off[n_regions];
-    if (n_regions == 0) {
-        C.valid = true;
-        return TB_OK;
-    }
     tr("host tables built");
-    TB_TRY(tb_h2d(ctx, C.d_ext_start, C.ext_start.data(), sizeof(i64) * n_regions));
-    TB_TRY(tb_h2d(ctx, C.d_ext_end, ext_end.data(), sizeof(i64) * n_regions));
-    TB_TRY(tb_h2d(ctx, C.d_ext_off, C.ext_off.data(), sizeof(i64) * (n_regions + 1)));
-    TB_TRY(tb_h2d(ctx, C.d_out_off, C.out_off.data(), sizeof(i64) * (n_regions + 1)));
-    TB_TRY(tb_h2d(ctx, C.d_win_off, C.win_off.data(), sizeof(i64) * (n_regions + 1)));
-    TB_TRY(tb_h2d(ctx, ctx->reg_a, tile_region.data(), sizeof(int32_t) * tile_region.size()));
-    TB_TRY(tb_h2d(ctx, ctx->reg_b, tile_start.data(), sizeof(int32_t) * tile_start.size()));
-    TB_TRY(tb_reserve(ctx, C.pile, (size_t)C.ext_total * 2 * sizeof(u32)));
-    TB_TRY(tb_reserve(ctx, C.biasraw, (size_t)C.ext_total * 2 * sizeof(double)));
-    TB_TRY(tb_reserve(ctx, C.fit, (size_t)C.n_windows * 2 * TB_FIT_REC * sizeof(double)));
-    TB_TRY(tb_reserve(ctx, C.tracks, (size_t)C.out_total * 8 * sizeof(double)));
-    TB_TRY(tb_reserve(ctx, C.prepost, (size_t)2 * 3 * 5 * L * sizeof(double)));
-    TB_CUDA(ctx, cudaMemsetAsync(C.prepost.p, 0, (size_t)2 * 3 * 5 * L * sizeof(double), ctx->stream));
-    if (sink_now)
-        for (int t = 0; t < 4; t++)
-            for (int s = 0; s < 2; s++)
-                if (C.sink_ptr[t][s]) TB_TRY(tb_reserve(ctx, C.dl[t][s], (size_t)C.out_total * (C.sink_f64 ? 8 : 4)));
-
-    tr("tables uploaded, buffers");
-    tb_timer_start(ctx);
-    tb_mark(ctx, 0);
-    TB_TRY(tb_pileup_device(ctx, n_regions, C.d_ext_start.as<i64>(), C.d_ext_end.as<i64>(), C.d_ext_off.as<i64>(), C.ext_total,
-                            shift_fwd, shift_rev, C.pile.as<u32>()));
-    tb_mark(ctx, 1);
-    TB_TRY(tb_score_device(ctx, C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), n_regions, C.ext_total, 3, 0,
-                           C.biasraw.as<double>(), C.biasraw.as<double>() + C.ext_total));
-    tb_mark(ctx, 2);
-    tr("K1 + K3a enqueued");
+    TB_TRY(tb_reserve(ctx, ctx->reg_a, sizeof(int32_t) * tile_region.size()));
+    TB_TRY(tb_reserve(ctx, ctx->reg_b, sizeof(int32_t) * tile_start.size()));
+    TB_CUDA(ctx, cudaMemcpyAsync(C.d_out_off.p, C.out_off.data(), sizeof(i64) * (n_regions + 1), cudaMemcpyHostToDevice, ctx->copy_stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(C.d_win_off.p, C.win_off.data(), sizeof(i64) * (n_regions + 1), cudaMemcpyHostToDevice, ctx->copy_stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(ctx->reg_a.p, tile_region.data(), sizeof(int32_t) * tile_region.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(ctx->reg_b.p, tile_start.data(), sizeof(int32_t) * tile_start.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[7], ctx->copy_stream));
+    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[7], 0));
+    tr("second tables uploaded");
     tb_cor_view V{C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), C.d_out_off.as<i64>(), C.d_win_off.as<i64>(),
                   n_regions, C.ext_total, C.out_total, C.n_windows, k_flank, window, L, f_extend};
     // window fits: lm_exact_order 0 -> one-pass fits with forward-difference inner products (fit_form 1: the DWM default), 1 -> MINPACK-exact

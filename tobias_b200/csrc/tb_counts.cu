@@ -570,13 +570,15 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     const size_t n_out = is_dwm ? (size_t)4 * 25 * L * L : (size_t)4 * 5 * L;
     memset(counts_out, 0, n_out * sizeof(int64_t));
     memset(scalars_out, 0, 5 * sizeof(int64_t));
-    std::vector<i64> ls, le;
+    std::vector<i64> &ls = ctx->h64[0], &le = ctx->h64[1];
     const tb_tracer tr(ctx, "tb_bias_counts");
     TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
     if (n_regions == 0 || ctx->n_reads == 0) return TB_OK;
 
     const i64 ext = (i64)k_flank + bg_shift;
-    std::vector<i64> es(n_regions), ee(n_regions);
+    std::vector<i64> &es = ctx->h64[2], &ee = ctx->h64[3];
+    es.resize(n_regions);
+    ee.resize(n_regions);
     for (i64 i = 0; i < n_regions; i++) {
         int c = contig[i];
         i64 lo = ctx->contig_off[c], hi = lo + ctx->contig_len[c];
@@ -646,7 +648,9 @@ extern "C" int tb_bias_counts(tb_ctx *ctx, int64_t n_regions, const int32_t *con
     int tile = TB_K2_TILE;
     if (tb_opt(ctx, "k2_tile", 0) >= 64) tile = (int)(tb_opt(ctx, "k2_tile", 0) & ~63LL);             // tests: force several tiles per region
     if (tile > TB_K2_TILE) tile = TB_K2_TILE;
-    std::vector<int32_t> unit_region, unit_tile;
+    std::vector<int32_t> &unit_region = ctx->h32[0], &unit_tile = ctx->h32[1];
+    unit_region.clear();
+    unit_tile.clear();
     unit_region.reserve(n_regions);
     unit_tile.reserve(n_regions);
     for (i64 i = 0; i < n_regions; i++) {

@@ -129,7 +129,7 @@ static int tb_pileup_any(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, 
 extern "C" int tb_count_reads(tb_ctx *ctx, int64_t n_regions, const int32_t *contig, const int64_t *start, const int64_t *end,
                               int shift_fwd, int shift_rev, int64_t *count_out) {
     if (!ctx || !count_out) return TB_ERR_ARG;
-    std::vector<i64> ls, le;
+    std::vector<i64> &ls = ctx->h64[0], &le = ctx->h64[1];
     const tb_tracer tr(ctx, "tb_count_reads");
     TB_TRY(tb_linear_regions(ctx, n_regions, contig, start, end, ls, le, false));
     *count_out = 0;
