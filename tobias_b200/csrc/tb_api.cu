@@ -58,6 +58,18 @@ int tb_h2d(tb_ctx *ctx, tb_dbuf &dst, const void *src, size_t bytes) {
     return TB_OK;
 }
 
+int tb_h2d_aux(tb_ctx *ctx, tb_dbuf &dst, const void *src, size_t bytes) {
+    TB_TRY(tb_reserve(ctx, dst, bytes));
+    if (bytes) TB_CUDA(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->aux_stream));
+    return TB_OK;
+}
+
+int tb_aux_join(tb_ctx *ctx) {
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
+    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
+    return TB_OK;
+}
+
 int tb_d2h(tb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (bytes) TB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -132,6 +144,8 @@ extern "C" int tb_init(int device, tb_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
         return tb_fail(nullptr, TB_ERR_CUDA, "tb_init: stream/event creation failed");
@@ -187,6 +201,8 @@ extern "C" void tb_destroy(tb_ctx *ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_copy);
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     for (auto &e : ctx->ev_chunk)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->contig_ready)

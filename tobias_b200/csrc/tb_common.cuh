@@ -64,6 +64,8 @@ struct tb_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // device-to-host copies that overlap with later kernels (tb_correct_download_begin)
+    cudaStream_t aux_stream = nullptr;       // small table uploads that must not wait for the compute stream (a pageable copy synchronises its stream first)
+    cudaEvent_t ev_aux = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // chunks of a run handed to the copy stream
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -179,6 +181,8 @@ struct tb_tracer {
 };
 
 int tb_h2d(tb_ctx *ctx, tb_dbuf &dst, const void *src, size_t bytes);          // reserve + async copy on ctx->stream
+int tb_h2d_aux(tb_ctx *ctx, tb_dbuf &dst, const void *src, size_t bytes);      // reserve + copy on the aux stream: the host does not wait for the compute stream
+int tb_aux_join(tb_ctx *ctx);                                                  // the compute stream waits for the aux copies issued so far
 int tb_d2h(tb_ctx *ctx, void *dst, const void *src, size_t bytes);            // sync copy
 int tb_sync(tb_ctx *ctx, const char *what);
 void tb_timer_start(tb_ctx *ctx);

@@ -957,6 +957,7 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
     };
     ctx->cor.valid = false;
+    TB_TRY(tb_sync(ctx, "tb_correct_run (entry)"));              // a kernel of an earlier call may still read the tables this run replaces
     const bool sink_now = ctx->cor.sink_on;                      // a sink serves this run only, whatever its outcome
     ctx->cor.sink_on = false;
     ctx->cor.pp_dst = nullptr;
@@ -1074,14 +1075,11 @@ extern "C" int tb_correct_run(tb_ctx *ctx, int64_t n_regions, const int32_t *con
         }
     }
     tr("host tables built");
-    TB_TRY(tb_reserve(ctx, ctx->reg_a, sizeof(int32_t) * tile_region.size()));
-    TB_TRY(tb_reserve(ctx, ctx->reg_b, sizeof(int32_t) * tile_start.size()));
-    TB_CUDA(ctx, cudaMemcpyAsync(C.d_out_off.p, C.out_off.data(), sizeof(i64) * (n_regions + 1), cudaMemcpyHostToDevice, ctx->copy_stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(C.d_win_off.p, C.win_off.data(), sizeof(i64) * (n_regions + 1), cudaMemcpyHostToDevice, ctx->copy_stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(ctx->reg_a.p, tile_region.data(), sizeof(int32_t) * tile_region.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(ctx->reg_b.p, tile_start.data(), sizeof(int32_t) * tile_start.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[7], ctx->copy_stream));
-    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[7], 0));
+    TB_TRY(tb_h2d_aux(ctx, C.d_out_off, C.out_off.data(), sizeof(i64) * (n_regions + 1)));
+    TB_TRY(tb_h2d_aux(ctx, C.d_win_off, C.win_off.data(), sizeof(i64) * (n_regions + 1)));
+    TB_TRY(tb_h2d_aux(ctx, ctx->reg_a, tile_region.data(), sizeof(int32_t) * tile_region.size()));
+    TB_TRY(tb_h2d_aux(ctx, ctx->reg_b, tile_start.data(), sizeof(int32_t) * tile_start.size()));
+    TB_TRY(tb_aux_join(ctx));
     tr("second tables uploaded");
     tb_cor_view V{C.d_ext_start.as<i64>(), C.d_ext_off.as<i64>(), C.d_out_off.as<i64>(), C.d_win_off.as<i64>(),
                   n_regions, C.ext_total, C.out_total, C.n_windows, k_flank, window, L, f_extend};
